@@ -1,0 +1,119 @@
+/*
+ * wendy_b200.h -- C ABI of libwendy_b200.so, the B200-native (sm_100a) replacement for the
+ * approximate-integration hot path of jobovy/wendy.
+ *
+ * The boundary this library replaces is the reference's single FFI call
+ *     void _wendy_nbody_approx_onestep(...)          reference wendy/wendy.h:29-34,
+ *                                                    wendy/wendy.c:385-418,
+ *                                                    bound by ctypes at wendy/wendy.py:76-93
+ * which the Python generator _nbody_approx calls once per output step
+ * (wendy/wendy.py:424-433).  Two entry styles are exported:
+ *
+ *  (1) COMPAT:   _wendy_nbody_approx_onestep with the reference's exact 16-argument
+ *                signature on HOST pointers (H2D, nleap sub-steps on the GPU, D2H), so the
+ *                reference's own ctypes binding can load this library unchanged
+ *                (INTEGRATION.md shows the two-line change).
+ *  (2) RESIDENT: a handle API that keeps (x, v, m, id) in HBM across calls; this is what
+ *                wendy_b200.nbody() uses.
+ *
+ * Plain C types only; no CUDA or torch types appear in any signature (streams and device
+ * pointers cross as void* / double*).  All functions return 0 on success and a negative
+ * WENDY_E_* code on failure; wendy_cuda_last_error() gives the message.  A handle is not
+ * thread-safe; distinct handles are independent (the reference C side is stateless too,
+ * SURVEY.md section 8b).
+ */
+#ifndef WENDY_B200_H
+#define WENDY_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wendy_cuda_handle wendy_cuda_handle;
+
+#define WENDY_OK 0
+#define WENDY_E_CUDA (-1)       /* a CUDA runtime call failed */
+#define WENDY_E_ARG (-2)        /* invalid argument */
+#define WENDY_E_OVERFLOW (-3)   /* a bucket cannot hold its particles even after re-balancing
+                                   (more than ~cap/4 exactly coincident particles) */
+#define WENDY_RETRY 1           /* wendy_cuda_substep only: layout was re-balanced, storage
+                                   slots moved; re-evaluate a_ext and call again */
+
+/* sort modes (flags & 0xf) */
+#define WENDY_SORT_AUTO 0    /* bucket fast path, radix sort to (re)build the layout */
+#define WENDY_SORT_RADIX 1   /* full LSD radix sort every sub-step (A/B and fallback) */
+
+/* Mirror of the reference record, wendy/wendy.h:12-16 (int idx; 4 bytes pad; double val). */
+struct wendy_array_w_index {
+  int idx;
+  double val;
+};
+
+/* ---- (2) resident API ------------------------------------------------------------------ */
+
+/* Create device state from HOST arrays in particle-index order.
+ *   N          total particles (all segments), N < 2^31 (ids are int, wendy/wendy.h:14)
+ *   m          masses ALREADY multiplied by twopiG (wendy/wendy.py:371)
+ *   totmass    n_segments values; the reference passes numpy.sum(m) (wendy/wendy.py:383)
+ *   omega2     < 0: no harmonic term (wendy/wendy.py:363-366, wendy/wendy.c:375)
+ *   n_segments independent realisations of N/n_segments particles each, laid out
+ *              contiguously (1 for a single system)
+ *   flags      WENDY_SORT_*
+ *   cap, fill  bucket capacity (0: default 2048; 256 for tests) and target fill (0: 3/4 cap)
+ *   cuda_stream cudaStream_t to run on (NULL: the legacy default stream)                   */
+int wendy_cuda_create(wendy_cuda_handle **h, long long N, const double *x, const double *v,
+                      const double *m, const double *totmass, double omega2, int n_segments,
+                      int flags, int cap, int fill, void *cuda_stream);
+
+/* One call of the reference entry point: drift dt/2, nleap x [force, kick, drift], with the
+ * last drift dt/2 (wendy/wendy.c:398-411).  Synchronous; *time_elapsed (may be NULL) gets the
+ * wall seconds of the call (wendy/wendy.c:396,416-417).  No external force. */
+int wendy_cuda_step(wendy_cuda_handle *h, double dt_leap, int nleap, double *time_elapsed);
+
+/* External-force stepping, one sub-step at a time (the caller evaluates F on device memory):
+ *   wendy_cuda_force_positions: positions at the next force evaluation, as a DEVICE array of
+ *       *n_slots doubles (storage order; slots not holding a particle contain finite junk).
+ *       first_substep != 0 applies the leading half drift of a call (wendy/wendy.c:398).
+ *   wendy_cuda_substep: force + kick(dt_kick) + drift(dt_drift); a_ext_dev is a DEVICE array
+ *       in the same storage order (or NULL); h_next is the half drift the NEXT call will
+ *       start with (dt_leap/2 after the last sub-step of a call, else 0).
+ *       Returns WENDY_RETRY if the layout had to be re-balanced (see above). */
+int wendy_cuda_force_positions(wendy_cuda_handle *h, double dt_leap, int first_substep,
+                               double **x_dev, long long *n_slots);
+int wendy_cuda_substep(wendy_cuda_handle *h, double dt_kick, double dt_drift, double h_next,
+                       const double *a_ext_dev);
+
+/* De-sort (wendy/wendy.c:413-415) and copy to HOST arrays of N doubles (either may be NULL). */
+int wendy_cuda_read(wendy_cuda_handle *h, double *x_host, double *v_host);
+/* Same, into DEVICE arrays of N doubles (no host copy). */
+int wendy_cuda_read_dev(wendy_cuda_handle *h, double *x_dev, double *v_dev);
+
+/* Diagnostics of the synchronised state, per the formulas of wendy/wendy.py:458-475,491 with
+ * the stored (twopiG-scaled) masses: out[0] kinetic, out[1] harmonic, out[2] potential,
+ * out[3] momentum, each summed over all segments.  E_reference = (out0+out1+out2)/twopiG. */
+int wendy_cuda_energy(wendy_cuda_handle *h, double out[4]);
+
+/* Counters: out[0] sub-steps, [1] layout rebuilds, [2] failed (re-run) sub-steps,
+ * [3] max bucket count seen, [4] particles that left the 32-bucket window,
+ * [5] kernels launched, [6] bucket capacity, [7] buckets. */
+int wendy_cuda_stats(wendy_cuda_handle *h, long long *out, int n);
+
+void wendy_cuda_destroy(wendy_cuda_handle *h);
+const char *wendy_cuda_last_error(void);
+
+/* Stand-alone argsort of HOST keys by (value, index): the radix sort of this library, exposed
+ * for parity tests against the reference's argsort (wendy/wendy.c:341-357). */
+int wendy_cuda_argsort(const double *x_host, long long N, int *perm_out);
+
+/* ---- (1) compat export: the reference's own symbol and signature ----------------------- */
+void _wendy_nbody_approx_onestep(int N, struct wendy_array_w_index *xi, double *x, double *v,
+                                 double *m, double *a, double totmass, double dt, int nleap,
+                                 double *t0, double omega2,
+                                 double (*ext_force)(int N, double *x, double t, double *a),
+                                 int sort_type, int *err, double *time_elapsed,
+                                 double *cumulmass);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WENDY_B200_H */

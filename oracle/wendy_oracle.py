@@ -207,22 +207,18 @@ def exact_prefix(ms):
     integer arithmetic on the fp64 significands."""
     if len(ms) == 0:
         return numpy.zeros(0)
+    import math
     mant, expo = numpy.frexp(ms)
     emin = int(expo.min()) - 53
+    ints = numpy.ldexp(mant, 53).astype(numpy.int64).tolist()  # exact 53-bit significands
+    shifts = (expo - 53 - emin).tolist()
     out = numpy.empty(len(ms))
     acc = 0
     for i in range(len(ms)):
-        out[i] = _int_to_double(acc, emin)
-        acc += int(numpy.ldexp(mant[i], 53)) << (int(expo[i]) - 53 - emin)
+        # int -> float is correctly rounded (nearest even) in CPython; ldexp is then exact
+        out[i] = math.ldexp(float(acc), emin)
+        acc += ints[i] << shifts[i]
     return out
-
-
-def _int_to_double(n, e):
-    """float(n * 2**e) rounded to nearest even, for arbitrary-size int n."""
-    from fractions import Fraction
-    if n == 0:
-        return 0.
-    return float(Fraction(n) * (Fraction(2) ** e))
 
 
 def energy(x, v, m, twopiG=1., omega=None):

@@ -1,0 +1,75 @@
+"""CPU: the C-ABI library loads and exports every symbol include/wendy_b200.h declares
+(no compute calls -- there is no GPU here), and argument validation works without a device."""
+import ctypes
+import os
+import re
+
+import numpy
+import pytest
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope='module')
+def lib():
+    import __graft_entry__
+    if not os.path.exists(os.path.join(ROOT, 'wendy_b200', 'libwendy_b200.so')):
+        __graft_entry__.build()
+    from wendy_b200 import _lib
+    return _lib.load()
+
+
+def test_header_symbols_all_exported(lib):
+    from wendy_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'wendy_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(_?wendy_[a-z_]+)\s*\(', hdr))
+    assert declared == set(_lib.EXPORTED)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+
+
+def test_no_torch_or_cuda_types_in_signatures():
+    hdr = open(os.path.join(ROOT, 'include', 'wendy_b200.h')).read()
+    code = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    assert 'cudaStream_t' not in code and 'torch' not in code and 'at::' not in code
+
+
+def test_argument_validation_needs_no_device(lib):
+    h = ctypes.c_void_p()
+    x = numpy.zeros(4)
+    tot = numpy.ones(1)
+    rc = lib.wendy_cuda_create(ctypes.byref(h), 4, x, x, x, tot, -1., 3, 0, 0, 0, None)
+    assert rc == -2 and b'multiple' in lib.wendy_cuda_last_error()
+    rc = lib.wendy_cuda_create(ctypes.byref(h), 4, x, x, x, tot, -1., 1, 0, 100, 0, None)
+    assert rc == -2 and b'cap' in lib.wendy_cuda_last_error()
+
+
+def test_record_layout_matches_reference_struct():
+    """struct array_w_index is {int idx; double val;} = 16 bytes (reference wendy/wendy.h:12-16)."""
+    from wendy_b200 import _lib
+    assert _lib.XI_DTYPE.itemsize == 16 and _lib.XI_DTYPE.fields['val'][1] == 8
+
+
+def test_product_path_has_no_oracle_or_cpu_fallback():
+    for fn in os.listdir(os.path.join(ROOT, 'wendy_b200')):
+        if fn.endswith('.py'):
+            src = open(os.path.join(ROOT, 'wendy_b200', fn)).read()
+            assert 'import oracle' not in src and 'from oracle' not in src, fn
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from wendy_b200 import _lib
+    monkeypatch.setattr(_lib, '_lib', None)
+    monkeypatch.setattr(_lib, 'LIB_PATH', '/nonexistent/libwendy_b200.so')
+    with pytest.raises(ImportError):
+        _lib.load()
+
+
+def test_nbody_argument_errors():
+    import wendy_b200
+    with pytest.raises(ValueError) as e:  # message pinned by reference tests/test_approx.py:187-196
+        next(wendy_b200.nbody([0.], [0.], [1.], 0.1, approx=True))
+    assert 'nleap' in str(e.value)
+    with pytest.raises(NotImplementedError):
+        next(wendy_b200.nbody([0.], [0.], [1.], 0.1))

@@ -1,0 +1,300 @@
+"""GPU: parity of the CUDA path (through the C ABI, via wendy_b200.nbody / ctypes) against
+  * the golden vectors generated from the unmodified reference (tests/golden), and
+  * the CPU oracle on the same seeded inputs.
+
+Tolerances (north star): sort permutation bit-exact; x, v relative 1e-12 after one step and
+1e-9 after ten.  The relative error is taken against max(|ref|, 1e-3) so that particles that
+happen to sit near x=0 do not turn an absolute 1e-16 into a huge relative number.
+"""
+import ctypes
+
+import numpy
+import pytest
+
+from conftest import load_golden
+from oracle import wendy_oracle as wo
+
+pytestmark = pytest.mark.gpu
+
+EXT_TORCH = {
+    'kat_c': lambda x, t: -1.21 * x + 0.1 * t,
+    'sech2_1000_ext': lambda x, t: -0.7 * __import__('torch').tanh(0.5 * x) + 0.05 * t,
+}
+SORTS = ['gpu', 'gpu-radix']
+CAPS = [0, 256]  # production bucket capacity, and a tiny one that forces many buckets
+
+
+def relerr(a, b):
+    return numpy.max(numpy.abs(a - b) / numpy.maximum(1e-3, numpy.abs(b)))
+
+
+def _kw(g, name):
+    om = float(g['omega']) if 'omega' in g else numpy.nan
+    return dict(omega=None if numpy.isnan(om) else om, ext_force=EXT_TORCH.get(name),
+                t0=float(g['t0']) if 't0' in g else 0.,
+                twopiG=float(g['twopiG']) if 'twopiG' in g else 1.)
+
+
+# ---- sort --------------------------------------------------------------------------------
+@pytest.mark.parametrize('n', [1, 2, 33, 4096, 4097, 100003, 1 << 20])
+def test_radix_argsort_bit_exact(n):
+    import wendy_b200
+    rs = numpy.random.RandomState(n)
+    x = rs.normal(size=n) * 10. ** rs.randint(-3, 4, size=n)
+    if n > 40:  # ties, signed zeros, extremes
+        x[::7] = x[3]
+        x[5], x[11] = 0., -0.
+        x[13], x[17] = 1e308, -1e308
+        x[19] = 5e-324
+    perm = wendy_b200.argsort(x)
+    assert numpy.array_equal(perm, wo.argsort_key_then_index(x))
+
+
+def test_radix_argsort_matches_reference_first_sort():
+    """The permutation the reference itself produced at its last force evaluation."""
+    import wendy_b200
+    g = load_golden('sech2_1000_nleap1')
+    # one reference call with nleap=1: sorted at x0 + dt/2 v0
+    x = g['x0'] + (0.05 / 2.) * g['v0']
+    perm = wendy_b200.argsort(x)
+    if wo.reference_available():
+        r = wo.Reference(g['x0'], g['v0'], g['m'], 0.05, 1)
+        r.step()
+        assert numpy.array_equal(perm, r.xi['idx'])
+    assert numpy.array_equal(perm, wo.argsort_key_then_index(x))
+
+
+# ---- full path vs reference goldens --------------------------------------------------------
+GOLDEN_CASES = ['kat_a', 'kat_b', 'kat_c', 'sech2_1000_nleap1', 'sech2_1000_nleap7_omega',
+                'sech2_1000_twopiG', 'sech2_1000_ext', 'config1_sech2_1e4', 'slab_4096', 'ties',
+                'tracers']
+
+
+@pytest.mark.parametrize('cap', CAPS)
+@pytest.mark.parametrize('sort', SORTS)
+@pytest.mark.parametrize('name', GOLDEN_CASES)
+def test_against_reference_golden(name, sort, cap):
+    import wendy_b200
+    g = load_golden(name)
+    n = int(g['keep'][-1]) + 1 if 'keep' in g else len(g['xs'])
+    keep = list(g['keep']) if 'keep' in g else list(range(n))
+    gen = wendy_b200.nbody(g['x0'], g['v0'], g['m'], float(g['dt']), approx=True,
+                           nleap=int(g['nleap']), sort=sort, _cap=cap, **_kw(g, name))
+    j = 0
+    for i in range(n):
+        x, v = next(gen)
+        if i in keep:
+            substeps = (i + 1) * int(g['nleap'])
+            # north-star tolerances; chaotic growth is negligible over these few steps
+            tol = 1e-12 if substeps <= 1 else (1e-9 if substeps <= 100 else 1e-7)
+            assert relerr(x, g['xs'][j]) < tol, (name, i, relerr(x, g['xs'][j]))
+            assert relerr(v, g['vs'][j]) < tol, (name, i, relerr(v, g['vs'][j]))
+            j += 1
+    gen.close()
+
+
+@pytest.mark.parametrize('sort', SORTS)
+def test_first_steps_are_at_rounding_level(sort):
+    """Well inside the tolerances: after one sub-step the GPU result differs from the reference
+    only by the (better) rounding of the cumulative mass."""
+    import wendy_b200
+    g = load_golden('sech2_1000_nleap1')
+    gen = wendy_b200.nbody(g['x0'], g['v0'], g['m'], 0.05, approx=True, nleap=1, sort=sort)
+    x, v = next(gen)
+    assert relerr(x, g['xs'][0]) < 1e-14 and relerr(v, g['vs'][0]) < 1e-14
+    gen.close()
+
+
+# ---- vs the oracle restatement with the SAME (exact) scan: bit-for-bit ----------------------
+@pytest.mark.parametrize('cap', CAPS)
+@pytest.mark.parametrize('sort', SORTS)
+def test_bit_exact_vs_oracle_with_exact_scan(sort, cap):
+    import wendy_b200
+    x, v, m = wo.sech2_ic(3000, seed=7, mass_jitter=0.1)
+    gen = wendy_b200.nbody(x, v, m, 0.02, approx=True, nleap=3, omega=0.9, sort=sort, _cap=cap)
+    xo, vo = x, v
+    for _ in range(3):
+        xg, vg = next(gen)
+        xo, vo, _, _ = wo.numpy_onestep(xo, vo, m, numpy.sum(m), 0.02 / 3, 3, 0.9 ** 2, exact_scan=True)
+        assert numpy.array_equal(xg, xo) and numpy.array_equal(vg, vo)
+    gen.close()
+
+
+def test_bucket_and_radix_paths_agree_bitwise():
+    import wendy_b200
+    x, v, m = wo.sech2_ic(50000, seed=3, mass_jitter=0.2)
+    outs = []
+    for sort, cap in (('gpu', 0), ('gpu-radix', 0), ('gpu', 256)):
+        gen = wendy_b200.nbody(x, v, m, 0.05, approx=True, nleap=10, sort=sort, _cap=cap)
+        for _ in range(3):
+            xg, vg = next(gen)
+        outs.append((xg.copy(), vg.copy()))
+        gen.close()
+    for xo, vo in outs[1:]:
+        assert numpy.array_equal(outs[0][0], xo) and numpy.array_equal(outs[0][1], vo)
+
+
+@pytest.mark.parametrize('n', [100000, 1000000])
+def test_large_n_vs_oracle(n):
+    """Config-2-like sizes.  Bit-for-bit against the oracle restatement with the exact scan;
+    against the reference's serial fp64 running sum (itself ~8e-12 off the exact sum at
+    N=1e6 for equal masses) the ABSOLUTE difference after ten sub-steps stays
+    below dt * 2 * bias, i.e. the GPU result is the more accurate of the two."""
+    import wendy_b200
+    x, v, m = wo.slab_ic(n, seed=3)
+    gen = wendy_b200.nbody(x, v, m, 0.005, approx=True, nleap=1)
+    xo, vo = x, v
+    xs, vs = x, v
+    for i in range(10):
+        xg, vg = next(gen)
+        xo, vo, _, _ = wo.numpy_onestep(xo, vo, m, numpy.sum(m), 0.005, 1, exact_scan=True)
+        xs, vs, _, _ = wo.numpy_onestep(xs, vs, m, numpy.sum(m), 0.005, 1)
+        assert numpy.array_equal(xg, xo) and numpy.array_equal(vg, vo), i
+    bias = numpy.max(numpy.abs(numpy.cumsum(m) - numpy.arange(1, n + 1) / n))
+    assert numpy.max(numpy.abs(vg - vs)) <= 10 * 0.005 * 2 * bias + 1e-15
+    assert relerr(xg, xs) < 1e-9
+    gen.close()
+
+
+# ---- generator semantics ----------------------------------------------------------------------
+def test_generator_yields_same_buffers_and_full_output():
+    import wendy_b200
+    x, v, m = wo.sech2_ic(500, seed=1)
+    gen = wendy_b200.nbody(x, v, m, 0.05, approx=True, nleap=2, full_output=True)
+    a = next(gen)
+    b = next(gen)
+    assert a[0] is b[0] and a[1] is b[1]  # reference wendy/wendy.py:434-437
+    assert 0. < b[2] < 1.  # reference tests/test_approx.py:198-211
+    gen.close()
+
+
+def test_nleap_call_pattern_matters_like_the_reference():
+    """10 calls with nleap=1 differ from 1 call with nleap=10 at the 1e-14 level (SURVEY.md
+    section 3.1); both must match the oracle run with the same pattern bit-for-bit."""
+    import wendy_b200
+    x, v, m = wo.sech2_ic(400, seed=9, mass_jitter=0.1)
+    g1 = wendy_b200.nbody(x, v, m, 0.01, approx=True, nleap=1)
+    for _ in range(10):
+        x1, v1 = next(g1)
+    g10 = wendy_b200.nbody(x, v, m, 0.1, approx=True, nleap=10)
+    x10, v10 = next(g10)
+    xo, vo = x, v
+    for _ in range(10):
+        xo, vo, _, _ = wo.numpy_onestep(xo, vo, m, numpy.sum(m), 0.01, 1, exact_scan=True)
+    assert numpy.array_equal(x1, xo) and numpy.array_equal(v1, vo)
+    xo, vo, _, _ = wo.numpy_onestep(x, v, m, numpy.sum(m), 0.01, 10, exact_scan=True)
+    assert numpy.array_equal(x10, xo) and numpy.array_equal(v10, vo)
+
+
+# ---- energy / momentum -------------------------------------------------------------------------
+@pytest.mark.parametrize('omega', [None, 1.1])
+@pytest.mark.parametrize('n', [3, 1000, 100000])
+def test_energy_matches_reference_formula(n, omega):
+    import wendy_b200
+    x, v, m = wo.sech2_ic(n, seed=4, mass_jitter=0.1)
+    for tg in (1., 2.5):
+        E = wo.energy(x, v, m, twopiG=tg, omega=omega)
+        Eg = wendy_b200.energy(x, v, m, twopiG=tg, omega=omega)
+        assert abs(Eg - E) <= 1e-12 * abs(E), (Eg, E)
+
+
+def test_energy_and_momentum_conservation():
+    """Reference tests/test_approx.py:34-51 (energy 1e-6 over 100 outputs), :151-163 (momentum)."""
+    import wendy_b200
+    N = 101
+    rs = numpy.random.RandomState(2)
+    x = numpy.arctanh(2. * rs.uniform(size=N) - 1) * 2.
+    v = rs.normal(size=N)
+    v -= numpy.mean(v)
+    m = numpy.ones(N) / N * (1. + 0.1 * (2. * rs.uniform(size=N) - 1))
+    v -= numpy.sum(m * v) / numpy.sum(m)
+    E = wendy_b200.energy(x, v, m)
+    gen = wendy_b200.nbody(x, v, m, 0.05, approx=True, nleap=1000)
+    for _ in range(20):
+        tx, tv = next(gen)
+        assert abs(wo.energy(tx, tv, m) - E) / abs(E) < 1e-6
+        assert abs(wendy_b200.momentum(tv, m)) < 1e-10
+    gen.close()
+
+
+# ---- ensembles of independent realisations -------------------------------------------------------
+@pytest.mark.parametrize('sort', SORTS)
+def test_segments_equal_independent_runs(sort):
+    import wendy_b200
+    S, L = 5, 700
+    xs, vs, ms = zip(*[wo.sech2_ic(L, seed=20 + s, mass_jitter=0.1) for s in range(S)])
+    gen = wendy_b200.nbody(numpy.concatenate(xs), numpy.concatenate(vs), numpy.concatenate(ms),
+                           0.05, approx=True, nleap=4, omega=0.5, sort=sort, n_segments=S, _cap=256)
+    for _ in range(3):
+        X, V = next(gen)
+    gen.close()
+    for s in range(S):
+        g1 = wendy_b200.nbody(xs[s], vs[s], ms[s], 0.05, approx=True, nleap=4, omega=0.5, sort=sort)
+        for _ in range(3):
+            x1, v1 = next(g1)
+        g1.close()
+        assert numpy.array_equal(X[s * L:(s + 1) * L], x1) and numpy.array_equal(V[s * L:(s + 1) * L], v1)
+
+
+# ---- compat export: the reference's own C entry point --------------------------------------------
+def _compat_call(lib, xi, x, v, m, tot, dt, nleap, t0, omega2, cb):
+    from wendy_b200 import _lib
+    a = numpy.zeros(len(x))
+    cum = numpy.zeros(len(x))
+    err = ctypes.c_int(0)
+    te = ctypes.c_double(0.)
+    t0c = ctypes.c_double(t0)
+    lib._wendy_nbody_approx_onestep(len(x), xi.ctypes.data, x, v, m, a, tot, dt, nleap,
+                                    ctypes.byref(t0c), omega2,
+                                    ctypes.cast(cb, ctypes.c_void_p) if cb is not None else None,
+                                    1, ctypes.byref(err), ctypes.byref(te), cum)
+    assert err.value == 0, lib.wendy_cuda_last_error()
+    return t0c.value, te.value
+
+
+@pytest.mark.parametrize('with_ext', [False, True])
+def test_compat_export_same_signature_as_reference(with_ext):
+    """Drive OUR library exactly as reference wendy/wendy.py:425-433 drives wendy_c."""
+    from wendy_b200 import _lib
+    lib = _lib.load()
+    x0, v0, m = wo.sech2_ic(777, seed=12, mass_jitter=0.1)
+    ext = (lambda x, t: -0.5 * numpy.tanh(x) + 0.01 * t) if with_ext else None
+    ref = wo.COracle(x0, v0, m, 0.05, 4, t0=0.3, omega=1.1, ext_force=ext)
+    x, v = x0.copy(), v0.copy()
+    xi = numpy.zeros(len(x), dtype=_lib.XI_DTYPE)
+    xi['idx'] = numpy.arange(len(x), dtype='i4')
+    xi['val'] = x
+    cb = wo.wrap_ext_force(ext)
+    t0 = 0.3
+    for _ in range(3):
+        xr, vr = ref.step()
+        t0, te = _compat_call(lib, xi, x, v, m, numpy.sum(m), 0.05 / 4, 4, t0, 1.1 ** 2, cb)
+        assert relerr(x, xr) < 1e-12 and relerr(v, vr) < 1e-12
+        assert numpy.array_equal(xi['idx'], ref.sidx)            # sort order of the last force
+        assert numpy.array_equal(xi['val'], x[xi['idx']])        # wendy/wendy.c:413-415 invariant
+        assert te > 0.
+    assert t0 == (ref.t0.value if with_ext else 0.3)
+
+
+# ---- robustness ------------------------------------------------------------------------------------
+def test_overflow_recovery_by_rebalancing():
+    """A violently collapsing cold slab changes the density by orders of magnitude: buckets
+    overflow, the step is re-run after re-balancing, and the result still matches the oracle."""
+    import wendy_b200
+    x, v, m = wo.slab_ic(20000, seed=5)
+    st = wendy_b200.ApproxState(x, v, m, cap=256, fill=250)
+    xo, vo = x, v
+    for _ in range(6):
+        st.step(0.05, 5)
+        xo, vo, _, _ = wo.numpy_onestep(xo, vo, m, numpy.sum(m), 0.05, 5, exact_scan=True)
+    xg, vg = st.read()
+    s = st.stats()
+    st.close()
+    assert s['failed_substeps'] > 0 and s['rebuilds'] > 1, s
+    assert numpy.array_equal(xg, xo) and numpy.array_equal(vg, vo)
+
+
+def test_rejects_non_finite_input():
+    import wendy_b200
+    with pytest.raises(RuntimeError):
+        wendy_b200.ApproxState(numpy.array([0., numpy.nan]), numpy.zeros(2), numpy.ones(2))

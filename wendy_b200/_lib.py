@@ -1,0 +1,84 @@
+"""ctypes binding of libwendy_b200.so (C ABI: include/wendy_b200.h).
+
+Plays the role of the reference's loader + argtypes block, wendy/wendy.py:13-101.  There is
+deliberately NO fallback: if the CUDA library is missing or cannot be loaded, importing the
+product path raises (the reference also hard-fails without wendy_c, wendy/wendy.py:40).
+"""
+import ctypes
+import os
+
+import numpy
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libwendy_b200.so')
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_ll_p = ctypes.POINTER(ctypes.c_longlong)
+
+WENDY_RETRY = 1
+SORT_FLAGS = {'gpu': 0, 'gpu-bucket': 0, 'gpu-radix': 1}
+#: numpy mirror of struct wendy_array_w_index / reference wendy/wendy.h:12-16
+XI_DTYPE = numpy.dtype([('idx', 'i4'), ('val', 'f8')], align=True)
+
+_lib = None
+
+
+def _nd(dtype):
+    return numpy.ctypeslib.ndpointer(dtype=dtype, flags=('C_CONTIGUOUS',))
+
+
+def load():
+    """Load the shared library (once) and declare every prototype of include/wendy_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("wendy_b200: CUDA library %s not found -- build it with "
+                          "`python -c 'import __graft_entry__ as g; g.build()'` or "
+                          "`make -C wendy_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp = ctypes.c_void_p
+    lib.wendy_cuda_last_error.restype = ctypes.c_char_p
+    lib.wendy_cuda_last_error.argtypes = []
+    lib.wendy_cuda_create.restype = ctypes.c_int
+    lib.wendy_cuda_create.argtypes = [ctypes.POINTER(vp), ctypes.c_longlong, _nd('f8'), _nd('f8'),
+                                      _nd('f8'), _nd('f8'), ctypes.c_double, ctypes.c_int,
+                                      ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
+    lib.wendy_cuda_step.restype = ctypes.c_int
+    lib.wendy_cuda_step.argtypes = [vp, ctypes.c_double, ctypes.c_int, c_double_p]
+    lib.wendy_cuda_force_positions.restype = ctypes.c_int
+    lib.wendy_cuda_force_positions.argtypes = [vp, ctypes.c_double, ctypes.c_int,
+                                               ctypes.POINTER(vp), c_ll_p]
+    lib.wendy_cuda_substep.restype = ctypes.c_int
+    lib.wendy_cuda_substep.argtypes = [vp, ctypes.c_double, ctypes.c_double, ctypes.c_double, vp]
+    lib.wendy_cuda_read.restype = ctypes.c_int
+    lib.wendy_cuda_read.argtypes = [vp, vp, vp]
+    lib.wendy_cuda_read_dev.restype = ctypes.c_int
+    lib.wendy_cuda_read_dev.argtypes = [vp, vp, vp]
+    lib.wendy_cuda_energy.restype = ctypes.c_int
+    lib.wendy_cuda_energy.argtypes = [vp, _nd('f8')]
+    lib.wendy_cuda_stats.restype = ctypes.c_int
+    lib.wendy_cuda_stats.argtypes = [vp, _nd('i8'), ctypes.c_int]
+    lib.wendy_cuda_destroy.restype = None
+    lib.wendy_cuda_destroy.argtypes = [vp]
+    lib.wendy_cuda_argsort.restype = ctypes.c_int
+    lib.wendy_cuda_argsort.argtypes = [_nd('f8'), ctypes.c_longlong, _nd('i4')]
+    lib._wendy_nbody_approx_onestep.restype = None
+    lib._wendy_nbody_approx_onestep.argtypes = [
+        ctypes.c_int, vp, _nd('f8'), _nd('f8'), _nd('f8'), _nd('f8'), ctypes.c_double,
+        ctypes.c_double, ctypes.c_int, c_double_p, ctypes.c_double, vp, ctypes.c_int,
+        ctypes.POINTER(ctypes.c_int), c_double_p, _nd('f8')]
+    _lib = lib
+    return lib
+
+
+#: every symbol include/wendy_b200.h declares (checked by tests/test_abi.py)
+EXPORTED = ['wendy_cuda_create', 'wendy_cuda_step', 'wendy_cuda_force_positions',
+            'wendy_cuda_substep', 'wendy_cuda_read', 'wendy_cuda_read_dev', 'wendy_cuda_energy',
+            'wendy_cuda_stats', 'wendy_cuda_destroy', 'wendy_cuda_last_error',
+            'wendy_cuda_argsort', '_wendy_nbody_approx_onestep']
+
+
+def check(rc):
+    if rc < 0:
+        raise RuntimeError('wendy_b200: %s (code %d)' % (load().wendy_cuda_last_error().decode(), rc))
+    return rc

@@ -1,0 +1,635 @@
+// api.cu -- handle, step orchestration and the C ABI of libwendy_b200.so
+// (include/wendy_b200.h).  Host logic only; the kernels are in tile.cu and radix.cu.
+//
+// Step structure follows the reference driver wendy/wendy.c:385-418 exactly:
+//   drift dt/2 ; (nleap-1) x [force, kick dt, drift dt] ; force, kick dt, drift dt/2 ; de-sort
+// with the leading half drift folded into the first sub-step's key computation (h_pre) and
+// the de-sort deferred to wendy_cuda_read().
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "../../include/wendy_b200.h"
+#include "common.cuh"
+#include "internal.h"
+
+using namespace wendy;
+
+static thread_local std::string g_err;
+static int set_err(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = (call);                                                                      \
+    if (e__ != cudaSuccess)                                                                        \
+      return set_err(WENDY_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));           \
+  } while (0)
+
+namespace wendy {
+void launch_iota(cudaStream_t st, int *id, long long n);
+void launch_gather_by_id(cudaStream_t st, const double *a_by_id, const int *id, const unsigned *cnt,
+                         int cap, int nb, double *a_slots);
+}
+
+struct wendy_cuda_handle {
+  long long N = 0, seg_len = 0;
+  int nseg = 1, mode = 0, fxE = 0;
+  double omega2 = -1.;
+  int cap = 0, fill = 0, nb = 0, nbps = 0;
+  size_t slots = 0;
+  cudaStream_t st = nullptr;
+  int sm_count = 148;
+  // state
+  double *x[2] = {nullptr, nullptr}, *v[2] = {nullptr, nullptr}, *m[2] = {nullptr, nullptr};
+  int *id[2] = {nullptr, nullptr};
+  int cur = 0;
+  unsigned *cnt[3] = {nullptr, nullptr, nullptr};
+  int ccur = 0;
+  bool dense = true;       // state is the dense upload in buffer `cur` (no layout yet)
+  bool has_split = false;  // splitters are valid for key = x + bucket_h * v
+  double bucket_h = 0.;
+  double *split = nullptr, *tot = nullptr;
+  // cross-CTA machinery
+  unsigned *ticket = nullptr;  // [3]
+  int tcur = 0;
+  unsigned *status = nullptr;
+  Desc *desc = nullptr;
+  unsigned *flags = nullptr;    // [0] fail_seq, [1] max count, [2] outside-window count
+  unsigned *h_flags = nullptr;  // pinned mirror
+  unsigned seq = 1;
+  // scratch
+  unsigned long long *offs = nullptr;
+  RadixScratch rs;
+  double *xo = nullptr, *vo = nullptr;
+  double *epart = nullptr, *eout = nullptr, *h_eout = nullptr;
+  int *rank = nullptr;
+  // counters
+  long long n_sub = 0, n_rebuild = 0, n_fail = 0, max_cnt = 0, n_outside = 0, n_launch = 0;
+};
+typedef wendy_cuda_handle H;
+
+static int choose_fx_exponent(double sum_abs) {
+  if (!(sum_abs > 0.) || !std::isfinite(sum_abs)) return 0;
+  int e;
+  frexp(sum_abs, &e);  // sum_abs < 2^e
+  return 124 - e;
+}
+
+static int alloc_radix(H *h, size_t n) {
+  if (h->rs.n_alloc >= n) return 0;
+  for (int i = 0; i < 2; i++) {
+    if (h->rs.key[i]) cudaFree(h->rs.key[i]);
+    if (h->rs.val[i]) cudaFree(h->rs.val[i]);
+  }
+  if (h->rs.table) cudaFree(h->rs.table);
+  if (h->rs.sums) cudaFree(h->rs.sums);
+  for (int i = 0; i < 2; i++) {
+    CK(cudaMalloc(&h->rs.key[i], n * sizeof(uint64_t)));
+    CK(cudaMalloc(&h->rs.val[i], n * sizeof(uint32_t)));
+  }
+  CK(cudaMalloc(&h->rs.table, radix_table_entries(n) * sizeof(uint32_t)));
+  CK(cudaMalloc(&h->rs.sums, (radix_sums_entries(n) + 1) * sizeof(uint32_t)));
+  h->rs.n_alloc = n;
+  return 0;
+}
+
+static int seg_bits(const H *h) {
+  int bits = 0;
+  while ((1ll << bits) < h->nseg) bits++;
+  return h->nseg > 1 ? bits : 0;
+}
+
+// Sync and fetch {fail_seq, max count, outside count}.
+static int fetch_flags(H *h) {
+  CK(cudaMemcpyAsync(h->h_flags, h->flags, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  CK(cudaGetLastError());
+  if (h->h_flags[1] > h->max_cnt) h->max_cnt = h->h_flags[1];
+  return 0;
+}
+
+static int reset_flags(H *h) {
+  unsigned init[3] = {0xffffffffu, 0u, 0u};
+  h->n_outside += h->h_flags[2];
+  CK(cudaMemcpyAsync(h->flags, init, sizeof(init), cudaMemcpyHostToDevice, h->st));
+  CK(cudaMemsetAsync(h->ticket, 0, 3 * sizeof(unsigned), h->st));
+  CK(cudaStreamSynchronize(h->st));  // `init` is a stack buffer
+  h->tcur = 0;
+  return 0;
+}
+
+// keys (x + hkey*v) of the current state -> radix scratch buffer 0, compact segment-major order
+static int make_keys(H *h, double hkey, int val_mode) {
+  if (alloc_radix(h, (size_t)h->N)) return WENDY_E_CUDA;
+  if (h->dense) {
+    launch_make_keys(h->st, h->x[h->cur], h->v[h->cur], hkey, nullptr, nullptr, 0, 0, h->N,
+                     h->rs.key[0], h->rs.val[0], val_mode, h->seg_len, 0);
+  } else {
+    launch_scan_counts(h->st, h->cnt[h->ccur], h->nb, h->offs);
+    launch_make_keys(h->st, h->x[h->cur], h->v[h->cur], hkey, h->cnt[h->ccur], h->offs, h->cap,
+                     h->nb, 0, h->rs.key[0], h->rs.val[0], val_mode, h->seg_len, h->nbps);
+    h->n_launch += 1;
+  }
+  h->n_launch += 1;
+  return 0;
+}
+
+// (Re)build the bucket layout for key = x + hkey*v: exact quantile splitters from a radix
+// sort of the keys, then one streaming scatter of the state into the other buffer.
+static int rebucket(H *h, double hkey) {
+  if (make_keys(h, hkey, VAL_SEGMENT)) return WENDY_E_CUDA;
+  int res = radix_sort_pairs(h->st, h->rs, (size_t)h->N, seg_bits(h), 1u);
+  h->n_launch += 5 * (8 + (seg_bits(h) + 7) / 8);
+  launch_pick_splitters(h->st, h->rs.key[res], h->seg_len, h->fill, h->nbps, h->nb, h->split);
+  int c1 = (h->ccur + 1) % 3, c2 = (h->ccur + 2) % 3;
+  CK(cudaMemsetAsync(h->cnt[c1], 0, (size_t)h->nb * sizeof(unsigned), h->st));
+  CK(cudaMemsetAsync(h->cnt[c2], 0, (size_t)h->nb * sizeof(unsigned), h->st));
+  ScatterParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.xin = h->x[h->cur]; sp.vin = h->v[h->cur]; sp.min = h->m[h->cur]; sp.idin = h->id[h->cur];
+  sp.cnt_in = h->dense ? nullptr : h->cnt[h->ccur];
+  sp.n_dense = h->N; sp.cap_in = h->cap; sp.nb_in = h->nb; sp.nbps_in = h->nbps;
+  sp.h = hkey;
+  int o = h->cur ^ 1;
+  sp.xout = h->x[o]; sp.vout = h->v[o]; sp.mout = h->m[o]; sp.idout = h->id[o];
+  sp.cnt_out = h->cnt[c1]; sp.split = h->split; sp.cap_out = h->cap; sp.nbps_out = h->nbps;
+  sp.seg_len = h->seg_len; sp.fail_seq = h->flags; sp.seq = h->seq++;
+  launch_scatter(h->st, sp, h->sm_count);
+  h->n_launch += 2;
+  if (fetch_flags(h)) return WENDY_E_CUDA;
+  if (h->h_flags[0] != 0xffffffffu) {
+    reset_flags(h);
+    return set_err(WENDY_E_OVERFLOW, "bucket overflow while building the layout: too many exactly "
+                                     "coincident particles for one bucket");
+  }
+  h->cur = o; h->ccur = c1; h->dense = false; h->has_split = true; h->bucket_h = hkey;
+  h->n_rebuild++;
+  CK(cudaMemsetAsync(h->flags + 1, 0, sizeof(unsigned), h->st));  // max-count is per layout
+  h->h_flags[1] = 0;
+  return 0;
+}
+
+static void fill_tile_params(H *h, TileParams &p) {
+  memset(&p, 0, sizeof(p));
+  int c = h->cur, o = c ^ 1;
+  p.xin = h->x[c]; p.vin = h->v[c]; p.min = h->m[c]; p.idin = h->id[c];
+  p.xout = h->x[o]; p.vout = h->v[o]; p.mout = h->m[o]; p.idout = h->id[o];
+  p.cnt_in = h->cnt[h->ccur];
+  p.cnt_out = h->cnt[(h->ccur + 1) % 3];
+  p.cnt_zero = h->cnt[(h->ccur + 2) % 3];
+  p.split = h->split;
+  p.nb = h->nb; p.nbps = h->nbps; p.seg_len = h->seg_len;
+  p.omega2 = h->omega2; p.tot = h->tot; p.fxE = h->fxE;
+  p.status = h->status; p.desc = h->desc;
+  p.ticket = h->ticket + h->tcur; p.ticket_zero = h->ticket + (h->tcur + 2) % 3;
+  p.fail_seq = h->flags; p.stats = h->flags + 1;
+  p.seq = h->seq; p.epoch = h->seq;
+}
+
+static void advance_after_tile(H *h) {
+  h->seq++;
+  h->tcur = (h->tcur + 1) % 3;
+  h->n_launch++;
+}
+
+// One sub-step on the bucket fast path (asynchronous).
+static void launch_bucket_substep(H *h, double h_pre, double dt_kick, double dt_drift, double h_next,
+                                  const double *aext, int *rank_out) {
+  TileParams p;
+  fill_tile_params(h, p);
+  p.h_pre = h_pre; p.dt_kick = dt_kick; p.dt_drift = dt_drift; p.h_next = h_next;
+  p.aext = aext; p.rank_out = rank_out;
+  launch_tile(h->st, h->cap, LOAD_BUCKET, EMIT_SPLITTER, 1, p);
+  advance_after_tile(h);
+  h->cur ^= 1; h->ccur = (h->ccur + 1) % 3; h->bucket_h = h_next;
+  h->n_sub++;
+}
+
+// One sub-step on the radix path: full sort of (key, slot), then the same tile kernel fed
+// through the sorted permutation; the output is a compact sorted layout.
+static int launch_radix_substep(H *h, double h_pre, double dt_kick, double dt_drift, const double *aext,
+                                int *rank_out) {
+  if (make_keys(h, h_pre, VAL_SLOT)) return WENDY_E_CUDA;
+  unsigned seg_div = h->dense ? (unsigned)h->seg_len : (unsigned)((long long)h->nbps * h->cap);
+  int res = radix_sort_pairs(h->st, h->rs, (size_t)h->N, seg_bits(h), seg_div);
+  h->n_launch += 5 * (8 + (seg_bits(h) + 7) / 8);
+  TileParams p;
+  fill_tile_params(h, p);
+  p.perm = h->rs.val[res];
+  p.h_pre = h_pre; p.dt_kick = dt_kick; p.dt_drift = dt_drift; p.h_next = 0.;
+  p.aext = aext; p.rank_out = rank_out;
+  launch_tile(h->st, h->cap, LOAD_GATHER, EMIT_RANK, 1, p);
+  advance_after_tile(h);
+  h->cur ^= 1; h->ccur = (h->ccur + 1) % 3; h->dense = false; h->has_split = false;
+  h->n_sub++;
+  return 0;
+}
+
+extern "C" {
+
+const char *wendy_cuda_last_error(void) { return g_err.c_str(); }
+
+void wendy_cuda_destroy(wendy_cuda_handle *h) {
+  if (!h) return;
+  for (int i = 0; i < 2; i++) {
+    cudaFree(h->x[i]); cudaFree(h->v[i]); cudaFree(h->m[i]); cudaFree(h->id[i]);
+    cudaFree(h->rs.key[i]); cudaFree(h->rs.val[i]);
+  }
+  for (int i = 0; i < 3; i++) cudaFree(h->cnt[i]);
+  cudaFree(h->rs.table); cudaFree(h->rs.sums);
+  cudaFree(h->split); cudaFree(h->tot); cudaFree(h->ticket); cudaFree(h->status); cudaFree(h->desc);
+  cudaFree(h->flags); cudaFree(h->offs); cudaFree(h->xo); cudaFree(h->vo); cudaFree(h->epart);
+  cudaFree(h->eout); cudaFree(h->rank);
+  if (h->h_flags) cudaFreeHost(h->h_flags);
+  if (h->h_eout) cudaFreeHost(h->h_eout);
+  delete h;
+}
+
+int wendy_cuda_create(wendy_cuda_handle **out, long long N, const double *x, const double *v,
+                      const double *m, const double *totmass, double omega2, int n_segments, int flags,
+                      int cap, int fill, void *cuda_stream) {
+  if (!out || !x || !v || !m || !totmass) return set_err(WENDY_E_ARG, "null argument");
+  if (N <= 0 || N >= (1ll << 31)) return set_err(WENDY_E_ARG, "N must be in [1, 2^31)");
+  if (n_segments < 1 || N % n_segments) return set_err(WENDY_E_ARG, "N must be a multiple of n_segments");
+  if (cap == 0) cap = 2048;
+  if (!tile_cap_supported(cap)) return set_err(WENDY_E_ARG, "cap must be 2048 or 256");
+  if (fill == 0) fill = cap * 3 / 4;
+  if (fill < 1 || fill > cap) return set_err(WENDY_E_ARG, "fill must be in [1, cap]");
+  H *h = new H;
+  *out = nullptr;
+  h->N = N; h->nseg = n_segments; h->seg_len = N / n_segments; h->omega2 = omega2;
+  h->mode = flags & 0xf; h->cap = cap; h->fill = fill;
+  h->nbps = (int)((h->seg_len + fill - 1) / fill);
+  long long nb = (long long)h->nbps * n_segments;
+  if (nb * cap >= (1ll << 32)) { delete h; return set_err(WENDY_E_ARG, "too many storage slots for u32 indices"); }
+  h->nb = (int)nb; h->slots = (size_t)nb * cap;
+  h->st = (cudaStream_t)cuda_stream;
+  int dev = 0;
+#define CKD(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { std::string s__ = std::string(#call) + ": " + cudaGetErrorString(e__); wendy_cuda_destroy(h); return set_err(WENDY_E_CUDA, s__); } } while (0)
+  CKD(cudaGetDevice(&dev));
+  CKD(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev));
+  double sum_abs = 0.;
+  for (long long i = 0; i < N; i++) {
+    if (!std::isfinite(x[i]) || !std::isfinite(v[i]) || !std::isfinite(m[i])) {
+      wendy_cuda_destroy(h);
+      return set_err(WENDY_E_ARG, "x, v, m must be finite (NaN keys are undefined in the reference sort too)");
+    }
+  }
+  for (int s = 0; s < n_segments; s++) {
+    double a = 0.;
+    for (long long i = s * h->seg_len; i < (s + 1) * h->seg_len; i++) a += fabs(m[i]);
+    if (a > sum_abs) sum_abs = a;
+  }
+  h->fxE = choose_fx_exponent(sum_abs);
+  for (int i = 0; i < 2; i++) {
+    CKD(cudaMalloc(&h->x[i], h->slots * sizeof(double)));
+    CKD(cudaMalloc(&h->v[i], h->slots * sizeof(double)));
+    CKD(cudaMalloc(&h->m[i], h->slots * sizeof(double)));
+    CKD(cudaMalloc(&h->id[i], h->slots * sizeof(int)));
+    CKD(cudaMemsetAsync(h->x[i], 0, h->slots * sizeof(double), h->st));
+    CKD(cudaMemsetAsync(h->v[i], 0, h->slots * sizeof(double), h->st));
+  }
+  for (int i = 0; i < 3; i++) {
+    CKD(cudaMalloc(&h->cnt[i], (size_t)h->nb * sizeof(unsigned)));
+    CKD(cudaMemsetAsync(h->cnt[i], 0, (size_t)h->nb * sizeof(unsigned), h->st));
+  }
+  CKD(cudaMalloc(&h->split, (size_t)h->nb * sizeof(double)));
+  CKD(cudaMalloc(&h->tot, (size_t)n_segments * sizeof(double)));
+  CKD(cudaMalloc(&h->ticket, 3 * sizeof(unsigned)));
+  CKD(cudaMalloc(&h->status, (size_t)h->nb * sizeof(unsigned)));
+  CKD(cudaMalloc(&h->desc, (size_t)h->nb * sizeof(Desc)));
+  CKD(cudaMalloc(&h->flags, 4 * sizeof(unsigned)));
+  CKD(cudaMalloc(&h->offs, (size_t)h->nb * sizeof(unsigned long long)));
+  CKD(cudaMalloc(&h->epart, (size_t)h->nb * 4 * sizeof(double)));
+  CKD(cudaMalloc(&h->eout, 4 * sizeof(double)));
+  CKD(cudaMallocHost(&h->h_flags, 4 * sizeof(unsigned)));
+  CKD(cudaMallocHost(&h->h_eout, 4 * sizeof(double)));
+  memset(h->h_flags, 0, 4 * sizeof(unsigned));
+  CKD(cudaMemsetAsync(h->status, 0, (size_t)h->nb * sizeof(unsigned), h->st));
+  CKD(cudaMemcpyAsync(h->x[0], x, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  CKD(cudaMemcpyAsync(h->v[0], v, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  CKD(cudaMemcpyAsync(h->m[0], m, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  CKD(cudaMemcpyAsync(h->tot, totmass, (size_t)n_segments * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  launch_iota(h->st, h->id[0], N);
+  if (reset_flags(h)) { std::string s = g_err; wendy_cuda_destroy(h); return set_err(WENDY_E_CUDA, s); }
+  CKD(cudaGetLastError());
+#undef CKD
+  h->dense = true; h->cur = 0; h->ccur = 0;
+  *out = h;
+  return 0;
+}
+
+// Run sub-steps [k0, nleap) of one reference call; on a bucket overflow re-balance and resume.
+static int run_substeps(H *h, double dt, int nleap) {
+  int k = 0;
+  int attempts_at_k = 0;
+  while (k < nleap) {
+    // enqueue everything that is left, remembering where each sub-step started
+    std::vector<unsigned> seq_of;
+    std::vector<int> cur_of, ccur_of;
+    const int k_start = k;
+    if (h->mode != WENDY_SORT_RADIX) {
+      double need_h = (k == 0) ? dt / 2. : 0.;
+      if (h->dense || !h->has_split || h->bucket_h != need_h) {
+        int rc = rebucket(h, need_h);
+        if (rc) return rc;
+      }
+    }
+    for (int kk = k_start; kk < nleap; kk++) {
+      seq_of.push_back(h->seq);
+      cur_of.push_back(h->cur);
+      ccur_of.push_back(h->ccur);
+      double h_pre = (kk == 0) ? dt / 2. : 0.;
+      double dt_drift = (kk == nleap - 1) ? dt / 2. : dt;
+      if (h->mode == WENDY_SORT_RADIX) {
+        int rc = launch_radix_substep(h, h_pre, dt, dt_drift, nullptr, nullptr);
+        if (rc) return rc;
+      } else {
+        launch_bucket_substep(h, h_pre, dt, dt_drift, (kk == nleap - 1) ? dt / 2. : 0., nullptr, nullptr);
+      }
+    }
+    if (fetch_flags(h)) return WENDY_E_CUDA;
+    unsigned f = h->h_flags[0];
+    if (f == 0xffffffffu) break;
+    // launch f overflowed: the state it read is intact; everything after it did nothing
+    int kf = -1;
+    for (size_t i = 0; i < seq_of.size(); i++)
+      if (seq_of[i] == f) kf = k_start + (int)i;
+    if (kf < 0) return set_err(WENDY_E_CUDA, "internal: unknown failing launch");
+    h->n_fail++;
+    h->n_sub -= (nleap - kf);
+    h->cur = cur_of[kf - k_start];
+    h->ccur = ccur_of[kf - k_start];
+    h->has_split = false;  // force a rebuild for the key of sub-step kf
+    if (reset_flags(h)) return WENDY_E_CUDA;
+    attempts_at_k = (kf == k) ? attempts_at_k + 1 : 1;
+    if (attempts_at_k > 2)
+      return set_err(WENDY_E_OVERFLOW, "bucket overflow persists after re-balancing (time step far too "
+                                       "large for the bucket capacity, or massive coincidences)");
+    k = kf;
+  }
+  // cheap insurance: re-balance between calls when some bucket is nearly full
+  if (h->mode != WENDY_SORT_RADIX && h->h_flags[1] > (unsigned)(h->cap - (h->cap - h->fill) / 4)) {
+    int rc = rebucket(h, h->bucket_h);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int wendy_cuda_step(wendy_cuda_handle *h, double dt_leap, int nleap, double *time_elapsed) {
+  if (!h) return set_err(WENDY_E_ARG, "null handle");
+  if (nleap < 1) return set_err(WENDY_E_ARG, "nleap must be >= 1");
+  auto t0 = std::chrono::steady_clock::now();
+  int rc = run_substeps(h, dt_leap, nleap);
+  if (time_elapsed)
+    *time_elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return rc;
+}
+
+int wendy_cuda_force_positions(wendy_cuda_handle *h, double dt_leap, int first_substep, double **x_dev,
+                               long long *n_slots) {
+  if (!h || !x_dev || !n_slots) return set_err(WENDY_E_ARG, "null argument");
+  double need_h = first_substep ? dt_leap / 2. : 0.;
+  if (h->mode == WENDY_SORT_RADIX) {
+    // radix mode keeps no splitters; give it a (compact or bucketed) layout to expose
+    if (h->dense) { int rc = rebucket(h, need_h); if (rc) return rc; }
+  } else if (h->dense || !h->has_split || h->bucket_h != need_h) {
+    int rc = rebucket(h, need_h);
+    if (rc) return rc;
+  }
+  if (need_h != 0.) {  // materialise the half drift: keys become the stored positions
+    launch_apply_drift(h->st, h->x[h->cur], h->v[h->cur], need_h, h->cnt[h->ccur], h->cap, h->nb);
+    h->n_launch++;
+    h->bucket_h = 0.;
+  }
+  *x_dev = h->x[h->cur];
+  *n_slots = (long long)h->slots;
+  return 0;
+}
+
+int wendy_cuda_substep(wendy_cuda_handle *h, double dt_kick, double dt_drift, double h_next,
+                       const double *a_ext_dev) {
+  if (!h) return set_err(WENDY_E_ARG, "null handle");
+  if (h->dense) return set_err(WENDY_E_ARG, "call wendy_cuda_force_positions first");
+  int cur0 = h->cur, ccur0 = h->ccur;
+  if (h->mode == WENDY_SORT_RADIX) {
+    int rc = launch_radix_substep(h, 0., dt_kick, dt_drift, a_ext_dev, nullptr);
+    if (rc) return rc;
+    // radix mode applies no trailing re-bucket key: the next call's half drift goes via h_pre
+    if (fetch_flags(h)) return WENDY_E_CUDA;
+    return 0;
+  }
+  if (!h->has_split || h->bucket_h != 0.) return set_err(WENDY_E_ARG, "layout is not keyed on the stored positions");
+  launch_bucket_substep(h, 0., dt_kick, dt_drift, h_next, a_ext_dev, nullptr);
+  if (fetch_flags(h)) return WENDY_E_CUDA;
+  if (h->h_flags[0] != 0xffffffffu) {
+    h->n_fail++; h->n_sub--;
+    h->cur = cur0; h->ccur = ccur0;
+    if (reset_flags(h)) return WENDY_E_CUDA;
+    int rc = rebucket(h, 0.);
+    if (rc) return rc;
+    return WENDY_RETRY;
+  }
+  if (h->h_flags[1] > (unsigned)(h->cap - (h->cap - h->fill) / 4)) {
+    // nearly full bucket: re-balance now; the caller's next force_positions sees the new slots
+    int rc = rebucket(h, h_next);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int wendy_cuda_read_dev(wendy_cuda_handle *h, double *x_dev, double *v_dev) {
+  if (!h) return set_err(WENDY_E_ARG, "null handle");
+  if (!h->xo) {
+    CK(cudaMalloc(&h->xo, (size_t)h->N * sizeof(double)));
+    CK(cudaMalloc(&h->vo, (size_t)h->N * sizeof(double)));
+  }
+  double *xd = x_dev ? x_dev : h->xo, *vd = v_dev ? v_dev : h->vo;
+  if (h->dense) {
+    CK(cudaMemcpyAsync(xd, h->x[h->cur], (size_t)h->N * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    CK(cudaMemcpyAsync(vd, h->v[h->cur], (size_t)h->N * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+  } else {
+    launch_unsort(h->st, h->x[h->cur], h->v[h->cur], h->id[h->cur], h->cnt[h->ccur], h->cap, h->nb, xd, vd);
+    h->n_launch++;
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int wendy_cuda_read(wendy_cuda_handle *h, double *x_host, double *v_host) {
+  int rc = wendy_cuda_read_dev(h, nullptr, nullptr);
+  if (rc) return rc;
+  if (x_host) CK(cudaMemcpyAsync(x_host, h->xo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  if (v_host) CK(cudaMemcpyAsync(v_host, h->vo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+int wendy_cuda_energy(wendy_cuda_handle *h, double out[4]) {
+  if (!h || !out) return set_err(WENDY_E_ARG, "null argument");
+  // sort the synchronised positions (the layout may be keyed on x + h*v) and run the tile
+  // kernel in diagnostic mode through the sorted permutation
+  if (make_keys(h, 0., VAL_SLOT)) return WENDY_E_CUDA;
+  unsigned seg_div = h->dense ? (unsigned)h->seg_len : (unsigned)((long long)h->nbps * h->cap);
+  int res = radix_sort_pairs(h->st, h->rs, (size_t)h->N, seg_bits(h), seg_div);
+  h->n_launch += 5 * (8 + (seg_bits(h) + 7) / 8);
+  TileParams p;
+  fill_tile_params(h, p);
+  p.perm = h->rs.val[res];
+  p.cnt_out = nullptr; p.cnt_zero = nullptr; p.ticket_zero = h->ticket + (h->tcur + 2) % 3;
+  p.energy_part = h->epart;
+  launch_tile(h->st, h->cap, LOAD_GATHER, EMIT_NONE, 0, p);
+  advance_after_tile(h);
+  launch_reduce_energy(h->st, h->epart, h->nb, h->eout);
+  h->n_launch++;
+  CK(cudaMemcpyAsync(h->h_eout, h->eout, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  CK(cudaGetLastError());
+  for (int i = 0; i < 4; i++) out[i] = h->h_eout[i];
+  return 0;
+}
+
+int wendy_cuda_stats(wendy_cuda_handle *h, long long *out, int n) {
+  if (!h || !out) return set_err(WENDY_E_ARG, "null argument");
+  long long s[8] = {h->n_sub, h->n_rebuild, h->n_fail, h->max_cnt, h->n_outside + h->h_flags[2], h->n_launch,
+                    (long long)h->cap, (long long)h->nb};
+  for (int i = 0; i < n && i < 8; i++) out[i] = s[i];
+  return 0;
+}
+
+int wendy_cuda_argsort(const double *x_host, long long N, int *perm_out) {
+  if (!x_host || !perm_out || N < 0 || N >= (1ll << 31)) return set_err(WENDY_E_ARG, "bad argument");
+  if (N == 0) return 0;
+  H tmp;  // only the radix scratch is used
+  double *dx = nullptr;
+  if (alloc_radix(&tmp, (size_t)N)) return WENDY_E_CUDA;
+  int rc = 0;
+  do {
+    if (cudaMalloc(&dx, (size_t)N * sizeof(double)) != cudaSuccess) { rc = set_err(WENDY_E_CUDA, "cudaMalloc"); break; }
+    cudaMemcpy(dx, x_host, (size_t)N * sizeof(double), cudaMemcpyHostToDevice);
+    launch_make_keys(nullptr, dx, nullptr, 0., nullptr, nullptr, 0, 0, N, tmp.rs.key[0], tmp.rs.val[0],
+                     VAL_INDEX, N, 0);
+    int res = radix_sort_pairs(nullptr, tmp.rs, (size_t)N, 0, 1u);
+    cudaError_t e = cudaMemcpy(perm_out, tmp.rs.val[res], (size_t)N * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) rc = set_err(WENDY_E_CUDA, cudaGetErrorString(e));
+  } while (0);
+  cudaFree(dx);
+  for (int i = 0; i < 2; i++) { cudaFree(tmp.rs.key[i]); cudaFree(tmp.rs.val[i]); }
+  cudaFree(tmp.rs.table); cudaFree(tmp.rs.sums);
+  return rc;
+}
+
+// ---- compat export -------------------------------------------------------------------------------------
+// The reference's own entry point (wendy/wendy.c:385-393) on host pointers.  State does not
+// survive the call (the reference C side is stateless as well); use the resident API for
+// throughput.  `a` and `cumulmass` are scratch in the reference (never read by its Python
+// side, wendy/wendy.py:424-437) and are left untouched; `err` is never written on this path
+// in the reference either.  On a CUDA failure *err is set to -1 and the message is available
+// from wendy_cuda_last_error().
+void _wendy_nbody_approx_onestep(int N, struct wendy_array_w_index *xi, double *x, double *v, double *m,
+                                 double *a, double totmass, double dt, int nleap, double *t0,
+                                 double omega2, double (*ext_force)(int, double *, double, double *),
+                                 int sort_type, int *err, double *time_elapsed, double *cumulmass) {
+  (void)a; (void)cumulmass; (void)sort_type;
+  auto tb = std::chrono::steady_clock::now();
+  if (N <= 0) return;
+  std::vector<double> xs((size_t)N);
+  for (int i = 0; i < N; i++) xs[xi[i].idx] = xi[i].val;  // xi is the authoritative position state
+  const char *env = getenv("WENDY_B200_SORT");
+  int flags = (env && !strcmp(env, "radix")) ? WENDY_SORT_RADIX : WENDY_SORT_AUTO;
+  const char *ecap = getenv("WENDY_B200_CAP");
+  H *h = nullptr;
+  int rc = wendy_cuda_create(&h, N, xs.data(), v, m, &totmass, omega2, 1, flags, ecap ? atoi(ecap) : 0, 0, nullptr);
+  std::vector<int> rank((size_t)N);
+  if (!rc) rc = (cudaMalloc(&h->rank, (size_t)N * sizeof(int)) == cudaSuccess) ? 0 : WENDY_E_CUDA;
+  if (!rc && !ext_force) {
+    // sub-step by sub-step so that the sort order of the LAST force evaluation is recorded
+    for (int k = 0; k < nleap && !rc; k++) {
+      double *xd; long long ns;
+      rc = wendy_cuda_force_positions(h, dt, k == 0, &xd, &ns);
+      if (rc) break;
+      int tries = 0;
+      do {
+        int cur0 = h->cur, ccur0 = h->ccur;
+        if (h->mode == WENDY_SORT_RADIX) {
+          rc = launch_radix_substep(h, 0., dt, k == nleap - 1 ? dt / 2. : dt, nullptr, h->rank);
+          if (!rc) rc = fetch_flags(h);
+        } else {
+          launch_bucket_substep(h, 0., dt, k == nleap - 1 ? dt / 2. : dt, 0., nullptr, h->rank);
+          rc = fetch_flags(h);
+          if (!rc && h->h_flags[0] != 0xffffffffu) {
+            h->cur = cur0; h->ccur = ccur0;
+            rc = reset_flags(h);
+            if (!rc) rc = rebucket(h, 0.);
+            if (!rc) rc = WENDY_RETRY;
+          }
+        }
+      } while (rc == WENDY_RETRY && ++tries < 3);
+    }
+  } else if (!rc) {
+    std::vector<double> xh((size_t)N), ah((size_t)N);
+    double *a_id = nullptr, *a_slot = nullptr;
+    if (cudaMalloc(&a_id, (size_t)N * sizeof(double)) != cudaSuccess) rc = WENDY_E_CUDA;
+    for (int k = 0; k < nleap && !rc; k++) {
+      int tries = 0;
+      do {
+        double *xd; long long ns;
+        rc = wendy_cuda_force_positions(h, dt, k == 0, &xd, &ns);
+        if (rc) break;
+        if (!a_slot && cudaMalloc(&a_slot, (size_t)ns * sizeof(double)) != cudaSuccess) { rc = WENDY_E_CUDA; break; }
+        rc = wendy_cuda_read(h, xh.data(), nullptr);  // positions at force time, particle order
+        if (rc) break;
+        if (N > 10) {  // EXTERNAL_SWITCH, wendy/wendy.h:9-11 and wendy/wendy.c:362-370
+          ext_force(N, xh.data(), *t0, ah.data());
+        } else {
+          for (int i = 0; i < N; i++) ah[i] = ext_force(1, &xh[i], *t0, nullptr);
+        }
+        cudaMemcpyAsync(a_id, ah.data(), (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->st);
+        launch_gather_by_id(h->st, a_id, h->id[h->cur], h->cnt[h->ccur], h->cap, h->nb, a_slot);
+        if (h->mode == WENDY_SORT_RADIX) {
+          rc = launch_radix_substep(h, 0., dt, k == nleap - 1 ? dt / 2. : dt, a_slot, h->rank);
+          if (!rc) rc = fetch_flags(h);
+        } else {
+          int cur0 = h->cur, ccur0 = h->ccur;
+          launch_bucket_substep(h, 0., dt, k == nleap - 1 ? dt / 2. : dt, 0., a_slot, h->rank);
+          rc = fetch_flags(h);
+          if (!rc && h->h_flags[0] != 0xffffffffu) {
+            h->cur = cur0; h->ccur = ccur0;
+            rc = reset_flags(h);
+            if (!rc) rc = rebucket(h, 0.);
+            if (!rc) rc = WENDY_RETRY;
+          }
+        }
+      } while (rc == WENDY_RETRY && ++tries < 3);
+      if (!rc) *t0 += dt;  // wendy/wendy.c:403-404,409-410
+    }
+    cudaFree(a_id); cudaFree(a_slot);
+  }
+  if (!rc) rc = wendy_cuda_read(h, x, v);
+  if (!rc) {
+    cudaError_t e = cudaMemcpy(rank.data(), h->rank, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = set_err(WENDY_E_CUDA, cudaGetErrorString(e));
+  }
+  if (!rc) {
+    // xi: order of the last force evaluation, values after the final half drift
+    for (int i = 0; i < N; i++) {
+      xi[rank[i]].idx = i;
+      xi[rank[i]].val = x[i];
+    }
+  } else if (err) {
+    *err = -1;
+  }
+  wendy_cuda_destroy(h);
+  if (time_elapsed)
+    *time_elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - tb).count();
+}
+
+}  // extern "C"

@@ -1,0 +1,137 @@
+// common.cuh -- device helpers shared by the wendy_b200 kernels (sm_100a only).
+//
+//  * order-preserving fp64 -> u64 key transform (radix sort keys)
+//  * exact 128-bit fixed-point mass arithmetic: the cumulative mass of the force
+//    (reference wendy/wendy.c:359-360 is a serial fp64 running sum) is computed here as
+//    the CORRECTLY ROUNDED exact prefix sum, which makes it independent of tiling,
+//    of the order in which tiles finish, of the sort path taken and of the GPU count.
+//  * warp / block scan primitives on 128-bit integers
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef __int128 i128;
+typedef unsigned __int128 u128;
+
+#define WENDY_FULL_MASK 0xffffffffu
+
+// ---------------------------------------------------------------------------------
+// key transform: ascending u64 order == ascending fp64 order; -0.0 is canonicalised to
+// +0.0 first because the reference comparator (wendy/wendy.c:21) treats them as equal.
+__host__ __device__ __forceinline__ uint64_t key_from_double(double x) {
+  x = x + 0.0;  // -0.0 + 0.0 == +0.0 under round-to-nearest
+#ifdef __CUDA_ARCH__
+  uint64_t b = (uint64_t)__double_as_longlong(x);
+#else
+  uint64_t b;
+  memcpy(&b, &x, 8);
+#endif
+  uint64_t mask = (uint64_t)(-(int64_t)(b >> 63)) | 0x8000000000000000ull;
+  return b ^ mask;
+}
+
+__host__ __device__ __forceinline__ double double_from_key(uint64_t k) {
+  uint64_t mask = ((k >> 63) - 1ull) | 0x8000000000000000ull;
+  uint64_t b = k ^ mask;
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double((long long)b);
+#else
+  double x;
+  memcpy(&x, &b, 8);
+  return x;
+#endif
+}
+
+// ---------------------------------------------------------------------------------
+// fixed point: value * 2^E as a signed 128-bit integer.  E is chosen on the host so that
+// sum(|m|) * 2^E < 2^124 (api.cu: choose_fx_exponent); bits below 2^-E (masses more than
+// ~2^-70 times smaller than the total) are truncated towards zero.
+__device__ __forceinline__ i128 fx_from_double(double m, int E) {
+  long long bits = __double_as_longlong(m);
+  int ex = (int)((bits >> 52) & 0x7ff);
+  unsigned long long mant = (unsigned long long)bits & 0xFFFFFFFFFFFFFull;
+  if (ex == 0) {
+    if (mant == 0) return (i128)0;
+    ex = 1;  // subnormal
+  } else {
+    mant |= (1ull << 52);
+  }
+  int sh = ex - 1075 + E;  // value = mant * 2^(ex-1075)
+  u128 mag;
+  if (sh >= 0) {
+    if (sh > 73) sh = 73;  // unreachable for a valid E; keeps garbage input in range
+    mag = (u128)mant << sh;
+  } else {
+    mag = (sh > -64) ? (u128)(mant >> (-sh)) : (u128)0;
+  }
+  return bits < 0 ? -(i128)mag : (i128)mag;
+}
+
+// round-to-nearest-even conversion back to fp64 (one rounding in total).
+__device__ __forceinline__ double fx_to_double(i128 val, int E) {
+  if (val == 0) return 0.0;
+  bool neg = val < 0;
+  u128 mag = neg ? (u128)(-val) : (u128)val;
+  unsigned long long hi = (unsigned long long)(mag >> 64), lo = (unsigned long long)mag;
+  unsigned long long top;
+  int e2 = 0;
+  if (hi) {
+    int s = 64 - __clzll((long long)hi);  // 1..64 bits to drop so that the rest fits 64 bits
+    top = (unsigned long long)(mag >> s);
+    u128 dropped = mag & ((((u128)1) << s) - 1);
+    if (dropped) top |= 1ull;  // sticky bit (bit 0 is far below the fp64 rounding position)
+    e2 = s;
+  } else {
+    top = lo;
+  }
+  double d = scalbn(__ull2double_rn(top), e2 - E);
+  return neg ? -d : d;
+}
+
+// ---------------------------------------------------------------------------------
+// shuffles / scans on 128-bit integers
+__device__ __forceinline__ i128 shfl_up_i128(i128 v, int delta) {
+  unsigned long long lo = (unsigned long long)v, hi = (unsigned long long)((u128)v >> 64);
+  lo = __shfl_up_sync(WENDY_FULL_MASK, lo, delta);
+  hi = __shfl_up_sync(WENDY_FULL_MASK, hi, delta);
+  return (i128)(((u128)hi << 64) | lo);
+}
+__device__ __forceinline__ i128 shfl_i128(i128 v, int src) {
+  unsigned long long lo = (unsigned long long)v, hi = (unsigned long long)((u128)v >> 64);
+  lo = __shfl_sync(WENDY_FULL_MASK, lo, src);
+  hi = __shfl_sync(WENDY_FULL_MASK, hi, src);
+  return (i128)(((u128)hi << 64) | lo);
+}
+__device__ __forceinline__ i128 shfl_xor_i128(i128 v, int m) {
+  unsigned long long lo = (unsigned long long)v, hi = (unsigned long long)((u128)v >> 64);
+  lo = __shfl_xor_sync(WENDY_FULL_MASK, lo, m);
+  hi = __shfl_xor_sync(WENDY_FULL_MASK, hi, m);
+  return (i128)(((u128)hi << 64) | lo);
+}
+__device__ __forceinline__ i128 warp_inclusive_scan_i128(i128 v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    i128 u = shfl_up_i128(v, o);
+    if (lane >= o) v += u;
+  }
+  return v;
+}
+__device__ __forceinline__ unsigned warp_inclusive_scan_u32(unsigned v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned u = __shfl_up_sync(WENDY_FULL_MASK, v, o);
+    if (lane >= o) v += u;
+  }
+  return v;
+}
+
+// bank-conflict-free index for "8 consecutive items per thread" access to shared arrays
+__device__ __forceinline__ int pad8(int r) { return r + (r >> 3); }
+
+// global loads that must not hit a stale L1 line (cross-CTA communication)
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) {
+  return *(const volatile unsigned *)p;
+}
+__device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long *p) {
+  return __ldcg(p);
+}

@@ -1,0 +1,103 @@
+// internal.h -- host-side declarations shared by the translation units of
+// libwendy_b200.so.  Not part of the public C ABI (that is include/wendy_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace wendy {
+
+// ---- radix.cu -----------------------------------------------------------------------
+struct RadixScratch {
+  uint64_t *key[2] = {nullptr, nullptr};
+  uint32_t *val[2] = {nullptr, nullptr};
+  uint32_t *table = nullptr;  // [256][ntiles] digit-major histogram / offsets
+  uint32_t *sums = nullptr;
+  size_t n_alloc = 0;
+};
+size_t radix_table_entries(size_t n);
+size_t radix_sums_entries(size_t n);
+int radix_sort_pairs(cudaStream_t st, RadixScratch &s, size_t n, int seg_bits, unsigned seg_div);
+
+// ---- tile.cu ------------------------------------------------------------------------
+// One look-back descriptor per bucket: exact 128-bit mass sums and element counts.
+struct __align__(16) Desc {
+  unsigned long long agg_lo, agg_hi;  // this bucket's mass (fixed point)
+  unsigned long long inc_lo, inc_hi;  // inclusive prefix over the segment
+  long long agg_cnt, inc_cnt;
+};
+
+enum { LOAD_BUCKET = 0, LOAD_GATHER = 1 };
+enum { EMIT_SPLITTER = 0, EMIT_RANK = 1, EMIT_NONE = 2 };
+
+struct TileParams {
+  // input state (bucketed storage: bucket b owns slots [b*cap, b*cap + cnt_in[b]))
+  const double *xin, *vin, *min;
+  const int *idin;
+  const double *aext;       // external acceleration per storage slot, or null
+  const unsigned *cnt_in;   // LOAD_BUCKET
+  const uint32_t *perm;     // LOAD_GATHER: storage slots in (segment, key) order
+  // output state
+  double *xout, *vout, *mout;
+  int *idout;
+  unsigned *cnt_out;        // EMIT_SPLITTER: must be zero on entry; EMIT_RANK: written
+  unsigned *cnt_zero;       // array this launch clears for the launch after next (or null)
+  const double *split;      // EMIT_SPLITTER: split[b] = lower edge of bucket b
+  // geometry
+  int nb, nbps;             // buckets in total / per segment
+  long long seg_len;        // particles per segment
+  // physics (reference wendy/wendy.c:375-383 and :324-333)
+  double h_pre, dt_kick, dt_drift, h_next, omega2;
+  const double *tot;        // total mass per segment
+  int fxE;                  // fixed-point exponent
+  // cross-CTA machinery
+  unsigned *status;         // per bucket: (epoch << 2) | state
+  Desc *desc;
+  unsigned epoch;
+  unsigned *ticket, *ticket_zero;
+  unsigned *fail_seq;       // smallest launch sequence number that failed
+  unsigned seq;
+  unsigned *stats;          // [0] max bucket count seen, [1] emitted outside the window
+  // optional outputs
+  int *rank_out;            // rank_out[id] = rank within the segment at this force evaluation
+  double *energy_part;      // [nb][4]: kinetic, harmonic, potential, momentum partial sums
+};
+
+void launch_tile(cudaStream_t st, int cap, int load, int emit, int physics, const TileParams &p);
+size_t tile_smem_bytes(int cap);
+bool tile_cap_supported(int cap);
+
+struct ScatterParams {
+  const double *xin, *vin, *min;
+  const int *idin;
+  const unsigned *cnt_in;   // null: source is dense (n_dense elements, segment = i / seg_len)
+  long long n_dense;
+  int cap_in, nb_in, nbps_in;
+  double h;                 // bucket key = x + h*v
+  double *xout, *vout, *mout;
+  int *idout;
+  unsigned *cnt_out;
+  const double *split;
+  int cap_out, nbps_out;
+  long long seg_len;
+  unsigned *fail_seq;
+  unsigned seq;
+};
+void launch_scatter(cudaStream_t st, const ScatterParams &p, int sm_count);
+
+// keys for the radix sort, written in compact (segment-major) order
+void launch_make_keys(cudaStream_t st, const double *x, const double *v, double h,
+                      const unsigned *cnt_in, const unsigned long long *offs, int cap, int nb,
+                      long long n_dense, uint64_t *keys, uint32_t *vals, int val_mode,
+                      long long seg_len, int nbps);
+enum { VAL_SLOT = 0, VAL_SEGMENT = 1, VAL_INDEX = 2 };
+void launch_scan_counts(cudaStream_t st, const unsigned *cnt, int nb, unsigned long long *offs);
+void launch_pick_splitters(cudaStream_t st, const uint64_t *sorted_keys, long long seg_len,
+                           int fill, int nbps, int nb, double *split);
+void launch_apply_drift(cudaStream_t st, double *x, const double *v, double h,
+                        const unsigned *cnt, int cap, int nb);
+void launch_unsort(cudaStream_t st, const double *x, const double *v, const int *id,
+                   const unsigned *cnt, int cap, int nb, double *xo, double *vo);
+void launch_reduce_energy(cudaStream_t st, const double *part, int nb, double *out4);
+
+}  // namespace wendy

@@ -1,0 +1,785 @@
+// tile.cu -- the per-step hot kernel of the approximate integrator, plus the small
+// kernels around it.
+//
+// State lives in HBM as a *bucketed* structure-of-arrays (x, v, m, id): the x axis is cut
+// by splitters into buckets of at most CAP particles, bucket b owning storage slots
+// [b*CAP, b*CAP + cnt[b]).  Buckets are ordered, particles inside a bucket are not.
+//
+// One launch of tile_kernel<LOAD_BUCKET, EMIT_SPLITTER> is one leapfrog sub-step of the
+// reference (wendy/wendy.c:400-411), one CTA per bucket:
+//   load bucket -> [pre-drift] -> exact in-shared-memory sort by (x, id)      (wendy.c:341-357)
+//   -> exact 128-bit fixed-point exclusive mass scan, bucket prefix by decoupled
+//      look-back over the preceding buckets                                  (wendy.c:359-360)
+//   -> force  a = a_ext + (((M - 2 cum) - m) - omega^2 x)                     (wendy.c:375-383)
+//   -> kick v += dt a ; drift x += dt v                                       (wendy.c:324-333)
+//   -> re-bucket: every particle is appended to the bucket its NEW position falls in.
+// Because the per-step displacement is small, almost every particle stays in its bucket
+// or moves to a neighbour, so the "sort" costs one read and one write of the state.
+//
+// The same kernel body serves the radix path (LOAD_GATHER: particles arrive through the
+// radix-sorted permutation) and the energy diagnostic (EMIT_NONE).
+//
+// All arithmetic that reaches x or v is written with explicit __dmul_rn/__dadd_rn in the
+// reference's association order (no FMA contraction): SURVEY.md H2.
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace wendy {
+
+constexpr int DW = 32;  // destination buckets tracked with shared-memory counters
+
+template <int CAP, int THREADS>
+struct TileSmem {
+  static constexpr int E = CAP / THREADS;
+  static constexpr int PADN = CAP + CAP / E + 4;
+  double sx[CAP];  // sort keys (positions at force time), indexed by load slot
+  int sid[CAP];    // particle ids, indexed by load slot
+  union {
+    struct {
+      unsigned cnt[PADN];        // interpolation sub-bucket counters -> start offsets
+      unsigned short slot[CAP];  // load slots grouped by sub-bucket
+    } srt;
+    double mcum[PADN];  // masses in sorted order -> cumulative mass below
+  } u;
+  double ssplit[DW + 2];
+  unsigned dcnt[DW], dbase[DW];
+  unsigned long long wlo[32], whi[32];
+  unsigned uw[32];
+  double dred[4][32];
+  unsigned long long pre_lo, pre_hi;
+  long long pre_cnt;
+  unsigned utotal;
+  int bucket;
+};
+
+__device__ __forceinline__ i128 make_i128(unsigned long long lo, unsigned long long hi) {
+  return (i128)(((u128)hi << 64) | (u128)lo);
+}
+
+// Decoupled look-back over the buckets of one segment; called by all lanes of warp 0.
+// Returns the exclusive prefix (mass, count) of bucket b and publishes its inclusive one.
+// Sums are exact integers, so the result does not depend on which predecessors happened
+// to have published an inclusive prefix already.
+__device__ __forceinline__ void lookback(const TileParams &p, int b, int seg_lo, i128 agg,
+                                         long long n, int lane, i128 &P, long long &Pc) {
+  P = 0;
+  Pc = 0;
+  Desc *me = p.desc + b;
+  if (b > seg_lo) {
+    if (lane == 0) {
+      me->agg_lo = (unsigned long long)agg;
+      me->agg_hi = (unsigned long long)((u128)agg >> 64);
+      me->agg_cnt = n;
+      __threadfence();
+      *(volatile unsigned *)(p.status + b) = (p.epoch << 2) | 1u;
+    }
+    int j = b - 1;
+    while (true) {
+      int idx = j - lane;
+      unsigned st = 2u;  // lanes before the segment start act as "inclusive prefix 0"
+      i128 val = 0;
+      long long c = 0;
+      if (idx >= seg_lo) {
+        do {
+          st = ld_volatile_u32(p.status + idx);
+        } while ((st >> 2) != p.epoch);
+        st &= 3u;
+        __threadfence();
+        const Desc *d = p.desc + idx;
+        if (st == 2u) {
+          val = make_i128(__ldcg(&d->inc_lo), __ldcg(&d->inc_hi));
+          c = __ldcg(&d->inc_cnt);
+        } else {
+          val = make_i128(__ldcg(&d->agg_lo), __ldcg(&d->agg_hi));
+          c = __ldcg(&d->agg_cnt);
+        }
+      }
+      unsigned incl = __ballot_sync(WENDY_FULL_MASK, st == 2u);
+      int first = incl ? (__ffs(incl) - 1) : 32;
+      if (lane > first) {
+        val = 0;
+        c = 0;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        val += shfl_xor_i128(val, o);
+        c += __shfl_xor_sync(WENDY_FULL_MASK, c, o);
+      }
+      P += val;
+      Pc += c;
+      if (incl) break;
+      j -= 32;
+    }
+  }
+  if (lane == 0) {
+    i128 inc = P + agg;
+    me->inc_lo = (unsigned long long)inc;
+    me->inc_hi = (unsigned long long)((u128)inc >> 64);
+    me->inc_cnt = Pc + n;
+    __threadfence();
+    *(volatile unsigned *)(p.status + b) = (p.epoch << 2) | 2u;
+  }
+}
+
+template <int CAP, int THREADS, int LOAD, int EMIT, int PHYS>
+__global__ void __launch_bounds__(THREADS, (CAP * 48 <= 100 * 1024) ? 2 : 1)
+tile_kernel(const TileParams p) {
+  using SM = TileSmem<CAP, THREADS>;
+  constexpr int E = SM::E;
+  constexpr int NW = THREADS / 32;
+  constexpr int BK = CAP;  // interpolation sub-buckets
+  static_assert(E * THREADS == CAP && (E & (E - 1)) == 0, "CAP must be a power-of-two multiple of THREADS");
+  static_assert(CAP <= 65536, "load slots are stored as u16");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SM &S = *reinterpret_cast<SM *>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+
+  // A launch queued behind a failed one must not touch anything (host re-runs from there).
+  if (ld_volatile_u32(p.fail_seq) < p.seq) return;
+
+  if (tid == 0) S.bucket = (int)atomicAdd(p.ticket, 1u);
+  for (int i = tid; i < SM::PADN; i += THREADS) S.u.srt.cnt[i] = 0;
+  if (tid < DW) S.dcnt[tid] = 0;
+  __syncthreads();
+  const int b = S.bucket;
+  const int seg = b / p.nbps, kb = b - seg * p.nbps;
+  const int seg_lo = seg * p.nbps, seg_hi = seg_lo + p.nbps;
+  if (b == 0 && tid == 0 && p.ticket_zero) *p.ticket_zero = 0;
+
+  unsigned n;
+  if (LOAD == LOAD_BUCKET) {
+    n = p.cnt_in[b];
+    if (n > (unsigned)CAP) {  // cannot happen for a state produced by a successful launch
+      n = CAP;
+      if (tid == 0) atomicMin(p.fail_seq, p.seq);
+    }
+  } else {
+    long long rem = p.seg_len - (long long)kb * CAP;
+    n = rem <= 0 ? 0u : (rem > CAP ? (unsigned)CAP : (unsigned)rem);
+  }
+  if (tid == 0) {
+    if (p.cnt_zero) p.cnt_zero[b] = 0;
+    atomicMax(p.stats, n);
+    if (EMIT == EMIT_RANK) p.cnt_out[b] = n;
+  }
+
+  // destination window of splitters (EMIT_SPLITTER)
+  int wlo = 0, wn = 0;
+  if (EMIT == EMIT_SPLITTER) {
+    wlo = b - DW / 2;
+    if (wlo > seg_hi - DW) wlo = seg_hi - DW;
+    if (wlo < seg_lo) wlo = seg_lo;
+    wn = min(DW, seg_hi - wlo);
+    if (tid <= wn)
+      S.ssplit[tid] = (wlo + tid < seg_hi) ? p.split[wlo + tid] : CUDART_INF;
+  }
+
+  // ---- 1. load positions and ids; key = position at force time -----------------------
+  unsigned g[E];
+  double xk[E];
+  int id[E];
+  double lmin = CUDART_INF, lmax = -CUDART_INF;
+#pragma unroll
+  for (int k = 0; k < E; k++) {
+    unsigned i = tid + k * THREADS;
+    xk[k] = 0.0;
+    id[k] = 0;
+    g[k] = 0;
+    if (i < n) {
+      if (LOAD == LOAD_BUCKET)
+        g[k] = (unsigned)b * (unsigned)CAP + i;
+      else
+        g[k] = p.perm[(size_t)seg * p.seg_len + (size_t)kb * CAP + i];
+      double x = p.xin[g[k]];
+      id[k] = p.idin[g[k]];
+      if (p.h_pre != 0.0) x = __dadd_rn(x, __dmul_rn(p.h_pre, p.vin[g[k]]));
+      xk[k] = x;
+      lmin = fmin(lmin, x);
+      lmax = fmax(lmax, x);
+    }
+  }
+  // ---- 2. block min / max -------------------------------------------------------------
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lmin = fmin(lmin, __shfl_xor_sync(WENDY_FULL_MASK, lmin, o));
+    lmax = fmax(lmax, __shfl_xor_sync(WENDY_FULL_MASK, lmax, o));
+  }
+  if (lane == 0) {
+    S.dred[0][wid] = lmin;
+    S.dred[1][wid] = lmax;
+  }
+  __syncthreads();
+  double xmin = S.dred[0][0], xmax = S.dred[1][0];
+#pragma unroll
+  for (int w = 1; w < NW; w++) {
+    xmin = fmin(xmin, S.dred[0][w]);
+    xmax = fmax(xmax, S.dred[1][w]);
+  }
+  double range = xmax - xmin;
+  const double scale = (range > 0.0 && range < CUDART_INF) ? (double)(BK - 1) / range : 0.0;
+
+  // ---- 3. interpolation sub-bucket of every key (monotone in x), arrival slot -----------
+  unsigned pk[E];  // sub-bucket | arrival order << 16
+#pragma unroll
+  for (int k = 0; k < E; k++) {
+    pk[k] = 0;
+    if (tid + k * THREADS < n) {
+      int sub = (int)((xk[k] - xmin) * scale);
+      sub = max(0, min(BK - 1, sub));
+      unsigned o = atomicAdd(&S.u.srt.cnt[sub + sub / E], 1u);
+      pk[k] = (unsigned)sub | (o << 16);
+    }
+  }
+  __syncthreads();
+  // ---- 4. exclusive scan of the sub-bucket counters ------------------------------------
+  {
+    unsigned c[E], run = 0;
+    unsigned *cp = &S.u.srt.cnt[tid * (E + 1)];
+#pragma unroll
+    for (int q = 0; q < E; q++) {
+      c[q] = cp[q];
+      run += c[q];
+    }
+    unsigned inc = warp_inclusive_scan_u32(run, lane);
+    if (lane == 31) S.uw[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      unsigned t = lane < NW ? S.uw[lane] : 0u;
+      unsigned ti = warp_inclusive_scan_u32(t, lane);
+      if (lane < NW) S.uw[lane] = ti - t;
+    }
+    __syncthreads();
+    unsigned ex = inc - run + S.uw[wid];
+#pragma unroll
+    for (int q = 0; q < E; q++) {
+      cp[q] = ex;
+      ex += c[q];
+    }
+  }
+  __syncthreads();
+  // ---- 5. group load slots by sub-bucket -------------------------------------------------
+#pragma unroll
+  for (int k = 0; k < E; k++) {
+    unsigned i = tid + k * THREADS;
+    if (i < n) {
+      unsigned sub = pk[k] & 0xffffu;
+      unsigned pos = S.u.srt.cnt[sub + sub / E] + (pk[k] >> 16);
+      S.u.srt.slot[pos] = (unsigned short)i;
+      S.sx[i] = xk[k];
+      S.sid[i] = id[k];
+    }
+  }
+  __syncthreads();
+  // ---- 6. exact rank under the (x, id) order; masses are fetched meanwhile ---------------
+  double m[E];
+  unsigned r[E];
+#pragma unroll
+  for (int k = 0; k < E; k++) {
+    m[k] = 0.0;
+    if (tid + k * THREADS < n) m[k] = p.min[g[k]];
+  }
+#pragma unroll
+  for (int k = 0; k < E; k++) {
+    r[k] = 0;
+    if (tid + k * THREADS < n) {
+      unsigned sub = pk[k] & 0xffffu;
+      unsigned s0 = S.u.srt.cnt[sub + sub / E];
+      unsigned s1 = (sub + 1 < (unsigned)BK) ? S.u.srt.cnt[(sub + 1) + (sub + 1) / E] : n;
+      unsigned rr = s0;
+      const double xi = xk[k];
+      const int ii = id[k];
+      for (unsigned q = s0; q < s1; q++) {
+        unsigned j = S.u.srt.slot[q];
+        double xj = S.sx[j];
+        rr += (xj < xi || (xj == xi && S.sid[j] < ii)) ? 1u : 0u;
+      }
+      r[k] = rr;
+    }
+  }
+  __syncthreads();  // counters and slots are dead from here on; mcum aliases them
+  // ---- 7. masses into sorted order ----------------------------------------------------------
+#pragma unroll
+  for (int k = 0; k < E; k++)
+    if (tid + k * THREADS < n) S.u.mcum[r[k] + r[k] / E] = m[k];
+  __syncthreads();
+  // ---- 8. exact exclusive scan of the masses (128-bit fixed point) ----------------------------
+  i128 loc[E];
+  i128 tsum = 0;
+  {
+    double *mp = &S.u.mcum[tid * (E + 1)];
+#pragma unroll
+    for (int q = 0; q < E; q++) {
+      loc[q] = tsum;
+      if ((unsigned)(tid * E + q) < n) tsum += fx_from_double(mp[q], p.fxE);
+    }
+  }
+  i128 winc = warp_inclusive_scan_i128(tsum, lane);
+  if (lane == 31) {
+    S.wlo[wid] = (unsigned long long)winc;
+    S.whi[wid] = (unsigned long long)((u128)winc >> 64);
+  }
+  __syncthreads();
+  // ---- 9. warp 0: scan of the warp totals, then look-back for the bucket prefix --------------
+  if (wid == 0) {
+    i128 t = lane < NW ? make_i128(S.wlo[lane], S.whi[lane]) : (i128)0;
+    i128 ti = warp_inclusive_scan_i128(t, lane);
+    i128 agg = shfl_i128(ti, 31);
+    i128 tex = ti - t;
+    if (lane < NW) {
+      S.wlo[lane] = (unsigned long long)tex;
+      S.whi[lane] = (unsigned long long)((u128)tex >> 64);
+    }
+    i128 P;
+    long long Pc;
+    lookback(p, b, seg_lo, agg, (long long)n, lane, P, Pc);
+    if (lane == 0) {
+      S.pre_lo = (unsigned long long)P;
+      S.pre_hi = (unsigned long long)((u128)P >> 64);
+      S.pre_cnt = Pc;
+    }
+  }
+  __syncthreads();
+  // ---- 10. cumulative mass below every sorted position, correctly rounded ---------------------
+  {
+    i128 base = make_i128(S.pre_lo, S.pre_hi) + make_i128(S.wlo[wid], S.whi[wid]) + (winc - tsum);
+    double *mp = &S.u.mcum[tid * (E + 1)];
+#pragma unroll
+    for (int q = 0; q < E; q++)
+      if ((unsigned)(tid * E + q) < n) mp[q] = fx_to_double(base + loc[q], p.fxE);
+  }
+  const long long Pc = S.pre_cnt;
+  __syncthreads();
+  // ---- 11. force, kick, drift (or diagnostics) ----------------------------------------------------
+  const double tot = p.tot[seg];
+  double x2[E], v2[E], xb[E];
+  double e_ke = 0.0, e_he = 0.0, e_pe = 0.0, e_mom = 0.0;
+#pragma unroll
+  for (int k = 0; k < E; k++) {
+    x2[k] = v2[k] = xb[k] = 0.0;
+    if (tid + k * THREADS < n) {
+      const double c = S.u.mcum[r[k] + r[k] / E];
+      const double v = p.vin[g[k]];
+      double grav = __dsub_rn(__dsub_rn(tot, __dmul_rn(2.0, c)), m[k]);
+      if (PHYS) {
+        double acc = grav;
+        if (p.omega2 >= 0.0) acc = __dsub_rn(acc, __dmul_rn(p.omega2, xk[k]));
+        if (p.aext) acc = __dadd_rn(p.aext[g[k]], acc);
+        v2[k] = __dadd_rn(v, __dmul_rn(p.dt_kick, acc));
+        x2[k] = __dadd_rn(xk[k], __dmul_rn(p.dt_drift, v2[k]));
+        xb[k] = (p.h_next != 0.0) ? __dadd_rn(x2[k], __dmul_rn(p.h_next, v2[k])) : x2[k];
+      } else {
+        v2[k] = v;
+        x2[k] = (p.h_pre != 0.0) ? p.xin[g[k]] : xk[k];
+        xb[k] = xk[k];
+      }
+      if (EMIT == EMIT_NONE) {  // energy terms, reference wendy/wendy.py:458-475
+        e_ke += 0.5 * m[k] * v * v;
+        if (p.omega2 >= 0.0) e_he += 0.5 * m[k] * p.omega2 * xk[k] * xk[k];
+        e_pe -= m[k] * xk[k] * grav;
+        e_mom += m[k] * v;
+      }
+      if (p.rank_out) p.rank_out[id[k]] = (int)(Pc + (long long)r[k]);
+    }
+  }
+  if (EMIT == EMIT_NONE) {
+    if (p.energy_part) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        e_ke += __shfl_xor_sync(WENDY_FULL_MASK, e_ke, o);
+        e_he += __shfl_xor_sync(WENDY_FULL_MASK, e_he, o);
+        e_pe += __shfl_xor_sync(WENDY_FULL_MASK, e_pe, o);
+        e_mom += __shfl_xor_sync(WENDY_FULL_MASK, e_mom, o);
+      }
+      if (lane == 0) {
+        S.dred[0][wid] = e_ke;
+        S.dred[1][wid] = e_he;
+        S.dred[2][wid] = e_pe;
+        S.dred[3][wid] = e_mom;
+      }
+      __syncthreads();
+      if (tid < 4) {
+        double s = 0.0;
+        for (int w = 0; w < NW; w++) s += S.dred[tid][w];
+        p.energy_part[(size_t)b * 4 + tid] = s;
+      }
+    }
+    return;
+  }
+  // ---- 12. emission ------------------------------------------------------------------------------------
+  if (EMIT == EMIT_RANK) {  // compact sorted layout: slot = rank inside this tile
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+      if (tid + k * THREADS < n) {
+        size_t o = (size_t)b * CAP + r[k];
+        p.xout[o] = x2[k];
+        p.vout[o] = v2[k];
+        p.mout[o] = m[k];
+        p.idout[o] = id[k];
+      }
+    }
+    return;
+  }
+  // EMIT_SPLITTER: append every particle to the bucket that contains its new key
+  int dest[E];
+  unsigned lpos[E];
+  unsigned outside = 0;
+#pragma unroll
+  for (int k = 0; k < E; k++) {
+    int d = -1;
+    if (tid + k * THREADS < n) {
+      const double key = xb[k];
+      const int rel = b - wlo;
+      if (key >= S.ssplit[rel] && key < S.ssplit[rel + 1]) {
+        d = b;
+      } else if (key >= S.ssplit[0] && key < S.ssplit[wn]) {
+        int lo = 0, hi = wn;
+        while (hi - lo > 1) {
+          int mid = (lo + hi) >> 1;
+          if (S.ssplit[mid] <= key) lo = mid; else hi = mid;
+        }
+        d = wlo + lo;
+      } else {  // far move: search the whole segment (split[seg_lo] is -inf)
+        int lo = seg_lo, hi = seg_hi;
+        while (hi - lo > 1) {
+          int mid = (lo + hi) >> 1;
+          if (__ldg(p.split + mid) <= key) lo = mid; else hi = mid;
+        }
+        d = lo;
+      }
+    }
+    dest[k] = d;
+    unsigned mask = __match_any_sync(WENDY_FULL_MASK, d);
+    int leader = __ffs(mask) - 1;
+    unsigned basel = 0;
+    const bool inwin = (d >= wlo && d < wlo + wn);
+    if (lane == leader && d >= 0) {
+      if (inwin) {
+        basel = atomicAdd(&S.dcnt[d - wlo], (unsigned)__popc(mask));
+      } else {
+        basel = atomicAdd(&p.cnt_out[d], (unsigned)__popc(mask));
+        outside += __popc(mask);
+      }
+    }
+    basel = __shfl_sync(WENDY_FULL_MASK, basel, leader);
+    lpos[k] = basel + __popc(mask & lt);
+  }
+  __syncthreads();
+  if (tid < wn && S.dcnt[tid]) S.dbase[tid] = atomicAdd(&p.cnt_out[wlo + tid], S.dcnt[tid]);
+  if (outside) atomicAdd(p.stats + 1, outside);
+  __syncthreads();
+  bool overflow = false;
+#pragma unroll
+  for (int k = 0; k < E; k++) {
+    const int d = dest[k];
+    if (d >= 0) {
+      unsigned pos = lpos[k];
+      if (d >= wlo && d < wlo + wn) pos += S.dbase[d - wlo];
+      if (pos < (unsigned)CAP) {
+        size_t o = (size_t)d * CAP + pos;
+        p.xout[o] = x2[k];
+        p.vout[o] = v2[k];
+        p.mout[o] = m[k];
+        p.idout[o] = id[k];
+      } else {
+        overflow = true;
+      }
+    }
+  }
+  if (overflow) atomicMin(p.fail_seq, p.seq);
+}
+
+// ---- dispatch -------------------------------------------------------------------------------------------
+template <int CAP, int THREADS>
+static void launch_tile_cap(cudaStream_t st, int load, int emit, int physics, const TileParams &p) {
+  size_t sm = sizeof(TileSmem<CAP, THREADS>);
+#define WENDY_LAUNCH(L, EM, PH)                                                                   \
+  do {                                                                                              \
+    static bool attr_set = false;                                                                   \
+    if (!attr_set) {                                                                                \
+      cudaFuncSetAttribute(tile_kernel<CAP, THREADS, L, EM, PH>,                                    \
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                   \
+      attr_set = true;                                                                              \
+    }                                                                                               \
+    tile_kernel<CAP, THREADS, L, EM, PH><<<p.nb, THREADS, sm, st>>>(p);                             \
+  } while (0)
+  if (load == LOAD_BUCKET && emit == EMIT_SPLITTER && physics) WENDY_LAUNCH(LOAD_BUCKET, EMIT_SPLITTER, 1);
+  else if (load == LOAD_GATHER && emit == EMIT_RANK && physics) WENDY_LAUNCH(LOAD_GATHER, EMIT_RANK, 1);
+  else if (load == LOAD_GATHER && emit == EMIT_RANK && !physics) WENDY_LAUNCH(LOAD_GATHER, EMIT_RANK, 0);
+  else if (load == LOAD_GATHER && emit == EMIT_NONE && !physics) WENDY_LAUNCH(LOAD_GATHER, EMIT_NONE, 0);
+#undef WENDY_LAUNCH
+}
+
+bool tile_cap_supported(int cap) { return cap == 2048 || cap == 256; }
+
+size_t tile_smem_bytes(int cap) {
+  return cap == 2048 ? sizeof(TileSmem<2048, 512>) : sizeof(TileSmem<256, 64>);
+}
+
+void launch_tile(cudaStream_t st, int cap, int load, int emit, int physics, const TileParams &p) {
+  if (p.nb <= 0) return;
+  if (cap == 2048) launch_tile_cap<2048, 512>(st, load, emit, physics, p);
+  else launch_tile_cap<256, 64>(st, load, emit, physics, p);
+}
+
+// =========================================================================================================
+// Re-bucketing: stream every particle of a source layout into the bucket its key falls in.
+// Used when the layout is (re)built: at start-up, when a bucket would overflow, or when the
+// pending pre-drift changes.  Not on the steady-state path.
+__global__ void __launch_bounds__(256)
+scatter_kernel(const ScatterParams p) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  if (ld_volatile_u32(p.fail_seq) < p.seq) return;
+  const long long total = p.cnt_in ? (long long)p.nb_in * p.cap_in : p.n_dense;
+  const long long span = (long long)gridDim.x * blockDim.x;
+  const long long rounds = (total + span - 1) / span;
+  bool overflow = false;
+  for (long long rd = 0; rd < rounds; rd++) {
+    long long i = rd * span + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int d = -1;
+    double x = 0, v = 0;
+    if (i < total) {
+      long long seg;
+      bool ok = true;
+      if (p.cnt_in) {
+        int bi = (int)(i / p.cap_in);
+        ok = (unsigned)(i - (long long)bi * p.cap_in) < p.cnt_in[bi];
+        seg = bi / p.nbps_in;
+      } else {
+        seg = i / p.seg_len;
+      }
+      if (ok) {
+        x = p.xin[i];
+        v = p.vin[i];
+        double key = (p.h != 0.0) ? __dadd_rn(x, __dmul_rn(p.h, v)) : x;
+        int lo = (int)seg * p.nbps_out, hi = lo + p.nbps_out;
+        while (hi - lo > 1) {
+          int mid = (lo + hi) >> 1;
+          if (__ldg(p.split + mid) <= key) lo = mid; else hi = mid;
+        }
+        d = lo;
+      }
+    }
+    unsigned mask = __match_any_sync(WENDY_FULL_MASK, d);
+    int leader = __ffs(mask) - 1;
+    unsigned basel = 0;
+    if (lane == leader && d >= 0) basel = atomicAdd(&p.cnt_out[d], (unsigned)__popc(mask));
+    basel = __shfl_sync(WENDY_FULL_MASK, basel, leader);
+    if (d >= 0) {
+      unsigned pos = basel + __popc(mask & lt);
+      if (pos < (unsigned)p.cap_out) {
+        size_t o = (size_t)d * p.cap_out + pos;
+        p.xout[o] = x;
+        p.vout[o] = v;
+        p.mout[o] = p.min[i];
+        p.idout[o] = p.idin[i];
+      } else {
+        overflow = true;
+      }
+    }
+  }
+  if (overflow) atomicMin(p.fail_seq, p.seq);
+}
+
+void launch_scatter(cudaStream_t st, const ScatterParams &p, int sm_count) {
+  long long total = p.cnt_in ? (long long)p.nb_in * p.cap_in : p.n_dense;
+  if (total <= 0) return;
+  long long blocks = (total + 255) / 256;
+  long long maxb = (long long)sm_count * 16;
+  scatter_kernel<<<(unsigned)(blocks < maxb ? blocks : maxb), 256, 0, st>>>(p);
+}
+
+// ---- radix keys in compact (segment-major) order ----------------------------------------------------------
+__global__ void __launch_bounds__(256)
+make_keys_kernel(const double *__restrict__ x, const double *__restrict__ v, double h,
+                 const unsigned *__restrict__ cnt_in, const unsigned long long *__restrict__ offs,
+                 int cap, long long total, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                 int val_mode, long long seg_len, int nbps) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long o = i;
+    long long seg;
+    if (cnt_in) {
+      int bi = (int)(i / cap);
+      unsigned s = (unsigned)(i - (long long)bi * cap);
+      if (s >= cnt_in[bi]) continue;
+      o = (long long)offs[bi] + s;
+      seg = bi / nbps;
+    } else {
+      seg = i / seg_len;
+    }
+    double xx = x[i];
+    if (h != 0.0) xx = __dadd_rn(xx, __dmul_rn(h, v[i]));
+    keys[o] = key_from_double(xx);
+    vals[o] = val_mode == VAL_SEGMENT ? (uint32_t)seg : (uint32_t)i;
+  }
+}
+
+void launch_make_keys(cudaStream_t st, const double *x, const double *v, double h,
+                      const unsigned *cnt_in, const unsigned long long *offs, int cap, int nb,
+                      long long n_dense, uint64_t *keys, uint32_t *vals, int val_mode,
+                      long long seg_len, int nbps) {
+  long long total = cnt_in ? (long long)nb * cap : n_dense;
+  if (total <= 0) return;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  make_keys_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, v, h, cnt_in, offs, cap, total, keys, vals,
+                                                     val_mode, seg_len, nbps);
+}
+
+// exclusive scan of the bucket counts (single block; nb is N/fill, at most a few 1e5)
+__global__ void __launch_bounds__(1024)
+scan_counts_kernel(const unsigned *__restrict__ cnt, int nb, unsigned long long *__restrict__ offs) {
+  __shared__ unsigned long long wt[32];
+  __shared__ unsigned long long carry;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += 1024) {
+    int i = base + threadIdx.x;
+    unsigned long long v = i < nb ? cnt[i] : 0ull, inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned long long u = __shfl_up_sync(WENDY_FULL_MASK, inc, o);
+      if (lane >= o) inc += u;
+    }
+    if (lane == 31) wt[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      unsigned long long t = wt[lane], ti = t;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long u = __shfl_up_sync(WENDY_FULL_MASK, ti, o);
+        if (lane >= o) ti += u;
+      }
+      wt[lane] = ti - t;
+    }
+    __syncthreads();
+    if (i < nb) offs[i] = carry + wt[wid] + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += wt[31] + inc;
+    __syncthreads();
+  }
+}
+
+void launch_scan_counts(cudaStream_t st, const unsigned *cnt, int nb, unsigned long long *offs) {
+  if (nb > 0) scan_counts_kernel<<<1, 1024, 0, st>>>(cnt, nb, offs);
+}
+
+// splitters = exact quantiles of the sorted keys: bucket k of a segment starts at rank k*fill
+__global__ void pick_splitters_kernel(const uint64_t *__restrict__ sorted, long long seg_len, int fill,
+                                      int nbps, int nb, double *__restrict__ split) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  int seg = b / nbps, k = b - seg * nbps;
+  long long rk = (long long)k * fill;
+  double s;
+  if (k == 0) s = -CUDART_INF;
+  else if (rk < seg_len) s = double_from_key(sorted[(long long)seg * seg_len + rk]);
+  else s = CUDART_INF;  // unused tail bucket: never selected for a finite key
+  split[b] = s;
+}
+
+void launch_pick_splitters(cudaStream_t st, const uint64_t *sorted_keys, long long seg_len, int fill,
+                           int nbps, int nb, double *split) {
+  if (nb > 0) pick_splitters_kernel<<<(nb + 255) / 256, 256, 0, st>>>(sorted_keys, seg_len, fill, nbps, nb, split);
+}
+
+// x += h*v on every live slot (materialises the pending half drift, wendy/wendy.c:398)
+__global__ void apply_drift_kernel(double *__restrict__ x, const double *__restrict__ v, double h,
+                                   const unsigned *__restrict__ cnt, int cap, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int bi = (int)(i / cap);
+    if ((unsigned)(i - (long long)bi * cap) < cnt[bi]) x[i] = __dadd_rn(x[i], __dmul_rn(h, v[i]));
+  }
+}
+
+void launch_apply_drift(cudaStream_t st, double *x, const double *v, double h, const unsigned *cnt,
+                        int cap, int nb) {
+  long long total = (long long)nb * cap;
+  if (total <= 0) return;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  apply_drift_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, v, h, cnt, cap, total);
+}
+
+// de-sort: x_out[id] = x, v_out[id] = v (reference wendy/wendy.c:413-415)
+__global__ void unsort_kernel(const double *__restrict__ x, const double *__restrict__ v,
+                              const int *__restrict__ id, const unsigned *__restrict__ cnt, int cap,
+                              long long total, double *__restrict__ xo, double *__restrict__ vo) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int bi = (int)(i / cap);
+    if ((unsigned)(i - (long long)bi * cap) < cnt[bi]) {
+      int j = id[i];
+      xo[j] = x[i];
+      vo[j] = v[i];
+    }
+  }
+}
+
+void launch_unsort(cudaStream_t st, const double *x, const double *v, const int *id, const unsigned *cnt,
+                   int cap, int nb, double *xo, double *vo) {
+  long long total = (long long)nb * cap;
+  if (total <= 0) return;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  unsort_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, v, id, cnt, cap, total, xo, vo);
+}
+
+__global__ void iota_kernel(int *__restrict__ id, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    id[i] = (int)i;
+}
+void launch_iota(cudaStream_t st, int *id, long long n) {
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (n > 0) iota_kernel<<<(unsigned)blocks, 256, 0, st>>>(id, n);
+}
+
+// a_slots[slot] = a_by_id[id[slot]] (compat path: host callback results -> storage order)
+__global__ void gather_by_id_kernel(const double *__restrict__ a_by_id, const int *__restrict__ id,
+                                    const unsigned *__restrict__ cnt, int cap, long long total,
+                                    double *__restrict__ a_slots) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int bi = (int)(i / cap);
+    if ((unsigned)(i - (long long)bi * cap) < cnt[bi]) a_slots[i] = a_by_id[id[i]];
+  }
+}
+void launch_gather_by_id(cudaStream_t st, const double *a_by_id, const int *id, const unsigned *cnt,
+                         int cap, int nb, double *a_slots) {
+  long long total = (long long)nb * cap;
+  if (total <= 0) return;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  gather_by_id_kernel<<<(unsigned)blocks, 256, 0, st>>>(a_by_id, id, cnt, cap, total, a_slots);
+}
+
+// fixed-order final reduction of the per-bucket energy partials (deterministic)
+__global__ void __launch_bounds__(256)
+reduce_energy_kernel(const double *__restrict__ part, int nb, double *__restrict__ out4) {
+  __shared__ double s[4][256];
+  double a[4] = {0, 0, 0, 0};
+  for (int b = threadIdx.x; b < nb; b += 256)
+    for (int c = 0; c < 4; c++) a[c] += part[(size_t)b * 4 + c];
+  for (int c = 0; c < 4; c++) s[c][threadIdx.x] = a[c];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o)
+      for (int c = 0; c < 4; c++) s[c][threadIdx.x] += s[c][threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x < 4) out4[threadIdx.x] = s[threadIdx.x][0];
+}
+
+void launch_reduce_energy(cudaStream_t st, const double *part, int nb, double *out4) {
+  reduce_energy_kernel<<<1, 256, 0, st>>>(part, nb, out4);
+}
+
+}  // namespace wendy
