@@ -1,0 +1,257 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the approximate-integration hot path on B200.
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): sech^2
+self-gravitating disk with a harmonic term (omega=1.1), N=1e8 per GPU, fp64, seeded numpy ICs
+(SURVEY.md section 8d).  A bench "step" is ONE call of the reference entry point
+(wendy/wendy.c:385-418) with nleap leapfrog sub-steps; particle-steps = N * nleap * steps.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path
+  python bench.py --impl reference ...                          the reference's own C path on the host
+
+N>1 is launched by torchrun (one rank per GPU).  Until the NCCL sample-sort mode lands, ranks run
+independent realisations (BASELINE.json configs[4]-style ensemble, no data-path collective), so
+scaling is "weak".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES = 40.  # algorithmic bytes per particle-step: read x,v,m + write x,v
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--n', type=float, default=1e8, help='particles per GPU')
+    ap.add_argument('--nleap', type=int, default=10)
+    ap.add_argument('--dt-leap', type=float, default=1e-3)
+    ap.add_argument('--omega', type=float, default=1.1)
+    ap.add_argument('--sort', default='gpu', choices=['gpu', 'gpu-radix'])
+    ap.add_argument('--ref-n', type=float, default=1e7, help='particles in the CPU sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--variants', action='store_true', help='also time other dt_leap / sort settings')
+    return ap.parse_args()
+
+
+def sech2_ic(n, seed):
+    """reference examples/WendyScaling.ipynb:57-65."""
+    rs = numpy.random.RandomState(seed)
+    x = numpy.arctanh(2. * rs.uniform(size=n) - 1.) * 2.
+    v = rs.normal(size=n)
+    v -= numpy.mean(v)
+    m = numpy.full(n, 1. / n)
+    return x, v, m
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_ev = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_ev.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            self._stop_ev.wait(0.2)
+
+    def stop(self):
+        self._stop_ev.set()
+        self.join(timeout=6)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit())
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [nm for i, nm in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == 'Active' for r in self.rows)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None,
+                'sm_max_mhz': float(self.rows[0][1]) if self.rows else None,
+                'reasons': reasons, 'samples': len(self.rows)}
+
+
+def time_reference(x, v, m, omega, dt_leap, steps, warmup):
+    """The reference's own C path (oracle/_ref/wendy_c.so, sort='parallel', all host threads)."""
+    from oracle import wendy_oracle as wo
+    kind = 'reference' if wo.reference_available() else 'port'
+    if kind == 'reference':
+        r = wo.Reference(x, v, m, dt_leap, 1, omega=omega, sort='parallel')
+    else:
+        subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'oracle'), 'oracle'])
+        r = wo.COracle(x, v, m, dt_leap, 1, omega=omega)
+    for _ in range(warmup):
+        r.step()
+    t = time.perf_counter()
+    for _ in range(steps):
+        r.step()
+    el = time.perf_counter() - t
+    return len(x) * steps / el, el / steps, kind
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    n = int(a.n)
+    cores = os.cpu_count()
+
+    if a.impl == 'reference':
+        if rank != 0:
+            return
+        os.environ.pop('OMP_NUM_THREADS', None)
+        nr = int(a.ref_n)
+        x, v, m = sech2_ic(nr, 2)
+        val, per, kind = time_reference(x, v, m, a.omega, a.dt_leap, a.steps, a.warmup)
+        sample = ('N=%d of the N=%d workload, one sub-step per step, sort=parallel '
+                  '(PARALLEL_SORT_NUM_THREADS=32 default), OMP threads=%d' % (nr, n, cores))
+        print(json.dumps({
+            'impl': 'reference', 'metric': 'particle-steps/s', 'value': val, 'unit': 'particle-steps/s',
+            'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': per * 1e3,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic',
+            'config': {'workload': 'sech2 disk + harmonic omega=%g, dt_leap=%g (CPU sample N=%d)' % (a.omega, a.dt_leap, nr)},
+            'cpu_baseline': {'value': val, 'unit': 'particle-steps/s', 'cores': cores, 'kind': kind, 'sample': sample},
+            'e2e': {'value': val, 'unit': 'particle-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    import wendy_b200
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(t):
+        if world == 1:
+            return t
+        tt = torch.tensor([t], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    x, v, m = sech2_ic(n, 2 + rank)
+    omega2 = a.omega ** 2
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def run(dt_leap, sort, steps, warmup, nleap):
+        st = wendy_b200.ApproxState(x, v, m, omega2=omega2, sort=sort, stream=stream)
+        for _ in range(warmup):
+            st.step(dt_leap, nleap)
+        s0 = st.stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            st.step(dt_leap, nleap)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        s1 = st.stats()
+        st.close()
+        d = {k: s1[k] - s0[k] for k in ('substeps', 'rebuilds', 'failed_substeps', 'kernel_launches', 'radix_fallbacks')}
+        d['max_bucket_count'] = s1['max_bucket_count']
+        d['left_window'] = s1['left_window'] - s0['left_window']
+        return ms, d
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, d = run(a.dt_leap, a.sort, a.steps, a.warmup, a.nleap)
+    clocks = sampler.stop() if sampler else None
+    psteps = float(n) * world * a.nleap * a.steps
+    value = psteps / (ms * 1e-3)
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = peaks.get('hbm_gbs', 6650.)
+    # dominant kernel: tile_kernel (one launch per sub-step on the bucket path).  Its average
+    # duration is the timed region / sub-steps when nothing else ran (rebuilds == 0).
+    launches_tile = d['substeps']
+    ms_per_launch = ms / max(1, launches_tile)
+    achieved = ALG_BYTES * n / (ms_per_launch * 1e-3) / 1e9
+    out = {
+        'metric': 'particle-steps/s', 'value': value, 'unit': 'particle-steps/s', 'n_gpus': world,
+        'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms / a.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'sech2 disk + harmonic omega=%g, N=%d per GPU, dt_leap=%g, nleap=%d, sort=%s'
+                               % (a.omega, n, a.dt_leap, a.nleap, a.sort),
+                   'parallelism': 'independent realisations, one per GPU' if world > 1 else 'single GPU',
+                   'l2': 'state (%.1f GB) is far larger than L2' % (n * 28 / 1e9)},
+        'gpu_launches': d['kernel_launches'],
+        'path_stats': d,
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak,
+                     'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback', 'unit': 'GB/s',
+                     'frac': achieved / peak, 'traffic': None,
+                     'kernel': 'tile_kernel<LOAD_BUCKET,EMIT_SPLITTER>' if a.sort == 'gpu' else 'radix passes + tile_kernel<LOAD_GATHER>',
+                     'ms_per_launch': ms_per_launch},
+        'clocks': clocks,
+    }
+
+    if a.variants and world == 1:
+        var = {}
+        for dtl, srt in ((1e-5, 'gpu'), (1e-3, 'gpu'), (5e-3, 'gpu'), (1e-3, 'gpu-radix')):
+            vms, vd = run(dtl, srt, max(1, a.steps // 2), 1, a.nleap if srt == 'gpu' else 2)
+            nl = a.nleap if srt == 'gpu' else 2
+            var['dt_leap=%g,%s' % (dtl, srt)] = {'value': float(n) * nl * max(1, a.steps // 2) / (vms * 1e-3), 'stats': vd}
+        out['variants'] = var
+
+    # ---- end to end through the public generator API, host buffers --------------------------
+    if not a.no_e2e:
+        steps_e = max(2, min(a.steps, 4))
+        barrier()
+        t0 = time.perf_counter()
+        g = wendy_b200.nbody(x, v, m, a.dt_leap * a.nleap, approx=True, nleap=a.nleap, omega=a.omega, sort=a.sort)
+        for _ in range(steps_e):
+            xo, vo = next(g)
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        g.close()
+        el = max_over_ranks(el)
+        out['e2e'] = {'value': float(n) * world * a.nleap * steps_e / el, 'unit': 'particle-steps/s',
+                      'h2d_bytes_per_step': 24. * n / steps_e, 'd2h_bytes_per_step': 16. * n,
+                      'note': 'wendy_b200.nbody(): generator construction (H2D of x,v,m, amortised over %d steps) '
+                              '+ next() x %d, each with nleap=%d sub-steps and a D2H of x,v' % (steps_e, steps_e, a.nleap)}
+
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        os.environ.pop('OMP_NUM_THREADS', None)
+        nr = int(min(a.ref_n, n))
+        val, per, kind = time_reference(x[:nr] if nr < n else x, v[:nr], m[:nr] * (n / nr), a.omega, a.dt_leap, 3, 1)
+        out['cpu_baseline'] = {'value': val, 'unit': 'particle-steps/s', 'cores': cores, 'kind': kind,
+                               'sample': 'first %d particles of the workload (masses rescaled), 1 warm-up + 3 timed '
+                                         'sub-steps, reference sort=parallel, %.2f s per sub-step' % (nr, per)}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -95,7 +95,8 @@ int wendy_cuda_energy(wendy_cuda_handle *h, double out[4]);
 
 /* Counters: out[0] sub-steps, [1] layout rebuilds, [2] failed (re-run) sub-steps,
  * [3] max bucket count seen, [4] particles that left the 32-bucket window,
- * [5] kernels launched, [6] bucket capacity, [7] buckets. */
+ * [5] kernels launched, [6] bucket capacity, [7] buckets, [8] sub-steps that fell back to the
+ * radix path because a freshly balanced layout still overflowed. */
 int wendy_cuda_stats(wendy_cuda_handle *h, long long *out, int n);
 
 void wendy_cuda_destroy(wendy_cuda_handle *h);

@@ -72,6 +72,7 @@ struct wendy_cuda_handle {
   int *rank = nullptr;
   // counters
   long long n_sub = 0, n_rebuild = 0, n_fail = 0, max_cnt = 0, n_outside = 0, n_launch = 0;
+  long long n_radix_fallback = 0;
 };
 typedef wendy_cuda_handle H;
 
@@ -370,10 +371,18 @@ static int run_substeps(H *h, double dt, int nleap) {
     h->has_split = false;  // force a rebuild for the key of sub-step kf
     if (reset_flags(h)) return WENDY_E_CUDA;
     attempts_at_k = (kf == k) ? attempts_at_k + 1 : 1;
-    if (attempts_at_k > 2)
-      return set_err(WENDY_E_OVERFLOW, "bucket overflow persists after re-balancing (time step far too "
-                                       "large for the bucket capacity, or massive coincidences)");
     k = kf;
+    if (attempts_at_k >= 2) {
+      // even a freshly balanced layout overflows within this one sub-step (the density changes
+      // by more than the bucket head-room): take it on the radix path, which cannot overflow
+      double h_pre = (k == 0) ? dt / 2. : 0.;
+      int rc = launch_radix_substep(h, h_pre, dt, (k == nleap - 1) ? dt / 2. : dt, nullptr, nullptr);
+      if (rc) return rc;
+      if (fetch_flags(h)) return WENDY_E_CUDA;
+      h->n_radix_fallback++;
+      k++;
+      attempts_at_k = 0;
+    }
   }
   // cheap insurance: re-balance between calls when some bucket is nearly full
   if (h->mode != WENDY_SORT_RADIX && h->h_flags[1] > (unsigned)(h->cap - (h->cap - h->fill) / 4)) {
@@ -498,9 +507,9 @@ int wendy_cuda_energy(wendy_cuda_handle *h, double out[4]) {
 
 int wendy_cuda_stats(wendy_cuda_handle *h, long long *out, int n) {
   if (!h || !out) return set_err(WENDY_E_ARG, "null argument");
-  long long s[8] = {h->n_sub, h->n_rebuild, h->n_fail, h->max_cnt, h->n_outside + h->h_flags[2], h->n_launch,
-                    (long long)h->cap, (long long)h->nb};
-  for (int i = 0; i < n && i < 8; i++) out[i] = s[i];
+  long long s[9] = {h->n_sub, h->n_rebuild, h->n_fail, h->max_cnt, h->n_outside + h->h_flags[2], h->n_launch,
+                    (long long)h->cap, (long long)h->nb, h->n_radix_fallback};
+  for (int i = 0; i < n && i < 9; i++) out[i] = s[i];
   return 0;
 }
 

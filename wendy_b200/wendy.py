@@ -121,10 +121,10 @@ class ApproxState(object):
         return out
 
     def stats(self):
-        out = numpy.zeros(8, dtype=numpy.int64)
-        _lib.check(self._lib.wendy_cuda_stats(self._h, out, 8))
+        out = numpy.zeros(9, dtype=numpy.int64)
+        _lib.check(self._lib.wendy_cuda_stats(self._h, out, 9))
         keys = ['substeps', 'rebuilds', 'failed_substeps', 'max_bucket_count', 'left_window',
-                'kernel_launches', 'cap', 'buckets']
+                'kernel_launches', 'cap', 'buckets', 'radix_fallbacks']
         return dict(zip(keys, (int(o) for o in out)))
 
 
