@@ -42,6 +42,9 @@ typedef struct wendy_cuda_handle wendy_cuda_handle;
 /* sort modes (flags & 0xf) */
 #define WENDY_SORT_AUTO 0    /* bucket fast path, radix sort to (re)build the layout */
 #define WENDY_SORT_RADIX 1   /* full LSD radix sort every sub-step (A/B and fallback) */
+/* When all masses are bit-identical the library uses cum = RN(rank * m0), which equals the
+ * correctly rounded exact prefix sum of the general path; this flag forces the general path. */
+#define WENDY_FLAG_GENERAL_MASSES 0x10
 
 /* Mirror of the reference record, wendy/wendy.h:12-16 (int idx; 4 bytes pad; double val). */
 struct wendy_array_w_index {

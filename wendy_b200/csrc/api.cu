@@ -41,6 +41,8 @@ void launch_gather_by_id(cudaStream_t st, const double *a_by_id, const int *id, 
 struct wendy_cuda_handle {
   long long N = 0, seg_len = 0;
   int nseg = 1, mode = 0, fxE = 0;
+  bool eqm = false;        // all masses identical: no mass arrays, cum = rank * m0
+  double m0 = 0.;
   double omega2 = -1.;
   int cap = 0, fill = 0, nb = 0, nbps = 0;
   size_t slots = 0;
@@ -61,6 +63,7 @@ struct wendy_cuda_handle {
   int tcur = 0;
   unsigned *status = nullptr;
   Desc *desc = nullptr;
+  unsigned long long *cdesc = nullptr;
   unsigned *flags = nullptr;    // [0] fail_seq, [1] max count, [2] outside-window count
   unsigned *h_flags = nullptr;  // pinned mirror
   unsigned seq = 1;
@@ -188,7 +191,8 @@ static void fill_tile_params(H *h, TileParams &p) {
   p.split = h->split;
   p.nb = h->nb; p.nbps = h->nbps; p.seg_len = h->seg_len;
   p.omega2 = h->omega2; p.tot = h->tot; p.fxE = h->fxE;
-  p.status = h->status; p.desc = h->desc;
+  p.status = h->status; p.desc = h->desc; p.cdesc = h->cdesc;
+  p.eqm = h->eqm ? 1 : 0; p.m0 = h->m0;
   p.ticket = h->ticket + h->tcur; p.ticket_zero = h->ticket + (h->tcur + 2) % 3;
   p.fail_seq = h->flags; p.stats = h->flags + 1;
   p.seq = h->seq; p.epoch = h->seq;
@@ -246,6 +250,7 @@ void wendy_cuda_destroy(wendy_cuda_handle *h) {
   for (int i = 0; i < 3; i++) cudaFree(h->cnt[i]);
   cudaFree(h->rs.table); cudaFree(h->rs.sums);
   cudaFree(h->split); cudaFree(h->tot); cudaFree(h->ticket); cudaFree(h->status); cudaFree(h->desc);
+  cudaFree(h->cdesc);
   cudaFree(h->flags); cudaFree(h->offs); cudaFree(h->xo); cudaFree(h->vo); cudaFree(h->epart);
   cudaFree(h->eout); cudaFree(h->rank);
   if (h->h_flags) cudaFreeHost(h->h_flags);
@@ -289,10 +294,13 @@ int wendy_cuda_create(wendy_cuda_handle **out, long long N, const double *x, con
     if (a > sum_abs) sum_abs = a;
   }
   h->fxE = choose_fx_exponent(sum_abs);
+  h->eqm = !(flags & WENDY_FLAG_GENERAL_MASSES);
+  for (long long i = 1; i < N && h->eqm; i++) h->eqm = (m[i] == m[0]);
+  h->m0 = m[0];
   for (int i = 0; i < 2; i++) {
     CKD(cudaMalloc(&h->x[i], h->slots * sizeof(double)));
     CKD(cudaMalloc(&h->v[i], h->slots * sizeof(double)));
-    CKD(cudaMalloc(&h->m[i], h->slots * sizeof(double)));
+    if (!h->eqm) CKD(cudaMalloc(&h->m[i], h->slots * sizeof(double)));
     CKD(cudaMalloc(&h->id[i], h->slots * sizeof(int)));
     CKD(cudaMemsetAsync(h->x[i], 0, h->slots * sizeof(double), h->st));
     CKD(cudaMemsetAsync(h->v[i], 0, h->slots * sizeof(double), h->st));
@@ -306,6 +314,8 @@ int wendy_cuda_create(wendy_cuda_handle **out, long long N, const double *x, con
   CKD(cudaMalloc(&h->ticket, 3 * sizeof(unsigned)));
   CKD(cudaMalloc(&h->status, (size_t)h->nb * sizeof(unsigned)));
   CKD(cudaMalloc(&h->desc, (size_t)h->nb * sizeof(Desc)));
+  CKD(cudaMalloc(&h->cdesc, (size_t)h->nb * sizeof(unsigned long long)));
+  CKD(cudaMemsetAsync(h->cdesc, 0, (size_t)h->nb * sizeof(unsigned long long), h->st));
   CKD(cudaMalloc(&h->flags, 4 * sizeof(unsigned)));
   CKD(cudaMalloc(&h->offs, (size_t)h->nb * sizeof(unsigned long long)));
   CKD(cudaMalloc(&h->epart, (size_t)h->nb * 4 * sizeof(double)));
@@ -316,7 +326,7 @@ int wendy_cuda_create(wendy_cuda_handle **out, long long N, const double *x, con
   CKD(cudaMemsetAsync(h->status, 0, (size_t)h->nb * sizeof(unsigned), h->st));
   CKD(cudaMemcpyAsync(h->x[0], x, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->st));
   CKD(cudaMemcpyAsync(h->v[0], v, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->st));
-  CKD(cudaMemcpyAsync(h->m[0], m, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  if (!h->eqm) CKD(cudaMemcpyAsync(h->m[0], m, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->st));
   CKD(cudaMemcpyAsync(h->tot, totmass, (size_t)n_segments * sizeof(double), cudaMemcpyHostToDevice, h->st));
   launch_iota(h->st, h->id[0], N);
   if (reset_flags(h)) { std::string s = g_err; wendy_cuda_destroy(h); return set_err(WENDY_E_CUDA, s); }

@@ -84,7 +84,11 @@ __device__ __forceinline__ double fx_to_double(i128 val, int E) {
   } else {
     top = lo;
   }
-  double d = scalbn(__ull2double_rn(top), e2 - E);
+  // scale by 2^(e2-E): one exact multiply when that power of two is a normal double
+  const int k = e2 - E;
+  double d = __ull2double_rn(top);
+  if (k > -1000 && k < 1000) d *= __hiloint2double((1023 + k) << 20, 0);
+  else d = scalbn(d, k);
   return neg ? -d : d;
 }
 

@@ -50,9 +50,12 @@ struct TileParams {
   double h_pre, dt_kick, dt_drift, h_next, omega2;
   const double *tot;        // total mass per segment
   int fxE;                  // fixed-point exponent
+  int eqm;                  // all masses equal m0: cumulative mass = rank * m0 (no mass arrays)
+  double m0;
   // cross-CTA machinery
-  unsigned *status;         // per bucket: (epoch << 2) | state
+  unsigned *status;         // per bucket: (epoch << 2) | state   (mass look-back)
   Desc *desc;
+  unsigned long long *cdesc;  // per bucket: packed count look-back word
   unsigned epoch;
   unsigned *ticket, *ticket_zero;
   unsigned *fail_seq;       // smallest launch sequence number that failed

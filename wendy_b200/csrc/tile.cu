@@ -123,7 +123,45 @@ __device__ __forceinline__ void lookback(const TileParams &p, int b, int seg_lo,
   }
 }
 
-template <int CAP, int THREADS, int LOAD, int EMIT, int PHYS>
+// Count look-back through one packed 64-bit word per bucket: epoch(30) | state(2) | value(32).
+// Counts are known when a CTA starts, so this runs at kernel entry and never waits for
+// a predecessor's sort.  Called by all lanes of warp 0; returns the exclusive prefix.
+__device__ __forceinline__ unsigned long long pack_cnt(unsigned epoch, unsigned state, unsigned v) {
+  return ((unsigned long long)epoch << 34) | ((unsigned long long)state << 32) | v;
+}
+__device__ __forceinline__ unsigned count_lookback(const TileParams &p, int b, int seg_lo, unsigned n,
+                                                   int lane) {
+  unsigned Pc = 0;
+  volatile unsigned long long *cd = p.cdesc;
+  if (b > seg_lo) {
+    if (lane == 0) cd[b] = pack_cnt(p.epoch, 1u, n);
+    int j = b - 1;
+    while (true) {
+      int idx = j - lane;
+      unsigned st = 2u, val = 0u;
+      if (idx >= seg_lo) {
+        unsigned long long w;
+        do {
+          w = cd[idx];
+        } while ((unsigned)(w >> 34) != p.epoch);
+        st = (unsigned)(w >> 32) & 3u;
+        val = (unsigned)w;
+      }
+      unsigned incl = __ballot_sync(WENDY_FULL_MASK, st == 2u);
+      int first = incl ? (__ffs(incl) - 1) : 32;
+      if (lane > first) val = 0u;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(WENDY_FULL_MASK, val, o);
+      Pc += val;
+      if (incl) break;
+      j -= 32;
+    }
+  }
+  if (lane == 0) cd[b] = pack_cnt(p.epoch, 2u, Pc + n);
+  return Pc;
+}
+
+template <int CAP, int THREADS, int LOAD, int EMIT, int PHYS, int EQM>
 __global__ void __launch_bounds__(THREADS, (CAP * 48 <= 100 * 1024) ? 2 : 1)
 tile_kernel(const TileParams p) {
   using SM = TileSmem<CAP, THREADS>;
@@ -145,9 +183,9 @@ tile_kernel(const TileParams p) {
   if (tid < DW) S.dcnt[tid] = 0;
   __syncthreads();
   const int b = S.bucket;
-  const int seg = b / p.nbps, kb = b - seg * p.nbps;
+  const int seg = (p.nbps == p.nb) ? 0 : b / p.nbps;
+  const int kb = b - seg * p.nbps;
   const int seg_lo = seg * p.nbps, seg_hi = seg_lo + p.nbps;
-  if (b == 0 && tid == 0 && p.ticket_zero) *p.ticket_zero = 0;
 
   unsigned n;
   if (LOAD == LOAD_BUCKET) {
@@ -161,8 +199,9 @@ tile_kernel(const TileParams p) {
     n = rem <= 0 ? 0u : (rem > CAP ? (unsigned)CAP : (unsigned)rem);
   }
   if (tid == 0) {
+    if (b == 0 && p.ticket_zero) *p.ticket_zero = 0;
     if (p.cnt_zero) p.cnt_zero[b] = 0;
-    atomicMax(p.stats, n);
+    if (n > (unsigned)(CAP - CAP / 8)) atomicMax(p.stats, n);
     if (EMIT == EMIT_RANK) p.cnt_out[b] = n;
   }
 
@@ -181,7 +220,6 @@ tile_kernel(const TileParams p) {
   unsigned g[E];
   double xk[E];
   int id[E];
-  double lmin = CUDART_INF, lmax = -CUDART_INF;
 #pragma unroll
   for (int k = 0; k < E; k++) {
     unsigned i = tid + k * THREADS;
@@ -197,28 +235,58 @@ tile_kernel(const TileParams p) {
       id[k] = p.idin[g[k]];
       if (p.h_pre != 0.0) x = __dadd_rn(x, __dmul_rn(p.h_pre, p.vin[g[k]]));
       xk[k] = x;
-      lmin = fmin(lmin, x);
-      lmax = fmax(lmax, x);
     }
   }
-  // ---- 2. block min / max -------------------------------------------------------------
+  // ---- 1b. number of particles in the preceding buckets of the segment -------------------
+  // (known at entry: published and resolved while the loads above are in flight)
+  if (wid == 0) {
+    unsigned pc = (LOAD == LOAD_BUCKET) ? count_lookback(p, b, seg_lo, n, lane) : (unsigned)kb * (unsigned)CAP;
+    if (lane == 0) S.pre_cnt = (long long)pc;
+  }
+  // ---- 2. key range of the bucket ----------------------------------------------------------
+  // Interior buckets of a splitter layout know their range [split[b], split[b+1]) a priori;
+  // otherwise (edge buckets, gathered tiles) reduce min / max over the block.
+  double xmin = -CUDART_INF, xmax = CUDART_INF;
+  if (LOAD == LOAD_BUCKET && EMIT == EMIT_SPLITTER) {
+    xmin = __ldg(p.split + b);
+    if (b + 1 < seg_hi) xmax = __ldg(p.split + b + 1);
+  }
+  if (!(xmin > -CUDART_INF && xmax < CUDART_INF)) {  // uniform over the block
+    double lmin = CUDART_INF, lmax = -CUDART_INF;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    lmin = fmin(lmin, __shfl_xor_sync(WENDY_FULL_MASK, lmin, o));
-    lmax = fmax(lmax, __shfl_xor_sync(WENDY_FULL_MASK, lmax, o));
-  }
-  if (lane == 0) {
-    S.dred[0][wid] = lmin;
-    S.dred[1][wid] = lmax;
-  }
-  __syncthreads();
-  double xmin = S.dred[0][0], xmax = S.dred[1][0];
+    for (int k = 0; k < E; k++)
+      if (tid + k * THREADS < n) {
+        lmin = fmin(lmin, xk[k]);
+        lmax = fmax(lmax, xk[k]);
+      }
 #pragma unroll
-  for (int w = 1; w < NW; w++) {
-    xmin = fmin(xmin, S.dred[0][w]);
-    xmax = fmax(xmax, S.dred[1][w]);
+    for (int o = 16; o > 0; o >>= 1) {
+      lmin = fmin(lmin, __shfl_xor_sync(WENDY_FULL_MASK, lmin, o));
+      lmax = fmax(lmax, __shfl_xor_sync(WENDY_FULL_MASK, lmax, o));
+    }
+    if (lane == 0) {
+      S.dred[0][wid] = lmin;
+      S.dred[1][wid] = lmax;
+    }
+    __syncthreads();
+    if (wid == 0) {
+      lmin = lane < NW ? S.dred[0][lane] : CUDART_INF;
+      lmax = lane < NW ? S.dred[1][lane] : -CUDART_INF;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lmin = fmin(lmin, __shfl_xor_sync(WENDY_FULL_MASK, lmin, o));
+        lmax = fmax(lmax, __shfl_xor_sync(WENDY_FULL_MASK, lmax, o));
+      }
+      if (lane == 0) {
+        S.dred[2][0] = lmin;
+        S.dred[2][1] = lmax;
+      }
+    }
+    __syncthreads();
+    xmin = S.dred[2][0];
+    xmax = S.dred[2][1];
   }
-  double range = xmax - xmin;
+  const double range = xmax - xmin;
   const double scale = (range > 0.0 && range < CUDART_INF) ? (double)(BK - 1) / range : 0.0;
 
   // ---- 3. interpolation sub-bucket of every key (monotone in x), arrival slot -----------
@@ -276,10 +344,12 @@ tile_kernel(const TileParams p) {
   // ---- 6. exact rank under the (x, id) order; masses are fetched meanwhile ---------------
   double m[E];
   unsigned r[E];
+  if (!EQM) {
 #pragma unroll
-  for (int k = 0; k < E; k++) {
-    m[k] = 0.0;
-    if (tid + k * THREADS < n) m[k] = p.min[g[k]];
+    for (int k = 0; k < E; k++) {
+      m[k] = 0.0;
+      if (tid + k * THREADS < n) m[k] = p.min[g[k]];
+    }
   }
 #pragma unroll
   for (int k = 0; k < E; k++) {
@@ -289,69 +359,78 @@ tile_kernel(const TileParams p) {
       unsigned s0 = S.u.srt.cnt[sub + sub / E];
       unsigned s1 = (sub + 1 < (unsigned)BK) ? S.u.srt.cnt[(sub + 1) + (sub + 1) / E] : n;
       unsigned rr = s0;
-      const double xi = xk[k];
-      const int ii = id[k];
-      for (unsigned q = s0; q < s1; q++) {
-        unsigned j = S.u.srt.slot[q];
-        double xj = S.sx[j];
-        rr += (xj < xi || (xj == xi && S.sid[j] < ii)) ? 1u : 0u;
+      if (s1 - s0 > 1u) {  // shared sub-bucket: count the members that sort before this one
+        const double xi = xk[k];
+        const int ii = id[k];
+        for (unsigned q = s0; q < s1; q++) {
+          unsigned j = S.u.srt.slot[q];
+          double xj = S.sx[j];
+          rr += (xj < xi || (xj == xi && S.sid[j] < ii)) ? 1u : 0u;
+        }
       }
       r[k] = rr;
     }
   }
-  __syncthreads();  // counters and slots are dead from here on; mcum aliases them
-  // ---- 7. masses into sorted order ----------------------------------------------------------
+  long long Pc;
+  if (EQM) {
+    // Equal masses: the exact prefix sum below sorted position k is k*m0, so its correctly
+    // rounded value is one fp64 multiply -- bit-identical to the general path below.
+    __syncthreads();  // S.pre_cnt (written by warp 0 long ago) is visible to everyone
+    Pc = S.pre_cnt;
+  } else {
+    __syncthreads();  // counters and slots are dead from here on; mcum aliases them
+    // ---- 7. masses into sorted order --------------------------------------------------------
 #pragma unroll
-  for (int k = 0; k < E; k++)
-    if (tid + k * THREADS < n) S.u.mcum[r[k] + r[k] / E] = m[k];
-  __syncthreads();
-  // ---- 8. exact exclusive scan of the masses (128-bit fixed point) ----------------------------
-  i128 loc[E];
-  i128 tsum = 0;
-  {
-    double *mp = &S.u.mcum[tid * (E + 1)];
+    for (int k = 0; k < E; k++)
+      if (tid + k * THREADS < n) S.u.mcum[r[k] + r[k] / E] = m[k];
+    __syncthreads();
+    // ---- 8. exact exclusive scan of the masses (128-bit fixed point) --------------------------
+    i128 loc[E];
+    i128 tsum = 0;
+    {
+      double *mp = &S.u.mcum[tid * (E + 1)];
 #pragma unroll
-    for (int q = 0; q < E; q++) {
-      loc[q] = tsum;
-      if ((unsigned)(tid * E + q) < n) tsum += fx_from_double(mp[q], p.fxE);
+      for (int q = 0; q < E; q++) {
+        loc[q] = tsum;
+        if ((unsigned)(tid * E + q) < n) tsum += fx_from_double(mp[q], p.fxE);
+      }
     }
-  }
-  i128 winc = warp_inclusive_scan_i128(tsum, lane);
-  if (lane == 31) {
-    S.wlo[wid] = (unsigned long long)winc;
-    S.whi[wid] = (unsigned long long)((u128)winc >> 64);
-  }
-  __syncthreads();
-  // ---- 9. warp 0: scan of the warp totals, then look-back for the bucket prefix --------------
-  if (wid == 0) {
-    i128 t = lane < NW ? make_i128(S.wlo[lane], S.whi[lane]) : (i128)0;
-    i128 ti = warp_inclusive_scan_i128(t, lane);
-    i128 agg = shfl_i128(ti, 31);
-    i128 tex = ti - t;
-    if (lane < NW) {
-      S.wlo[lane] = (unsigned long long)tex;
-      S.whi[lane] = (unsigned long long)((u128)tex >> 64);
+    i128 winc = warp_inclusive_scan_i128(tsum, lane);
+    if (lane == 31) {
+      S.wlo[wid] = (unsigned long long)winc;
+      S.whi[wid] = (unsigned long long)((u128)winc >> 64);
     }
-    i128 P;
-    long long Pc;
-    lookback(p, b, seg_lo, agg, (long long)n, lane, P, Pc);
-    if (lane == 0) {
-      S.pre_lo = (unsigned long long)P;
-      S.pre_hi = (unsigned long long)((u128)P >> 64);
-      S.pre_cnt = Pc;
+    __syncthreads();
+    // ---- 9. warp 0: scan of the warp totals, then look-back for the bucket prefix ------------
+    if (wid == 0) {
+      i128 t = lane < NW ? make_i128(S.wlo[lane], S.whi[lane]) : (i128)0;
+      i128 ti = warp_inclusive_scan_i128(t, lane);
+      i128 agg = shfl_i128(ti, 31);
+      i128 tex = ti - t;
+      if (lane < NW) {
+        S.wlo[lane] = (unsigned long long)tex;
+        S.whi[lane] = (unsigned long long)((u128)tex >> 64);
+      }
+      i128 P;
+      long long Pcm;
+      lookback(p, b, seg_lo, agg, (long long)n, lane, P, Pcm);
+      if (lane == 0) {
+        S.pre_lo = (unsigned long long)P;
+        S.pre_hi = (unsigned long long)((u128)P >> 64);
+      }
     }
-  }
-  __syncthreads();
-  // ---- 10. cumulative mass below every sorted position, correctly rounded ---------------------
-  {
-    i128 base = make_i128(S.pre_lo, S.pre_hi) + make_i128(S.wlo[wid], S.whi[wid]) + (winc - tsum);
-    double *mp = &S.u.mcum[tid * (E + 1)];
+    __syncthreads();
+    // ---- 10. cumulative mass below every sorted position, correctly rounded -------------------
+    {
+      i128 base = make_i128(S.pre_lo, S.pre_hi) + make_i128(S.wlo[wid], S.whi[wid]) + (winc - tsum);
+      double *mp = &S.u.mcum[tid * (E + 1)];
 #pragma unroll
-    for (int q = 0; q < E; q++)
-      if ((unsigned)(tid * E + q) < n) mp[q] = fx_to_double(base + loc[q], p.fxE);
+      for (int q = 0; q < E; q++)
+        if ((unsigned)(tid * E + q) < n) mp[q] = fx_to_double(base + loc[q], p.fxE);
+    }
+    Pc = S.pre_cnt;
+    __syncthreads();
   }
-  const long long Pc = S.pre_cnt;
-  __syncthreads();
   // ---- 11. force, kick, drift (or diagnostics) ----------------------------------------------------
   const double tot = p.tot[seg];
   double x2[E], v2[E], xb[E];
@@ -360,9 +439,16 @@ tile_kernel(const TileParams p) {
   for (int k = 0; k < E; k++) {
     x2[k] = v2[k] = xb[k] = 0.0;
     if (tid + k * THREADS < n) {
-      const double c = S.u.mcum[r[k] + r[k] / E];
+      double c, mk;
+      if (EQM) {
+        mk = p.m0;
+        c = __dmul_rn((double)(Pc + (long long)r[k]), p.m0);
+      } else {
+        mk = m[k];
+        c = S.u.mcum[r[k] + r[k] / E];
+      }
       const double v = p.vin[g[k]];
-      double grav = __dsub_rn(__dsub_rn(tot, __dmul_rn(2.0, c)), m[k]);
+      double grav = __dsub_rn(__dsub_rn(tot, __dmul_rn(2.0, c)), mk);
       if (PHYS) {
         double acc = grav;
         if (p.omega2 >= 0.0) acc = __dsub_rn(acc, __dmul_rn(p.omega2, xk[k]));
@@ -376,12 +462,13 @@ tile_kernel(const TileParams p) {
         xb[k] = xk[k];
       }
       if (EMIT == EMIT_NONE) {  // energy terms, reference wendy/wendy.py:458-475
-        e_ke += 0.5 * m[k] * v * v;
-        if (p.omega2 >= 0.0) e_he += 0.5 * m[k] * p.omega2 * xk[k] * xk[k];
-        e_pe -= m[k] * xk[k] * grav;
-        e_mom += m[k] * v;
+        e_ke += 0.5 * mk * v * v;
+        if (p.omega2 >= 0.0) e_he += 0.5 * mk * p.omega2 * xk[k] * xk[k];
+        e_pe -= mk * xk[k] * grav;
+        e_mom += mk * v;
       }
       if (p.rank_out) p.rank_out[id[k]] = (int)(Pc + (long long)r[k]);
+      if (!EQM) m[k] = mk;
     }
   }
   if (EMIT == EMIT_NONE) {
@@ -416,7 +503,7 @@ tile_kernel(const TileParams p) {
         size_t o = (size_t)b * CAP + r[k];
         p.xout[o] = x2[k];
         p.vout[o] = v2[k];
-        p.mout[o] = m[k];
+        if (!EQM) p.mout[o] = m[k];
         p.idout[o] = id[k];
       }
     }
@@ -426,13 +513,15 @@ tile_kernel(const TileParams p) {
   int dest[E];
   unsigned lpos[E];
   unsigned outside = 0;
+  const int rel = b - wlo;
+  const double home_lo = S.ssplit[rel], home_hi = S.ssplit[rel + 1];
 #pragma unroll
   for (int k = 0; k < E; k++) {
     int d = -1;
-    if (tid + k * THREADS < n) {
+    const bool ok = tid + k * THREADS < n;
+    if (ok) {
       const double key = xb[k];
-      const int rel = b - wlo;
-      if (key >= S.ssplit[rel] && key < S.ssplit[rel + 1]) {
+      if (key >= home_lo && key < home_hi) {
         d = b;
       } else if (key >= S.ssplit[0] && key < S.ssplit[wn]) {
         int lo = 0, hi = wn;
@@ -451,11 +540,19 @@ tile_kernel(const TileParams p) {
       }
     }
     dest[k] = d;
-    unsigned mask = __match_any_sync(WENDY_FULL_MASK, d);
-    int leader = __ffs(mask) - 1;
-    unsigned basel = 0;
+    // slot allocation, aggregated per warp and destination
+    unsigned basel = 0, mask;
+    int leader;
+    const unsigned valid = __ballot_sync(WENDY_FULL_MASK, ok);
+    if (__all_sync(WENDY_FULL_MASK, d == b || !ok)) {  // whole warp stays home (the common case)
+      mask = ok ? valid : 0u;
+      leader = __ffs(valid) - 1;
+    } else {
+      mask = __match_any_sync(WENDY_FULL_MASK, d);
+      leader = __ffs(mask) - 1;
+    }
     const bool inwin = (d >= wlo && d < wlo + wn);
-    if (lane == leader && d >= 0) {
+    if (ok && lane == leader) {
       if (inwin) {
         basel = atomicAdd(&S.dcnt[d - wlo], (unsigned)__popc(mask));
       } else {
@@ -463,7 +560,7 @@ tile_kernel(const TileParams p) {
         outside += __popc(mask);
       }
     }
-    basel = __shfl_sync(WENDY_FULL_MASK, basel, leader);
+    basel = __shfl_sync(WENDY_FULL_MASK, basel, leader < 0 ? 0 : leader);
     lpos[k] = basel + __popc(mask & lt);
   }
   __syncthreads();
@@ -481,7 +578,7 @@ tile_kernel(const TileParams p) {
         size_t o = (size_t)d * CAP + pos;
         p.xout[o] = x2[k];
         p.vout[o] = v2[k];
-        p.mout[o] = m[k];
+        if (!EQM) p.mout[o] = m[k];
         p.idout[o] = id[k];
       } else {
         overflow = true;
@@ -492,22 +589,21 @@ tile_kernel(const TileParams p) {
 }
 
 // ---- dispatch -------------------------------------------------------------------------------------------
-template <int CAP, int THREADS>
+template <int CAP, int THREADS, int EQM>
 static void launch_tile_cap(cudaStream_t st, int load, int emit, int physics, const TileParams &p) {
   size_t sm = sizeof(TileSmem<CAP, THREADS>);
 #define WENDY_LAUNCH(L, EM, PH)                                                                   \
   do {                                                                                              \
     static bool attr_set = false;                                                                   \
     if (!attr_set) {                                                                                \
-      cudaFuncSetAttribute(tile_kernel<CAP, THREADS, L, EM, PH>,                                    \
+      cudaFuncSetAttribute(tile_kernel<CAP, THREADS, L, EM, PH, EQM>,                               \
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                   \
       attr_set = true;                                                                              \
     }                                                                                               \
-    tile_kernel<CAP, THREADS, L, EM, PH><<<p.nb, THREADS, sm, st>>>(p);                             \
+    tile_kernel<CAP, THREADS, L, EM, PH, EQM><<<p.nb, THREADS, sm, st>>>(p);                        \
   } while (0)
   if (load == LOAD_BUCKET && emit == EMIT_SPLITTER && physics) WENDY_LAUNCH(LOAD_BUCKET, EMIT_SPLITTER, 1);
   else if (load == LOAD_GATHER && emit == EMIT_RANK && physics) WENDY_LAUNCH(LOAD_GATHER, EMIT_RANK, 1);
-  else if (load == LOAD_GATHER && emit == EMIT_RANK && !physics) WENDY_LAUNCH(LOAD_GATHER, EMIT_RANK, 0);
   else if (load == LOAD_GATHER && emit == EMIT_NONE && !physics) WENDY_LAUNCH(LOAD_GATHER, EMIT_NONE, 0);
 #undef WENDY_LAUNCH
 }
@@ -520,8 +616,13 @@ size_t tile_smem_bytes(int cap) {
 
 void launch_tile(cudaStream_t st, int cap, int load, int emit, int physics, const TileParams &p) {
   if (p.nb <= 0) return;
-  if (cap == 2048) launch_tile_cap<2048, 512>(st, load, emit, physics, p);
-  else launch_tile_cap<256, 64>(st, load, emit, physics, p);
+  if (cap == 2048) {
+    if (p.eqm) launch_tile_cap<2048, 512, 1>(st, load, emit, physics, p);
+    else launch_tile_cap<2048, 512, 0>(st, load, emit, physics, p);
+  } else {
+    if (p.eqm) launch_tile_cap<256, 64, 1>(st, load, emit, physics, p);
+    else launch_tile_cap<256, 64, 0>(st, load, emit, physics, p);
+  }
 }
 
 // =========================================================================================================
@@ -574,7 +675,7 @@ scatter_kernel(const ScatterParams p) {
         size_t o = (size_t)d * p.cap_out + pos;
         p.xout[o] = x;
         p.vout[o] = v;
-        p.mout[o] = p.min[i];
+        if (p.min) p.mout[o] = p.min[i];
         p.idout[o] = p.idin[i];
       } else {
         overflow = true;

@@ -39,7 +39,8 @@ class _CudaArrayView(object):
 class ApproxState(object):
     """Device-resident particle state + the step driver (one per generator)."""
 
-    def __init__(self, x, v, m, omega2=-1., n_segments=1, sort='gpu', cap=0, fill=0, stream=None):
+    def __init__(self, x, v, m, omega2=-1., n_segments=1, sort='gpu', cap=0, fill=0, stream=None,
+                 general_masses=False):
         self._lib = _lib.load()
         x = numpy.require(x, dtype=numpy.float64, requirements=['C'])
         v = numpy.require(v, dtype=numpy.float64, requirements=['C'])
@@ -58,7 +59,8 @@ class ApproxState(object):
         self._h = ctypes.c_void_p()
         _lib.check(self._lib.wendy_cuda_create(ctypes.byref(self._h), self.N, x, v, m, tot,
                                                float(omega2), self.n_segments,
-                                               _lib.SORT_FLAGS[sort], int(cap), int(fill),
+                                               _lib.SORT_FLAGS[sort] | (0x10 if general_masses else 0),
+                                               int(cap), int(fill),
                                                ctypes.c_void_p(stream) if stream else None))
         self.time_elapsed = 0.
 
@@ -131,7 +133,7 @@ class ApproxState(object):
 def nbody(x, v, m, dt, t0=0., twopiG=1., omega=None, ext_force=None,
           approx=False, nleap=None, sort='gpu',
           maxcoll=100000, warn_maxcoll=False,
-          full_output=False, n_segments=1, _cap=0, _fill=0):
+          full_output=False, n_segments=1, _cap=0, _fill=0, _general_masses=False):
     """
     NAME:
        nbody
@@ -160,19 +162,20 @@ def nbody(x, v, m, dt, t0=0., twopiG=1., omega=None, ext_force=None,
         raise ValueError('When approx is True, the number of leapfrog steps nleap= per output time step needs to be set')
     for item in _nbody_approx(x, v, m, dt, nleap, t0=t0, sort=sort, omega=omega,
                               ext_force=ext_force, twopiG=twopiG, full_output=full_output,
-                              n_segments=n_segments, _cap=_cap, _fill=_fill):
+                              n_segments=n_segments, _cap=_cap, _fill=_fill,
+                              _general_masses=_general_masses):
         yield item
 
 
 def _nbody_approx(x, v, m, dt, nleap, t0=0., omega=None, ext_force=None, sort='gpu',
-                  twopiG=1., full_output=False, n_segments=1, _cap=0, _fill=0):
+                  twopiG=1., full_output=False, n_segments=1, _cap=0, _fill=0, _general_masses=False):
     """Setup follows reference wendy/wendy.py:363-387,422; loop follows :424-437."""
     omega2 = -1. if omega is None else omega ** 2.
     x = numpy.require(numpy.array(x, dtype=numpy.float64), requirements=['C', 'W'])
     v = numpy.require(numpy.array(v, dtype=numpy.float64), requirements=['C', 'W'])
     ms = numpy.require(twopiG * numpy.array(m, dtype=numpy.float64), requirements=['C', 'W'])
     state = ApproxState(x, v, ms, omega2=omega2, n_segments=n_segments, sort=sort, cap=_cap,
-                        fill=_fill)
+                        fill=_fill, general_masses=_general_masses)
     dt_leap = dt / nleap
     try:
         while True:
