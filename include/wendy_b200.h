@@ -62,7 +62,8 @@ struct wendy_array_w_index {
  *   n_segments independent realisations of N/n_segments particles each, laid out
  *              contiguously (1 for a single system)
  *   flags      WENDY_SORT_*
- *   cap, fill  bucket capacity (0: default 2048; 256 for tests) and target fill (0: 3/4 cap)
+ *   cap, fill  bucket capacity (0: default 256 = one warp per bucket; 2048 = one CTA per bucket)
+ *              and target fill (0: 128 of 256, 1536 of 2048)
  *   cuda_stream cudaStream_t to run on (NULL: the legacy default stream)                   */
 int wendy_cuda_create(wendy_cuda_handle **h, long long N, const double *x, const double *v,
                       const double *m, const double *totmass, double omega2, int n_segments,
@@ -101,6 +102,10 @@ int wendy_cuda_energy(wendy_cuda_handle *h, double out[4]);
  * [5] kernels launched, [6] bucket capacity, [7] buckets, [8] sub-steps that fell back to the
  * radix path because a freshly balanced layout still overflowed. */
 int wendy_cuda_stats(wendy_cuda_handle *h, long long *out, int n);
+
+/* Test/diagnostic hook: copies the per-bucket particle counts and lower splitters of the current
+ * layout to HOST arrays of nb_max entries; returns the number of buckets (0: no layout yet). */
+int wendy_cuda_debug_layout(wendy_cuda_handle *h, unsigned *counts, double *splitters, int nb_max);
 
 void wendy_cuda_destroy(wendy_cuda_handle *h);
 const char *wendy_cuda_last_error(void);

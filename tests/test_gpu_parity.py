@@ -24,7 +24,7 @@ EXT_TORCH = {
     'sech2_1000_ext': lambda x, t: -0.7 * __import__('torch').tanh(0.5 * x) + 0.05 * t,
 }
 SORTS = ['gpu', 'gpu-radix']
-CAPS = [0, 256]  # production bucket capacity, and a tiny one that forces many buckets
+CAPS = [0, 2048]  # warp-per-bucket kernel (cap 256, default) and CTA-per-bucket kernel
 
 
 def relerr(a, b):

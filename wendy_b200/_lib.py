@@ -58,6 +58,8 @@ def load():
     lib.wendy_cuda_energy.argtypes = [vp, _nd('f8')]
     lib.wendy_cuda_stats.restype = ctypes.c_int
     lib.wendy_cuda_stats.argtypes = [vp, _nd('i8'), ctypes.c_int]
+    lib.wendy_cuda_debug_layout.restype = ctypes.c_int
+    lib.wendy_cuda_debug_layout.argtypes = [vp, _nd('u4'), _nd('f8'), ctypes.c_int]
     lib.wendy_cuda_destroy.restype = None
     lib.wendy_cuda_destroy.argtypes = [vp]
     lib.wendy_cuda_argsort.restype = ctypes.c_int
@@ -74,7 +76,7 @@ def load():
 #: every symbol include/wendy_b200.h declares (checked by tests/test_abi.py)
 EXPORTED = ['wendy_cuda_create', 'wendy_cuda_step', 'wendy_cuda_force_positions',
             'wendy_cuda_substep', 'wendy_cuda_read', 'wendy_cuda_read_dev', 'wendy_cuda_energy',
-            'wendy_cuda_stats', 'wendy_cuda_destroy', 'wendy_cuda_last_error',
+            'wendy_cuda_stats', 'wendy_cuda_debug_layout', 'wendy_cuda_destroy', 'wendy_cuda_last_error',
             'wendy_cuda_argsort', '_wendy_nbody_approx_onestep']
 
 

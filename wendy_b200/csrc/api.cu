@@ -64,6 +64,9 @@ struct wendy_cuda_handle {
   unsigned *status = nullptr;
   Desc *desc = nullptr;
   unsigned long long *cdesc = nullptr;
+  unsigned *cpre = nullptr;            // exclusive prefix of the current bucket counts
+  unsigned long long *cp_desc = nullptr;  // look-back words of the count_prefix kernel
+  unsigned *cp_ticket = nullptr;
   unsigned *flags = nullptr;    // [0] fail_seq, [1] max count, [2] outside-window count
   unsigned *h_flags = nullptr;  // pinned mirror
   unsigned seq = 1;
@@ -211,7 +214,13 @@ static void launch_bucket_substep(H *h, double h_pre, double dt_kick, double dt_
   fill_tile_params(h, p);
   p.h_pre = h_pre; p.dt_kick = dt_kick; p.dt_drift = dt_drift; p.h_next = h_next;
   p.aext = aext; p.rank_out = rank_out;
-  launch_tile(h->st, h->cap, LOAD_BUCKET, EMIT_SPLITTER, 1, p);
+  if (wstep_cap_supported(h->cap)) {
+    launch_count_prefix(h->st, p.cnt_in, h->nb, h->cpre, h->cp_desc, h->cp_ticket, p.epoch);
+    h->n_launch++;
+    p.cpre = h->cpre;
+    launch_wstep(h->st, h->cap, p);
+  }
+  else launch_tile(h->st, h->cap, LOAD_BUCKET, EMIT_SPLITTER, 1, p);
   advance_after_tile(h);
   h->cur ^= 1; h->ccur = (h->ccur + 1) % 3; h->bucket_h = h_next;
   h->n_sub++;
@@ -250,7 +259,7 @@ void wendy_cuda_destroy(wendy_cuda_handle *h) {
   for (int i = 0; i < 3; i++) cudaFree(h->cnt[i]);
   cudaFree(h->rs.table); cudaFree(h->rs.sums);
   cudaFree(h->split); cudaFree(h->tot); cudaFree(h->ticket); cudaFree(h->status); cudaFree(h->desc);
-  cudaFree(h->cdesc);
+  cudaFree(h->cdesc); cudaFree(h->cpre); cudaFree(h->cp_desc); cudaFree(h->cp_ticket);
   cudaFree(h->flags); cudaFree(h->offs); cudaFree(h->xo); cudaFree(h->vo); cudaFree(h->epart);
   cudaFree(h->eout); cudaFree(h->rank);
   if (h->h_flags) cudaFreeHost(h->h_flags);
@@ -264,9 +273,12 @@ int wendy_cuda_create(wendy_cuda_handle **out, long long N, const double *x, con
   if (!out || !x || !v || !m || !totmass) return set_err(WENDY_E_ARG, "null argument");
   if (N <= 0 || N >= (1ll << 31)) return set_err(WENDY_E_ARG, "N must be in [1, 2^31)");
   if (n_segments < 1 || N % n_segments) return set_err(WENDY_E_ARG, "N must be a multiple of n_segments");
-  if (cap == 0) cap = 2048;
+  if (cap == 0) cap = 256;
   if (!tile_cap_supported(cap)) return set_err(WENDY_E_ARG, "cap must be 2048 or 256");
-  if (fill == 0) fill = cap * 3 / 4;
+  // Splitters are exact quantiles of ONE random sample, so bucket widths carry their own
+  // 1/sqrt(fill) noise and the steady-state count variance is 2*fill (measured: DESIGN.md).
+  // Defaults leave >= 8 sigma of head-room: 128 + 8*sqrt(256) = 256, 1536 + 9*sqrt(3072) < 2048.
+  if (fill == 0) fill = (cap == 256) ? 128 : cap * 3 / 4;
   if (fill < 1 || fill > cap) return set_err(WENDY_E_ARG, "fill must be in [1, cap]");
   H *h = new H;
   *out = nullptr;
@@ -316,6 +328,11 @@ int wendy_cuda_create(wendy_cuda_handle **out, long long N, const double *x, con
   CKD(cudaMalloc(&h->desc, (size_t)h->nb * sizeof(Desc)));
   CKD(cudaMalloc(&h->cdesc, (size_t)h->nb * sizeof(unsigned long long)));
   CKD(cudaMemsetAsync(h->cdesc, 0, (size_t)h->nb * sizeof(unsigned long long), h->st));
+  CKD(cudaMalloc(&h->cpre, (size_t)h->nb * sizeof(unsigned)));
+  CKD(cudaMalloc(&h->cp_desc, (size_t)(count_prefix_tiles(h->nb) + 1) * sizeof(unsigned long long)));
+  CKD(cudaMemsetAsync(h->cp_desc, 0, (size_t)(count_prefix_tiles(h->nb) + 1) * sizeof(unsigned long long), h->st));
+  CKD(cudaMalloc(&h->cp_ticket, sizeof(unsigned)));
+  CKD(cudaMemsetAsync(h->cp_ticket, 0, sizeof(unsigned), h->st));
   CKD(cudaMalloc(&h->flags, 4 * sizeof(unsigned)));
   CKD(cudaMalloc(&h->offs, (size_t)h->nb * sizeof(unsigned long long)));
   CKD(cudaMalloc(&h->epart, (size_t)h->nb * 4 * sizeof(double)));
@@ -395,7 +412,7 @@ static int run_substeps(H *h, double dt, int nleap) {
     }
   }
   // cheap insurance: re-balance between calls when some bucket is nearly full
-  if (h->mode != WENDY_SORT_RADIX && h->h_flags[1] > (unsigned)(h->cap - (h->cap - h->fill) / 4)) {
+  if (h->mode != WENDY_SORT_RADIX && h->h_flags[1] > (unsigned)(h->cap - (h->cap - h->fill) / 16)) {
     int rc = rebucket(h, h->bucket_h);
     if (rc) return rc;
   }
@@ -456,7 +473,7 @@ int wendy_cuda_substep(wendy_cuda_handle *h, double dt_kick, double dt_drift, do
     if (rc) return rc;
     return WENDY_RETRY;
   }
-  if (h->h_flags[1] > (unsigned)(h->cap - (h->cap - h->fill) / 4)) {
+  if (h->h_flags[1] > (unsigned)(h->cap - (h->cap - h->fill) / 16)) {
     // nearly full bucket: re-balance now; the caller's next force_positions sees the new slots
     int rc = rebucket(h, h_next);
     if (rc) return rc;
@@ -521,6 +538,16 @@ int wendy_cuda_stats(wendy_cuda_handle *h, long long *out, int n) {
                     (long long)h->cap, (long long)h->nb, h->n_radix_fallback};
   for (int i = 0; i < n && i < 9; i++) out[i] = s[i];
   return 0;
+}
+
+int wendy_cuda_debug_layout(wendy_cuda_handle *h, unsigned *counts, double *splitters, int nb_max) {
+  if (!h) return set_err(WENDY_E_ARG, "null handle");
+  if (h->dense) return 0;
+  int nb = h->nb < nb_max ? h->nb : nb_max;
+  CK(cudaStreamSynchronize(h->st));
+  if (counts) CK(cudaMemcpy(counts, h->cnt[h->ccur], (size_t)nb * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  if (splitters) CK(cudaMemcpy(splitters, h->split, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost));
+  return nb;
 }
 
 int wendy_cuda_argsort(const double *x_host, long long N, int *perm_out) {

@@ -56,6 +56,7 @@ struct TileParams {
   unsigned *status;         // per bucket: (epoch << 2) | state   (mass look-back)
   Desc *desc;
   unsigned long long *cdesc;  // per bucket: packed count look-back word
+  const unsigned *cpre;       // wstep: exclusive prefix of cnt_in over ALL buckets (count_prefix kernel)
   unsigned epoch;
   unsigned *ticket, *ticket_zero;
   unsigned *fail_seq;       // smallest launch sequence number that failed
@@ -68,6 +69,13 @@ struct TileParams {
 
 void launch_tile(cudaStream_t st, int cap, int load, int emit, int physics, const TileParams &p);
 size_t tile_smem_bytes(int cap);
+// wstep.cu: warp-per-bucket sub-step (cap 256)
+void launch_wstep(cudaStream_t st, int cap, const TileParams &p);
+// exclusive prefix sum of the bucket counts (single pass, decoupled look-back over CTA tiles)
+void launch_count_prefix(cudaStream_t st, const unsigned *cnt, int nb, unsigned *cpre,
+                         unsigned long long *tile_desc, unsigned *ticket, unsigned epoch);
+int count_prefix_tiles(int nb);
+bool wstep_cap_supported(int cap);
 bool tile_cap_supported(int cap);
 
 struct ScatterParams {

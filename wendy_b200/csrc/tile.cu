@@ -25,6 +25,7 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "lookback.cuh"
 
 namespace wendy {
 
@@ -53,113 +54,6 @@ struct TileSmem {
   unsigned utotal;
   int bucket;
 };
-
-__device__ __forceinline__ i128 make_i128(unsigned long long lo, unsigned long long hi) {
-  return (i128)(((u128)hi << 64) | (u128)lo);
-}
-
-// Decoupled look-back over the buckets of one segment; called by all lanes of warp 0.
-// Returns the exclusive prefix (mass, count) of bucket b and publishes its inclusive one.
-// Sums are exact integers, so the result does not depend on which predecessors happened
-// to have published an inclusive prefix already.
-__device__ __forceinline__ void lookback(const TileParams &p, int b, int seg_lo, i128 agg,
-                                         long long n, int lane, i128 &P, long long &Pc) {
-  P = 0;
-  Pc = 0;
-  Desc *me = p.desc + b;
-  if (b > seg_lo) {
-    if (lane == 0) {
-      me->agg_lo = (unsigned long long)agg;
-      me->agg_hi = (unsigned long long)((u128)agg >> 64);
-      me->agg_cnt = n;
-      __threadfence();
-      *(volatile unsigned *)(p.status + b) = (p.epoch << 2) | 1u;
-    }
-    int j = b - 1;
-    while (true) {
-      int idx = j - lane;
-      unsigned st = 2u;  // lanes before the segment start act as "inclusive prefix 0"
-      i128 val = 0;
-      long long c = 0;
-      if (idx >= seg_lo) {
-        do {
-          st = ld_volatile_u32(p.status + idx);
-        } while ((st >> 2) != p.epoch);
-        st &= 3u;
-        __threadfence();
-        const Desc *d = p.desc + idx;
-        if (st == 2u) {
-          val = make_i128(__ldcg(&d->inc_lo), __ldcg(&d->inc_hi));
-          c = __ldcg(&d->inc_cnt);
-        } else {
-          val = make_i128(__ldcg(&d->agg_lo), __ldcg(&d->agg_hi));
-          c = __ldcg(&d->agg_cnt);
-        }
-      }
-      unsigned incl = __ballot_sync(WENDY_FULL_MASK, st == 2u);
-      int first = incl ? (__ffs(incl) - 1) : 32;
-      if (lane > first) {
-        val = 0;
-        c = 0;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        val += shfl_xor_i128(val, o);
-        c += __shfl_xor_sync(WENDY_FULL_MASK, c, o);
-      }
-      P += val;
-      Pc += c;
-      if (incl) break;
-      j -= 32;
-    }
-  }
-  if (lane == 0) {
-    i128 inc = P + agg;
-    me->inc_lo = (unsigned long long)inc;
-    me->inc_hi = (unsigned long long)((u128)inc >> 64);
-    me->inc_cnt = Pc + n;
-    __threadfence();
-    *(volatile unsigned *)(p.status + b) = (p.epoch << 2) | 2u;
-  }
-}
-
-// Count look-back through one packed 64-bit word per bucket: epoch(30) | state(2) | value(32).
-// Counts are known when a CTA starts, so this runs at kernel entry and never waits for
-// a predecessor's sort.  Called by all lanes of warp 0; returns the exclusive prefix.
-__device__ __forceinline__ unsigned long long pack_cnt(unsigned epoch, unsigned state, unsigned v) {
-  return ((unsigned long long)epoch << 34) | ((unsigned long long)state << 32) | v;
-}
-__device__ __forceinline__ unsigned count_lookback(const TileParams &p, int b, int seg_lo, unsigned n,
-                                                   int lane) {
-  unsigned Pc = 0;
-  volatile unsigned long long *cd = p.cdesc;
-  if (b > seg_lo) {
-    if (lane == 0) cd[b] = pack_cnt(p.epoch, 1u, n);
-    int j = b - 1;
-    while (true) {
-      int idx = j - lane;
-      unsigned st = 2u, val = 0u;
-      if (idx >= seg_lo) {
-        unsigned long long w;
-        do {
-          w = cd[idx];
-        } while ((unsigned)(w >> 34) != p.epoch);
-        st = (unsigned)(w >> 32) & 3u;
-        val = (unsigned)w;
-      }
-      unsigned incl = __ballot_sync(WENDY_FULL_MASK, st == 2u);
-      int first = incl ? (__ffs(incl) - 1) : 32;
-      if (lane > first) val = 0u;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(WENDY_FULL_MASK, val, o);
-      Pc += val;
-      if (incl) break;
-      j -= 32;
-    }
-  }
-  if (lane == 0) cd[b] = pack_cnt(p.epoch, 2u, Pc + n);
-  return Pc;
-}
 
 template <int CAP, int THREADS, int LOAD, int EMIT, int PHYS, int EQM>
 __global__ void __launch_bounds__(THREADS, (CAP * 48 <= 100 * 1024) ? 2 : 1)
@@ -201,7 +95,7 @@ tile_kernel(const TileParams p) {
   if (tid == 0) {
     if (b == 0 && p.ticket_zero) *p.ticket_zero = 0;
     if (p.cnt_zero) p.cnt_zero[b] = 0;
-    if (n > (unsigned)(CAP - CAP / 8)) atomicMax(p.stats, n);
+    if (n > (unsigned)(CAP - CAP / 16)) atomicMax(p.stats, n);
     if (EMIT == EMIT_RANK) p.cnt_out[b] = n;
   }
 
@@ -240,7 +134,7 @@ tile_kernel(const TileParams p) {
   // ---- 1b. number of particles in the preceding buckets of the segment -------------------
   // (known at entry: published and resolved while the loads above are in flight)
   if (wid == 0) {
-    unsigned pc = (LOAD == LOAD_BUCKET) ? count_lookback(p, b, seg_lo, n, lane) : (unsigned)kb * (unsigned)CAP;
+    unsigned pc = (LOAD == LOAD_BUCKET) ? count_lookback(p.cdesc, p.epoch, b, seg_lo, n, lane) : (unsigned)kb * (unsigned)CAP;
     if (lane == 0) S.pre_cnt = (long long)pc;
   }
   // ---- 2. key range of the bucket ----------------------------------------------------------

@@ -1,0 +1,452 @@
+// wstep.cu -- the steady-state hot kernel: one leapfrog sub-step, ONE WARP PER BUCKET.
+//
+// Same algorithm as tile_kernel<LOAD_BUCKET, EMIT_SPLITTER> (tile.cu), re-shaped for the
+// SM: a bucket holds at most WCAP = 256 particles and is owned by a single warp, so the
+// whole sub-step -- stage, sort, scan, force, kick, drift, re-bucket -- needs no block barrier.
+// 32 independent warps per SM sit in different phases and hide each other's latencies.
+//
+//   stage   lane 0 issues TMA bulk copies (cp.async.bulk, mbarrier complete_tx) of the bucket's
+//           x, v, id (and m) segments into the warp's private shared-memory slab
+//   prefix  while the copies fly: count look-back (packed 64-bit words) and, for general
+//           masses, the order-independent bucket mass is published early (lookback.cuh)
+//   sort    interpolation counting sort on the key range [split[b], split[b+1]) + exact rank
+//           under (x, id) by comparison inside a sub-bucket                    (wendy.c:341-357)
+//   scan    equal masses: cum = RN(rank * m0); general: exact 128-bit warp scan (wendy.c:359-360)
+//   step    a = a_ext + (((M - 2 cum) - m) - omega^2 x); v += dt a; x += dt v   (wendy.c:375-383,324-333)
+//   emit    destination bucket by splitter search (registers + shuffles for the 31 nearest
+//           buckets, galloping search beyond), slots by warp-aggregated atomics, stores
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "internal.h"
+#include "lookback.cuh"
+
+namespace wendy {
+
+template <int WCAP, int EQM>
+struct __align__(16) WarpSlab {
+  static constexpr int E = WCAP / 32;
+  static constexpr int PADN = WCAP + WCAP / E + 8;
+  double sx[WCAP];
+  double sv[WCAP];
+  double sm[EQM ? 2 : WCAP];   // masses by load slot
+  double so[EQM ? 2 : PADN];   // masses in sorted order -> cumulative mass (padded)
+  int sid[WCAP];
+  union {
+    unsigned cnt[PADN];      // sort phase: sub-bucket counters -> start offsets
+    struct {                 // emit phase (the counters are dead by then)
+      double wsp[33];        // lower splitters of the 32 buckets around the home bucket (+ upper end)
+      unsigned dcnt[32], dbase[32];
+    } w;
+  };
+  unsigned short slot[WCAP];
+  unsigned long long mbar;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+
+// largest d in [lo0, hi0) with split[d] <= key, starting from a guess (split[lo0] is -inf)
+__device__ __forceinline__ int gallop_search(const double *__restrict__ split, double key, int guess,
+                                             int lo0, int hi0) {
+  int lo = min(max(guess, lo0), hi0 - 1), hi;
+  int step = 1;
+  if (__ldg(split + lo) <= key) {
+    hi = lo + 1;
+    while (hi < hi0 && __ldg(split + hi) <= key) {
+      lo = hi;
+      step <<= 1;
+      hi = lo + step;
+    }
+    if (hi > hi0) hi = hi0;
+  } else {
+    hi = lo;
+    lo = hi - 1;
+    while (lo > lo0 && __ldg(split + lo) > key) {
+      hi = lo;
+      step <<= 1;
+      lo = hi - step;
+    }
+    if (lo < lo0) lo = lo0;
+  }
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(split + mid) <= key) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+template <int WCAP, int WARPS, int EQM>
+__global__ void __launch_bounds__(WARPS * 32, 1024 / (WARPS * 32))
+wstep_kernel(const TileParams p) {
+  using SL = WarpSlab<WCAP, EQM>;
+  constexpr int E = SL::E;
+  constexpr int BK = WCAP;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ unsigned s_ticket;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  SL &S = reinterpret_cast<SL *>(smem_raw)[wid];
+
+  if (ld_volatile_u32(p.fail_seq) < p.seq) return;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(p.ticket, 1u);
+  __syncthreads();  // the only block-wide barrier
+  const int b = (int)s_ticket * WARPS + wid;
+  if (b >= p.nb) return;
+  const int seg = (p.nbps == p.nb) ? 0 : b / p.nbps;
+  const int seg_lo = seg * p.nbps, seg_hi = seg_lo + p.nbps;
+
+  unsigned n = p.cnt_in[b];
+  if (n > (unsigned)WCAP) {
+    n = WCAP;
+    if (lane == 0) atomicMin(p.fail_seq, p.seq);
+  }
+  const size_t base = (size_t)b * WCAP;
+  const uint32_t bar = smem_u32(&S.mbar);
+  // ---- stage: TMA bulk copies of the live part of the bucket --------------------------------
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (b == 0 && p.ticket_zero) *p.ticket_zero = 0;
+    if (p.cnt_zero) p.cnt_zero[b] = 0;
+    if (n > (unsigned)(WCAP - WCAP / 16)) atomicMax(p.stats, n);
+    if (n) {
+      const uint32_t b8 = (n * 8u + 15u) & ~15u, b4 = (n * 4u + 15u) & ~15u;
+      const uint32_t total = b8 * (EQM ? 2u : 3u) + b4;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(total) : "memory");
+      tma_load_1d(S.sx, p.xin + base, b8, bar);
+      tma_load_1d(S.sv, p.vin + base, b8, bar);
+      if (!EQM) tma_load_1d(S.sm, p.min + base, b8, bar);
+      tma_load_1d(S.sid, p.idin + base, b4, bar);
+    }
+  }
+#pragma unroll
+  for (int i = lane; i < SL::PADN; i += 32) S.cnt[i] = 0;
+  // particles in the preceding buckets of the segment (count_prefix kernel ran just before)
+  const long long Pc = (long long)p.cpre[b] - (long long)seg * p.seg_len;
+  // lower splitters of the 32 buckets around b, in shared memory (only leaving lanes search)
+  int wlo = b - 15;
+  if (wlo > seg_hi - 32) wlo = seg_hi - 32;
+  if (wlo < seg_lo) wlo = seg_lo;
+  const double wsp_reg = (wlo + lane < seg_hi) ? __ldg(p.split + wlo + lane) : CUDART_INF;
+  const double wsp_end = (wlo + 32 < seg_hi) ? __ldg(p.split + wlo + 32) : CUDART_INF;
+  const double home_lo = __ldg(p.split + b);
+  const double home_hi = (b + 1 < seg_hi) ? __ldg(p.split + b + 1) : CUDART_INF;
+  const double tot = p.tot[seg];
+  __syncwarp();
+  if (n == 0) {
+    if (!EQM) {
+      i128 P; long long pc2;
+      lookback(p, b, seg_lo, (i128)0, 0ll, lane, P, pc2);
+    }
+    return;
+  }
+  mbar_wait(bar, 0);
+
+  // ---- keys: position at force time; key range -------------------------------------------------
+  double xmin = home_lo, xmax = home_hi;
+  if (p.h_pre != 0.0) {
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+      const unsigned i = lane + 32 * k;
+      if (i < n) S.sx[i] = __dadd_rn(S.sx[i], __dmul_rn(p.h_pre, S.sv[i]));
+    }
+  }
+  if (!(xmin > -CUDART_INF && xmax < CUDART_INF)) {  // edge bucket: reduce min / max in the warp
+    double lmin = CUDART_INF, lmax = -CUDART_INF;
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+      const unsigned i = lane + 32 * k;
+      if (i < n) {
+        lmin = fmin(lmin, S.sx[i]);
+        lmax = fmax(lmax, S.sx[i]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lmin = fmin(lmin, __shfl_xor_sync(WENDY_FULL_MASK, lmin, o));
+      lmax = fmax(lmax, __shfl_xor_sync(WENDY_FULL_MASK, lmax, o));
+    }
+    xmin = lmin;
+    xmax = lmax;
+  }
+  const double range = xmax - xmin;
+  const double scale = (range > 0.0 && range < CUDART_INF) ? (double)(BK - 1) / range : 0.0;
+
+  // general masses: the bucket's mass does not depend on the order -> publish it now and
+  // resolve the prefix while the sort runs on the other warps
+  i128 P = 0;
+  if (!EQM) {
+    i128 agg = 0;
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+      const unsigned i = lane + 32 * k;
+      if (i < n) agg += fx_from_double(S.sm[i], p.fxE);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) agg += shfl_xor_i128(agg, o);
+    long long pc2;
+    lookback(p, b, seg_lo, agg, (long long)n, lane, P, pc2);
+  }
+
+  // ---- sort: interpolation sub-bucket, arrival slot ------------------------------------------------
+  unsigned pk[E];
+#pragma unroll
+  for (int k = 0; k < E; k++) {
+    const unsigned i = lane + 32 * k;
+    pk[k] = 0;
+    if (32u * k < n && i < n) {
+      int sub = (int)((S.sx[i] - xmin) * scale);
+      sub = max(0, min(BK - 1, sub));
+      unsigned o = atomicAdd(&S.cnt[sub + sub / E], 1u);
+      pk[k] = (unsigned)sub | (o << 16);
+    }
+  }
+  __syncwarp();
+  {  // exclusive scan of the sub-bucket counters: E consecutive (padded) entries per lane
+    unsigned c[E], run = 0;
+    unsigned *cp = &S.cnt[lane * (E + 1)];
+#pragma unroll
+    for (int q = 0; q < E; q++) {
+      c[q] = cp[q];
+      run += c[q];
+    }
+    unsigned ex = warp_inclusive_scan_u32(run, lane) - run;
+#pragma unroll
+    for (int q = 0; q < E; q++) {
+      cp[q] = ex;
+      ex += c[q];
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < E; k++) {
+    const unsigned i = lane + 32 * k;
+    if (32u * k < n && i < n) {
+      const unsigned sub = pk[k] & 0xffffu;
+      S.slot[S.cnt[sub + sub / E] + (pk[k] >> 16)] = (unsigned short)i;
+    }
+  }
+  __syncwarp();
+  // exact rank under (x, id)
+  unsigned r[E];
+#pragma unroll
+  for (int k = 0; k < E; k++) {
+    const unsigned i = lane + 32 * k;
+    r[k] = 0;
+    if (32u * k < n && i < n) {
+      const unsigned sub = pk[k] & 0xffffu;
+      const unsigned s0 = S.cnt[sub + sub / E];
+      const unsigned s1 = (sub + 1 < (unsigned)BK) ? S.cnt[(sub + 1) + (sub + 1) / E] : n;
+      unsigned rr = s0;
+      if (s1 - s0 > 1u) {
+        const double xi = S.sx[i];
+        const int ii = S.sid[i];
+        for (unsigned q = s0; q < s1; q++) {
+          const unsigned j = S.slot[q];
+          const double xj = S.sx[j];
+          rr += (xj < xi || (xj == xi && S.sid[j] < ii)) ? 1u : 0u;
+        }
+      }
+      r[k] = rr;
+    }
+  }
+  // ---- scan (general masses): exact 128-bit prefix in sorted order ------------------------------------
+  if (!EQM) {
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+      const unsigned i = lane + 32 * k;
+      if (i < n) S.so[r[k] + r[k] / E] = S.sm[i];
+    }
+    __syncwarp();
+    i128 loc[E], tsum = 0;
+    double *mp = &S.so[lane * (E + 1)];
+#pragma unroll
+    for (int q = 0; q < E; q++) {
+      loc[q] = tsum;
+      if ((unsigned)(lane * E + q) < n) tsum += fx_from_double(mp[q], p.fxE);
+    }
+    const i128 bs = P + (warp_inclusive_scan_i128(tsum, lane) - tsum);
+#pragma unroll
+    for (int q = 0; q < E; q++)
+      if ((unsigned)(lane * E + q) < n) mp[q] = fx_to_double(bs + loc[q], p.fxE);
+    __syncwarp();
+  }
+  // ---- step + destination -------------------------------------------------------------------------------
+  __syncwarp();  // the sort counters are dead: their storage becomes the emit window
+  S.w.wsp[lane] = wsp_reg;
+  if (lane == 0) S.w.wsp[32] = wsp_end;
+  S.w.dcnt[lane] = 0;
+  __syncwarp();
+  int dest[E];
+  unsigned hoff[E];
+  unsigned hc = 0, outside = 0;
+#pragma unroll
+  for (int k = 0; k < E; k++) {
+    dest[k] = -1;
+    hoff[k] = 0;
+    if (32u * k < n) {  // warp-uniform: rounds past the live part of the bucket are skipped
+      const unsigned i = lane + 32 * k;
+      const bool ok = i < n;
+      int d = -1;
+      if (ok) {
+        const double xk = S.sx[i], v = S.sv[i];
+        double c, mk;
+        if (EQM) {
+          mk = p.m0;
+          c = __dmul_rn((double)(Pc + (long long)r[k]), p.m0);
+        } else {
+          mk = S.sm[i];
+          c = S.so[r[k] + r[k] / E];
+        }
+        double acc = __dsub_rn(__dsub_rn(tot, __dmul_rn(2.0, c)), mk);
+        if (p.omega2 >= 0.0) acc = __dsub_rn(acc, __dmul_rn(p.omega2, xk));
+        if (p.aext) acc = __dadd_rn(p.aext[base + i], acc);
+        const double v2 = __dadd_rn(v, __dmul_rn(p.dt_kick, acc));
+        const double x2 = __dadd_rn(xk, __dmul_rn(p.dt_drift, v2));
+        const double key = (p.h_next != 0.0) ? __dadd_rn(x2, __dmul_rn(p.h_next, v2)) : x2;
+        S.sx[i] = x2;
+        S.sv[i] = v2;
+        if (p.rank_out) p.rank_out[S.sid[i]] = (int)(Pc + (long long)r[k]);
+        if (key >= home_lo && key < home_hi) {
+          d = b;
+        } else if (key >= S.w.wsp[0] && key < S.w.wsp[32]) {  // one of the 32 nearby buckets
+          int lo = 0, hi = 32;
+#pragma unroll
+          for (int s = 0; s < 5; s++) {
+            const int mid = (lo + hi) >> 1;
+            if (S.w.wsp[mid] <= key) lo = mid; else hi = mid;
+          }
+          d = wlo + lo;
+          hoff[k] = atomicAdd(&S.w.dcnt[lo], 1u);
+        } else {  // beyond the window: guess from the local bucket width, then gallop
+          const double wdt = home_hi - home_lo;
+          double gq = (wdt > 0.0 && wdt < CUDART_INF) ? (key - home_lo) / wdt : (key < home_lo ? -32.0 : 32.0);
+          gq = fmax(-2.0e9, fmin(2.0e9, gq));
+          const long long gg = (long long)b + (long long)floor(gq);
+          const int guess = (int)max((long long)seg_lo, min((long long)seg_hi - 1, gg));
+          d = gallop_search(p.split, key, guess, seg_lo, seg_hi);
+          hoff[k] = atomicAdd(&p.cnt_out[d], 1u);  // final slot
+          outside++;
+        }
+      }
+      dest[k] = d;
+      const unsigned home = __ballot_sync(WENDY_FULL_MASK, d == b);
+      if (d == b) hoff[k] = hc + __popc(home & lt);
+      hc += __popc(home);
+    }
+  }
+  // ---- slots: one global atomic per destination bucket of the window, all in one round trip ----------
+  __syncwarp();
+  {
+    unsigned c = S.w.dcnt[lane];
+    if (lane == b - wlo) c += hc;  // in-window away particles were counted first: home goes after
+    if (c) S.w.dbase[lane] = atomicAdd(&p.cnt_out[wlo + lane], c);
+  }
+  if (outside) atomicAdd(p.stats + 1, outside);
+  __syncwarp();
+  const unsigned home_shift = S.w.dcnt[b - wlo];
+  // ---- stores ----------------------------------------------------------------------------------------------
+  bool overflow = false;
+#pragma unroll
+  for (int k = 0; k < E; k++) {
+    if (32u * k < n) {
+      const unsigned i = lane + 32 * k;
+      const int d = dest[k];
+      if (d >= 0) {
+        unsigned pos = hoff[k];
+        if (d == b) pos += S.w.dbase[b - wlo] + home_shift;
+        else if (d >= wlo && d < wlo + 32) pos += S.w.dbase[d - wlo];
+        if (pos < (unsigned)WCAP) {
+          const size_t o = (size_t)d * WCAP + pos;
+          p.xout[o] = S.sx[i];
+          p.vout[o] = S.sv[i];
+          if (!EQM) p.mout[o] = S.sm[i];
+          p.idout[o] = S.sid[i];
+        } else {
+          overflow = true;
+        }
+      }
+    }
+  }
+  if (overflow) atomicMin(p.fail_seq, p.seq);
+}
+
+// ---- exclusive prefix of the bucket counts: one pass, look-back over CTA tiles ---------------------------
+constexpr int CP_T = 1024, CP_I = 4, CP_TILE = CP_T * CP_I;
+__global__ void __launch_bounds__(CP_T)
+count_prefix_kernel(const unsigned *__restrict__ cnt, int nb, unsigned *__restrict__ cpre,
+                    unsigned long long *desc, unsigned *ticket, unsigned epoch) {
+  __shared__ unsigned s_t, s_w[32], s_pre;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_t = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const int t = (int)s_t;
+  if (t == (int)gridDim.x - 1 && threadIdx.x == 0) *ticket = 0;  // every ticket is taken: re-arm
+  const int i0 = t * CP_TILE + threadIdx.x * CP_I;
+  unsigned c[CP_I], run = 0;
+#pragma unroll
+  for (int q = 0; q < CP_I; q++) {
+    c[q] = (i0 + q < nb) ? cnt[i0 + q] : 0u;
+    run += c[q];
+  }
+  const unsigned inc = warp_inclusive_scan_u32(run, lane);
+  if (lane == 31) s_w[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    const unsigned w = s_w[lane];
+    const unsigned wi = warp_inclusive_scan_u32(w, lane);
+    s_w[lane] = wi - w;
+    const unsigned total = __shfl_sync(WENDY_FULL_MASK, wi, 31);
+    const unsigned pre = count_lookback(desc, epoch, t, 0, total, lane);
+    if (lane == 0) s_pre = pre;
+  }
+  __syncthreads();
+  unsigned ex = s_pre + s_w[wid] + inc - run;
+#pragma unroll
+  for (int q = 0; q < CP_I; q++) {
+    if (i0 + q < nb) cpre[i0 + q] = ex;
+    ex += c[q];
+  }
+}
+
+int count_prefix_tiles(int nb) { return (nb + CP_TILE - 1) / CP_TILE; }
+
+void launch_count_prefix(cudaStream_t st, const unsigned *cnt, int nb, unsigned *cpre,
+                         unsigned long long *tile_desc, unsigned *ticket, unsigned epoch) {
+  if (nb > 0) count_prefix_kernel<<<count_prefix_tiles(nb), CP_T, 0, st>>>(cnt, nb, cpre, tile_desc, ticket, epoch);
+}
+
+template <int WCAP, int WARPS, int EQM>
+static void launch_wstep_t(cudaStream_t st, const TileParams &p) {
+  static bool attr_set = false;
+  const size_t sm = sizeof(WarpSlab<WCAP, EQM>) * WARPS;
+  if (!attr_set) {
+    cudaFuncSetAttribute(wstep_kernel<WCAP, WARPS, EQM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    attr_set = true;
+  }
+  const int grid = (p.nb + WARPS - 1) / WARPS;
+  wstep_kernel<WCAP, WARPS, EQM><<<grid, WARPS * 32, sm, st>>>(p);
+}
+
+bool wstep_cap_supported(int cap) { return cap == 256; }
+
+void launch_wstep(cudaStream_t st, int cap, const TileParams &p) {
+  if (p.nb <= 0) return;
+  if (p.eqm) launch_wstep_t<256, 8, 1>(st, p);
+  else launch_wstep_t<256, 8, 0>(st, p);
+}
+
+}  // namespace wendy

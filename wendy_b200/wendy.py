@@ -122,6 +122,14 @@ class ApproxState(object):
         _lib.check(self._lib.wendy_cuda_energy(self._h, out))
         return out
 
+    def layout(self):
+        """(counts, splitters) of the current bucket layout (diagnostic)."""
+        nb = self.stats()['buckets']
+        cnt = numpy.zeros(nb, dtype=numpy.uint32)
+        spl = numpy.zeros(nb)
+        nb = _lib.check(self._lib.wendy_cuda_debug_layout(self._h, cnt, spl, nb))
+        return cnt[:nb], spl[:nb]
+
     def stats(self):
         out = numpy.zeros(9, dtype=numpy.int64)
         _lib.check(self._lib.wendy_cuda_stats(self._h, out, 9))
