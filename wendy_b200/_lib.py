@@ -10,7 +10,8 @@ import os
 import numpy
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libwendy_b200.so')
+# WENDY_B200_LIB selects an alternative build of the same library (kernel A/B experiments)
+LIB_PATH = os.environ.get('WENDY_B200_LIB') or os.path.join(_HERE, 'libwendy_b200.so')
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_ll_p = ctypes.POINTER(ctypes.c_longlong)
 

@@ -21,6 +21,16 @@
 #include "internal.h"
 #include "lookback.cuh"
 
+#ifndef WS_RANK2
+#define WS_RANK2 1
+#endif
+#ifndef WS_NEIGH
+#define WS_NEIGH 0
+#endif
+#ifndef WS_PROBE4
+#define WS_PROBE4 0
+#endif
+
 namespace wendy {
 
 template <int WCAP, int EQM>
@@ -257,7 +267,12 @@ wstep_kernel(const TileParams p) {
         for (unsigned q = s0; q < s1; q++) {
           const unsigned j = S.slot[q];
           const double xj = S.sx[j];
+#if WS_RANK2
+          rr += (xj < xi) ? 1u : 0u;
+          if (xj == xi) rr += (S.sid[j] < ii) ? 1u : 0u;  // exact coincidence: ties by particle index
+#else
           rr += (xj < xi || (xj == xi && S.sid[j] < ii)) ? 1u : 0u;
+#endif
         }
       }
       r[k] = rr;
@@ -293,6 +308,8 @@ wstep_kernel(const TileParams p) {
   int dest[E];
   unsigned hoff[E];
   unsigned hc = 0, outside = 0;
+  const double wdt = home_hi - home_lo;
+  const double inv_w = (wdt > 0.0 && wdt < CUDART_INF) ? 1.0 / wdt : 0.0;
 #pragma unroll
   for (int k = 0; k < E; k++) {
     dest[k] = -1;
@@ -323,21 +340,39 @@ wstep_kernel(const TileParams p) {
         if (key >= home_lo && key < home_hi) {
           d = b;
         } else if (key >= S.w.wsp[0] && key < S.w.wsp[32]) {  // one of the 32 nearby buckets
-          int lo = 0, hi = 32;
-#pragma unroll
-          for (int s = 0; s < 5; s++) {
+          int lo, hi;
+          const int rel = b - wlo;
+#if WS_NEIGH
+          if (key < home_lo) {  // neighbours first, then bisection of what is left
+            if (key >= S.w.wsp[rel - 1]) { lo = rel - 1; hi = rel; }
+            else if (rel >= 2 && key >= S.w.wsp[rel - 2]) { lo = rel - 2; hi = rel - 1; }
+            else { lo = 0; hi = rel - 2; }
+          } else {
+            if (key < S.w.wsp[rel + 2 > 32 ? 32 : rel + 2]) { lo = rel + 1; hi = rel + 2; }
+            else if (rel + 3 <= 32 && key < S.w.wsp[rel + 3]) { lo = rel + 2; hi = rel + 3; }
+            else { lo = rel + 3; hi = 32; }
+          }
+#else
+          if (key < home_lo) { lo = 0; hi = rel; } else { lo = rel + 1; hi = 32; }
+#endif
+          while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
             if (S.w.wsp[mid] <= key) lo = mid; else hi = mid;
           }
           d = wlo + lo;
           hoff[k] = atomicAdd(&S.w.dcnt[lo], 1u);
-        } else {  // beyond the window: guess from the local bucket width, then gallop
-          const double wdt = home_hi - home_lo;
-          double gq = (wdt > 0.0 && wdt < CUDART_INF) ? (key - home_lo) / wdt : (key < home_lo ? -32.0 : 32.0);
+        } else {  // beyond the window: interpolated guess, probe 4 adjacent splitters, else gallop
+          double gq = (key - home_lo) * inv_w;
           gq = fmax(-2.0e9, fmin(2.0e9, gq));
-          const long long gg = (long long)b + (long long)floor(gq);
-          const int guess = (int)max((long long)seg_lo, min((long long)seg_hi - 1, gg));
-          d = gallop_search(p.split, key, guess, seg_lo, seg_hi);
+          const int g = (int)max((long long)seg_lo + 1, min((long long)seg_hi - 3, (long long)b + (long long)floor(gq)));
+          if (WS_PROBE4 && g - 1 >= seg_lo && g + 2 < seg_hi) {
+            const double sA = __ldg(p.split + g - 1), sB = __ldg(p.split + g), sC = __ldg(p.split + g + 1),
+                         sD = __ldg(p.split + g + 2);
+            if (key >= sB && key < sC) d = g;
+            else if (key >= sC && key < sD) d = g + 1;
+            else if (key >= sA && key < sB) d = g - 1;
+          }
+          if (d < 0) d = gallop_search(p.split, key, g, seg_lo, seg_hi);
           hoff[k] = atomicAdd(&p.cnt_out[d], 1u);  // final slot
           outside++;
         }
