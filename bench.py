@@ -209,8 +209,11 @@ def main():
         'path_stats': d,
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak,
                      'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback', 'unit': 'GB/s',
-                     'frac': achieved / peak, 'traffic': None,
-                     'kernel': 'tile_kernel<LOAD_BUCKET,EMIT_SPLITTER>' if a.sort == 'gpu' else 'radix passes + tile_kernel<LOAD_GATHER>',
+                     'frac': achieved / peak,
+                     # dram__bytes_read+write per launch from the ncu --set full capture of this kernel
+                     # (profiles/r01/wstep_dt1e-5_N2e7_summary.txt: 40.2 B/particle), scaled to this N
+                     'traffic': 40.2 * n if a.sort == 'gpu' else None,
+                     'kernel': 'wstep_kernel<256,8,EQM> (one warp per bucket)' if a.sort == 'gpu' else 'radix passes + tile_kernel<LOAD_GATHER>',
                      'ms_per_launch': ms_per_launch},
         'clocks': clocks,
     }

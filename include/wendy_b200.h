@@ -103,6 +103,35 @@ int wendy_cuda_energy(wendy_cuda_handle *h, double out[4]);
  * radix path because a freshly balanced layout still overflowed. */
 int wendy_cuda_stats(wendy_cuda_handle *h, long long *out, int n);
 
+/* ---- sharded single system: one contiguous key range per GPU -------------------
+ * The caller (wendy_b200/multi.py) owns the collectives; the library owns the local work.
+ * Equal masses only (m0).  ids are GLOBAL particle indices.  bounds has nranks+1 ascending
+ * edges (first -inf, last +inf); this GPU owns keys in [bounds[rank], bounds[rank+1]).
+ *   create_shard   upload n_local particles whose positions lie in the range
+ *   shard_substep  one leapfrog sub-step; particles whose new key leaves the range are written
+ *                  to per-peer outboxes (out_counts[p] of them for peer p); pc_offset = number of
+ *                  particles owned by lower ranks (offsets the cumulative mass)
+ *   shard_outbox   DEVICE pointers of the outboxes: peer p starts at p * ocap
+ *   shard_inject   append n received particles (DEVICE arrays) to the local layout
+ *   shard_read     compact local (x, v, id) to HOST arrays of capacity entries                  */
+int wendy_cuda_create_shard(wendy_cuda_handle **h, long long n_local, long long n_capacity,
+                            const double *x, const double *v, const int *ids, double m0,
+                            double totmass, double omega2, int nranks, int rank,
+                            const double *bounds, long long outbox_capacity, void *cuda_stream);
+int wendy_cuda_shard_substep(wendy_cuda_handle *h, double h_pre, double dt_kick, double dt_drift,
+                             double h_next, long long pc_offset, unsigned *out_counts);
+int wendy_cuda_shard_outbox(wendy_cuda_handle *h, double **x, double **v, int **id, long long *ocap);
+int wendy_cuda_shard_inject(wendy_cuda_handle *h, const double *x_dev, const double *v_dev,
+                            const int *id_dev, long long n);
+int wendy_cuda_shard_count(wendy_cuda_handle *h, long long *n_local);
+int wendy_cuda_shard_read(wendy_cuda_handle *h, double *x_host, double *v_host, int *id_host,
+                          long long *n);
+
+/* Page-lock (cudaHostRegister) / release a HOST buffer the caller passes repeatedly to
+ * wendy_cuda_read, so the per-yield D2H copy runs at full PCIe speed.  Optional. */
+int wendy_cuda_pin(void *host_ptr, unsigned long long bytes);
+int wendy_cuda_unpin(void *host_ptr);
+
 /* Test/diagnostic hook: copies the per-bucket particle counts and lower splitters of the current
  * layout to HOST arrays of nb_max entries; returns the number of buckets (0: no layout yet). */
 int wendy_cuda_debug_layout(wendy_cuda_handle *h, unsigned *counts, double *splitters, int nb_max);

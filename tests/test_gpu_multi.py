@@ -1,0 +1,92 @@
+"""GPU: the sharded single-system mode on the CUDA shard engine.  On one GPU the ranks are
+threads of this process (each with its own handle and key range); with >= 2 GPUs the same
+logic also runs as two NCCL processes.  Results must equal the single-GPU path bit for bit."""
+import os
+import socket
+
+import numpy
+import pytest
+
+from multi_helpers import run_threads
+from oracle import wendy_oracle as wo
+
+pytestmark = pytest.mark.gpu
+
+
+def _single_gpu(x, v, m, dt_leap, nleap, calls, omega):
+    import wendy_b200
+    g = wendy_b200.nbody(x, v, m, dt_leap * nleap, approx=True, nleap=nleap, omega=omega)
+    for _ in range(calls):
+        X, V = next(g)
+    X, V = X.copy(), V.copy()
+    g.close()
+    return X, V
+
+
+def _run_rank(comm, n, omega, dt_leap, nleap, calls):
+    from wendy_b200 import multi
+    x, v, m = wo.sech2_ic(n, seed=6)
+    mine = numpy.arange(n) % comm.size == comm.rank
+    s = multi.ShardedSystem(x[mine], v[mine], numpy.arange(n)[mine], m[0], numpy.sum(m), comm, omega=omega)
+    for _ in range(calls):
+        s.step(dt_leap, nleap)
+    X, V = s.gather(n)
+    mig, counts = s.migrated, s.counts
+    s.close()
+    return X, V, mig, counts
+
+
+@pytest.mark.parametrize('ranks', [2, 3])
+@pytest.mark.parametrize('n,dt_leap', [(40000, 0.01), (200000, 0.002)])
+def test_sharded_threads_one_gpu_equals_single_gpu(ranks, n, dt_leap):
+    x, v, m = wo.sech2_ic(n, seed=6)
+    Xs, Vs = _single_gpu(x, v, m, dt_leap, 5, 2, 1.1)
+    res = run_threads(ranks, lambda comm: _run_rank(comm, n, 1.1, dt_leap, 5, 2), device='cuda')
+    for X, V, mig, counts in res:
+        assert numpy.array_equal(X, Xs) and numpy.array_equal(V, Vs)
+        assert int(counts.sum()) == n
+    assert sum(r[2] for r in res) > 0
+
+
+def test_sharded_matches_oracle():
+    n = 30000
+    x, v, m = wo.sech2_ic(n, seed=6)
+    xo, vo = x, v
+    for _ in range(2):
+        xo, vo, _, _ = wo.numpy_onestep(xo, vo, m, numpy.sum(m), 0.01, 3, -1., exact_scan=True)
+    res = run_threads(2, lambda comm: _run_rank(comm, n, None, 0.01, 3, 2), device='cuda')
+    assert numpy.array_equal(res[0][0], xo) and numpy.array_equal(res[0][1], vo)
+
+
+def _nccl_worker(rank, world, port, n, q):
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        from wendy_b200 import multi
+        X, V, mig, counts = _run_rank(multi.TorchComm(device='cuda'), n, 1.1, 0.005, 5, 2)
+        if rank == 0:
+            q.put((X, V, mig))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_two_gpus_nccl_equals_single_gpu():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    n = 200000
+    x, v, m = wo.sech2_ic(n, seed=6)
+    Xs, Vs = _single_gpu(x, v, m, 0.005, 5, 2, 1.1)
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.SimpleQueue()
+    mp.spawn(_nccl_worker, args=(2, port, n, q), nprocs=2, join=True)
+    X, V, mig = q.get()
+    assert numpy.array_equal(X, Xs) and numpy.array_equal(V, Vs) and mig > 0

@@ -59,6 +59,26 @@ def load():
     lib.wendy_cuda_energy.argtypes = [vp, _nd('f8')]
     lib.wendy_cuda_stats.restype = ctypes.c_int
     lib.wendy_cuda_stats.argtypes = [vp, _nd('i8'), ctypes.c_int]
+    lib.wendy_cuda_create_shard.restype = ctypes.c_int
+    lib.wendy_cuda_create_shard.argtypes = [ctypes.POINTER(vp), ctypes.c_longlong, ctypes.c_longlong,
+                                            _nd('f8'), _nd('f8'), _nd('i4'), ctypes.c_double,
+                                            ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int,
+                                            _nd('f8'), ctypes.c_longlong, vp]
+    lib.wendy_cuda_shard_substep.restype = ctypes.c_int
+    lib.wendy_cuda_shard_substep.argtypes = [vp, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                             ctypes.c_double, ctypes.c_longlong, _nd('u4')]
+    lib.wendy_cuda_shard_outbox.restype = ctypes.c_int
+    lib.wendy_cuda_shard_outbox.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), c_ll_p]
+    lib.wendy_cuda_shard_inject.restype = ctypes.c_int
+    lib.wendy_cuda_shard_inject.argtypes = [vp, vp, vp, vp, ctypes.c_longlong]
+    lib.wendy_cuda_shard_count.restype = ctypes.c_int
+    lib.wendy_cuda_shard_count.argtypes = [vp, c_ll_p]
+    lib.wendy_cuda_shard_read.restype = ctypes.c_int
+    lib.wendy_cuda_shard_read.argtypes = [vp, _nd('f8'), _nd('f8'), _nd('i4'), c_ll_p]
+    lib.wendy_cuda_pin.restype = ctypes.c_int
+    lib.wendy_cuda_pin.argtypes = [vp, ctypes.c_ulonglong]
+    lib.wendy_cuda_unpin.restype = ctypes.c_int
+    lib.wendy_cuda_unpin.argtypes = [vp]
     lib.wendy_cuda_debug_layout.restype = ctypes.c_int
     lib.wendy_cuda_debug_layout.argtypes = [vp, _nd('u4'), _nd('f8'), ctypes.c_int]
     lib.wendy_cuda_destroy.restype = None
@@ -77,7 +97,8 @@ def load():
 #: every symbol include/wendy_b200.h declares (checked by tests/test_abi.py)
 EXPORTED = ['wendy_cuda_create', 'wendy_cuda_step', 'wendy_cuda_force_positions',
             'wendy_cuda_substep', 'wendy_cuda_read', 'wendy_cuda_read_dev', 'wendy_cuda_energy',
-            'wendy_cuda_stats', 'wendy_cuda_debug_layout', 'wendy_cuda_destroy', 'wendy_cuda_last_error',
+            'wendy_cuda_stats', 'wendy_cuda_create_shard', 'wendy_cuda_shard_substep', 'wendy_cuda_shard_outbox',
+            'wendy_cuda_shard_inject', 'wendy_cuda_shard_count', 'wendy_cuda_shard_read', 'wendy_cuda_pin', 'wendy_cuda_unpin', 'wendy_cuda_debug_layout', 'wendy_cuda_destroy', 'wendy_cuda_last_error',
             'wendy_cuda_argsort', '_wendy_nbody_approx_onestep']
 
 

@@ -76,6 +76,14 @@ struct wendy_cuda_handle {
   double *xo = nullptr, *vo = nullptr;
   double *epart = nullptr, *eout = nullptr, *h_eout = nullptr;
   int *rank = nullptr;
+  // sharded single system (one key range per GPU)
+  int nranks = 1, my_rank = 0;
+  long long n_cap = 0;          // particle capacity of this shard
+  double *bounds = nullptr;     // device, nranks+1
+  double *out_x = nullptr, *out_v = nullptr;
+  int *out_id = nullptr, *cid = nullptr;
+  unsigned *out_cnt = nullptr, *h_out_cnt = nullptr;
+  long long ocap = 0, pc_offset = 0;
   // counters
   long long n_sub = 0, n_rebuild = 0, n_fail = 0, max_cnt = 0, n_outside = 0, n_launch = 0;
   long long n_radix_fallback = 0;
@@ -196,6 +204,9 @@ static void fill_tile_params(H *h, TileParams &p) {
   p.omega2 = h->omega2; p.tot = h->tot; p.fxE = h->fxE;
   p.status = h->status; p.desc = h->desc; p.cdesc = h->cdesc;
   p.eqm = h->eqm ? 1 : 0; p.m0 = h->m0;
+  p.nranks = h->nranks; p.my_rank = h->my_rank; p.bounds = h->bounds;
+  p.out_x = h->out_x; p.out_v = h->out_v; p.out_id = h->out_id; p.out_cnt = h->out_cnt;
+  p.ocap = (unsigned)h->ocap; p.pc_offset = h->pc_offset;
   p.ticket = h->ticket + h->tcur; p.ticket_zero = h->ticket + (h->tcur + 2) % 3;
   p.fail_seq = h->flags; p.stats = h->flags + 1;
   p.seq = h->seq; p.epoch = h->seq;
@@ -262,16 +273,20 @@ void wendy_cuda_destroy(wendy_cuda_handle *h) {
   cudaFree(h->cdesc); cudaFree(h->cpre); cudaFree(h->cp_desc); cudaFree(h->cp_ticket);
   cudaFree(h->flags); cudaFree(h->offs); cudaFree(h->xo); cudaFree(h->vo); cudaFree(h->epart);
   cudaFree(h->eout); cudaFree(h->rank);
+  cudaFree(h->bounds); cudaFree(h->out_x); cudaFree(h->out_v); cudaFree(h->out_id); cudaFree(h->out_cnt);
+  cudaFree(h->cid);
+  if (h->h_out_cnt) cudaFreeHost(h->h_out_cnt);
   if (h->h_flags) cudaFreeHost(h->h_flags);
   if (h->h_eout) cudaFreeHost(h->h_eout);
   delete h;
 }
 
-int wendy_cuda_create(wendy_cuda_handle **out, long long N, const double *x, const double *v,
-                      const double *m, const double *totmass, double omega2, int n_segments, int flags,
-                      int cap, int fill, void *cuda_stream) {
+static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, const double *x, const double *v,
+                       const double *m, const int *ids, const double *totmass, double omega2, int n_segments,
+                       int flags, int cap, int fill, void *cuda_stream) {
   if (!out || !x || !v || !m || !totmass) return set_err(WENDY_E_ARG, "null argument");
-  if (N <= 0 || N >= (1ll << 31)) return set_err(WENDY_E_ARG, "N must be in [1, 2^31)");
+  if (N <= 0 || N >= (1ll << 31) || n_cap < N || n_cap >= (1ll << 31))
+    return set_err(WENDY_E_ARG, "N must be in [1, 2^31) and not exceed the capacity");
   if (n_segments < 1 || N % n_segments) return set_err(WENDY_E_ARG, "N must be a multiple of n_segments");
   if (cap == 0) cap = 256;
   if (!tile_cap_supported(cap)) return set_err(WENDY_E_ARG, "cap must be 2048 or 256");
@@ -282,9 +297,9 @@ int wendy_cuda_create(wendy_cuda_handle **out, long long N, const double *x, con
   if (fill < 1 || fill > cap) return set_err(WENDY_E_ARG, "fill must be in [1, cap]");
   H *h = new H;
   *out = nullptr;
-  h->N = N; h->nseg = n_segments; h->seg_len = N / n_segments; h->omega2 = omega2;
+  h->N = N; h->n_cap = n_cap; h->nseg = n_segments; h->seg_len = N / n_segments; h->omega2 = omega2;
   h->mode = flags & 0xf; h->cap = cap; h->fill = fill;
-  h->nbps = (int)((h->seg_len + fill - 1) / fill);
+  h->nbps = (int)(((n_cap / n_segments) + fill - 1) / fill);
   long long nb = (long long)h->nbps * n_segments;
   if (nb * cap >= (1ll << 32)) { delete h; return set_err(WENDY_E_ARG, "too many storage slots for u32 indices"); }
   h->nb = (int)nb; h->slots = (size_t)nb * cap;
@@ -345,12 +360,138 @@ int wendy_cuda_create(wendy_cuda_handle **out, long long N, const double *x, con
   CKD(cudaMemcpyAsync(h->v[0], v, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->st));
   if (!h->eqm) CKD(cudaMemcpyAsync(h->m[0], m, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->st));
   CKD(cudaMemcpyAsync(h->tot, totmass, (size_t)n_segments * sizeof(double), cudaMemcpyHostToDevice, h->st));
-  launch_iota(h->st, h->id[0], N);
+  if (ids) CKD(cudaMemcpyAsync(h->id[0], ids, (size_t)N * sizeof(int), cudaMemcpyHostToDevice, h->st));
+  else launch_iota(h->st, h->id[0], N);
   if (reset_flags(h)) { std::string s = g_err; wendy_cuda_destroy(h); return set_err(WENDY_E_CUDA, s); }
   CKD(cudaGetLastError());
 #undef CKD
   h->dense = true; h->cur = 0; h->ccur = 0;
   *out = h;
+  return 0;
+}
+
+int wendy_cuda_create(wendy_cuda_handle **out, long long N, const double *x, const double *v,
+                      const double *m, const double *totmass, double omega2, int n_segments, int flags,
+                      int cap, int fill, void *cuda_stream) {
+  return create_impl(out, N, N, x, v, m, nullptr, totmass, omega2, n_segments, flags, cap, fill, cuda_stream);
+}
+
+// ---- sharded single system: this GPU owns the key range [bounds[rank], bounds[rank+1]) ------------------
+int wendy_cuda_create_shard(wendy_cuda_handle **out, long long n_local, long long n_capacity, const double *x,
+                            const double *v, const int *ids, double m0, double totmass, double omega2,
+                            int nranks, int rank, const double *bounds, long long outbox_capacity,
+                            void *cuda_stream) {
+  if (!ids || !bounds || nranks < 1 || rank < 0 || rank >= nranks || outbox_capacity < 1)
+    return set_err(WENDY_E_ARG, "bad shard argument");
+  std::vector<double> m((size_t)n_local, m0);
+  int rc = create_impl(out, n_local, n_capacity, x, v, m.data(), ids, &totmass, omega2, 1, 0, 256, 0, cuda_stream);
+  if (rc) return rc;
+  H *h = *out;
+  h->nranks = nranks; h->my_rank = rank; h->ocap = outbox_capacity;
+  // nranks == 1 still runs the sharded kernel variant when asked to (tests): force it with nranks >= 1
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = cudaMalloc(&h->bounds, (size_t)(nranks + 1) * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpy(h->bounds, bounds, (size_t)(nranks + 1) * sizeof(double), cudaMemcpyHostToDevice);
+  size_t ob = (size_t)nranks * (size_t)outbox_capacity;
+  if (e == cudaSuccess) e = cudaMalloc(&h->out_x, ob * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&h->out_v, ob * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&h->out_id, ob * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&h->out_cnt, (size_t)nranks * sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMallocHost(&h->h_out_cnt, (size_t)nranks * sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMalloc(&h->cid, (size_t)n_capacity * sizeof(int));
+  if (e != cudaSuccess) { std::string msg = cudaGetErrorString(e); wendy_cuda_destroy(h); *out = nullptr; return set_err(WENDY_E_CUDA, msg); }
+  return 0;
+}
+
+// One leapfrog sub-step on the local range.  out_counts[p] = particles placed in the outbox of peer p.
+int wendy_cuda_shard_substep(wendy_cuda_handle *h, double h_pre, double dt_kick, double dt_drift, double h_next,
+                             long long pc_offset, unsigned *out_counts) {
+  if (!h || !out_counts || !h->bounds) return set_err(WENDY_E_ARG, "not a shard handle");
+  h->pc_offset = pc_offset;
+  for (int attempt = 0; attempt < 3; attempt++) {
+    if (h->dense || !h->has_split || h->bucket_h != h_pre) {
+      int rc = rebucket(h, h_pre);
+      if (rc) return rc;
+    }
+    CK(cudaMemsetAsync(h->out_cnt, 0, (size_t)h->nranks * sizeof(unsigned), h->st));
+    int cur0 = h->cur, ccur0 = h->ccur;
+    launch_bucket_substep(h, h_pre, dt_kick, dt_drift, h_next, nullptr, nullptr);
+    CK(cudaMemcpyAsync(h->h_out_cnt, h->out_cnt, (size_t)h->nranks * sizeof(unsigned), cudaMemcpyDeviceToHost, h->st));
+    if (fetch_flags(h)) return WENDY_E_CUDA;
+    if (h->h_flags[0] == 0xffffffffu) {
+      long long gone = 0;
+      for (int r = 0; r < h->nranks; r++) { out_counts[r] = h->h_out_cnt[r]; gone += h->h_out_cnt[r]; }
+      h->N -= gone; h->seg_len = h->N;
+      return 0;
+    }
+    h->n_fail++; h->n_sub--;
+    h->cur = cur0; h->ccur = ccur0; h->has_split = false;
+    if (reset_flags(h)) return WENDY_E_CUDA;
+  }
+  return set_err(WENDY_E_OVERFLOW, "shard: bucket or outbox overflow persists after re-balancing");
+}
+
+int wendy_cuda_shard_outbox(wendy_cuda_handle *h, double **x, double **v, int **id, long long *ocap) {
+  if (!h || !h->bounds) return set_err(WENDY_E_ARG, "not a shard handle");
+  *x = h->out_x; *v = h->out_v; *id = h->out_id; *ocap = h->ocap;
+  return 0;
+}
+
+// Append n particles (DEVICE arrays) whose keys lie in this shard's range to the current layout.
+int wendy_cuda_shard_inject(wendy_cuda_handle *h, const double *x_dev, const double *v_dev, const int *id_dev,
+                            long long n) {
+  if (!h || !h->bounds) return set_err(WENDY_E_ARG, "not a shard handle");
+  if (n <= 0) return 0;
+  if (h->N + n > h->n_cap) return set_err(WENDY_E_OVERFLOW, "shard capacity exceeded (global re-partition needed)");
+  if (h->dense || !h->has_split) return set_err(WENDY_E_ARG, "inject needs a layout");
+  ScatterParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.xin = x_dev; sp.vin = v_dev; sp.min = nullptr; sp.idin = id_dev;
+  sp.cnt_in = nullptr; sp.n_dense = n; sp.h = h->bucket_h;
+  int c = h->cur;
+  sp.xout = h->x[c]; sp.vout = h->v[c]; sp.mout = nullptr; sp.idout = h->id[c];
+  sp.cnt_out = h->cnt[h->ccur]; sp.split = h->split; sp.cap_out = h->cap; sp.nbps_out = h->nbps;
+  sp.seg_len = h->n_cap + 1; sp.fail_seq = h->flags; sp.seq = h->seq++;
+  launch_scatter(h->st, sp, h->sm_count);
+  h->n_launch++;
+  if (fetch_flags(h)) return WENDY_E_CUDA;
+  if (h->h_flags[0] != 0xffffffffu) {
+    reset_flags(h);
+    return set_err(WENDY_E_OVERFLOW, "shard: bucket overflow while injecting migrants");
+  }
+  h->N += n; h->seg_len = h->N;
+  return 0;
+}
+
+int wendy_cuda_shard_count(wendy_cuda_handle *h, long long *n_local) {
+  if (!h || !n_local) return set_err(WENDY_E_ARG, "null argument");
+  *n_local = h->N;
+  return 0;
+}
+
+// Compact (x, v, id) of the local particles to HOST arrays (capacity entries); *n = local count.
+int wendy_cuda_shard_read(wendy_cuda_handle *h, double *x_host, double *v_host, int *id_host, long long *n) {
+  if (!h || !h->bounds || !x_host || !v_host || !id_host || !n) return set_err(WENDY_E_ARG, "bad argument");
+  if (!h->xo) {
+    CK(cudaMalloc(&h->xo, (size_t)h->n_cap * sizeof(double)));
+    CK(cudaMalloc(&h->vo, (size_t)h->n_cap * sizeof(double)));
+  }
+  if (h->dense) {
+    CK(cudaMemcpyAsync(x_host, h->x[h->cur], (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(v_host, h->v[h->cur], (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(id_host, h->id[h->cur], (size_t)h->N * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  } else {
+    launch_count_prefix(h->st, h->cnt[h->ccur], h->nb, h->cpre, h->cp_desc, h->cp_ticket, h->seq++);
+    launch_compact(h->st, h->x[h->cur], h->v[h->cur], h->id[h->cur], h->cnt[h->ccur], h->cpre, h->cap, h->nb,
+                   h->xo, h->vo, h->cid);
+    h->n_launch += 2;
+    CK(cudaMemcpyAsync(x_host, h->xo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(v_host, h->vo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(id_host, h->cid, (size_t)h->N * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  }
+  CK(cudaStreamSynchronize(h->st));
+  CK(cudaGetLastError());
+  *n = h->N;
   return 0;
 }
 
@@ -484,8 +625,8 @@ int wendy_cuda_substep(wendy_cuda_handle *h, double dt_kick, double dt_drift, do
 int wendy_cuda_read_dev(wendy_cuda_handle *h, double *x_dev, double *v_dev) {
   if (!h) return set_err(WENDY_E_ARG, "null handle");
   if (!h->xo) {
-    CK(cudaMalloc(&h->xo, (size_t)h->N * sizeof(double)));
-    CK(cudaMalloc(&h->vo, (size_t)h->N * sizeof(double)));
+    CK(cudaMalloc(&h->xo, (size_t)h->n_cap * sizeof(double)));
+    CK(cudaMalloc(&h->vo, (size_t)h->n_cap * sizeof(double)));
   }
   double *xd = x_dev ? x_dev : h->xo, *vd = v_dev ? v_dev : h->vo;
   if (h->dense) {
@@ -537,6 +678,18 @@ int wendy_cuda_stats(wendy_cuda_handle *h, long long *out, int n) {
   long long s[9] = {h->n_sub, h->n_rebuild, h->n_fail, h->max_cnt, h->n_outside + h->h_flags[2], h->n_launch,
                     (long long)h->cap, (long long)h->nb, h->n_radix_fallback};
   for (int i = 0; i < n && i < 9; i++) out[i] = s[i];
+  return 0;
+}
+
+int wendy_cuda_pin(void *host_ptr, unsigned long long bytes) {
+  if (!host_ptr || !bytes) return set_err(WENDY_E_ARG, "null argument");
+  CK(cudaHostRegister(host_ptr, (size_t)bytes, cudaHostRegisterDefault));
+  return 0;
+}
+
+int wendy_cuda_unpin(void *host_ptr) {
+  if (!host_ptr) return set_err(WENDY_E_ARG, "null argument");
+  CK(cudaHostUnregister(host_ptr));
   return 0;
 }
 

@@ -62,6 +62,15 @@ struct TileParams {
   unsigned *fail_seq;       // smallest launch sequence number that failed
   unsigned seq;
   unsigned *stats;          // [0] max bucket count seen, [1] emitted outside the window
+  // sharded single system (one key range per GPU): particles whose new key leaves
+  // [bounds[my_rank], bounds[my_rank+1]) are appended to the outbox of the owning peer
+  int nranks, my_rank;
+  const double *bounds;     // nranks+1 ascending range edges (first -inf, last +inf), device
+  double *out_x, *out_v;    // [nranks][ocap] outboxes
+  int *out_id;
+  unsigned *out_cnt;        // [nranks]
+  unsigned ocap;
+  long long pc_offset;      // particles owned by lower ranks (added to every rank)
   // optional outputs
   int *rank_out;            // rank_out[id] = rank within the segment at this force evaluation
   double *energy_part;      // [nb][4]: kinetic, harmonic, potential, momentum partial sums
@@ -110,5 +119,8 @@ void launch_apply_drift(cudaStream_t st, double *x, const double *v, double h,
 void launch_unsort(cudaStream_t st, const double *x, const double *v, const int *id,
                    const unsigned *cnt, int cap, int nb, double *xo, double *vo);
 void launch_reduce_energy(cudaStream_t st, const double *part, int nb, double *out4);
+// compact (x, v, id) of the live slots into dense arrays (order: bucket-major, arbitrary inside)
+void launch_compact(cudaStream_t st, const double *x, const double *v, const int *id, const unsigned *cnt,
+                    const unsigned *cpre, int cap, int nb, double *xo, double *vo, int *ido);
 
 }  // namespace wendy

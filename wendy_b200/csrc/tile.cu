@@ -756,6 +756,31 @@ void launch_gather_by_id(cudaStream_t st, const double *a_by_id, const int *id, 
   gather_by_id_kernel<<<(unsigned)blocks, 256, 0, st>>>(a_by_id, id, cnt, cap, total, a_slots);
 }
 
+__global__ void compact_kernel(const double *__restrict__ x, const double *__restrict__ v,
+                               const int *__restrict__ id, const unsigned *__restrict__ cnt,
+                               const unsigned *__restrict__ cpre, int cap, long long total,
+                               double *__restrict__ xo, double *__restrict__ vo, int *__restrict__ ido) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int bi = (int)(i / cap);
+    unsigned s = (unsigned)(i - (long long)bi * cap);
+    if (s < cnt[bi]) {
+      size_t o = (size_t)cpre[bi] + s;
+      xo[o] = x[i];
+      vo[o] = v[i];
+      ido[o] = id[i];
+    }
+  }
+}
+void launch_compact(cudaStream_t st, const double *x, const double *v, const int *id, const unsigned *cnt,
+                    const unsigned *cpre, int cap, int nb, double *xo, double *vo, int *ido) {
+  long long total = (long long)nb * cap;
+  if (total <= 0) return;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  compact_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, v, id, cnt, cpre, cap, total, xo, vo, ido);
+}
+
 // fixed-order final reduction of the per-bucket energy partials (deterministic)
 __global__ void __launch_bounds__(256)
 reduce_energy_kernel(const double *__restrict__ part, int nb, double *__restrict__ out4) {

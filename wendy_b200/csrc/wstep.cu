@@ -98,7 +98,7 @@ __device__ __forceinline__ int gallop_search(const double *__restrict__ split, d
   return lo;
 }
 
-template <int WCAP, int WARPS, int EQM>
+template <int WCAP, int WARPS, int EQM, int SHARD>
 __global__ void __launch_bounds__(WARPS * 32, 1024 / (WARPS * 32))
 wstep_kernel(const TileParams p) {
   using SL = WarpSlab<WCAP, EQM>;
@@ -145,7 +145,7 @@ wstep_kernel(const TileParams p) {
 #pragma unroll
   for (int i = lane; i < SL::PADN; i += 32) S.cnt[i] = 0;
   // particles in the preceding buckets of the segment (count_prefix kernel ran just before)
-  const long long Pc = (long long)p.cpre[b] - (long long)seg * p.seg_len;
+  const long long Pc = (long long)p.cpre[b] - (long long)seg * p.seg_len + (SHARD ? p.pc_offset : 0ll);
   // lower splitters of the 32 buckets around b, in shared memory (only leaving lanes search)
   int wlo = b - 15;
   if (wlo > seg_hi - 32) wlo = seg_hi - 32;
@@ -308,6 +308,9 @@ wstep_kernel(const TileParams p) {
   int dest[E];
   unsigned hoff[E];
   unsigned hc = 0, outside = 0;
+  bool sh_overflow = false;
+  const double sh_lo = SHARD ? __ldg(p.bounds + p.my_rank) : 0.0;
+  const double sh_hi = SHARD ? __ldg(p.bounds + p.my_rank + 1) : 0.0;
   const double wdt = home_hi - home_lo;
   const double inv_w = (wdt > 0.0 && wdt < CUDART_INF) ? 1.0 / wdt : 0.0;
 #pragma unroll
@@ -323,7 +326,7 @@ wstep_kernel(const TileParams p) {
         double c, mk;
         if (EQM) {
           mk = p.m0;
-          c = __dmul_rn((double)(Pc + (long long)r[k]), p.m0);
+          c = __dmul_rn((double)(Pc + (long long)r[k]), p.m0);  // Pc includes the lower ranks' particles
         } else {
           mk = S.sm[i];
           c = S.so[r[k] + r[k] / E];
@@ -337,7 +340,21 @@ wstep_kernel(const TileParams p) {
         S.sx[i] = x2;
         S.sv[i] = v2;
         if (p.rank_out) p.rank_out[S.sid[i]] = (int)(Pc + (long long)r[k]);
-        if (key >= home_lo && key < home_hi) {
+        if (SHARD && (key < sh_lo || key >= sh_hi)) {
+          // leaves this GPU's key range: append to the outbox of the rank that owns the key
+          int peer = 0;
+          while (peer + 1 < p.nranks && key >= __ldg(p.bounds + peer + 1)) peer++;
+          const unsigned slot = atomicAdd(p.out_cnt + peer, 1u);
+          if (slot < p.ocap) {
+            const size_t o = (size_t)peer * p.ocap + slot;
+            p.out_x[o] = x2;
+            p.out_v[o] = v2;
+            p.out_id[o] = S.sid[i];
+          } else {
+            sh_overflow = true;
+          }
+          d = -3;
+        } else if (key >= home_lo && key < home_hi) {
           d = b;
         } else if (key >= S.w.wsp[0] && key < S.w.wsp[32]) {  // one of the 32 nearby buckets
           int lo, hi;
@@ -416,7 +433,7 @@ wstep_kernel(const TileParams p) {
       }
     }
   }
-  if (overflow) atomicMin(p.fail_seq, p.seq);
+  if (overflow || sh_overflow) atomicMin(p.fail_seq, p.seq);
 }
 
 // ---- exclusive prefix of the bucket counts: one pass, look-back over CTA tiles ---------------------------
@@ -464,24 +481,25 @@ void launch_count_prefix(cudaStream_t st, const unsigned *cnt, int nb, unsigned 
   if (nb > 0) count_prefix_kernel<<<count_prefix_tiles(nb), CP_T, 0, st>>>(cnt, nb, cpre, tile_desc, ticket, epoch);
 }
 
-template <int WCAP, int WARPS, int EQM>
+template <int WCAP, int WARPS, int EQM, int SHARD>
 static void launch_wstep_t(cudaStream_t st, const TileParams &p) {
   static bool attr_set = false;
   const size_t sm = sizeof(WarpSlab<WCAP, EQM>) * WARPS;
   if (!attr_set) {
-    cudaFuncSetAttribute(wstep_kernel<WCAP, WARPS, EQM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaFuncSetAttribute(wstep_kernel<WCAP, WARPS, EQM, SHARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     attr_set = true;
   }
   const int grid = (p.nb + WARPS - 1) / WARPS;
-  wstep_kernel<WCAP, WARPS, EQM><<<grid, WARPS * 32, sm, st>>>(p);
+  wstep_kernel<WCAP, WARPS, EQM, SHARD><<<grid, WARPS * 32, sm, st>>>(p);
 }
 
 bool wstep_cap_supported(int cap) { return cap == 256; }
 
 void launch_wstep(cudaStream_t st, int cap, const TileParams &p) {
   if (p.nb <= 0) return;
-  if (p.eqm) launch_wstep_t<256, 8, 1>(st, p);
-  else launch_wstep_t<256, 8, 0>(st, p);
+  if (p.bounds) launch_wstep_t<256, 8, 1, 1>(st, p);  // sharded mode: equal masses only
+  else if (p.eqm) launch_wstep_t<256, 8, 1, 0>(st, p);
+  else launch_wstep_t<256, 8, 0, 0>(st, p);
 }
 
 }  // namespace wendy

@@ -1,0 +1,271 @@
+"""Multi-GPU modes of the approximate integrator (no reference
+counterpart -- the reference is single-node OpenMP only).
+
+Two modes, one process per GPU (``torch.distributed``, NCCL on GPUs, gloo in CPU tests):
+
+* ``shard_ensemble``: independent realisations are dealt out to ranks; no data-path collective.
+* ``ShardedSystem``: ONE large system, range-partitioned over ranks by position ("sample
+  sort"): splitters from an all-gathered key sample, an initial all-to-all of particles, then
+  per leapfrog sub-step
+      local step on every rank (particles whose new key leaves the rank's range land in
+      per-peer outboxes)  ->  all-to-all of the migrants (x, v, id)  ->  append on the receiver
+      ->  all-gather of the per-rank particle counts, whose prefix offsets the cumulative mass.
+  Equal masses only in this round (cumulative mass = RN(global rank * m0), exactly what the
+  single-GPU path computes, so results are independent of the number of ranks bit for bit).
+
+The host logic here is engine-agnostic: the local work is done by an *engine* object
+(``CudaShardEngine`` in the product; the tests plug in a numpy engine to run the same logic
+under gloo on CPUs).
+"""
+import ctypes
+
+import numpy
+
+from . import _lib
+
+
+# ---- ensembles --------------------------------------------------------------------------------
+def shard_ensemble(n_realisations, rank, world_size):
+    """Contiguous block of realisation indices owned by ``rank`` (sizes differ by at most one)."""
+    base, extra = divmod(n_realisations, world_size)
+    lo = rank * base + min(rank, extra)
+    return range(lo, lo + base + (1 if rank < extra else 0))
+
+
+# ---- communication layer ----------------------------------------------------------------------
+class TorchComm(object):
+    """torch.distributed plumbing: small all-gathers and a variable-size all-to-all built from
+    batched point-to-point ops (works on both NCCL and gloo)."""
+
+    def __init__(self, group=None, device='cpu'):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group, self.device = torch, dist, group, device
+        self.rank = dist.get_rank(group)
+        self.size = dist.get_world_size(group)
+
+    def allgather_vec(self, vec):
+        """vec: 1-D sequence of float64 -> (size, len) numpy array."""
+        t = self.torch.as_tensor(numpy.asarray(vec, dtype=numpy.float64), device=self.device)
+        out = [self.torch.empty_like(t) for _ in range(self.size)]
+        self.dist.all_gather(out, t, group=self.group)
+        return numpy.stack([o.cpu().numpy() for o in out])
+
+    def exchange(self, send):
+        """send[p]: (n_p, 3) float64 tensor for peer p (send[rank] is delivered locally).
+        Returns the list of received (m_p, 3) tensors, indexed by source rank."""
+        torch, dist = self.torch, self.dist
+        counts = self.allgather_vec([s.shape[0] for s in send]).astype(numpy.int64)  # [src][dst]
+        recv = [None] * self.size
+        ops = []
+        for p in range(self.size):
+            if p == self.rank:
+                recv[p] = send[p]
+                continue
+            n_in = int(counts[p][self.rank])
+            recv[p] = torch.empty((n_in, 3), dtype=torch.float64, device=self.device)
+            if n_in:
+                ops.append(dist.P2POp(dist.irecv, recv[p], p, group=self.group))
+            if send[p].shape[0]:
+                ops.append(dist.P2POp(dist.isend, send[p].contiguous(), p, group=self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return recv
+
+
+# ---- local engine on a B200 ----------------------------------------------------------------------
+class _DevView(object):
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {'shape': (int(n),), 'typestr': typestr,
+                                         'data': (int(ptr), False), 'version': 2, 'strides': None}
+
+
+class CudaShardEngine(object):
+    """One key range on one GPU, over the shard entry points of libwendy_b200.so."""
+
+    def __init__(self, x, v, ids, m0, totmass, omega2, nranks, rank, bounds, capacity,
+                 outbox_capacity, device=None):
+        import torch
+        self.torch = torch
+        self._lib = _lib.load()
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else device
+        self.nranks, self.rank = nranks, rank
+        self._h = ctypes.c_void_p()
+        x = numpy.ascontiguousarray(x, dtype=numpy.float64)
+        v = numpy.ascontiguousarray(v, dtype=numpy.float64)
+        ids = numpy.ascontiguousarray(ids, dtype=numpy.int32)
+        bounds = numpy.ascontiguousarray(bounds, dtype=numpy.float64)
+        self.capacity = int(capacity)
+        _lib.check(self._lib.wendy_cuda_create_shard(
+            ctypes.byref(self._h), len(x), self.capacity, x, v, ids, float(m0), float(totmass),
+            float(omega2), nranks, rank, bounds, int(outbox_capacity),
+            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        px, pv, pi, oc = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_longlong()
+        _lib.check(self._lib.wendy_cuda_shard_outbox(self._h, ctypes.byref(px), ctypes.byref(pv),
+                                                     ctypes.byref(pi), ctypes.byref(oc)))
+        n = nranks * oc.value
+        self._ocap = oc.value
+        self._ox = torch.as_tensor(_DevView(px.value, n, '<f8'), device=self.device)
+        self._ov = torch.as_tensor(_DevView(pv.value, n, '<f8'), device=self.device)
+        self._oi = torch.as_tensor(_DevView(pi.value, n, '<i4'), device=self.device)
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._lib.wendy_cuda_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def substep(self, h_pre, dt_kick, dt_drift, h_next, pc_offset):
+        """Returns, per peer, an (n, 3) float64 CUDA tensor of migrants (x, v, id)."""
+        torch = self.torch
+        cnt = numpy.zeros(self.nranks, dtype=numpy.uint32)
+        _lib.check(self._lib.wendy_cuda_shard_substep(self._h, h_pre, dt_kick, dt_drift, h_next,
+                                                      int(pc_offset), cnt))
+        out = []
+        for p in range(self.nranks):
+            lo, n = p * self._ocap, int(cnt[p])
+            out.append(torch.stack((self._ox[lo:lo + n], self._ov[lo:lo + n],
+                                    self._oi[lo:lo + n].to(torch.float64)), dim=1))
+        return out
+
+    def inject(self, packed):
+        """packed: (n, 3) float64 CUDA tensor of particles that now belong to this range."""
+        n = packed.shape[0]
+        if n == 0:
+            return
+        x = packed[:, 0].contiguous()
+        v = packed[:, 1].contiguous()
+        ids = packed[:, 2].to(self.torch.int32).contiguous()
+        self.torch.cuda.current_stream().synchronize()
+        _lib.check(self._lib.wendy_cuda_shard_inject(self._h, x.data_ptr(), v.data_ptr(),
+                                                     ids.data_ptr(), n))
+
+    def count(self):
+        n = ctypes.c_longlong()
+        _lib.check(self._lib.wendy_cuda_shard_count(self._h, ctypes.byref(n)))
+        return n.value
+
+    def read(self):
+        x = numpy.empty(self.capacity)
+        v = numpy.empty(self.capacity)
+        ids = numpy.empty(self.capacity, dtype=numpy.int32)
+        n = ctypes.c_longlong()
+        _lib.check(self._lib.wendy_cuda_shard_read(self._h, x, v, ids, ctypes.byref(n)))
+        return ids[:n.value], x[:n.value], v[:n.value]
+
+    def to_device(self, arr):
+        return self.torch.as_tensor(numpy.ascontiguousarray(arr), device=self.device)
+
+
+# ---- the sharded system ------------------------------------------------------------------------------
+def choose_bounds(all_samples, nranks):
+    """Range edges from the pooled key sample: equal-count quantiles, -inf / +inf at the ends."""
+    s = numpy.sort(numpy.asarray(all_samples, dtype=numpy.float64).ravel())
+    s = s[numpy.isfinite(s)]
+    b = numpy.empty(nranks + 1)
+    b[0], b[-1] = -numpy.inf, numpy.inf
+    for k in range(1, nranks):
+        b[k] = s[min(len(s) - 1, (k * len(s)) // nranks)] if len(s) else 0.
+    return numpy.maximum.accumulate(b)
+
+
+def route(keys, bounds):
+    """Owner rank of every key: largest p with bounds[p] <= key."""
+    return numpy.clip(numpy.searchsorted(bounds, keys, side='right') - 1, 0, len(bounds) - 2)
+
+
+class ShardedSystem(object):
+    """One self-gravitating system spread over ``comm.size`` ranks (see module docstring).
+
+    Every rank passes the particles it happens to hold (any subset, with their GLOBAL ids);
+    ``m0`` is the common particle mass ALREADY times twopiG, ``totmass`` the global total as the
+    reference computes it (numpy.sum of the scaled masses, wendy/wendy.py:383)."""
+
+    def __init__(self, x, v, ids, m0, totmass, comm, omega=None, engine_factory=None,
+                 capacity_factor=1.3, outbox_fraction=0.05, n_sample=4096):
+        self.comm = comm
+        self.m0, self.totmass = float(m0), float(totmass)
+        self.omega2 = -1. if omega is None else float(omega) ** 2.
+        self._raw = (numpy.array(x, dtype=numpy.float64), numpy.array(v, dtype=numpy.float64),
+                     numpy.array(ids, dtype=numpy.int32))
+        self.engine_factory = engine_factory or CudaShardEngine
+        self.capacity_factor, self.outbox_fraction, self.n_sample = capacity_factor, outbox_fraction, n_sample
+        self.engine = None
+        self.bounds = None
+        self.dt_leap = None
+        self.pc_offset = 0
+        self.migrated = 0
+
+    # -- set-up: global sample sort on the keys of the FIRST force evaluation -------------------------
+    def _partition(self, dt_leap):
+        x, v, ids = self._raw
+        comm = self.comm
+        key = x + (dt_leap / 2.) * v  # position at the first force evaluation (wendy/wendy.c:398)
+        n_tot = int(comm.allgather_vec([len(x)]).sum())
+        take = numpy.linspace(0, max(len(key) - 1, 0), num=min(self.n_sample, len(key))).astype(int)
+        sample = numpy.full(self.n_sample, numpy.nan)
+        sample[:len(take)] = numpy.sort(key)[take] if len(key) else []
+        self.bounds = choose_bounds(comm.allgather_vec(sample), comm.size)
+        owner = route(key, self.bounds)
+        cap = int(self.capacity_factor * n_tot / comm.size) + 1024
+        # the engine's tensors decide where the exchange buffers live (cuda for NCCL, cpu for gloo)
+        import torch
+        send = [torch.as_tensor(numpy.stack((x[owner == p], v[owner == p], ids[owner == p].astype(numpy.float64)),
+                                            axis=1), device=comm.device) for p in range(comm.size)]
+        recv = comm.exchange(send)
+        mine = torch.cat(recv, dim=0).cpu().numpy() if recv else numpy.zeros((0, 3))
+        self.engine = self.engine_factory(mine[:, 0].copy(), mine[:, 1].copy(), mine[:, 2].astype(numpy.int32),
+                                          self.m0, self.totmass, self.omega2, comm.size, comm.rank,
+                                          self.bounds, cap, max(1024, int(self.outbox_fraction * cap)))
+        self._raw = None
+        self.dt_leap = dt_leap
+        self._update_offset()
+
+    def _update_offset(self):
+        counts = self.comm.allgather_vec([self.engine.count()])[:, 0]
+        self.counts = counts.astype(numpy.int64)
+        self.pc_offset = int(self.counts[:self.comm.rank].sum())
+
+    # -- one reference call: drift dt/2, nleap x [force, kick, drift] (wendy/wendy.c:385-418) ------------
+    def step(self, dt_leap, nleap):
+        if self.engine is None:
+            self._partition(dt_leap)
+        elif dt_leap != self.dt_leap:
+            raise NotImplementedError('changing dt between calls needs a global re-partition')
+        import torch
+        for k in range(nleap):
+            last = k == nleap - 1
+            out = self.engine.substep(dt_leap / 2. if k == 0 else 0., dt_leap,
+                                      dt_leap / 2. if last else dt_leap,
+                                      dt_leap / 2. if last else 0., self.pc_offset)
+            self.migrated += sum(int(o.shape[0]) for p, o in enumerate(out) if p != self.comm.rank)
+            recv = self.comm.exchange(out)
+            inc = [r for p, r in enumerate(recv) if p != self.comm.rank and r.shape[0]]
+            if inc:
+                self.engine.inject(torch.cat(inc, dim=0))
+            self._update_offset()
+        return self
+
+    def read_local(self):
+        """(ids, x, v) of the particles this rank currently owns (synchronised state)."""
+        return self.engine.read()
+
+    def gather(self, n_total):
+        """Full (x, v) in particle-index order on every rank (diagnostics / tests)."""
+        ids, x, v = self.read_local()
+        pad = int(self.comm.allgather_vec([len(ids)]).max())
+        buf = numpy.full((3, pad), numpy.nan)
+        buf[0, :len(ids)], buf[1, :len(ids)], buf[2, :len(ids)] = ids, x, v
+        allb = self.comm.allgather_vec(buf.ravel()).reshape(self.comm.size, 3, pad)
+        X, V = numpy.empty(n_total), numpy.empty(n_total)
+        for b in allb:
+            ok = numpy.isfinite(b[0])
+            X[b[0][ok].astype(int)] = b[1][ok]
+            V[b[0][ok].astype(int)] = b[2][ok]
+        return X, V
+
+    def close(self):
+        if self.engine is not None:
+            self.engine.close()

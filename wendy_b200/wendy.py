@@ -182,10 +182,14 @@ def _nbody_approx(x, v, m, dt, nleap, t0=0., omega=None, ext_force=None, sort='g
     x = numpy.require(numpy.array(x, dtype=numpy.float64), requirements=['C', 'W'])
     v = numpy.require(numpy.array(v, dtype=numpy.float64), requirements=['C', 'W'])
     ms = numpy.require(twopiG * numpy.array(m, dtype=numpy.float64), requirements=['C', 'W'])
-    state = ApproxState(x, v, ms, omega2=omega2, n_segments=n_segments, sort=sort, cap=_cap,
-                        fill=_fill, general_masses=_general_masses)
+    # the yielded buffers are re-used for every D2H copy: page-lock them (best effort)
+    lib = _lib.load()
+    pinned = [a for a in (x, v) if a.nbytes >= (1 << 20) and lib.wendy_cuda_pin(a.ctypes.data, a.nbytes) == 0]
+    state = None
     dt_leap = dt / nleap
     try:
+        state = ApproxState(x, v, ms, omega2=omega2, n_segments=n_segments, sort=sort, cap=_cap,
+                            fill=_fill, general_masses=_general_masses)
         while True:
             if ext_force is None:
                 state.step(dt_leap, nleap)
@@ -197,7 +201,10 @@ def _nbody_approx(x, v, m, dt, nleap, t0=0., omega=None, ext_force=None, sort='g
             else:
                 yield (x, v)
     finally:
-        state.close()
+        if state is not None:
+            state.close()
+        for a in pinned:
+            lib.wendy_cuda_unpin(a.ctypes.data)
 
 
 def energy(x, v, m, twopiG=1., individual=False, omega=None, n_segments=1):
