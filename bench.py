@@ -35,15 +35,18 @@ def parse():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--n', type=float, default=1e8, help='particles per GPU')
-    ap.add_argument('--nleap', type=int, default=10)
+    ap.add_argument('--particles', dest='n', type=float, default=1e8, help='particles per GPU')
+    ap.add_argument('--leap', dest='nleap', type=int, default=10)
     ap.add_argument('--dt-leap', type=float, default=1e-3)
     ap.add_argument('--omega', type=float, default=1.1)
     ap.add_argument('--sort', default='gpu', choices=['gpu', 'gpu-radix'])
-    ap.add_argument('--ref-n', type=float, default=1e7, help='particles in the CPU sample')
-    ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--ref-particles', dest='ref_n', type=float, default=1e7, help='particles in the CPU sample')
+    ap.add_argument('--skip-cpu-baseline', dest='no_cpu_baseline', action='store_true')
+    ap.add_argument('--skip-e2e', dest='no_e2e', action='store_true')
     ap.add_argument('--variants', action='store_true', help='also time other dt_leap / sort settings')
+    ap.add_argument('--mode', default='auto', choices=['auto', 'ensemble', 'sharded'],
+                    help='N>1: independent realisations per GPU, or ONE system of n*gpus particles '
+                         'range-partitioned over the GPUs (auto = sharded)')
     return ap.parse_args()
 
 
@@ -178,10 +181,39 @@ def main():
         d['left_window'] = s1['left_window'] - s0['left_window']
         return ms, d
 
+    def run_sharded(dt_leap, steps, warmup, nleap):
+        """ONE system of n*world particles, range-partitioned by position over the ranks."""
+        from wendy_b200 import multi
+        comm = multi.TorchComm(device='cuda')
+        ids = numpy.arange(n, dtype=numpy.int64) + rank * n
+        m0 = 1. / (n * world)
+        s = multi.ShardedSystem(x, v, ids.astype(numpy.int32), m0, m0 * n * world, comm, omega=a.omega)
+        for _ in range(warmup):
+            s.step(dt_leap, nleap)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        mig0 = s.migrated
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            s.step(dt_leap, nleap)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        d = {'substeps': steps * nleap, 'rebuilds': 0, 'failed_substeps': 0, 'kernel_launches': 2 * steps * nleap,
+             'radix_fallbacks': 0, 'max_bucket_count': 0, 'left_window': 0,
+             'migrants_per_substep_rank0': (s.migrated - mig0) / float(steps * nleap),
+             'particles_per_rank': [int(c) for c in s.counts]}
+        s.close()
+        return ms, d
+
+    sharded = world > 1 and a.mode in ('auto', 'sharded')
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms, d = run(a.dt_leap, a.sort, a.steps, a.warmup, a.nleap)
+    if sharded:
+        ms, d = run_sharded(a.dt_leap, a.steps, a.warmup, a.nleap)
+    else:
+        ms, d = run(a.dt_leap, a.sort, a.steps, a.warmup, a.nleap)
     clocks = sampler.stop() if sampler else None
     psteps = float(n) * world * a.nleap * a.steps
     value = psteps / (ms * 1e-3)
@@ -203,7 +235,9 @@ def main():
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': 'sech2 disk + harmonic omega=%g, N=%d per GPU, dt_leap=%g, nleap=%d, sort=%s'
                                % (a.omega, n, a.dt_leap, a.nleap, a.sort),
-                   'parallelism': 'independent realisations, one per GPU' if world > 1 else 'single GPU',
+                   'parallelism': ('one system of %d particles range-partitioned over %d GPUs (sample sort: all-to-all of '
+                                   'migrants + all-gather of counts per sub-step)' % (n * world, world)) if sharded
+                   else ('independent realisations, one per GPU' if world > 1 else 'single GPU'),
                    'l2': 'state (%.1f GB) is far larger than L2' % (n * 28 / 1e9)},
         'gpu_launches': d['kernel_launches'],
         'path_stats': d,
@@ -227,7 +261,7 @@ def main():
         out['variants'] = var
 
     # ---- end to end through the public generator API, host buffers --------------------------
-    if not a.no_e2e:
+    if not a.no_e2e and not sharded:
         steps_e = max(2, min(a.steps, 4))
         barrier()
         t0 = time.perf_counter()

@@ -73,7 +73,7 @@ class ThreadComm(object):
         self.w.barrier.wait()
         return out
 
-    def exchange(self, send):
+    def exchange(self, send, counts=None):
         for p in range(self.size):
             self.w.mail[p][self.rank] = send[p].clone()
         self.w.barrier.wait()

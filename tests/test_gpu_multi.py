@@ -58,7 +58,7 @@ def test_sharded_matches_oracle():
     assert numpy.array_equal(res[0][0], xo) and numpy.array_equal(res[0][1], vo)
 
 
-def _nccl_worker(rank, world, port, n, q):
+def _nccl_worker(rank, world, port, n, out_path):
     import torch
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'
@@ -68,8 +68,8 @@ def _nccl_worker(rank, world, port, n, q):
     try:
         from wendy_b200 import multi
         X, V, mig, counts = _run_rank(multi.TorchComm(device='cuda'), n, 1.1, 0.005, 5, 2)
-        if rank == 0:
-            q.put((X, V, mig))
+        if rank == 0:  # hand the result over through a file (a pipe would fill up before join)
+            numpy.savez(out_path, X=X, V=V, mig=mig)
     finally:
         dist.destroy_process_group()
 
@@ -85,8 +85,8 @@ def test_sharded_two_gpus_nccl_equals_single_gpu():
     with socket.socket() as s:
         s.bind(('127.0.0.1', 0))
         port = s.getsockname()[1]
-    ctx = mp.get_context('spawn')
-    q = ctx.SimpleQueue()
-    mp.spawn(_nccl_worker, args=(2, port, n, q), nprocs=2, join=True)
-    X, V, mig = q.get()
-    assert numpy.array_equal(X, Xs) and numpy.array_equal(V, Vs) and mig > 0
+    import tempfile
+    out_path = os.path.join(tempfile.mkdtemp(), 'r0.npz')
+    mp.spawn(_nccl_worker, args=(2, port, n, out_path), nprocs=2, join=True)
+    r = numpy.load(out_path)
+    assert numpy.array_equal(r['X'], Xs) and numpy.array_equal(r['V'], Vs) and int(r['mig']) > 0

@@ -51,11 +51,13 @@ class TorchComm(object):
         self.dist.all_gather(out, t, group=self.group)
         return numpy.stack([o.cpu().numpy() for o in out])
 
-    def exchange(self, send):
+    def exchange(self, send, counts=None):
         """send[p]: (n_p, 3) float64 tensor for peer p (send[rank] is delivered locally).
+        counts[src][dst] may be passed when it is already known (saves one all-gather).
         Returns the list of received (m_p, 3) tensors, indexed by source rank."""
         torch, dist = self.torch, self.dist
-        counts = self.allgather_vec([s.shape[0] for s in send]).astype(numpy.int64)  # [src][dst]
+        if counts is None:
+            counts = self.allgather_vec([s.shape[0] for s in send]).astype(numpy.int64)  # [src][dst]
         recv = [None] * self.size
         ops = []
         for p in range(self.size):
@@ -241,11 +243,16 @@ class ShardedSystem(object):
                                       dt_leap / 2. if last else dt_leap,
                                       dt_leap / 2. if last else 0., self.pc_offset)
             self.migrated += sum(int(o.shape[0]) for p, o in enumerate(out) if p != self.comm.rank)
-            recv = self.comm.exchange(out)
+            # ONE small all-gather per sub-step: every rank's outgoing counts and its particle count
+            # after the export; incoming counts and the new count prefix follow from it on the host
+            info = self.comm.allgather_vec([o.shape[0] for o in out] + [self.engine.count()]).astype(numpy.int64)
+            sent = info[:, :-1]
+            recv = self.comm.exchange(out, counts=sent)
             inc = [r for p, r in enumerate(recv) if p != self.comm.rank and r.shape[0]]
             if inc:
                 self.engine.inject(torch.cat(inc, dim=0))
-            self._update_offset()
+            self.counts = info[:, -1] + sent.sum(axis=0) - numpy.diag(sent)
+            self.pc_offset = int(self.counts[:self.comm.rank].sum())
         return self
 
     def read_local(self):
