@@ -262,7 +262,7 @@ def main():
 
     # ---- end to end through the public generator API, host buffers --------------------------
     if not a.no_e2e and not sharded:
-        steps_e = max(2, min(a.steps, 4))
+        steps_e = max(2, min(a.steps, 10))
         barrier()
         t0 = time.perf_counter()
         g = wendy_b200.nbody(x, v, m, a.dt_leap * a.nleap, approx=True, nleap=a.nleap, omega=a.omega, sort=a.sort)

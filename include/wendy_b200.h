@@ -74,6 +74,16 @@ int wendy_cuda_create(wendy_cuda_handle **h, long long N, const double *x, const
  * wall seconds of the call (wendy/wendy.c:396,416-417).  No external force. */
 int wendy_cuda_step(wendy_cuda_handle *h, double dt_leap, int nleap, double *time_elapsed);
 
+/* Asynchronous form of wendy_cuda_step: _begin enqueues the sub-steps and returns, _end waits,
+ * checks for bucket overflow and (rarely) re-runs.  wendy_cuda_read_begin / _end is the
+ * overlapped read-out: the de-sort runs on the compute stream, the D2H copies on a private copy
+ * stream, so   step_end(k); read_begin; step_begin(k+1); read_end   hides the copy behind the
+ * next call's kernels.  Host buffers should be page-locked (wendy_cuda_pin). */
+int wendy_cuda_step_begin(wendy_cuda_handle *h, double dt_leap, int nleap);
+int wendy_cuda_step_end(wendy_cuda_handle *h);
+int wendy_cuda_read_begin(wendy_cuda_handle *h, double *x_host, double *v_host);
+int wendy_cuda_read_end(wendy_cuda_handle *h);
+
 /* External-force stepping, one sub-step at a time (the caller evaluates F on device memory):
  *   wendy_cuda_force_positions: positions at the next force evaluation, as a DEVICE array of
  *       *n_slots doubles (storage order; slots not holding a particle contain finite junk).

@@ -46,6 +46,14 @@ def load():
                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
     lib.wendy_cuda_step.restype = ctypes.c_int
     lib.wendy_cuda_step.argtypes = [vp, ctypes.c_double, ctypes.c_int, c_double_p]
+    lib.wendy_cuda_step_begin.restype = ctypes.c_int
+    lib.wendy_cuda_step_begin.argtypes = [vp, ctypes.c_double, ctypes.c_int]
+    lib.wendy_cuda_step_end.restype = ctypes.c_int
+    lib.wendy_cuda_step_end.argtypes = [vp]
+    lib.wendy_cuda_read_begin.restype = ctypes.c_int
+    lib.wendy_cuda_read_begin.argtypes = [vp, vp, vp]
+    lib.wendy_cuda_read_end.restype = ctypes.c_int
+    lib.wendy_cuda_read_end.argtypes = [vp]
     lib.wendy_cuda_force_positions.restype = ctypes.c_int
     lib.wendy_cuda_force_positions.argtypes = [vp, ctypes.c_double, ctypes.c_int,
                                                ctypes.POINTER(vp), c_ll_p]
@@ -95,7 +103,8 @@ def load():
 
 
 #: every symbol include/wendy_b200.h declares (checked by tests/test_abi.py)
-EXPORTED = ['wendy_cuda_create', 'wendy_cuda_step', 'wendy_cuda_force_positions',
+EXPORTED = ['wendy_cuda_create', 'wendy_cuda_step', 'wendy_cuda_step_begin', 'wendy_cuda_step_end',
+            'wendy_cuda_read_begin', 'wendy_cuda_read_end', 'wendy_cuda_force_positions',
             'wendy_cuda_substep', 'wendy_cuda_read', 'wendy_cuda_read_dev', 'wendy_cuda_energy',
             'wendy_cuda_stats', 'wendy_cuda_create_shard', 'wendy_cuda_shard_substep', 'wendy_cuda_shard_outbox',
             'wendy_cuda_shard_inject', 'wendy_cuda_shard_count', 'wendy_cuda_shard_read', 'wendy_cuda_pin', 'wendy_cuda_unpin', 'wendy_cuda_debug_layout', 'wendy_cuda_destroy', 'wendy_cuda_last_error',

@@ -84,6 +84,14 @@ struct wendy_cuda_handle {
   int *out_id = nullptr, *cid = nullptr;
   unsigned *out_cnt = nullptr, *h_out_cnt = nullptr;
   long long ocap = 0, pc_offset = 0;
+  // asynchronous call in flight (wendy_cuda_step_begin / _end) and overlapped read-out
+  bool pending = false;
+  double p_dt = 0.;
+  int p_nleap = 0, p_k0 = 0;
+  std::vector<unsigned> p_seq;
+  std::vector<int> p_cur, p_ccur;
+  cudaStream_t st_copy = nullptr;
+  cudaEvent_t ev_unsort = nullptr;
   // counters
   long long n_sub = 0, n_rebuild = 0, n_fail = 0, max_cnt = 0, n_outside = 0, n_launch = 0;
   long long n_radix_fallback = 0;
@@ -276,6 +284,8 @@ void wendy_cuda_destroy(wendy_cuda_handle *h) {
   cudaFree(h->bounds); cudaFree(h->out_x); cudaFree(h->out_v); cudaFree(h->out_id); cudaFree(h->out_cnt);
   cudaFree(h->cid);
   if (h->h_out_cnt) cudaFreeHost(h->h_out_cnt);
+  if (h->st_copy) cudaStreamDestroy(h->st_copy);
+  if (h->ev_unsort) cudaEventDestroy(h->ev_unsort);
   if (h->h_flags) cudaFreeHost(h->h_flags);
   if (h->h_eout) cudaFreeHost(h->h_eout);
   delete h;
@@ -309,8 +319,11 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
   CKD(cudaGetDevice(&dev));
   CKD(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev));
   double sum_abs = 0.;
-  for (long long i = 0; i < N; i++) {
-    if (!std::isfinite(x[i]) || !std::isfinite(v[i]) || !std::isfinite(m[i])) {
+  {
+    // x*0 is 0 for finite x and NaN otherwise: one vectorisable pass instead of 3N isfinite calls
+    double probe = 0.;
+    for (long long i = 0; i < N; i++) probe += x[i] * 0. + v[i] * 0. + m[i] * 0.;
+    if (!(probe == 0.)) {
       wendy_cuda_destroy(h);
       return set_err(WENDY_E_ARG, "x, v, m must be finite (NaN keys are undefined in the reference sort too)");
     }
@@ -495,52 +508,57 @@ int wendy_cuda_shard_read(wendy_cuda_handle *h, double *x_host, double *v_host, 
   return 0;
 }
 
-// Run sub-steps [k0, nleap) of one reference call; on a bucket overflow re-balance and resume.
-static int run_substeps(H *h, double dt, int nleap) {
-  int k = 0;
-  int attempts_at_k = 0;
-  while (k < nleap) {
-    // enqueue everything that is left, remembering where each sub-step started
-    std::vector<unsigned> seq_of;
-    std::vector<int> cur_of, ccur_of;
-    const int k_start = k;
-    if (h->mode != WENDY_SORT_RADIX) {
-      double need_h = (k == 0) ? dt / 2. : 0.;
-      if (h->dense || !h->has_split || h->bucket_h != need_h) {
-        int rc = rebucket(h, need_h);
-        if (rc) return rc;
-      }
+// Enqueue sub-steps [k0, nleap) of one reference call (asynchronous apart from a layout rebuild).
+static int enqueue_substeps(H *h, double dt, int nleap, int k0) {
+  h->p_seq.clear(); h->p_cur.clear(); h->p_ccur.clear();
+  h->p_dt = dt; h->p_nleap = nleap; h->p_k0 = k0;
+  if (h->mode != WENDY_SORT_RADIX) {
+    double need_h = (k0 == 0) ? dt / 2. : 0.;
+    if (h->dense || !h->has_split || h->bucket_h != need_h) {
+      int rc = rebucket(h, need_h);
+      if (rc) return rc;
     }
-    for (int kk = k_start; kk < nleap; kk++) {
-      seq_of.push_back(h->seq);
-      cur_of.push_back(h->cur);
-      ccur_of.push_back(h->ccur);
-      double h_pre = (kk == 0) ? dt / 2. : 0.;
-      double dt_drift = (kk == nleap - 1) ? dt / 2. : dt;
-      if (h->mode == WENDY_SORT_RADIX) {
-        int rc = launch_radix_substep(h, h_pre, dt, dt_drift, nullptr, nullptr);
-        if (rc) return rc;
-      } else {
-        launch_bucket_substep(h, h_pre, dt, dt_drift, (kk == nleap - 1) ? dt / 2. : 0., nullptr, nullptr);
-      }
+  }
+  for (int kk = k0; kk < nleap; kk++) {
+    h->p_seq.push_back(h->seq);
+    h->p_cur.push_back(h->cur);
+    h->p_ccur.push_back(h->ccur);
+    double h_pre = (kk == 0) ? dt / 2. : 0.;
+    double dt_drift = (kk == nleap - 1) ? dt / 2. : dt;
+    if (h->mode == WENDY_SORT_RADIX) {
+      int rc = launch_radix_substep(h, h_pre, dt, dt_drift, nullptr, nullptr);
+      if (rc) return rc;
+    } else {
+      launch_bucket_substep(h, h_pre, dt, dt_drift, (kk == nleap - 1) ? dt / 2. : 0., nullptr, nullptr);
     }
+  }
+  return 0;
+}
+
+// Wait for the enqueued sub-steps; on a bucket overflow re-balance and resume from the failed one.
+static int finish_substeps(H *h) {
+  const double dt = h->p_dt;
+  const int nleap = h->p_nleap;
+  int last_fail = -1, attempts = 0;
+  while (true) {
     if (fetch_flags(h)) return WENDY_E_CUDA;
     unsigned f = h->h_flags[0];
     if (f == 0xffffffffu) break;
     // launch f overflowed: the state it read is intact; everything after it did nothing
     int kf = -1;
-    for (size_t i = 0; i < seq_of.size(); i++)
-      if (seq_of[i] == f) kf = k_start + (int)i;
+    for (size_t i = 0; i < h->p_seq.size(); i++)
+      if (h->p_seq[i] == f) kf = h->p_k0 + (int)i;
     if (kf < 0) return set_err(WENDY_E_CUDA, "internal: unknown failing launch");
     h->n_fail++;
     h->n_sub -= (nleap - kf);
-    h->cur = cur_of[kf - k_start];
-    h->ccur = ccur_of[kf - k_start];
+    h->cur = h->p_cur[kf - h->p_k0];
+    h->ccur = h->p_ccur[kf - h->p_k0];
     h->has_split = false;  // force a rebuild for the key of sub-step kf
     if (reset_flags(h)) return WENDY_E_CUDA;
-    attempts_at_k = (kf == k) ? attempts_at_k + 1 : 1;
-    k = kf;
-    if (attempts_at_k >= 2) {
+    attempts = (kf == last_fail) ? attempts + 1 : 1;
+    last_fail = kf;
+    int k = kf;
+    if (attempts >= 2) {
       // even a freshly balanced layout overflows within this one sub-step (the density changes
       // by more than the bucket head-room): take it on the radix path, which cannot overflow
       double h_pre = (k == 0) ? dt / 2. : 0.;
@@ -549,8 +567,11 @@ static int run_substeps(H *h, double dt, int nleap) {
       if (fetch_flags(h)) return WENDY_E_CUDA;
       h->n_radix_fallback++;
       k++;
-      attempts_at_k = 0;
+      attempts = 0;
+      last_fail = -1;
     }
+    int rc = enqueue_substeps(h, dt, nleap, k);
+    if (rc) return rc;
   }
   // cheap insurance: re-balance between calls when some bucket is nearly full
   if (h->mode != WENDY_SORT_RADIX && h->h_flags[1] > (unsigned)(h->cap - (h->cap - h->fill) / 16)) {
@@ -560,9 +581,33 @@ static int run_substeps(H *h, double dt, int nleap) {
   return 0;
 }
 
+static int run_substeps(H *h, double dt, int nleap) {
+  int rc = enqueue_substeps(h, dt, nleap, 0);
+  if (rc) return rc;
+  return finish_substeps(h);
+}
+
+int wendy_cuda_step_begin(wendy_cuda_handle *h, double dt_leap, int nleap) {
+  if (!h) return set_err(WENDY_E_ARG, "null handle");
+  if (nleap < 1) return set_err(WENDY_E_ARG, "nleap must be >= 1");
+  if (h->pending) return set_err(WENDY_E_ARG, "a call is already in flight");
+  int rc = enqueue_substeps(h, dt_leap, nleap, 0);
+  if (rc) return rc;
+  h->pending = true;
+  return 0;
+}
+
+int wendy_cuda_step_end(wendy_cuda_handle *h) {
+  if (!h) return set_err(WENDY_E_ARG, "null handle");
+  if (!h->pending) return 0;
+  h->pending = false;
+  return finish_substeps(h);
+}
+
 int wendy_cuda_step(wendy_cuda_handle *h, double dt_leap, int nleap, double *time_elapsed) {
   if (!h) return set_err(WENDY_E_ARG, "null handle");
   if (nleap < 1) return set_err(WENDY_E_ARG, "nleap must be >= 1");
+  if (h->pending) return set_err(WENDY_E_ARG, "a call is already in flight (wendy_cuda_step_end first)");
   auto t0 = std::chrono::steady_clock::now();
   int rc = run_substeps(h, dt_leap, nleap);
   if (time_elapsed)
@@ -646,6 +691,30 @@ int wendy_cuda_read(wendy_cuda_handle *h, double *x_host, double *v_host) {
   if (x_host) CK(cudaMemcpyAsync(x_host, h->xo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
   if (v_host) CK(cudaMemcpyAsync(v_host, h->vo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
+// Overlapped read-out: de-sort into staging on the compute stream, D2H on a private copy stream.
+// Between _begin and _end the caller may enqueue the next call (wendy_cuda_step_begin).
+int wendy_cuda_read_begin(wendy_cuda_handle *h, double *x_host, double *v_host) {
+  if (!h) return set_err(WENDY_E_ARG, "null handle");
+  if (h->pending) return set_err(WENDY_E_ARG, "finish the call in flight first");
+  if (!h->st_copy) {
+    CK(cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_unsort, cudaEventDisableTiming));
+  }
+  int rc = wendy_cuda_read_dev(h, nullptr, nullptr);
+  if (rc) return rc;
+  CK(cudaEventRecord(h->ev_unsort, h->st));
+  CK(cudaStreamWaitEvent(h->st_copy, h->ev_unsort, 0));
+  if (x_host) CK(cudaMemcpyAsync(x_host, h->xo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st_copy));
+  if (v_host) CK(cudaMemcpyAsync(v_host, h->vo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st_copy));
+  return 0;
+}
+
+int wendy_cuda_read_end(wendy_cuda_handle *h) {
+  if (!h) return set_err(WENDY_E_ARG, "null handle");
+  if (h->st_copy) CK(cudaStreamSynchronize(h->st_copy));
   return 0;
 }
 

@@ -212,16 +212,22 @@ wstep_kernel(const TileParams p) {
   }
 
   // ---- sort: interpolation sub-bucket, arrival slot ------------------------------------------------
+  // pk[k] packs, per particle: sub-bucket (bits 0-7), position in sub-bucket order (8-15),
+  // exact rank (16-23); all < 256 = WCAP.
+  static_assert(WCAP <= 256, "packed sort state assumes 8-bit indices");
   unsigned pk[E];
+  double xr[E];
 #pragma unroll
   for (int k = 0; k < E; k++) {
     const unsigned i = lane + 32 * k;
     pk[k] = 0;
+    xr[k] = 0.0;
     if (32u * k < n && i < n) {
-      int sub = (int)((S.sx[i] - xmin) * scale);
+      xr[k] = S.sx[i];
+      int sub = (int)((xr[k] - xmin) * scale);
       sub = max(0, min(BK - 1, sub));
       unsigned o = atomicAdd(&S.cnt[sub + sub / E], 1u);
-      pk[k] = (unsigned)sub | (o << 16);
+      pk[k] = (unsigned)sub | (o << 8);
     }
   }
   __syncwarp();
@@ -241,49 +247,47 @@ wstep_kernel(const TileParams p) {
     }
   }
   __syncwarp();
+  // keys move (through registers) into sub-bucket order IN PLACE: sx[pos] = key, slot[pos] = load slot
 #pragma unroll
   for (int k = 0; k < E; k++) {
     const unsigned i = lane + 32 * k;
     if (32u * k < n && i < n) {
-      const unsigned sub = pk[k] & 0xffffu;
-      S.slot[S.cnt[sub + sub / E] + (pk[k] >> 16)] = (unsigned short)i;
+      const unsigned sub = pk[k] & 0xffu;
+      const unsigned pos = S.cnt[sub + sub / E] + (pk[k] >> 8);
+      S.sx[pos] = xr[k];
+      S.slot[pos] = (unsigned short)i;
+      pk[k] = sub | (pos << 8);
     }
   }
   __syncwarp();
-  // exact rank under (x, id)
-  unsigned r[E];
+  // exact rank under (x, id): sub-bucket start + members that compare smaller
 #pragma unroll
   for (int k = 0; k < E; k++) {
     const unsigned i = lane + 32 * k;
-    r[k] = 0;
     if (32u * k < n && i < n) {
-      const unsigned sub = pk[k] & 0xffffu;
+      const unsigned sub = pk[k] & 0xffu;
       const unsigned s0 = S.cnt[sub + sub / E];
       const unsigned s1 = (sub + 1 < (unsigned)BK) ? S.cnt[(sub + 1) + (sub + 1) / E] : n;
       unsigned rr = s0;
       if (s1 - s0 > 1u) {
-        const double xi = S.sx[i];
-        const int ii = S.sid[i];
+        const double xi = xr[k];
         for (unsigned q = s0; q < s1; q++) {
-          const unsigned j = S.slot[q];
-          const double xj = S.sx[j];
-#if WS_RANK2
+          const double xj = S.sx[q];
           rr += (xj < xi) ? 1u : 0u;
-          if (xj == xi) rr += (S.sid[j] < ii) ? 1u : 0u;  // exact coincidence: ties by particle index
-#else
-          rr += (xj < xi || (xj == xi && S.sid[j] < ii)) ? 1u : 0u;
-#endif
+          if (xj == xi) rr += (S.sid[S.slot[q]] < S.sid[i]) ? 1u : 0u;  // coincidence: ties by particle index
         }
       }
-      r[k] = rr;
+      pk[k] |= rr << 16;
     }
   }
+#define WS_POS(k) ((pk[k] >> 8) & 0xffu)
+#define WS_RANK(k) (pk[k] >> 16)
   // ---- scan (general masses): exact 128-bit prefix in sorted order ------------------------------------
   if (!EQM) {
 #pragma unroll
     for (int k = 0; k < E; k++) {
       const unsigned i = lane + 32 * k;
-      if (i < n) S.so[r[k] + r[k] / E] = S.sm[i];
+      if (i < n) S.so[WS_RANK(k) + WS_RANK(k) / E] = S.sm[i];
     }
     __syncwarp();
     i128 loc[E], tsum = 0;
@@ -322,14 +326,15 @@ wstep_kernel(const TileParams p) {
       const bool ok = i < n;
       int d = -1;
       if (ok) {
-        const double xk = S.sx[i], v = S.sv[i];
+        const unsigned ps = WS_POS(k);
+        const double xk = S.sx[ps], v = S.sv[i];
         double c, mk;
         if (EQM) {
           mk = p.m0;
-          c = __dmul_rn((double)(Pc + (long long)r[k]), p.m0);  // Pc includes the lower ranks' particles
+          c = __dmul_rn((double)(Pc + (long long)WS_RANK(k)), p.m0);  // Pc includes the lower ranks' particles
         } else {
           mk = S.sm[i];
-          c = S.so[r[k] + r[k] / E];
+          c = S.so[WS_RANK(k) + WS_RANK(k) / E];
         }
         double acc = __dsub_rn(__dsub_rn(tot, __dmul_rn(2.0, c)), mk);
         if (p.omega2 >= 0.0) acc = __dsub_rn(acc, __dmul_rn(p.omega2, xk));
@@ -337,9 +342,9 @@ wstep_kernel(const TileParams p) {
         const double v2 = __dadd_rn(v, __dmul_rn(p.dt_kick, acc));
         const double x2 = __dadd_rn(xk, __dmul_rn(p.dt_drift, v2));
         const double key = (p.h_next != 0.0) ? __dadd_rn(x2, __dmul_rn(p.h_next, v2)) : x2;
-        S.sx[i] = x2;
+        S.sx[ps] = x2;
         S.sv[i] = v2;
-        if (p.rank_out) p.rank_out[S.sid[i]] = (int)(Pc + (long long)r[k]);
+        if (p.rank_out) p.rank_out[S.sid[i]] = (int)(Pc + (long long)WS_RANK(k));
         if (SHARD && (key < sh_lo || key >= sh_hi)) {
           // leaves this GPU's key range: append to the outbox of the rank that owns the key
           int peer = 0;
@@ -357,25 +362,11 @@ wstep_kernel(const TileParams p) {
         } else if (key >= home_lo && key < home_hi) {
           d = b;
         } else if (key >= S.w.wsp[0] && key < S.w.wsp[32]) {  // one of the 32 nearby buckets
-          int lo, hi;
-          const int rel = b - wlo;
-#if WS_NEIGH
-          if (key < home_lo) {  // neighbours first, then bisection of what is left
-            if (key >= S.w.wsp[rel - 1]) { lo = rel - 1; hi = rel; }
-            else if (rel >= 2 && key >= S.w.wsp[rel - 2]) { lo = rel - 2; hi = rel - 1; }
-            else { lo = 0; hi = rel - 2; }
-          } else {
-            if (key < S.w.wsp[rel + 2 > 32 ? 32 : rel + 2]) { lo = rel + 1; hi = rel + 2; }
-            else if (rel + 3 <= 32 && key < S.w.wsp[rel + 3]) { lo = rel + 2; hi = rel + 3; }
-            else { lo = rel + 3; hi = 32; }
-          }
-#else
-          if (key < home_lo) { lo = 0; hi = rel; } else { lo = rel + 1; hi = 32; }
-#endif
-          while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (S.w.wsp[mid] <= key) lo = mid; else hi = mid;
-          }
+          // interpolated guess from the home bucket's width, then a short walk to the exact bucket
+          int lo = (b - wlo) + (int)floor(fmax(-64.0, fmin(64.0, (key - home_lo) * inv_w)));
+          lo = max(0, min(31, lo));
+          while (lo > 0 && S.w.wsp[lo] > key) lo--;
+          while (lo < 31 && S.w.wsp[lo + 1] <= key) lo++;
           d = wlo + lo;
           hoff[k] = atomicAdd(&S.w.dcnt[lo], 1u);
         } else {  // beyond the window: interpolated guess, probe 4 adjacent splitters, else gallop
@@ -423,7 +414,7 @@ wstep_kernel(const TileParams p) {
         else if (d >= wlo && d < wlo + 32) pos += S.w.dbase[d - wlo];
         if (pos < (unsigned)WCAP) {
           const size_t o = (size_t)d * WCAP + pos;
-          p.xout[o] = S.sx[i];
+          p.xout[o] = S.sx[WS_POS(k)];
           p.vout[o] = S.sv[i];
           if (!EQM) p.mout[o] = S.sm[i];
           p.idout[o] = S.sid[i];
@@ -434,6 +425,8 @@ wstep_kernel(const TileParams p) {
     }
   }
   if (overflow || sh_overflow) atomicMin(p.fail_seq, p.seq);
+#undef WS_POS
+#undef WS_RANK
 }
 
 // ---- exclusive prefix of the bucket counts: one pass, look-back over CTA tiles ---------------------------

@@ -78,6 +78,23 @@ class ApproxState(object):
         self.time_elapsed = t.value
         return self
 
+    def step_begin(self, dt_leap, nleap):
+        """Enqueue one reference call without waiting for it (pair with step_end)."""
+        import time
+        self._t_begin = time.perf_counter()
+        _lib.check(self._lib.wendy_cuda_step_begin(self._h, dt_leap, nleap))
+
+    def step_end(self):
+        import time
+        _lib.check(self._lib.wendy_cuda_step_end(self._h))
+        self.time_elapsed = time.perf_counter() - getattr(self, '_t_begin', time.perf_counter())
+
+    def read_begin(self, x_out, v_out):
+        _lib.check(self._lib.wendy_cuda_read_begin(self._h, x_out.ctypes.data, v_out.ctypes.data))
+
+    def read_end(self):
+        _lib.check(self._lib.wendy_cuda_read_end(self._h))
+
     def step_ext(self, dt_leap, nleap, ext_force, t0):
         """Same, with a torch-vectorised external force; returns the advanced t0.
 
@@ -190,11 +207,22 @@ def _nbody_approx(x, v, m, dt, nleap, t0=0., omega=None, ext_force=None, sort='g
     try:
         state = ApproxState(x, v, ms, omega2=omega2, n_segments=n_segments, sort=sort, cap=_cap,
                             fill=_fill, general_masses=_general_masses)
+        if ext_force is None:
+            # The generator is infinite (reference wendy/wendy.py:424), so the call after this
+            # one is always needed: enqueue it before the D2H copy of this one has finished.
+            state.step_begin(dt_leap, nleap)
+            while True:
+                state.step_end()
+                te = state.time_elapsed
+                state.read_begin(x, v)
+                state.step_begin(dt_leap, nleap)
+                state.read_end()
+                if full_output:
+                    yield (x, v, te)
+                else:
+                    yield (x, v)
         while True:
-            if ext_force is None:
-                state.step(dt_leap, nleap)
-            else:
-                t0 = state.step_ext(dt_leap, nleap, ext_force, t0)
+            t0 = state.step_ext(dt_leap, nleap, ext_force, t0)
             state.read(x, v)
             if full_output:
                 yield (x, v, state.time_elapsed)
