@@ -41,6 +41,7 @@ void launch_gather_by_id(cudaStream_t st, const double *a_by_id, const int *id, 
 struct wendy_cuda_handle {
   long long N = 0, seg_len = 0;
   int nseg = 1, mode = 0, fxE = 0;
+  int nb_alloc = 0;
   bool eqm = false;        // all masses identical: no mass arrays, cum = rank * m0
   double m0 = 0.;
   double omega2 = -1.;
@@ -54,6 +55,10 @@ struct wendy_cuda_handle {
   int cur = 0;
   unsigned *cnt[3] = {nullptr, nullptr, nullptr};
   int ccur = 0;
+  bool adaptive = false;   // cap chosen by the library: 256 (warp kernel) <-> 2048 (CTA kernel)
+  int want_cap = 0;        // geometry to switch to at the next layout rebuild (0: keep)
+  int user_fill = 0, user_cap = 0;
+  double last_dt = 0.;
   bool dense = true;       // state is the dense upload in buffer `cur` (no layout yet)
   bool has_split = false;  // splitters are valid for key = x + bucket_h * v
   double bucket_h = 0.;
@@ -67,7 +72,7 @@ struct wendy_cuda_handle {
   unsigned *cpre = nullptr;            // exclusive prefix of the current bucket counts
   unsigned long long *cp_desc = nullptr;  // look-back words of the count_prefix kernel
   unsigned *cp_ticket = nullptr;
-  unsigned *flags = nullptr;    // [0] fail_seq, [1] max count, [2] outside-window count
+  unsigned *flags = nullptr;    // [0] fail_seq, [1] max count; [8..135] = 64 x u64 outside-window counters
   unsigned *h_flags = nullptr;  // pinned mirror
   unsigned seq = 1;
   // scratch
@@ -131,17 +136,26 @@ static int seg_bits(const H *h) {
 
 // Sync and fetch {fail_seq, max count, outside count}.
 static int fetch_flags(H *h) {
-  CK(cudaMemcpyAsync(h->h_flags, h->flags, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaMemcpyAsync(h->h_flags, h->flags, 136 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
   CK(cudaGetLastError());
   if (h->h_flags[1] > h->max_cnt) h->max_cnt = h->h_flags[1];
   return 0;
 }
 
+static long long outside_total(const H *h) {
+  long long t = 0;
+  const unsigned long long *c = (const unsigned long long *)(h->h_flags + 8);
+  for (int i = 0; i < 64; i++) t += (long long)c[i];
+  return t;
+}
+
 static int reset_flags(H *h) {
-  unsigned init[3] = {0xffffffffu, 0u, 0u};
-  h->n_outside += h->h_flags[2];
+  static const unsigned init[2] = {0xffffffffu, 0u};
+  h->n_outside += outside_total(h);
+  memset(h->h_flags + 8, 0, 128 * sizeof(unsigned));
   CK(cudaMemcpyAsync(h->flags, init, sizeof(init), cudaMemcpyHostToDevice, h->st));
+  CK(cudaMemsetAsync(h->flags + 8, 0, 128 * sizeof(unsigned), h->st));
   CK(cudaMemsetAsync(h->ticket, 0, 3 * sizeof(unsigned), h->st));
   CK(cudaStreamSynchronize(h->st));  // `init` is a stack buffer
   h->tcur = 0;
@@ -166,14 +180,24 @@ static int make_keys(H *h, double hkey, int val_mode) {
 
 // (Re)build the bucket layout for key = x + hkey*v: exact quantile splitters from a radix
 // sort of the keys, then one streaming scatter of the state into the other buffer.
+static int default_fill(const H *h, int cap) {
+  if (h->user_fill > 0 && cap == h->user_cap) return h->user_fill;
+  return cap == 256 ? 128 : cap * 3 / 4;
+}
+
 static int rebucket(H *h, double hkey) {
+  // target geometry (may differ from the geometry the state is currently stored in)
+  const int ncap = h->want_cap ? h->want_cap : h->cap;
+  const int nfill = (ncap == h->cap) ? h->fill : default_fill(h, ncap);
+  const int nnbps = (int)(((h->n_cap / h->nseg) + nfill - 1) / nfill);
+  const int nnb = nnbps * h->nseg;
   if (make_keys(h, hkey, VAL_SEGMENT)) return WENDY_E_CUDA;
   int res = radix_sort_pairs(h->st, h->rs, (size_t)h->N, seg_bits(h), 1u);
   h->n_launch += 5 * (8 + (seg_bits(h) + 7) / 8);
-  launch_pick_splitters(h->st, h->rs.key[res], h->seg_len, h->fill, h->nbps, h->nb, h->split);
+  launch_pick_splitters(h->st, h->rs.key[res], h->seg_len, nfill, nnbps, nnb, h->split);
   int c1 = (h->ccur + 1) % 3, c2 = (h->ccur + 2) % 3;
-  CK(cudaMemsetAsync(h->cnt[c1], 0, (size_t)h->nb * sizeof(unsigned), h->st));
-  CK(cudaMemsetAsync(h->cnt[c2], 0, (size_t)h->nb * sizeof(unsigned), h->st));
+  CK(cudaMemsetAsync(h->cnt[c1], 0, (size_t)h->nb_alloc * sizeof(unsigned), h->st));
+  CK(cudaMemsetAsync(h->cnt[c2], 0, (size_t)h->nb_alloc * sizeof(unsigned), h->st));
   ScatterParams sp;
   memset(&sp, 0, sizeof(sp));
   sp.xin = h->x[h->cur]; sp.vin = h->v[h->cur]; sp.min = h->m[h->cur]; sp.idin = h->id[h->cur];
@@ -182,7 +206,7 @@ static int rebucket(H *h, double hkey) {
   sp.h = hkey;
   int o = h->cur ^ 1;
   sp.xout = h->x[o]; sp.vout = h->v[o]; sp.mout = h->m[o]; sp.idout = h->id[o];
-  sp.cnt_out = h->cnt[c1]; sp.split = h->split; sp.cap_out = h->cap; sp.nbps_out = h->nbps;
+  sp.cnt_out = h->cnt[c1]; sp.split = h->split; sp.cap_out = ncap; sp.nbps_out = nnbps;
   sp.seg_len = h->seg_len; sp.fail_seq = h->flags; sp.seq = h->seq++;
   launch_scatter(h->st, sp, h->sm_count);
   h->n_launch += 2;
@@ -193,6 +217,7 @@ static int rebucket(H *h, double hkey) {
                                      "coincident particles for one bucket");
   }
   h->cur = o; h->ccur = c1; h->dense = false; h->has_split = true; h->bucket_h = hkey;
+  h->cap = ncap; h->fill = nfill; h->nbps = nnbps; h->nb = nnb; h->want_cap = 0;
   h->n_rebuild++;
   CK(cudaMemsetAsync(h->flags + 1, 0, sizeof(unsigned), h->st));  // max-count is per layout
   h->h_flags[1] = 0;
@@ -216,7 +241,7 @@ static void fill_tile_params(H *h, TileParams &p) {
   p.out_x = h->out_x; p.out_v = h->out_v; p.out_id = h->out_id; p.out_cnt = h->out_cnt;
   p.ocap = (unsigned)h->ocap; p.pc_offset = h->pc_offset;
   p.ticket = h->ticket + h->tcur; p.ticket_zero = h->ticket + (h->tcur + 2) % 3;
-  p.fail_seq = h->flags; p.stats = h->flags + 1;
+  p.fail_seq = h->flags; p.stats = h->flags + 1; p.outside = (unsigned long long *)(h->flags + 8);
   p.seq = h->seq; p.epoch = h->seq;
 }
 
@@ -233,12 +258,10 @@ static void launch_bucket_substep(H *h, double h_pre, double dt_kick, double dt_
   fill_tile_params(h, p);
   p.h_pre = h_pre; p.dt_kick = dt_kick; p.dt_drift = dt_drift; p.h_next = h_next;
   p.aext = aext; p.rank_out = rank_out;
-  if (wstep_cap_supported(h->cap)) {
-    launch_count_prefix(h->st, p.cnt_in, h->nb, h->cpre, h->cp_desc, h->cp_ticket, p.epoch);
-    h->n_launch++;
-    p.cpre = h->cpre;
-    launch_wstep(h->st, h->cap, p);
-  }
+  launch_count_prefix(h->st, p.cnt_in, h->nb, h->cpre, h->cp_desc, h->cp_ticket, p.epoch);
+  h->n_launch++;
+  p.cpre = h->cpre;
+  if (wstep_cap_supported(h->cap)) launch_wstep(h->st, h->cap, p);
   else launch_tile(h->st, h->cap, LOAD_BUCKET, EMIT_SPLITTER, 1, p);
   advance_after_tile(h);
   h->cur ^= 1; h->ccur = (h->ccur + 1) % 3; h->bucket_h = h_next;
@@ -298,21 +321,25 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
   if (N <= 0 || N >= (1ll << 31) || n_cap < N || n_cap >= (1ll << 31))
     return set_err(WENDY_E_ARG, "N must be in [1, 2^31) and not exceed the capacity");
   if (n_segments < 1 || N % n_segments) return set_err(WENDY_E_ARG, "N must be a multiple of n_segments");
+  const bool adaptive = (cap == 0);
   if (cap == 0) cap = 256;
   if (!tile_cap_supported(cap)) return set_err(WENDY_E_ARG, "cap must be 2048 or 256");
   // Splitters are exact quantiles of ONE random sample, so bucket widths carry their own
   // 1/sqrt(fill) noise and the steady-state count variance is 2*fill (measured: DESIGN.md).
   // Defaults leave >= 8 sigma of head-room: 128 + 8*sqrt(256) = 256, 1536 + 9*sqrt(3072) < 2048.
+  const int fill_arg = fill;
   if (fill == 0) fill = (cap == 256) ? 128 : cap * 3 / 4;
   if (fill < 1 || fill > cap) return set_err(WENDY_E_ARG, "fill must be in [1, cap]");
   H *h = new H;
   *out = nullptr;
+  h->user_fill = fill_arg; h->user_cap = cap;
   h->N = N; h->n_cap = n_cap; h->nseg = n_segments; h->seg_len = N / n_segments; h->omega2 = omega2;
   h->mode = flags & 0xf; h->cap = cap; h->fill = fill;
+  h->adaptive = adaptive && h->mode != WENDY_SORT_RADIX;
   h->nbps = (int)(((n_cap / n_segments) + fill - 1) / fill);
   long long nb = (long long)h->nbps * n_segments;
   if (nb * cap >= (1ll << 32)) { delete h; return set_err(WENDY_E_ARG, "too many storage slots for u32 indices"); }
-  h->nb = (int)nb; h->slots = (size_t)nb * cap;
+  h->nb = (int)nb; h->nb_alloc = (int)nb; h->slots = (size_t)nb * cap;
   h->st = (cudaStream_t)cuda_stream;
   int dev = 0;
 #define CKD(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { std::string s__ = std::string(#call) + ": " + cudaGetErrorString(e__); wendy_cuda_destroy(h); return set_err(WENDY_E_CUDA, s__); } } while (0)
@@ -361,13 +388,14 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
   CKD(cudaMemsetAsync(h->cp_desc, 0, (size_t)(count_prefix_tiles(h->nb) + 1) * sizeof(unsigned long long), h->st));
   CKD(cudaMalloc(&h->cp_ticket, sizeof(unsigned)));
   CKD(cudaMemsetAsync(h->cp_ticket, 0, sizeof(unsigned), h->st));
-  CKD(cudaMalloc(&h->flags, 4 * sizeof(unsigned)));
+  CKD(cudaMalloc(&h->flags, 136 * sizeof(unsigned)));
+  CKD(cudaMemsetAsync(h->flags, 0, 136 * sizeof(unsigned), h->st));
   CKD(cudaMalloc(&h->offs, (size_t)h->nb * sizeof(unsigned long long)));
   CKD(cudaMalloc(&h->epart, (size_t)h->nb * 4 * sizeof(double)));
   CKD(cudaMalloc(&h->eout, 4 * sizeof(double)));
-  CKD(cudaMallocHost(&h->h_flags, 4 * sizeof(unsigned)));
+  CKD(cudaMallocHost(&h->h_flags, 136 * sizeof(unsigned)));
   CKD(cudaMallocHost(&h->h_eout, 4 * sizeof(double)));
-  memset(h->h_flags, 0, 4 * sizeof(unsigned));
+  memset(h->h_flags, 0, 136 * sizeof(unsigned));
   CKD(cudaMemsetAsync(h->status, 0, (size_t)h->nb * sizeof(unsigned), h->st));
   CKD(cudaMemcpyAsync(h->x[0], x, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->st));
   CKD(cudaMemcpyAsync(h->v[0], v, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->st));
@@ -512,6 +540,16 @@ int wendy_cuda_shard_read(wendy_cuda_handle *h, double *x_host, double *v_host, 
 static int enqueue_substeps(H *h, double dt, int nleap, int k0) {
   h->p_seq.clear(); h->p_cur.clear(); h->p_ccur.clear();
   h->p_dt = dt; h->p_nleap = nleap; h->p_k0 = k0;
+  if (k0 == 0) {
+    h->n_outside += outside_total(h);
+    memset(h->h_flags + 8, 0, 128 * sizeof(unsigned));
+    CK(cudaMemsetAsync(h->flags + 8, 0, 128 * sizeof(unsigned), h->st));  // per-call window statistic
+    if (h->adaptive && h->last_dt != 0. && dt != h->last_dt && h->cap != 256) {
+      h->want_cap = 256;  // a new time step: start again from the fine layout and re-measure
+      h->has_split = false;
+    }
+    h->last_dt = dt;
+  }
   if (h->mode != WENDY_SORT_RADIX) {
     double need_h = (k0 == 0) ? dt / 2. : 0.;
     if (h->dense || !h->has_split || h->bucket_h != need_h) {
@@ -572,6 +610,17 @@ static int finish_substeps(H *h) {
     }
     int rc = enqueue_substeps(h, dt, nleap, k);
     if (rc) return rc;
+  }
+  // adaptive layout: when most particles leave the 32-bucket window of the warp kernel every
+  // sub-step (large N*dt), 2048-slot buckets with CTA-aggregated emission are faster
+  if (h->adaptive && h->cap == 256 && !h->dense) {
+    const double moved = (double)outside_total(h);
+    if (moved > 0.5 * (double)h->N * (double)nleap) {
+      h->want_cap = 2048;
+      int rc = rebucket(h, h->bucket_h);
+      if (rc) return rc;
+      return 0;
+    }
   }
   // cheap insurance: re-balance between calls when some bucket is nearly full
   if (h->mode != WENDY_SORT_RADIX && h->h_flags[1] > (unsigned)(h->cap - (h->cap - h->fill) / 16)) {
@@ -744,7 +793,7 @@ int wendy_cuda_energy(wendy_cuda_handle *h, double out[4]) {
 
 int wendy_cuda_stats(wendy_cuda_handle *h, long long *out, int n) {
   if (!h || !out) return set_err(WENDY_E_ARG, "null argument");
-  long long s[9] = {h->n_sub, h->n_rebuild, h->n_fail, h->max_cnt, h->n_outside + h->h_flags[2], h->n_launch,
+  long long s[9] = {h->n_sub, h->n_rebuild, h->n_fail, h->max_cnt, h->n_outside + outside_total(h), h->n_launch,
                     (long long)h->cap, (long long)h->nb, h->n_radix_fallback};
   for (int i = 0; i < n && i < 9; i++) out[i] = s[i];
   return 0;

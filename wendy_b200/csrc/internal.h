@@ -61,7 +61,8 @@ struct TileParams {
   unsigned *ticket, *ticket_zero;
   unsigned *fail_seq;       // smallest launch sequence number that failed
   unsigned seq;
-  unsigned *stats;          // [0] max bucket count seen, [1] emitted outside the window
+  unsigned *stats;          // [0] max bucket count seen
+  unsigned long long *outside;  // particles emitted outside the 32-bucket window (per call)
   // sharded single system (one key range per GPU): particles whose new key leaves
   // [bounds[my_rank], bounds[my_rank+1]) are appended to the outbox of the owning peer
   int nranks, my_rank;

@@ -134,7 +134,10 @@ tile_kernel(const TileParams p) {
   // ---- 1b. number of particles in the preceding buckets of the segment -------------------
   // (known at entry: published and resolved while the loads above are in flight)
   if (wid == 0) {
-    unsigned pc = (LOAD == LOAD_BUCKET) ? count_lookback(p.cdesc, p.epoch, b, seg_lo, n, lane) : (unsigned)kb * (unsigned)CAP;
+    unsigned pc;
+    if (LOAD != LOAD_BUCKET) pc = (unsigned)kb * (unsigned)CAP;
+    else if (p.cpre) pc = p.cpre[b] - (unsigned)((long long)seg * p.seg_len);  // count_prefix kernel ran before
+    else pc = count_lookback(p.cdesc, p.epoch, b, seg_lo, n, lane);
     if (lane == 0) S.pre_cnt = (long long)pc;
   }
   // ---- 2. key range of the bucket ----------------------------------------------------------
@@ -459,7 +462,10 @@ tile_kernel(const TileParams p) {
   }
   __syncthreads();
   if (tid < wn && S.dcnt[tid]) S.dbase[tid] = atomicAdd(&p.cnt_out[wlo + tid], S.dcnt[tid]);
-  if (outside) atomicAdd(p.stats + 1, outside);
+  {  // one atomic per warp, spread over 64 counters (a single hot address serialises in L2)
+    const unsigned wsum = __reduce_add_sync(WENDY_FULL_MASK, outside);
+    if (lane == 0 && wsum) atomicAdd(p.outside + (b & 63), (unsigned long long)wsum);
+  }
   __syncthreads();
   bool overflow = false;
 #pragma unroll

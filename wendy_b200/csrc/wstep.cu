@@ -398,7 +398,10 @@ wstep_kernel(const TileParams p) {
     if (lane == b - wlo) c += hc;  // in-window away particles were counted first: home goes after
     if (c) S.w.dbase[lane] = atomicAdd(&p.cnt_out[wlo + lane], c);
   }
-  if (outside) atomicAdd(p.stats + 1, outside);
+  {  // one atomic per warp, spread over 64 counters (a single hot address serialises in L2)
+    const unsigned wsum = __reduce_add_sync(WENDY_FULL_MASK, outside);
+    if (lane == 0 && wsum) atomicAdd(p.outside + (b & 63), (unsigned long long)wsum);
+  }
   __syncwarp();
   const unsigned home_shift = S.w.dcnt[b - wlo];
   // ---- stores ----------------------------------------------------------------------------------------------
