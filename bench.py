@@ -203,7 +203,8 @@ def main():
         d = {'substeps': steps * nleap, 'rebuilds': 0, 'failed_substeps': 0, 'kernel_launches': 2 * steps * nleap,
              'radix_fallbacks': 0, 'max_bucket_count': 0, 'left_window': 0,
              'migrants_per_substep_rank0': (s.migrated - mig0) / float(steps * nleap),
-             'particles_per_rank': [int(c) for c in s.counts]}
+             'particles_per_rank': [int(c) for c in s.counts],
+             'host_ms_per_substep_rank0': {k: 1e3 * t / max(1, (steps + warmup) * nleap) for k, t in s.timing.items()}}
         s.close()
         return ms, d
 

@@ -121,8 +121,9 @@ int wendy_cuda_stats(wendy_cuda_handle *h, long long *out, int n);
  *   shard_substep  one leapfrog sub-step; particles whose new key leaves the range are written
  *                  to per-peer outboxes (out_counts[p] of them for peer p); pc_offset = number of
  *                  particles owned by lower ranks (offsets the cumulative mass)
- *   shard_outbox   DEVICE pointers of the outboxes: peer p starts at p * ocap
- *   shard_inject   append n received particles (DEVICE arrays) to the local layout
+ *   shard_outbox   DEVICE pointer of the outboxes: packed (x, v, id-as-double) records of three
+ *                  doubles, peer p starts at record p * ocap
+ *   shard_inject   append n received particles (DEVICE array of packed records) to the layout
  *   shard_read     compact local (x, v, id) to HOST arrays of capacity entries                  */
 int wendy_cuda_create_shard(wendy_cuda_handle **h, long long n_local, long long n_capacity,
                             const double *x, const double *v, const int *ids, double m0,
@@ -130,9 +131,8 @@ int wendy_cuda_create_shard(wendy_cuda_handle **h, long long n_local, long long 
                             const double *bounds, long long outbox_capacity, void *cuda_stream);
 int wendy_cuda_shard_substep(wendy_cuda_handle *h, double h_pre, double dt_kick, double dt_drift,
                              double h_next, long long pc_offset, unsigned *out_counts);
-int wendy_cuda_shard_outbox(wendy_cuda_handle *h, double **x, double **v, int **id, long long *ocap);
-int wendy_cuda_shard_inject(wendy_cuda_handle *h, const double *x_dev, const double *v_dev,
-                            const int *id_dev, long long n);
+int wendy_cuda_shard_outbox(wendy_cuda_handle *h, double **records, long long *ocap);
+int wendy_cuda_shard_inject(wendy_cuda_handle *h, const double *records_dev, long long n);
 int wendy_cuda_shard_count(wendy_cuda_handle *h, long long *n_local);
 int wendy_cuda_shard_read(wendy_cuda_handle *h, double *x_host, double *v_host, int *id_host,
                           long long *n);

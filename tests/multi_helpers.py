@@ -37,6 +37,8 @@ class NumpyShardEngine(object):
         return out
 
     def inject(self, packed):
+        if packed.shape[0] == 0:
+            return
         a = packed.cpu().numpy()
         self.x = numpy.concatenate((self.x, a[:, 0]))
         self.v = numpy.concatenate((self.v, a[:, 1]))
@@ -77,9 +79,9 @@ class ThreadComm(object):
         for p in range(self.size):
             self.w.mail[p][self.rank] = send[p].clone()
         self.w.barrier.wait()
-        recv = [self.w.mail[self.rank][p] for p in range(self.size)]
+        recv = [self.w.mail[self.rank][p] for p in range(self.size) if p != self.rank]
         self.w.barrier.wait()
-        return recv
+        return torch.cat(recv, dim=0) if recv else torch.zeros((0, 3), dtype=torch.float64)
 
 
 def run_threads(size, fn, device='cpu'):

@@ -76,9 +76,9 @@ def load():
     lib.wendy_cuda_shard_substep.argtypes = [vp, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                              ctypes.c_double, ctypes.c_longlong, _nd('u4')]
     lib.wendy_cuda_shard_outbox.restype = ctypes.c_int
-    lib.wendy_cuda_shard_outbox.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp), c_ll_p]
+    lib.wendy_cuda_shard_outbox.argtypes = [vp, ctypes.POINTER(vp), c_ll_p]
     lib.wendy_cuda_shard_inject.restype = ctypes.c_int
-    lib.wendy_cuda_shard_inject.argtypes = [vp, vp, vp, vp, ctypes.c_longlong]
+    lib.wendy_cuda_shard_inject.argtypes = [vp, vp, ctypes.c_longlong]
     lib.wendy_cuda_shard_count.restype = ctypes.c_int
     lib.wendy_cuda_shard_count.argtypes = [vp, c_ll_p]
     lib.wendy_cuda_shard_read.restype = ctypes.c_int

@@ -36,6 +36,8 @@ namespace wendy {
 void launch_iota(cudaStream_t st, int *id, long long n);
 void launch_gather_by_id(cudaStream_t st, const double *a_by_id, const int *id, const unsigned *cnt,
                          int cap, int nb, double *a_slots);
+void launch_make_keys_packed(cudaStream_t st, const double *packed, double h, long long n, uint64_t *keys,
+                             uint32_t *vals);
 }
 
 struct wendy_cuda_handle {
@@ -57,6 +59,7 @@ struct wendy_cuda_handle {
   int ccur = 0;
   bool adaptive = false;   // cap chosen by the library: 256 (warp kernel) <-> 2048 (CTA kernel)
   int want_cap = 0;        // geometry to switch to at the next layout rebuild (0: keep)
+  bool rebuild_pending = false;  // shard: rebuild at the start of the next sub-step (state complete)
   int user_fill = 0, user_cap = 0;
   double last_dt = 0.;
   bool dense = true;       // state is the dense upload in buffer `cur` (no layout yet)
@@ -85,8 +88,8 @@ struct wendy_cuda_handle {
   int nranks = 1, my_rank = 0;
   long long n_cap = 0;          // particle capacity of this shard
   double *bounds = nullptr;     // device, nranks+1
-  double *out_x = nullptr, *out_v = nullptr;
-  int *out_id = nullptr, *cid = nullptr;
+  double *out_rec = nullptr;
+  int *cid = nullptr;
   unsigned *out_cnt = nullptr, *h_out_cnt = nullptr;
   long long ocap = 0, pc_offset = 0;
   // asynchronous call in flight (wendy_cuda_step_begin / _end) and overlapped read-out
@@ -185,16 +188,20 @@ static int default_fill(const H *h, int cap) {
   return cap == 256 ? 128 : cap * 3 / 4;
 }
 
-static int rebucket(H *h, double hkey) {
+static int rebucket(H *h, double hkey, const double *extra = nullptr, long long n_extra = 0) {
   // target geometry (may differ from the geometry the state is currently stored in)
   const int ncap = h->want_cap ? h->want_cap : h->cap;
   const int nfill = (ncap == h->cap) ? h->fill : default_fill(h, ncap);
   const int nnbps = (int)(((h->n_cap / h->nseg) + nfill - 1) / nfill);
   const int nnb = nnbps * h->nseg;
+  if (alloc_radix(h, (size_t)(h->N + n_extra))) return WENDY_E_CUDA;
   if (make_keys(h, hkey, VAL_SEGMENT)) return WENDY_E_CUDA;
-  int res = radix_sort_pairs(h->st, h->rs, (size_t)h->N, seg_bits(h), 1u);
+  if (n_extra > 0)  // shard inject: the layout is built from the union of local state and inbox
+    launch_make_keys_packed(h->st, extra, hkey, n_extra, h->rs.key[0] + h->N, h->rs.val[0] + h->N);
+  const long long n_all = h->N + n_extra;
+  int res = radix_sort_pairs(h->st, h->rs, (size_t)n_all, seg_bits(h), 1u);
   h->n_launch += 5 * (8 + (seg_bits(h) + 7) / 8);
-  launch_pick_splitters(h->st, h->rs.key[res], h->seg_len, nfill, nnbps, nnb, h->split);
+  launch_pick_splitters(h->st, h->rs.key[res], n_extra > 0 ? n_all : h->seg_len, nfill, nnbps, nnb, h->split);
   int c1 = (h->ccur + 1) % 3, c2 = (h->ccur + 2) % 3;
   CK(cudaMemsetAsync(h->cnt[c1], 0, (size_t)h->nb_alloc * sizeof(unsigned), h->st));
   CK(cudaMemsetAsync(h->cnt[c2], 0, (size_t)h->nb_alloc * sizeof(unsigned), h->st));
@@ -209,6 +216,11 @@ static int rebucket(H *h, double hkey) {
   sp.cnt_out = h->cnt[c1]; sp.split = h->split; sp.cap_out = ncap; sp.nbps_out = nnbps;
   sp.seg_len = h->seg_len; sp.fail_seq = h->flags; sp.seq = h->seq++;
   launch_scatter(h->st, sp, h->sm_count);
+  if (n_extra > 0) {
+    sp.packed_in = extra; sp.cnt_in = nullptr; sp.n_dense = n_extra; sp.min = nullptr;
+    sp.seg_len = h->n_cap + n_extra + 1; sp.seq = h->seq++;
+    launch_scatter(h->st, sp, h->sm_count);
+  }
   h->n_launch += 2;
   if (fetch_flags(h)) return WENDY_E_CUDA;
   if (h->h_flags[0] != 0xffffffffu) {
@@ -238,7 +250,7 @@ static void fill_tile_params(H *h, TileParams &p) {
   p.status = h->status; p.desc = h->desc; p.cdesc = h->cdesc;
   p.eqm = h->eqm ? 1 : 0; p.m0 = h->m0;
   p.nranks = h->nranks; p.my_rank = h->my_rank; p.bounds = h->bounds;
-  p.out_x = h->out_x; p.out_v = h->out_v; p.out_id = h->out_id; p.out_cnt = h->out_cnt;
+  p.out_rec = h->out_rec; p.out_cnt = h->out_cnt;
   p.ocap = (unsigned)h->ocap; p.pc_offset = h->pc_offset;
   p.ticket = h->ticket + h->tcur; p.ticket_zero = h->ticket + (h->tcur + 2) % 3;
   p.fail_seq = h->flags; p.stats = h->flags + 1; p.outside = (unsigned long long *)(h->flags + 8);
@@ -304,7 +316,7 @@ void wendy_cuda_destroy(wendy_cuda_handle *h) {
   cudaFree(h->cdesc); cudaFree(h->cpre); cudaFree(h->cp_desc); cudaFree(h->cp_ticket);
   cudaFree(h->flags); cudaFree(h->offs); cudaFree(h->xo); cudaFree(h->vo); cudaFree(h->epart);
   cudaFree(h->eout); cudaFree(h->rank);
-  cudaFree(h->bounds); cudaFree(h->out_x); cudaFree(h->out_v); cudaFree(h->out_id); cudaFree(h->out_cnt);
+  cudaFree(h->bounds); cudaFree(h->out_rec); cudaFree(h->out_cnt);
   cudaFree(h->cid);
   if (h->h_out_cnt) cudaFreeHost(h->h_out_cnt);
   if (h->st_copy) cudaStreamDestroy(h->st_copy);
@@ -425,7 +437,7 @@ int wendy_cuda_create_shard(wendy_cuda_handle **out, long long n_local, long lon
   if (!ids || !bounds || nranks < 1 || rank < 0 || rank >= nranks || outbox_capacity < 1)
     return set_err(WENDY_E_ARG, "bad shard argument");
   std::vector<double> m((size_t)n_local, m0);
-  int rc = create_impl(out, n_local, n_capacity, x, v, m.data(), ids, &totmass, omega2, 1, 0, 256, 0, cuda_stream);
+  int rc = create_impl(out, n_local, n_capacity, x, v, m.data(), ids, &totmass, omega2, 1, 0, 0, 0, cuda_stream);
   if (rc) return rc;
   H *h = *out;
   h->nranks = nranks; h->my_rank = rank; h->ocap = outbox_capacity;
@@ -434,9 +446,7 @@ int wendy_cuda_create_shard(wendy_cuda_handle **out, long long n_local, long lon
   if (e == cudaSuccess) e = cudaMalloc(&h->bounds, (size_t)(nranks + 1) * sizeof(double));
   if (e == cudaSuccess) e = cudaMemcpy(h->bounds, bounds, (size_t)(nranks + 1) * sizeof(double), cudaMemcpyHostToDevice);
   size_t ob = (size_t)nranks * (size_t)outbox_capacity;
-  if (e == cudaSuccess) e = cudaMalloc(&h->out_x, ob * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc(&h->out_v, ob * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc(&h->out_id, ob * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&h->out_rec, ob * 3 * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&h->out_cnt, (size_t)nranks * sizeof(unsigned));
   if (e == cudaSuccess) e = cudaMallocHost(&h->h_out_cnt, (size_t)nranks * sizeof(unsigned));
   if (e == cudaSuccess) e = cudaMalloc(&h->cid, (size_t)n_capacity * sizeof(int));
@@ -450,9 +460,10 @@ int wendy_cuda_shard_substep(wendy_cuda_handle *h, double h_pre, double dt_kick,
   if (!h || !out_counts || !h->bounds) return set_err(WENDY_E_ARG, "not a shard handle");
   h->pc_offset = pc_offset;
   for (int attempt = 0; attempt < 3; attempt++) {
-    if (h->dense || !h->has_split || h->bucket_h != h_pre) {
+    if (h->dense || !h->has_split || h->bucket_h != h_pre || h->rebuild_pending) {
       int rc = rebucket(h, h_pre);
       if (rc) return rc;
+      h->rebuild_pending = false;
     }
     CK(cudaMemsetAsync(h->out_cnt, 0, (size_t)h->nranks * sizeof(unsigned), h->st));
     int cur0 = h->cur, ccur0 = h->ccur;
@@ -463,6 +474,16 @@ int wendy_cuda_shard_substep(wendy_cuda_handle *h, double h_pre, double dt_kick,
       long long gone = 0;
       for (int r = 0; r < h->nranks; r++) { out_counts[r] = h->h_out_cnt[r]; gone += h->h_out_cnt[r]; }
       h->N -= gone; h->seg_len = h->N;
+      // adaptive layout (see finish_substeps): judged on this single sub-step
+      if (h->adaptive && h->cap == 256 && (double)outside_total(h) > 0.5 * (double)h->N) {
+        // switch to coarse buckets, but only once the incoming migrants have been injected: a
+        // layout built now would see a boundary region depleted of the particles in flight
+        h->want_cap = 2048;
+        h->rebuild_pending = true;
+      }
+      h->n_outside += outside_total(h);
+      memset(h->h_flags + 8, 0, 128 * sizeof(unsigned));
+      CK(cudaMemsetAsync(h->flags + 8, 0, 128 * sizeof(unsigned), h->st));
       return 0;
     }
     h->n_fail++; h->n_sub--;
@@ -472,33 +493,43 @@ int wendy_cuda_shard_substep(wendy_cuda_handle *h, double h_pre, double dt_kick,
   return set_err(WENDY_E_OVERFLOW, "shard: bucket or outbox overflow persists after re-balancing");
 }
 
-int wendy_cuda_shard_outbox(wendy_cuda_handle *h, double **x, double **v, int **id, long long *ocap) {
-  if (!h || !h->bounds) return set_err(WENDY_E_ARG, "not a shard handle");
-  *x = h->out_x; *v = h->out_v; *id = h->out_id; *ocap = h->ocap;
+int wendy_cuda_shard_outbox(wendy_cuda_handle *h, double **records, long long *ocap) {
+  if (!h || !h->bounds || !records || !ocap) return set_err(WENDY_E_ARG, "not a shard handle");
+  *records = h->out_rec; *ocap = h->ocap;
   return 0;
 }
 
 // Append n particles (DEVICE arrays) whose keys lie in this shard's range to the current layout.
-int wendy_cuda_shard_inject(wendy_cuda_handle *h, const double *x_dev, const double *v_dev, const int *id_dev,
-                            long long n) {
+int wendy_cuda_shard_inject(wendy_cuda_handle *h, const double *records_dev, long long n) {
   if (!h || !h->bounds) return set_err(WENDY_E_ARG, "not a shard handle");
   if (n <= 0) return 0;
   if (h->N + n > h->n_cap) return set_err(WENDY_E_OVERFLOW, "shard capacity exceeded (global re-partition needed)");
   if (h->dense || !h->has_split) return set_err(WENDY_E_ARG, "inject needs a layout");
   ScatterParams sp;
   memset(&sp, 0, sizeof(sp));
-  sp.xin = x_dev; sp.vin = v_dev; sp.min = nullptr; sp.idin = id_dev;
+  sp.packed_in = records_dev; sp.min = nullptr;
   sp.cnt_in = nullptr; sp.n_dense = n; sp.h = h->bucket_h;
   int c = h->cur;
   sp.xout = h->x[c]; sp.vout = h->v[c]; sp.mout = nullptr; sp.idout = h->id[c];
   sp.cnt_out = h->cnt[h->ccur]; sp.split = h->split; sp.cap_out = h->cap; sp.nbps_out = h->nbps;
   sp.seg_len = h->n_cap + 1; sp.fail_seq = h->flags; sp.seq = h->seq++;
+  // snapshot of the counts: an overflowing append is rolled back (slots beyond the counts are dead)
+  CK(cudaMemcpyAsync(h->cnt[(h->ccur + 2) % 3], h->cnt[h->ccur], (size_t)h->nb * sizeof(unsigned),
+                     cudaMemcpyDeviceToDevice, h->st));
   launch_scatter(h->st, sp, h->sm_count);
   h->n_launch++;
   if (fetch_flags(h)) return WENDY_E_CUDA;
   if (h->h_flags[0] != 0xffffffffu) {
-    reset_flags(h);
-    return set_err(WENDY_E_OVERFLOW, "shard: bucket overflow while injecting migrants");
+    // some bucket near the range edge cannot take its share of the migrants: rebuild the layout from
+    // the union of the local particles and the inbox
+    if (reset_flags(h)) return WENDY_E_CUDA;
+    CK(cudaMemcpyAsync(h->cnt[h->ccur], h->cnt[(h->ccur + 2) % 3], (size_t)h->nb * sizeof(unsigned),
+                       cudaMemcpyDeviceToDevice, h->st));
+    h->n_fail++;
+    int rc = rebucket(h, h->bucket_h, records_dev, n);
+    if (rc) return rc;
+  } else {
+    CK(cudaMemsetAsync(h->cnt[(h->ccur + 2) % 3], 0, (size_t)h->nb_alloc * sizeof(unsigned), h->st));
   }
   h->N += n; h->seg_len = h->N;
   return 0;

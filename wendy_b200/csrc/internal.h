@@ -67,8 +67,7 @@ struct TileParams {
   // [bounds[my_rank], bounds[my_rank+1]) are appended to the outbox of the owning peer
   int nranks, my_rank;
   const double *bounds;     // nranks+1 ascending range edges (first -inf, last +inf), device
-  double *out_x, *out_v;    // [nranks][ocap] outboxes
-  int *out_id;
+  double *out_rec;          // [nranks][ocap][3] outboxes of packed (x, v, id) records
   unsigned *out_cnt;        // [nranks]
   unsigned ocap;
   long long pc_offset;      // particles owned by lower ranks (added to every rank)
@@ -92,6 +91,7 @@ struct ScatterParams {
   const double *xin, *vin, *min;
   const int *idin;
   const unsigned *cnt_in;   // null: source is dense (n_dense elements, segment = i / seg_len)
+  const double *packed_in;  // non-null: dense source of packed (x, v, id) triples (migrants)
   long long n_dense;
   int cap_in, nb_in, nbps_in;
   double h;                 // bucket key = x + h*v

@@ -339,7 +339,7 @@ tile_kernel(const TileParams p) {
       double c, mk;
       if (EQM) {
         mk = p.m0;
-        c = __dmul_rn((double)(Pc + (long long)r[k]), p.m0);
+        c = __dmul_rn((double)(Pc + p.pc_offset + (long long)r[k]), p.m0);  // pc_offset: lower ranks (sharded)
       } else {
         mk = m[k];
         c = S.u.mcum[r[k] + r[k] / E];
@@ -412,13 +412,30 @@ tile_kernel(const TileParams p) {
   unsigned outside = 0;
   const int rel = b - wlo;
   const double home_lo = S.ssplit[rel], home_hi = S.ssplit[rel + 1];
+  bool sh_overflow = false;
+  const double sh_lo = p.bounds ? __ldg(p.bounds + p.my_rank) : 0.0;
+  const double sh_hi = p.bounds ? __ldg(p.bounds + p.my_rank + 1) : 0.0;
 #pragma unroll
   for (int k = 0; k < E; k++) {
     int d = -1;
     const bool ok = tid + k * THREADS < n;
     if (ok) {
       const double key = xb[k];
-      if (key >= home_lo && key < home_hi) {
+      if (p.bounds && (key < sh_lo || key >= sh_hi)) {
+        // sharded system: the key leaves this GPU's range -> outbox of the owning rank
+        int peer = 0;
+        while (peer + 1 < p.nranks && key >= __ldg(p.bounds + peer + 1)) peer++;
+        const unsigned slot = atomicAdd(p.out_cnt + peer, 1u);
+        if (slot < p.ocap) {
+          double *rec = p.out_rec + ((size_t)peer * p.ocap + slot) * 3;
+          rec[0] = x2[k];
+          rec[1] = v2[k];
+          rec[2] = (double)id[k];
+        } else {
+          sh_overflow = true;
+        }
+        d = -3;
+      } else if (key >= home_lo && key < home_hi) {
         d = b;
       } else if (key >= S.ssplit[0] && key < S.ssplit[wn]) {
         int lo = 0, hi = wn;
@@ -449,7 +466,7 @@ tile_kernel(const TileParams p) {
       leader = __ffs(mask) - 1;
     }
     const bool inwin = (d >= wlo && d < wlo + wn);
-    if (ok && lane == leader) {
+    if (ok && d >= 0 && lane == leader) {
       if (inwin) {
         basel = atomicAdd(&S.dcnt[d - wlo], (unsigned)__popc(mask));
       } else {
@@ -485,7 +502,7 @@ tile_kernel(const TileParams p) {
       }
     }
   }
-  if (overflow) atomicMin(p.fail_seq, p.seq);
+  if (overflow || sh_overflow) atomicMin(p.fail_seq, p.seq);
 }
 
 // ---- dispatch -------------------------------------------------------------------------------------------
@@ -553,8 +570,13 @@ scatter_kernel(const ScatterParams p) {
         seg = i / p.seg_len;
       }
       if (ok) {
-        x = p.xin[i];
-        v = p.vin[i];
+        if (p.packed_in) {
+          x = p.packed_in[3 * i];
+          v = p.packed_in[3 * i + 1];
+        } else {
+          x = p.xin[i];
+          v = p.vin[i];
+        }
         double key = (p.h != 0.0) ? __dadd_rn(x, __dmul_rn(p.h, v)) : x;
         int lo = (int)seg * p.nbps_out, hi = lo + p.nbps_out;
         while (hi - lo > 1) {
@@ -576,7 +598,7 @@ scatter_kernel(const ScatterParams p) {
         p.xout[o] = x;
         p.vout[o] = v;
         if (p.min) p.mout[o] = p.min[i];
-        p.idout[o] = p.idin[i];
+        p.idout[o] = p.packed_in ? (int)p.packed_in[3 * i + 2] : p.idin[i];
       } else {
         overflow = true;
       }
@@ -629,6 +651,25 @@ void launch_make_keys(cudaStream_t st, const double *x, const double *v, double 
   if (blocks > 148 * 32) blocks = 148 * 32;
   make_keys_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, v, h, cnt_in, offs, cap, total, keys, vals,
                                                      val_mode, seg_len, nbps);
+}
+
+// keys of packed (x, v, id) migrant records (segment 0)
+__global__ void make_keys_packed_kernel(const double *__restrict__ packed, double h, long long n,
+                                        uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    double xx = packed[3 * i];
+    if (h != 0.0) xx = __dadd_rn(xx, __dmul_rn(h, packed[3 * i + 1]));
+    keys[i] = key_from_double(xx);
+    vals[i] = 0u;
+  }
+}
+void launch_make_keys_packed(cudaStream_t st, const double *packed, double h, long long n, uint64_t *keys,
+                             uint32_t *vals) {
+  if (n <= 0) return;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  make_keys_packed_kernel<<<(unsigned)blocks, 256, 0, st>>>(packed, h, n, keys, vals);
 }
 
 // exclusive scan of the bucket counts (single block; nb is N/fill, at most a few 1e5)

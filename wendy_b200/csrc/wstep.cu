@@ -351,10 +351,10 @@ wstep_kernel(const TileParams p) {
           while (peer + 1 < p.nranks && key >= __ldg(p.bounds + peer + 1)) peer++;
           const unsigned slot = atomicAdd(p.out_cnt + peer, 1u);
           if (slot < p.ocap) {
-            const size_t o = (size_t)peer * p.ocap + slot;
-            p.out_x[o] = x2;
-            p.out_v[o] = v2;
-            p.out_id[o] = S.sid[i];
+            double *rec = p.out_rec + ((size_t)peer * p.ocap + slot) * 3;  // packed (x, v, id) record
+            rec[0] = x2;
+            rec[1] = v2;
+            rec[2] = (double)S.sid[i];
           } else {
             sh_overflow = true;
           }

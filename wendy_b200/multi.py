@@ -54,26 +54,34 @@ class TorchComm(object):
     def exchange(self, send, counts=None):
         """send[p]: (n_p, 3) float64 tensor for peer p (send[rank] is delivered locally).
         counts[src][dst] may be passed when it is already known (saves one all-gather).
-        Returns the list of received (m_p, 3) tensors, indexed by source rank."""
+        Returns ONE contiguous (m, 3) tensor with everything received from the other ranks."""
         torch, dist = self.torch, self.dist
         if counts is None:
             counts = self.allgather_vec([s.shape[0] for s in send]).astype(numpy.int64)  # [src][dst]
-        recv = [None] * self.size
-        ops = []
+        n_in = [int(counts[p][self.rank]) if p != self.rank else 0 for p in range(self.size)]
+        n_out = [int(send[p].shape[0]) if p != self.rank else 0 for p in range(self.size)]
+        total = sum(n_in)
+        if getattr(self, '_inbox', None) is None or self._inbox.shape[0] < total:
+            self._inbox = torch.empty((max(total, 1024) * 2, 3), dtype=torch.float64, device=self.device)
+        inbox = self._inbox[:total]
+        if total == 0 and sum(n_out) == 0:
+            return inbox
+        if dist.get_backend(self.group) == 'nccl':
+            sendbuf = torch.cat([send[p] for p in range(self.size) if n_out[p]], dim=0) if sum(n_out) \
+                else torch.empty((0, 3), dtype=torch.float64, device=self.device)
+            dist.all_to_all_single(inbox, sendbuf, output_split_sizes=n_in, input_split_sizes=n_out,
+                                   group=self.group)
+            return inbox
+        ops, off = [], 0
         for p in range(self.size):
-            if p == self.rank:
-                recv[p] = send[p]
-                continue
-            n_in = int(counts[p][self.rank])
-            recv[p] = torch.empty((n_in, 3), dtype=torch.float64, device=self.device)
-            if n_in:
-                ops.append(dist.P2POp(dist.irecv, recv[p], p, group=self.group))
-            if send[p].shape[0]:
+            if n_in[p]:
+                ops.append(dist.P2POp(dist.irecv, inbox[off:off + n_in[p]], p, group=self.group))
+                off += n_in[p]
+            if n_out[p]:
                 ops.append(dist.P2POp(dist.isend, send[p].contiguous(), p, group=self.group))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
-        return recv
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        return inbox
 
 
 # ---- local engine on a B200 ----------------------------------------------------------------------
@@ -103,14 +111,12 @@ class CudaShardEngine(object):
             ctypes.byref(self._h), len(x), self.capacity, x, v, ids, float(m0), float(totmass),
             float(omega2), nranks, rank, bounds, int(outbox_capacity),
             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        px, pv, pi, oc = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_longlong()
-        _lib.check(self._lib.wendy_cuda_shard_outbox(self._h, ctypes.byref(px), ctypes.byref(pv),
-                                                     ctypes.byref(pi), ctypes.byref(oc)))
-        n = nranks * oc.value
+        pr, oc = ctypes.c_void_p(), ctypes.c_longlong()
+        _lib.check(self._lib.wendy_cuda_shard_outbox(self._h, ctypes.byref(pr), ctypes.byref(oc)))
         self._ocap = oc.value
-        self._ox = torch.as_tensor(_DevView(px.value, n, '<f8'), device=self.device)
-        self._ov = torch.as_tensor(_DevView(pv.value, n, '<f8'), device=self.device)
-        self._oi = torch.as_tensor(_DevView(pi.value, n, '<i4'), device=self.device)
+        # zero-copy view of the packed (x, v, id) outbox records: [peer][slot][3]
+        self._orec = torch.as_tensor(_DevView(pr.value, nranks * oc.value * 3, '<f8'),
+                                     device=self.device).view(nranks, oc.value, 3)
 
     def close(self):
         if getattr(self, '_h', None):
@@ -125,24 +131,16 @@ class CudaShardEngine(object):
         cnt = numpy.zeros(self.nranks, dtype=numpy.uint32)
         _lib.check(self._lib.wendy_cuda_shard_substep(self._h, h_pre, dt_kick, dt_drift, h_next,
                                                       int(pc_offset), cnt))
-        out = []
-        for p in range(self.nranks):
-            lo, n = p * self._ocap, int(cnt[p])
-            out.append(torch.stack((self._ox[lo:lo + n], self._ov[lo:lo + n],
-                                    self._oi[lo:lo + n].to(torch.float64)), dim=1))
-        return out
+        return [self._orec[p, :int(cnt[p])] for p in range(self.nranks)]
 
     def inject(self, packed):
-        """packed: (n, 3) float64 CUDA tensor of particles that now belong to this range."""
+        """packed: contiguous (n, 3) float64 CUDA tensor of particles that now belong to this range."""
         n = packed.shape[0]
         if n == 0:
             return
-        x = packed[:, 0].contiguous()
-        v = packed[:, 1].contiguous()
-        ids = packed[:, 2].to(self.torch.int32).contiguous()
+        packed = packed.contiguous()
         self.torch.cuda.current_stream().synchronize()
-        _lib.check(self._lib.wendy_cuda_shard_inject(self._h, x.data_ptr(), v.data_ptr(),
-                                                     ids.data_ptr(), n))
+        _lib.check(self._lib.wendy_cuda_shard_inject(self._h, packed.data_ptr(), n))
 
     def count(self):
         n = ctypes.c_longlong()
@@ -208,7 +206,7 @@ class ShardedSystem(object):
         n_tot = int(comm.allgather_vec([len(x)]).sum())
         take = numpy.linspace(0, max(len(key) - 1, 0), num=min(self.n_sample, len(key))).astype(int)
         sample = numpy.full(self.n_sample, numpy.nan)
-        sample[:len(take)] = numpy.sort(key)[take] if len(key) else []
+        sample[:len(take)] = key[take] if len(key) else []  # a strided subset is an unbiased key sample
         self.bounds = choose_bounds(comm.allgather_vec(sample), comm.size)
         owner = route(key, self.bounds)
         cap = int(self.capacity_factor * n_tot / comm.size) + 1024
@@ -216,8 +214,8 @@ class ShardedSystem(object):
         import torch
         send = [torch.as_tensor(numpy.stack((x[owner == p], v[owner == p], ids[owner == p].astype(numpy.float64)),
                                             axis=1), device=comm.device) for p in range(comm.size)]
-        recv = comm.exchange(send)
-        mine = torch.cat(recv, dim=0).cpu().numpy() if recv else numpy.zeros((0, 3))
+        keep = send[comm.rank]
+        mine = torch.cat((keep, comm.exchange(send)), dim=0).cpu().numpy()
         self.engine = self.engine_factory(mine[:, 0].copy(), mine[:, 1].copy(), mine[:, 2].astype(numpy.int32),
                                           self.m0, self.totmass, self.omega2, comm.size, comm.rank,
                                           self.bounds, cap, max(1024, int(self.outbox_fraction * cap)))
@@ -236,21 +234,25 @@ class ShardedSystem(object):
             self._partition(dt_leap)
         elif dt_leap != self.dt_leap:
             raise NotImplementedError('changing dt between calls needs a global re-partition')
-        import torch
+        import time
+        tm = self.timing = getattr(self, 'timing', {'substep': 0., 'allgather': 0., 'exchange+inject': 0.})
         for k in range(nleap):
             last = k == nleap - 1
+            t0 = time.perf_counter()
             out = self.engine.substep(dt_leap / 2. if k == 0 else 0., dt_leap,
                                       dt_leap / 2. if last else dt_leap,
                                       dt_leap / 2. if last else 0., self.pc_offset)
+            t1 = time.perf_counter()
             self.migrated += sum(int(o.shape[0]) for p, o in enumerate(out) if p != self.comm.rank)
             # ONE small all-gather per sub-step: every rank's outgoing counts and its particle count
             # after the export; incoming counts and the new count prefix follow from it on the host
             info = self.comm.allgather_vec([o.shape[0] for o in out] + [self.engine.count()]).astype(numpy.int64)
             sent = info[:, :-1]
-            recv = self.comm.exchange(out, counts=sent)
-            inc = [r for p, r in enumerate(recv) if p != self.comm.rank and r.shape[0]]
-            if inc:
-                self.engine.inject(torch.cat(inc, dim=0))
+            t2 = time.perf_counter()
+            self.engine.inject(self.comm.exchange(out, counts=sent))
+            tm['substep'] += t1 - t0
+            tm['allgather'] += t2 - t1
+            tm['exchange+inject'] += time.perf_counter() - t2
             self.counts = info[:, -1] + sent.sum(axis=0) - numpy.diag(sent)
             self.pc_offset = int(self.counts[:self.comm.rank].sum())
         return self
