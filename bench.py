@@ -177,6 +177,7 @@ def main():
         ms = max_over_ranks(e0.elapsed_time(e1))
         s1 = st.stats()
         st.close()
+        run.cap = s1['cap']
         d = {k: s1[k] - s0[k] for k in ('substeps', 'rebuilds', 'failed_substeps', 'kernel_launches', 'radix_fallbacks')}
         d['max_bucket_count'] = s1['max_bucket_count']
         d['left_window'] = s1['left_window'] - s0['left_window']
@@ -246,10 +247,12 @@ def main():
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak,
                      'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback', 'unit': 'GB/s',
                      'frac': achieved / peak,
-                     # dram__bytes_read+write per launch from the ncu --set full capture of this kernel
-                     # (profiles/r01/wstep_dt1e-5_N2e7_summary.txt: 40.2 B/particle), scaled to this N
-                     'traffic': 40.2 * n if a.sort == 'gpu' else None,
-                     'kernel': 'wstep_kernel<256,8,EQM> (one warp per bucket)' if a.sort == 'gpu' else 'radix passes + tile_kernel<LOAD_GATHER>',
+                     # dram__bytes_read+write per launch from the ncu --set full captures under profiles/r01
+                     # (wstep: 40.2 B/particle, CTA kernel: 40.6 B/particle), scaled to this N
+                     'traffic': (40.2 if getattr(run, 'cap', 256) == 256 else 40.6) * n if a.sort == 'gpu' else None,
+                     'kernel': ('radix passes + tile_kernel<LOAD_GATHER>' if a.sort != 'gpu' else
+                                'wstep_kernel<256,8,EQM> (one warp per bucket)' if getattr(run, 'cap', 256) == 256 else
+                                'tile_kernel<2048,512,LOAD_BUCKET,EMIT_SPLITTER,EQM> (one CTA per bucket; layout chosen adaptively)'),
                      'ms_per_launch': ms_per_launch},
         'clocks': clocks,
     }

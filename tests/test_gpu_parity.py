@@ -314,6 +314,24 @@ def test_overflow_recovery_by_rebalancing():
     assert numpy.array_equal(xg, xo) and numpy.array_equal(vg, vo)
 
 
+def test_adaptive_layout_switches_to_coarse_buckets_and_stays_exact():
+    """With a large N*dt most particles leave the 32-bucket window of the warp kernel; the library
+    then rebuilds the layout with 2048-slot buckets (CTA kernel).  Results must not change."""
+    import wendy_b200
+    x, v, m = wo.sech2_ic(400000, seed=13)
+    st = wendy_b200.ApproxState(x, v, m, omega2=1.21)
+    xo, vo = x, v
+    caps = []
+    for _ in range(3):
+        st.step(0.1, 3)
+        caps.append(st.stats()['cap'])
+        xo, vo, _, _ = wo.numpy_onestep(xo, vo, m, numpy.sum(m), 0.1, 3, 1.21, exact_scan=True)
+    xg, vg = st.read()
+    st.close()
+    assert caps[0] in (256, 2048) and caps[-1] == 2048, caps
+    assert numpy.array_equal(xg, xo) and numpy.array_equal(vg, vo)
+
+
 def test_rejects_non_finite_input():
     import wendy_b200
     with pytest.raises(RuntimeError):

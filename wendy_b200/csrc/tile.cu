@@ -29,7 +29,13 @@
 
 namespace wendy {
 
-constexpr int DW = 32;  // destination buckets tracked with shared-memory counters
+#ifndef TK_DW
+#define TK_DW 256
+#endif
+#ifndef TK_INTERP
+#define TK_INTERP 1
+#endif
+constexpr int DW = TK_DW;  // destination buckets tracked with shared-memory counters
 
 template <int CAP, int THREADS>
 struct TileSmem {
@@ -55,6 +61,42 @@ struct TileSmem {
   int bucket;
 };
 
+#ifndef TK_RANK2
+#define TK_RANK2 1
+#endif
+#ifndef TK_GALLOP
+#define TK_GALLOP 1
+#endif
+// largest d in [lo0, hi0) with split[d] <= key, starting from a guess (split[lo0] is -inf)
+__device__ __forceinline__ int gallop_search_tile(const double *__restrict__ split, double key, int guess,
+                                                  int lo0, int hi0) {
+  int lo = min(max(guess, lo0), hi0 - 1), hi;
+  int step = 1;
+  if (__ldg(split + lo) <= key) {
+    hi = lo + 1;
+    while (hi < hi0 && __ldg(split + hi) <= key) {
+      lo = hi;
+      step <<= 1;
+      hi = lo + step;
+    }
+    if (hi > hi0) hi = hi0;
+  } else {
+    hi = lo;
+    lo = hi - 1;
+    while (lo > lo0 && __ldg(split + lo) > key) {
+      hi = lo;
+      step <<= 1;
+      lo = hi - step;
+    }
+    if (lo < lo0) lo = lo0;
+  }
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(split + mid) <= key) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
 template <int CAP, int THREADS, int LOAD, int EMIT, int PHYS, int EQM>
 __global__ void __launch_bounds__(THREADS, (CAP * 48 <= 100 * 1024) ? 2 : 1)
 tile_kernel(const TileParams p) {
@@ -74,7 +116,7 @@ tile_kernel(const TileParams p) {
 
   if (tid == 0) S.bucket = (int)atomicAdd(p.ticket, 1u);
   for (int i = tid; i < SM::PADN; i += THREADS) S.u.srt.cnt[i] = 0;
-  if (tid < DW) S.dcnt[tid] = 0;
+  for (int i = tid; i < DW; i += THREADS) S.dcnt[i] = 0;
   __syncthreads();
   const int b = S.bucket;
   const int seg = (p.nbps == p.nb) ? 0 : b / p.nbps;
@@ -106,8 +148,8 @@ tile_kernel(const TileParams p) {
     if (wlo > seg_hi - DW) wlo = seg_hi - DW;
     if (wlo < seg_lo) wlo = seg_lo;
     wn = min(DW, seg_hi - wlo);
-    if (tid <= wn)
-      S.ssplit[tid] = (wlo + tid < seg_hi) ? p.split[wlo + tid] : CUDART_INF;
+    for (int i = tid; i <= wn; i += THREADS)
+      S.ssplit[i] = (wlo + i < seg_hi) ? p.split[wlo + i] : CUDART_INF;
   }
 
   // ---- 1. load positions and ids; key = position at force time -----------------------
@@ -262,7 +304,12 @@ tile_kernel(const TileParams p) {
         for (unsigned q = s0; q < s1; q++) {
           unsigned j = S.u.srt.slot[q];
           double xj = S.sx[j];
+#if TK_RANK2
+          rr += (xj < xi) ? 1u : 0u;
+          if (xj == xi) rr += (S.sid[j] < ii) ? 1u : 0u;  // exact coincidence: ties by particle index
+#else
           rr += (xj < xi || (xj == xi && S.sid[j] < ii)) ? 1u : 0u;
+#endif
         }
       }
       r[k] = rr;
@@ -413,6 +460,8 @@ tile_kernel(const TileParams p) {
   const int rel = b - wlo;
   const double home_lo = S.ssplit[rel], home_hi = S.ssplit[rel + 1];
   bool sh_overflow = false;
+  const double wdt = home_hi - home_lo;
+  const double inv_w = (wdt > 0.0 && wdt < CUDART_INF) ? 1.0 / wdt : 0.0;
   const double sh_lo = p.bounds ? __ldg(p.bounds + p.my_rank) : 0.0;
   const double sh_hi = p.bounds ? __ldg(p.bounds + p.my_rank + 1) : 0.0;
 #pragma unroll
@@ -438,19 +487,33 @@ tile_kernel(const TileParams p) {
       } else if (key >= home_lo && key < home_hi) {
         d = b;
       } else if (key >= S.ssplit[0] && key < S.ssplit[wn]) {
+#if TK_INTERP
+        int lo = rel + (int)floor(fmax(-256.0, fmin(256.0, (key - home_lo) * inv_w)));
+        lo = max(0, min(wn - 1, lo));
+        while (lo > 0 && S.ssplit[lo] > key) lo--;
+        while (lo < wn - 1 && S.ssplit[lo + 1] <= key) lo++;
+#else
         int lo = 0, hi = wn;
         while (hi - lo > 1) {
           int mid = (lo + hi) >> 1;
           if (S.ssplit[mid] <= key) lo = mid; else hi = mid;
         }
+#endif
         d = wlo + lo;
-      } else {  // far move: search the whole segment (split[seg_lo] is -inf)
+      } else {  // far move (split[seg_lo] is -inf)
+#if TK_GALLOP
+        // interpolated guess from the home bucket's width, then a galloping search around it
+        double gq = fmax(-2.0e9, fmin(2.0e9, (key - home_lo) * inv_w));
+        const int g = (int)max((long long)seg_lo, min((long long)seg_hi - 1, (long long)b + (long long)floor(gq)));
+        d = gallop_search_tile(p.split, key, g, seg_lo, seg_hi);
+#else
         int lo = seg_lo, hi = seg_hi;
         while (hi - lo > 1) {
           int mid = (lo + hi) >> 1;
           if (__ldg(p.split + mid) <= key) lo = mid; else hi = mid;
         }
         d = lo;
+#endif
       }
     }
     dest[k] = d;
@@ -478,7 +541,8 @@ tile_kernel(const TileParams p) {
     lpos[k] = basel + __popc(mask & lt);
   }
   __syncthreads();
-  if (tid < wn && S.dcnt[tid]) S.dbase[tid] = atomicAdd(&p.cnt_out[wlo + tid], S.dcnt[tid]);
+  for (int i = tid; i < wn; i += THREADS)
+    if (S.dcnt[i]) S.dbase[i] = atomicAdd(&p.cnt_out[wlo + i], S.dcnt[i]);
   {  // one atomic per warp, spread over 64 counters (a single hot address serialises in L2)
     const unsigned wsum = __reduce_add_sync(WENDY_FULL_MASK, outside);
     if (lane == 0 && wsum) atomicAdd(p.outside + (b & 63), (unsigned long long)wsum);
