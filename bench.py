@@ -263,6 +263,34 @@ def main():
             vms, vd = run(dtl, srt, max(1, a.steps // 2), 1, a.nleap if srt == 'gpu' else 2)
             nl = a.nleap if srt == 'gpu' else 2
             var['dt_leap=%g,%s' % (dtl, srt)] = {'value': float(n) * nl * max(1, a.steps // 2) / (vms * 1e-3), 'stats': vd}
+        # general (unequal) masses: the exact 128-bit scan path
+        rs = numpy.random.RandomState(5)
+        mj = m * (1. + 0.1 * (2. * rs.uniform(size=n) - 1.))
+        for dtl in (1e-5, 1e-3):
+            st = wendy_b200.ApproxState(x, v, mj, omega2=omega2, stream=stream)
+            st.step(dtl, a.nleap); st.step(dtl, a.nleap)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(2):
+                st.step(dtl, a.nleap)
+            e1.record(); torch.cuda.synchronize()
+            var['general masses, dt_leap=%g' % dtl] = {'value': float(n) * a.nleap * 2 / (e0.elapsed_time(e1) * 1e-3),
+                                                        'stats': st.stats()}
+            st.close()
+        # BASELINE config 5 shape: independent realisations of 1e5 particles + torch ext_force (Gaia spiral)
+        S, L = max(1, int(n // 100000 // 2)), 100000
+        xs = numpy.arctanh(2. * rs.uniform(size=S * L) - 1.) * 2.
+        vs = rs.normal(size=S * L) + 1.0
+        ms = numpy.full(S * L, 0.3 / L)
+        F = lambda xx, t: -0.7 * torch.tanh(0.5 * xx)  # noqa: E731
+        g = wendy_b200.nbody(xs, vs, ms, 0.05, approx=True, nleap=10, ext_force=F, n_segments=S)
+        next(g)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(2):
+            next(g)
+        torch.cuda.synchronize(); el = time.perf_counter() - t0
+        g.close()
+        var['ensemble %d x 1e5 + torch ext_force, dt_leap=0.005 (generator, incl. D2H)' % S] = {'value': S * L * 10 * 2 / el}
         out['variants'] = var
 
     # ---- end to end through the public generator API, host buffers --------------------------

@@ -296,6 +296,66 @@ def test_compat_export_same_signature_as_reference(with_ext):
     assert t0 == (ref.t0.value if with_ext else 0.3)
 
 
+# ---- adversarial inputs for the in-bucket interpolation sort and the splitter logic -----------------
+def _nasty(kind, n, rs):
+    if kind == 'duplicates':      # many exactly coincident particles (identical x AND v: they stay tied)
+        x = numpy.repeat(rs.normal(size=n // 20), 20)
+        v = numpy.repeat(rs.normal(size=n // 20), 20)
+    elif kind == 'two_clumps':    # two tight clumps far apart + a thin background
+        x = numpy.concatenate((rs.normal(-50., 1e-6, n // 2), rs.normal(80., 1e-3, n // 2 - 100), rs.uniform(-100, 100, 100)))
+        v = rs.normal(size=n) * 0.01
+    elif kind == 'heavy_tails':   # Cauchy positions: huge dynamic range inside edge buckets
+        x = rs.standard_cauchy(size=n) * 1e3
+        v = rs.standard_cauchy(size=n)
+    elif kind == 'tiny_scale':    # everything within a few thousand ulps of 1.0
+        x = 1.0 + rs.randint(0, 4000, size=n) * 2.0 ** -52
+        v = rs.normal(size=n) * 1e-14
+    elif kind == 'signed_zero':   # mixture of +0.0, -0.0 and denormals
+        x = rs.choice([0.0, -0.0, 5e-324, -5e-324, 1e-310], size=n)
+        v = rs.normal(size=n) * 1e-300
+    return x, v
+
+
+@pytest.mark.parametrize('cap', CAPS)
+@pytest.mark.parametrize('kind', ['duplicates', 'two_clumps', 'heavy_tails', 'tiny_scale', 'signed_zero'])
+def test_adversarial_distributions_bit_exact(kind, cap):
+    import wendy_b200
+    rs = numpy.random.RandomState(99)
+    n = 4000
+    x, v = _nasty(kind, n, rs)
+    m = rs.uniform(0.5, 1.5, size=n) / n
+    gen = wendy_b200.nbody(x, v, m, 0.03, approx=True, nleap=3, omega=0.3, _cap=cap)
+    xo, vo = x, v
+    for _ in range(2):
+        xg, vg = next(gen)
+        xo, vo, _, _ = wo.numpy_onestep(xo, vo, m, numpy.sum(m), 0.01, 3, 0.09, exact_scan=True)
+        assert numpy.array_equal(xg, xo) and numpy.array_equal(vg, vo), kind
+    gen.close()
+
+
+def test_ext_force_on_an_ensemble_matches_separate_runs():
+    """Config-5 shape in miniature: several realisations, torch-vectorised external force."""
+    import torch
+    import wendy_b200
+    S, L = 4, 3000
+    F = lambda x, t: -0.7 * torch.tanh(0.5 * x) + 0.01 * t  # noqa: E731
+    Fn = lambda x, t: -0.7 * numpy.tanh(0.5 * x) + 0.01 * t  # noqa: E731
+    ics = [wo.sech2_ic(L, seed=40 + s) for s in range(S)]
+    X = numpy.concatenate([i[0] for i in ics]); V = numpy.concatenate([i[1] for i in ics])
+    M = numpy.concatenate([0.3 * i[2] for i in ics])
+    gen = wendy_b200.nbody(X, V, M, 0.05, approx=True, nleap=5, ext_force=F, t0=0.2, n_segments=S)
+    for _ in range(2):
+        Xg, Vg = next(gen)
+    gen.close()
+    for s in range(S):
+        xo, vo, t0 = ics[s][0], ics[s][1], 0.2
+        for _ in range(2):
+            xo, vo, t0, _ = wo.numpy_onestep(xo, vo, 0.3 * ics[s][2], numpy.sum(0.3 * ics[s][2]), 0.01, 5, -1., Fn, t0,
+                                             exact_scan=True)
+        # torch.tanh and numpy.tanh may differ in the last bit: tolerance instead of bit equality
+        assert relerr(Xg[s * L:(s + 1) * L], xo) < 1e-12 and relerr(Vg[s * L:(s + 1) * L], vo) < 1e-12
+
+
 # ---- robustness ------------------------------------------------------------------------------------
 def test_overflow_recovery_by_rebalancing():
     """A violently collapsing cold slab changes the density by orders of magnitude: buckets

@@ -38,6 +38,9 @@ void launch_gather_by_id(cudaStream_t st, const double *a_by_id, const int *id, 
                          int cap, int nb, double *a_slots);
 void launch_make_keys_packed(cudaStream_t st, const double *packed, double h, long long n, uint64_t *keys,
                              uint32_t *vals);
+void launch_make_keys_by_id(cudaStream_t st, const double *x, const double *v, const int *id, const unsigned *cnt,
+                            int cap, int nb, long long n, double h, uint32_t *inv_scratch, uint64_t *keys,
+                            uint32_t *vals);
 }
 
 struct wendy_cuda_handle {
@@ -284,7 +287,16 @@ static void launch_bucket_substep(H *h, double h_pre, double dt_kick, double dt_
 // through the sorted permutation; the output is a compact sorted layout.
 static int launch_radix_substep(H *h, double h_pre, double dt_kick, double dt_drift, const double *aext,
                                 int *rank_out) {
-  if (make_keys(h, h_pre, VAL_SLOT)) return WENDY_E_CUDA;
+  if (h->dense || h->bounds) {
+    // dense upload: slots ARE particle ids, so the stable sort already breaks ties by index
+    if (make_keys(h, h_pre, VAL_SLOT)) return WENDY_E_CUDA;
+  } else {
+    // keys generated in particle-id order (segment-major, ids are contiguous per segment)
+    if (alloc_radix(h, (size_t)h->N)) return WENDY_E_CUDA;
+    launch_make_keys_by_id(h->st, h->x[h->cur], h->v[h->cur], h->id[h->cur], h->cnt[h->ccur], h->cap, h->nb,
+                           h->N, h_pre, h->rs.val[1], h->rs.key[0], h->rs.val[0]);
+    h->n_launch += 2;
+  }
   unsigned seg_div = h->dense ? (unsigned)h->seg_len : (unsigned)((long long)h->nbps * h->cap);
   int res = radix_sort_pairs(h->st, h->rs, (size_t)h->N, seg_bits(h), seg_div);
   h->n_launch += 5 * (8 + (seg_bits(h) + 7) / 8);

@@ -717,6 +717,42 @@ void launch_make_keys(cudaStream_t st, const double *x, const double *v, double 
                                                      val_mode, seg_len, nbps);
 }
 
+// Radix keys in PARTICLE-ID order: inv[id] = slot, then keys[j] = key(x[inv[j]] + h v[inv[j]]) with value
+// inv[j].  A stable LSD sort started from this order yields the (key, id) order everywhere, so
+// exact coincidences are ordered by particle index even across tile boundaries.
+__global__ void invert_ids_kernel(const int *__restrict__ id, const unsigned *__restrict__ cnt, int cap,
+                                  long long total, uint32_t *__restrict__ inv) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int bi = (int)(i / cap);
+    if ((unsigned)(i - (long long)bi * cap) < cnt[bi]) inv[id[i]] = (uint32_t)i;
+  }
+}
+__global__ void make_keys_by_id_kernel(const double *__restrict__ x, const double *__restrict__ v, double h,
+                                       const uint32_t *__restrict__ inv, long long n,
+                                       uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+       j += (long long)gridDim.x * blockDim.x) {
+    const uint32_t s = inv[j];
+    double xx = x[s];
+    if (h != 0.0) xx = __dadd_rn(xx, __dmul_rn(h, v[s]));
+    keys[j] = key_from_double(xx);
+    vals[j] = s;
+  }
+}
+void launch_make_keys_by_id(cudaStream_t st, const double *x, const double *v, const int *id, const unsigned *cnt,
+                            int cap, int nb, long long n, double h, uint32_t *inv_scratch, uint64_t *keys,
+                            uint32_t *vals) {
+  long long total = (long long)nb * cap;
+  if (total <= 0 || n <= 0) return;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  invert_ids_kernel<<<(unsigned)blocks, 256, 0, st>>>(id, cnt, cap, total, inv_scratch);
+  blocks = (n + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  make_keys_by_id_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, v, h, inv_scratch, n, keys, vals);
+}
+
 // keys of packed (x, v, id) migrant records (segment 0)
 __global__ void make_keys_packed_kernel(const double *__restrict__ packed, double h, long long n,
                                         uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
