@@ -64,6 +64,12 @@ struct TileSmem {
 #ifndef TK_RANK2
 #define TK_RANK2 1
 #endif
+#ifndef TK_TIE2
+#define TK_TIE2 1
+#endif
+#ifndef TK_EARLY_V
+#define TK_EARLY_V 1
+#endif
 #ifndef TK_GALLOP
 #define TK_GALLOP 1
 #endif
@@ -283,6 +289,14 @@ tile_kernel(const TileParams p) {
   // ---- 6. exact rank under the (x, id) order; masses are fetched meanwhile ---------------
   double m[E];
   unsigned r[E];
+#if TK_EARLY_V
+  double vreg[E];  // velocities are fetched now so that the load overlaps the ranking
+#pragma unroll
+  for (int k = 0; k < E; k++) {
+    vreg[k] = 0.0;
+    if (tid + k * THREADS < n) vreg[k] = p.vin[g[k]];
+  }
+#endif
   if (!EQM) {
 #pragma unroll
     for (int k = 0; k < E; k++) {
@@ -301,6 +315,22 @@ tile_kernel(const TileParams p) {
       if (s1 - s0 > 1u) {  // shared sub-bucket: count the members that sort before this one
         const double xi = xk[k];
         const int ii = id[k];
+#if TK_TIE2
+        unsigned eq = 0;
+        for (unsigned q = s0; q < s1; q++) {
+          const double xj = S.sx[S.u.srt.slot[q]];
+          rr += (xj < xi) ? 1u : 0u;
+          eq += (xj == xi) ? 1u : 0u;
+        }
+        // every particle ties with itself once; anything beyond that is an exact coincidence,
+        // ordered by particle index in a second (rare) pass
+        if (eq > 1u) {
+          for (unsigned q = s0; q < s1; q++) {
+            const unsigned j = S.u.srt.slot[q];
+            if (S.sx[j] == xi) rr += (S.sid[j] < ii) ? 1u : 0u;
+          }
+        }
+#else
         for (unsigned q = s0; q < s1; q++) {
           unsigned j = S.u.srt.slot[q];
           double xj = S.sx[j];
@@ -311,6 +341,7 @@ tile_kernel(const TileParams p) {
           rr += (xj < xi || (xj == xi && S.sid[j] < ii)) ? 1u : 0u;
 #endif
         }
+#endif
       }
       r[k] = rr;
     }
@@ -391,7 +422,11 @@ tile_kernel(const TileParams p) {
         mk = m[k];
         c = S.u.mcum[r[k] + r[k] / E];
       }
+#if TK_EARLY_V
+      const double v = vreg[k];
+#else
       const double v = p.vin[g[k]];
+#endif
       double grav = __dsub_rn(__dsub_rn(tot, __dmul_rn(2.0, c)), mk);
       if (PHYS) {
         double acc = grav;

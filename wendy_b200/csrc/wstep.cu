@@ -24,6 +24,9 @@
 #ifndef WS_RANK2
 #define WS_RANK2 1
 #endif
+#ifndef WS_TIE2
+#define WS_TIE2 1
+#endif
 #ifndef WS_NEIGH
 #define WS_NEIGH 0
 #endif
@@ -271,11 +274,25 @@ wstep_kernel(const TileParams p) {
       unsigned rr = s0;
       if (s1 - s0 > 1u) {
         const double xi = xr[k];
+#if WS_TIE2
+        unsigned eq = 0;
+        for (unsigned q = s0; q < s1; q++) {
+          const double xj = S.sx[q];
+          rr += (xj < xi) ? 1u : 0u;
+          eq += (xj == xi) ? 1u : 0u;
+        }
+        if (eq > 1u) {  // every particle ties with itself; real coincidences are ordered by particle index
+          const int ii = S.sid[i];
+          for (unsigned q = s0; q < s1; q++)
+            if (S.sx[q] == xi) rr += (S.sid[S.slot[q]] < ii) ? 1u : 0u;
+        }
+#else
         for (unsigned q = s0; q < s1; q++) {
           const double xj = S.sx[q];
           rr += (xj < xi) ? 1u : 0u;
           if (xj == xi) rr += (S.sid[S.slot[q]] < S.sid[i]) ? 1u : 0u;  // coincidence: ties by particle index
         }
+#endif
       }
       pk[k] |= rr << 16;
     }
