@@ -78,6 +78,9 @@ struct wendy_cuda_handle {
   unsigned *cpre = nullptr;            // exclusive prefix of the current bucket counts
   unsigned long long *cp_desc = nullptr;  // look-back words of the count_prefix kernel
   unsigned *cp_ticket = nullptr;
+  ulonglong2 *magg = nullptr, *mpre = nullptr;  // general masses: bucket masses and their prefix
+  Desc *mp_desc = nullptr;
+  unsigned *mp_status = nullptr, *mp_ticket = nullptr;
   unsigned *flags = nullptr;    // [0] fail_seq, [1] max count; [8..135] = 64 x u64 outside-window counters
   unsigned *h_flags = nullptr;  // pinned mirror
   unsigned seq = 1;
@@ -276,6 +279,12 @@ static void launch_bucket_substep(H *h, double h_pre, double dt_kick, double dt_
   launch_count_prefix(h->st, p.cnt_in, h->nb, h->cpre, h->cp_desc, h->cp_ticket, p.epoch);
   h->n_launch++;
   p.cpre = h->cpre;
+  if (!h->eqm) {
+    launch_mass_prefix(h->st, p.min, p.cnt_in, h->cap, h->nb, h->fxE, h->magg, h->mpre, h->mp_desc, h->mp_status,
+                       h->mp_ticket, p.epoch);
+    h->n_launch += 2;
+    p.mpre = h->mpre;
+  }
   if (wstep_cap_supported(h->cap)) launch_wstep(h->st, h->cap, p);
   else launch_tile(h->st, h->cap, LOAD_BUCKET, EMIT_SPLITTER, 1, p);
   advance_after_tile(h);
@@ -326,6 +335,7 @@ void wendy_cuda_destroy(wendy_cuda_handle *h) {
   cudaFree(h->rs.table); cudaFree(h->rs.sums);
   cudaFree(h->split); cudaFree(h->tot); cudaFree(h->ticket); cudaFree(h->status); cudaFree(h->desc);
   cudaFree(h->cdesc); cudaFree(h->cpre); cudaFree(h->cp_desc); cudaFree(h->cp_ticket);
+  cudaFree(h->magg); cudaFree(h->mpre); cudaFree(h->mp_desc); cudaFree(h->mp_status); cudaFree(h->mp_ticket);
   cudaFree(h->flags); cudaFree(h->offs); cudaFree(h->xo); cudaFree(h->vo); cudaFree(h->epart);
   cudaFree(h->eout); cudaFree(h->rank);
   cudaFree(h->bounds); cudaFree(h->out_rec); cudaFree(h->out_cnt);
@@ -412,6 +422,16 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
   CKD(cudaMemsetAsync(h->cp_desc, 0, (size_t)(count_prefix_tiles(h->nb) + 1) * sizeof(unsigned long long), h->st));
   CKD(cudaMalloc(&h->cp_ticket, sizeof(unsigned)));
   CKD(cudaMemsetAsync(h->cp_ticket, 0, sizeof(unsigned), h->st));
+  if (!h->eqm) {
+    const size_t mt = (size_t)mass_prefix_tiles(h->nb) + 1;
+    CKD(cudaMalloc(&h->magg, (size_t)h->nb * sizeof(ulonglong2)));
+    CKD(cudaMalloc(&h->mpre, (size_t)h->nb * sizeof(ulonglong2)));
+    CKD(cudaMalloc(&h->mp_desc, mt * sizeof(Desc)));
+    CKD(cudaMalloc(&h->mp_status, mt * sizeof(unsigned)));
+    CKD(cudaMemsetAsync(h->mp_status, 0, mt * sizeof(unsigned), h->st));
+    CKD(cudaMalloc(&h->mp_ticket, sizeof(unsigned)));
+    CKD(cudaMemsetAsync(h->mp_ticket, 0, sizeof(unsigned), h->st));
+  }
   CKD(cudaMalloc(&h->flags, 136 * sizeof(unsigned)));
   CKD(cudaMemsetAsync(h->flags, 0, 136 * sizeof(unsigned), h->st));
   CKD(cudaMalloc(&h->offs, (size_t)h->nb * sizeof(unsigned long long)));

@@ -56,7 +56,8 @@ struct TileParams {
   unsigned *status;         // per bucket: (epoch << 2) | state   (mass look-back)
   Desc *desc;
   unsigned long long *cdesc;  // per bucket: packed count look-back word
-  const unsigned *cpre;       // wstep: exclusive prefix of cnt_in over ALL buckets (count_prefix kernel)
+  const unsigned *cpre;       // exclusive prefix of cnt_in over ALL buckets (count_prefix kernel)
+  const ulonglong2 *mpre;     // general masses: exclusive 128-bit mass prefix over ALL buckets, or null
   unsigned epoch;
   unsigned *ticket, *ticket_zero;
   unsigned *fail_seq;       // smallest launch sequence number that failed
@@ -84,6 +85,11 @@ void launch_wstep(cudaStream_t st, int cap, const TileParams &p);
 void launch_count_prefix(cudaStream_t st, const unsigned *cnt, int nb, unsigned *cpre,
                          unsigned long long *tile_desc, unsigned *ticket, unsigned epoch);
 int count_prefix_tiles(int nb);
+// general masses: exact bucket masses (one read of m) and their exclusive 128-bit prefix
+void launch_mass_prefix(cudaStream_t st, const double *m, const unsigned *cnt, int cap, int nb, int fxE,
+                        ulonglong2 *magg, ulonglong2 *mpre, Desc *desc, unsigned *status, unsigned *ticket,
+                        unsigned epoch);
+int mass_prefix_tiles(int nb);
 bool wstep_cap_supported(int cap);
 bool tile_cap_supported(int cap);
 

@@ -19,18 +19,18 @@ __device__ __forceinline__ i128 make_i128(unsigned long long lo, unsigned long l
 // Returns the exclusive prefix (mass, count) of bucket b and publishes its inclusive one.
 // Sums are exact integers, so the result does not depend on which predecessors happened
 // to have published an inclusive prefix already.
-__device__ __forceinline__ void lookback(const TileParams &p, int b, int seg_lo, i128 agg,
-                                         long long n, int lane, i128 &P, long long &Pc) {
+__device__ __forceinline__ void lookback(Desc *descs, unsigned *status, unsigned epoch, int b, int seg_lo,
+                                         i128 agg, long long n, int lane, i128 &P, long long &Pc) {
   P = 0;
   Pc = 0;
-  Desc *me = p.desc + b;
+  Desc *me = descs + b;
   if (b > seg_lo) {
     if (lane == 0) {
       me->agg_lo = (unsigned long long)agg;
       me->agg_hi = (unsigned long long)((u128)agg >> 64);
       me->agg_cnt = n;
       __threadfence();
-      *(volatile unsigned *)(p.status + b) = (p.epoch << 2) | 1u;
+      *(volatile unsigned *)(status + b) = (epoch << 2) | 1u;
     }
     int j = b - 1;
     while (true) {
@@ -40,11 +40,11 @@ __device__ __forceinline__ void lookback(const TileParams &p, int b, int seg_lo,
       long long c = 0;
       if (idx >= seg_lo) {
         do {
-          st = ld_volatile_u32(p.status + idx);
-        } while ((st >> 2) != p.epoch);
+          st = ld_volatile_u32(status + idx);
+        } while ((st >> 2) != epoch);
         st &= 3u;
         __threadfence();
-        const Desc *d = p.desc + idx;
+        const Desc *d = descs + idx;
         if (st == 2u) {
           val = make_i128(__ldcg(&d->inc_lo), __ldcg(&d->inc_hi));
           c = __ldcg(&d->inc_cnt);
@@ -76,7 +76,7 @@ __device__ __forceinline__ void lookback(const TileParams &p, int b, int seg_lo,
     me->inc_hi = (unsigned long long)((u128)inc >> 64);
     me->inc_cnt = Pc + n;
     __threadfence();
-    *(volatile unsigned *)(p.status + b) = (p.epoch << 2) | 2u;
+    *(volatile unsigned *)(status + b) = (epoch << 2) | 2u;
   }
 }
 

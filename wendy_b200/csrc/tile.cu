@@ -388,7 +388,12 @@ tile_kernel(const TileParams p) {
       }
       i128 P;
       long long Pcm;
-      lookback(p, b, seg_lo, agg, (long long)n, lane, P, Pcm);
+      if (p.mpre) {  // bucket mass prefix precomputed (bucket_mass + mass_prefix kernels): no look-back
+        const ulonglong2 a = p.mpre[b], z = p.mpre[seg_lo];
+        P = make_i128(a.x, a.y) - make_i128(z.x, z.y);
+      } else {
+        lookback(p.desc, p.status, p.epoch, b, seg_lo, agg, (long long)n, lane, P, Pcm);
+      }
       if (lane == 0) {
         S.pre_lo = (unsigned long long)P;
         S.pre_hi = (unsigned long long)((u128)P >> 64);

@@ -160,9 +160,9 @@ wstep_kernel(const TileParams p) {
   const double tot = p.tot[seg];
   __syncwarp();
   if (n == 0) {
-    if (!EQM) {
+    if (!EQM && !p.mpre) {
       i128 P; long long pc2;
-      lookback(p, b, seg_lo, (i128)0, 0ll, lane, P, pc2);
+      lookback(p.desc, p.status, p.epoch, b, seg_lo, (i128)0, 0ll, lane, P, pc2);
     }
     return;
   }
@@ -202,16 +202,21 @@ wstep_kernel(const TileParams p) {
   // resolve the prefix while the sort runs on the other warps
   i128 P = 0;
   if (!EQM) {
-    i128 agg = 0;
+    if (p.mpre) {  // exact bucket-mass prefix precomputed by bucket_mass + mass_prefix kernels
+      const ulonglong2 a = p.mpre[b], z = p.mpre[seg_lo];
+      P = make_i128(a.x, a.y) - make_i128(z.x, z.y);
+    } else {
+      i128 agg = 0;
 #pragma unroll
-    for (int k = 0; k < E; k++) {
-      const unsigned i = lane + 32 * k;
-      if (i < n) agg += fx_from_double(S.sm[i], p.fxE);
+      for (int k = 0; k < E; k++) {
+        const unsigned i = lane + 32 * k;
+        if (i < n) agg += fx_from_double(S.sm[i], p.fxE);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) agg += shfl_xor_i128(agg, o);
+      long long pc2;
+      lookback(p.desc, p.status, p.epoch, b, seg_lo, agg, (long long)n, lane, P, pc2);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) agg += shfl_xor_i128(agg, o);
-    long long pc2;
-    lookback(p, b, seg_lo, agg, (long long)n, lane, P, pc2);
   }
 
   // ---- sort: interpolation sub-bucket, arrival slot ------------------------------------------------
@@ -488,6 +493,89 @@ count_prefix_kernel(const unsigned *__restrict__ cnt, int nb, unsigned *__restri
 }
 
 int count_prefix_tiles(int nb) { return (nb + CP_TILE - 1) / CP_TILE; }
+
+// ---- general masses: exact 128-bit mass of every bucket, then its exclusive prefix ---------------------------
+// (one extra coalesced read of m per sub-step; replaces a decoupled look-back whose chains are long at
+// one-warp-per-bucket granularity)
+__global__ void __launch_bounds__(256)
+bucket_mass_kernel(const double *__restrict__ m, const unsigned *__restrict__ cnt, int cap, int nb, int fxE,
+                   ulonglong2 *__restrict__ magg) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= nb) return;
+  const unsigned n = min(cnt[b], (unsigned)cap);
+  const double *mp = m + (size_t)b * cap;
+  i128 agg = 0;
+  for (unsigned i = lane; i < n; i += 32) agg += fx_from_double(mp[i], fxE);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) agg += shfl_xor_i128(agg, o);
+  if (lane == 0) magg[b] = make_ulonglong2((unsigned long long)agg, (unsigned long long)((u128)agg >> 64));
+}
+
+constexpr int MP_T = 256, MP_I = 4, MP_TILE = MP_T * MP_I;
+__global__ void __launch_bounds__(MP_T)
+mass_prefix_kernel(const ulonglong2 *__restrict__ magg, int nb, ulonglong2 *__restrict__ mpre, Desc *desc,
+                   unsigned *status, unsigned *ticket, unsigned epoch) {
+  __shared__ unsigned s_t;
+  __shared__ unsigned long long s_lo[8], s_hi[8], s_plo, s_phi;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_t = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const int t = (int)s_t;
+  if (t == (int)gridDim.x - 1 && threadIdx.x == 0) *ticket = 0;
+  const int i0 = t * MP_TILE + threadIdx.x * MP_I;
+  i128 loc[MP_I], run = 0;
+#pragma unroll
+  for (int q = 0; q < MP_I; q++) {
+    loc[q] = run;
+    if (i0 + q < nb) {
+      const ulonglong2 a = magg[i0 + q];
+      run += make_i128(a.x, a.y);
+    }
+  }
+  const i128 inc = warp_inclusive_scan_i128(run, lane);
+  if (lane == 31) {
+    s_lo[wid] = (unsigned long long)inc;
+    s_hi[wid] = (unsigned long long)((u128)inc >> 64);
+  }
+  __syncthreads();
+  if (wid == 0) {
+    i128 w = lane < MP_T / 32 ? make_i128(s_lo[lane], s_hi[lane]) : (i128)0;
+    const i128 wi = warp_inclusive_scan_i128(w, lane);
+    const i128 total = shfl_i128(wi, 31);
+    const i128 wex = wi - w;
+    if (lane < MP_T / 32) {
+      s_lo[lane] = (unsigned long long)wex;
+      s_hi[lane] = (unsigned long long)((u128)wex >> 64);
+    }
+    i128 P;
+    long long pc;
+    lookback(desc, status, epoch, t, 0, total, 0ll, lane, P, pc);
+    if (lane == 0) {
+      s_plo = (unsigned long long)P;
+      s_phi = (unsigned long long)((u128)P >> 64);
+    }
+  }
+  __syncthreads();
+  const i128 base = make_i128(s_plo, s_phi) + make_i128(s_lo[wid], s_hi[wid]) + (inc - run);
+#pragma unroll
+  for (int q = 0; q < MP_I; q++) {
+    if (i0 + q < nb) {
+      const i128 e = base + loc[q];
+      mpre[i0 + q] = make_ulonglong2((unsigned long long)e, (unsigned long long)((u128)e >> 64));
+    }
+  }
+}
+
+int mass_prefix_tiles(int nb) { return (nb + MP_TILE - 1) / MP_TILE; }
+
+void launch_mass_prefix(cudaStream_t st, const double *m, const unsigned *cnt, int cap, int nb, int fxE,
+                        ulonglong2 *magg, ulonglong2 *mpre, Desc *desc, unsigned *status, unsigned *ticket,
+                        unsigned epoch) {
+  if (nb <= 0) return;
+  bucket_mass_kernel<<<(nb + 7) / 8, 256, 0, st>>>(m, cnt, cap, nb, fxE, magg);
+  mass_prefix_kernel<<<mass_prefix_tiles(nb), MP_T, 0, st>>>(magg, nb, mpre, desc, status, ticket, epoch);
+}
 
 void launch_count_prefix(cudaStream_t st, const unsigned *cnt, int nb, unsigned *cpre,
                          unsigned long long *tile_desc, unsigned *ticket, unsigned epoch) {

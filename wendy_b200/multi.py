@@ -61,9 +61,12 @@ class TorchComm(object):
         n_in = [int(counts[p][self.rank]) if p != self.rank else 0 for p in range(self.size)]
         n_out = [int(send[p].shape[0]) if p != self.rank else 0 for p in range(self.size)]
         total = sum(n_in)
-        if getattr(self, '_inbox', None) is None or self._inbox.shape[0] < total:
-            self._inbox = torch.empty((max(total, 1024) * 2, 3), dtype=torch.float64, device=self.device)
-        inbox = self._inbox[:total]
+        if total > (1 << 22):  # the one-off initial partition: do not keep gigabytes around
+            inbox = torch.empty((total, 3), dtype=torch.float64, device=self.device)
+        else:
+            if getattr(self, '_inbox', None) is None or self._inbox.shape[0] < total:
+                self._inbox = torch.empty((max(total, 1024) * 2, 3), dtype=torch.float64, device=self.device)
+            inbox = self._inbox[:total]
         if total == 0 and sum(n_out) == 0:
             return inbox
         if dist.get_backend(self.group) == 'nccl':
