@@ -187,7 +187,7 @@ class ShardedSystem(object):
     reference computes it (numpy.sum of the scaled masses, wendy/wendy.py:383)."""
 
     def __init__(self, x, v, ids, m0, totmass, comm, omega=None, engine_factory=None,
-                 capacity_factor=1.3, outbox_fraction=0.05, n_sample=4096):
+                 capacity_factor=1.3, outbox_fraction=0.05, n_sample=65536):
         self.comm = comm
         self.m0, self.totmass = float(m0), float(totmass)
         self.omega2 = -1. if omega is None else float(omega) ** 2.
