@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <chrono>
 #include <string>
 #include <vector>
@@ -69,6 +70,13 @@ struct wendy_cuda_handle {
   bool has_split = false;  // splitters are valid for key = x + bucket_h * v
   double bucket_h = 0.;
   double *split = nullptr, *tot = nullptr;
+  // Lagrangian splitters (advect_on): second edge buffer + per-cell flow statistics
+  double *split_alt = nullptr, *knot_sum = nullptr, *knot_x = nullptr, *knot_y = nullptr;
+  unsigned *knot_n = nullptr;
+  bool advect_on = false;
+  // sticky radix fallback: sub-steps still to run on the radix path, and the current back-off length
+  int radix_left = 0, radix_streak = 0;
+  long long fail_mark = 0;
   // cross-CTA machinery
   unsigned *ticket = nullptr;  // [3]
   int tcur = 0;
@@ -189,6 +197,12 @@ static int make_keys(H *h, double hkey, int val_mode) {
 
 // (Re)build the bucket layout for key = x + hkey*v: exact quantile splitters from a radix
 // sort of the keys, then one streaming scatter of the state into the other buffer.
+// WENDY_B200_ADVECT=0 disables the Lagrangian splitters (A/B experiments)
+static bool advect_allowed() {
+  const char *e = getenv("WENDY_B200_ADVECT");
+  return !(e && e[0] == '0');
+}
+
 static int default_fill(const H *h, int cap) {
   if (h->user_fill > 0 && cap == h->user_cap) return h->user_fill;
   return cap == 256 ? 128 : cap * 3 / 4;
@@ -236,6 +250,11 @@ static int rebucket(H *h, double hkey, const double *extra = nullptr, long long 
   }
   h->cur = o; h->ccur = c1; h->dense = false; h->has_split = true; h->bucket_h = hkey;
   h->cap = ncap; h->fill = nfill; h->nbps = nnbps; h->nb = nnb; h->want_cap = 0;
+  {
+    const size_t nc = (size_t)h->nb_alloc / 8 + 8;  // flow statistics belong to the old layout
+    CK(cudaMemsetAsync(h->knot_sum, 0, nc * sizeof(double), h->st));
+    CK(cudaMemsetAsync(h->knot_n, 0, nc * sizeof(unsigned), h->st));
+  }
   h->n_rebuild++;
   CK(cudaMemsetAsync(h->flags + 1, 0, sizeof(unsigned), h->st));  // max-count is per layout
   h->h_flags[1] = 0;
@@ -250,7 +269,7 @@ static void fill_tile_params(H *h, TileParams &p) {
   p.cnt_in = h->cnt[h->ccur];
   p.cnt_out = h->cnt[(h->ccur + 1) % 3];
   p.cnt_zero = h->cnt[(h->ccur + 2) % 3];
-  p.split = h->split;
+  p.split = h->split; p.split_in = h->split;
   p.nb = h->nb; p.nbps = h->nbps; p.seg_len = h->seg_len;
   p.omega2 = h->omega2; p.tot = h->tot; p.fxE = h->fxE;
   p.status = h->status; p.desc = h->desc; p.cdesc = h->cdesc;
@@ -276,6 +295,16 @@ static void launch_bucket_substep(H *h, double h_pre, double dt_kick, double dt_
   fill_tile_params(h, p);
   p.h_pre = h_pre; p.dt_kick = dt_kick; p.dt_drift = dt_drift; p.h_next = h_next;
   p.aext = aext; p.rank_out = rank_out;
+  if (h->advect_on && h->nseg == 1) {
+    // move the bucket edges with the flow measured by the previous sub-step: input layout = h->split,
+    // output layout = the advected copy
+    const int G = (h->cap == 256) ? 64 : 8;
+    launch_advect_splitters(h->st, h->split, h->split_alt, h->nb, G, h->knot_sum, h->knot_n, h->knot_x, h->knot_y);
+    h->n_launch += 2;
+    p.split_in = h->split; p.split = h->split_alt;
+    p.knot_sum = h->knot_sum; p.knot_n = h->knot_n; p.knot_g = G;
+    std::swap(h->split, h->split_alt);
+  }
   launch_count_prefix(h->st, p.cnt_in, h->nb, h->cpre, h->cp_desc, h->cp_ticket, p.epoch);
   h->n_launch++;
   p.cpre = h->cpre;
@@ -333,6 +362,7 @@ void wendy_cuda_destroy(wendy_cuda_handle *h) {
   }
   for (int i = 0; i < 3; i++) cudaFree(h->cnt[i]);
   cudaFree(h->rs.table); cudaFree(h->rs.sums);
+  cudaFree(h->split_alt); cudaFree(h->knot_sum); cudaFree(h->knot_x); cudaFree(h->knot_y); cudaFree(h->knot_n);
   cudaFree(h->split); cudaFree(h->tot); cudaFree(h->ticket); cudaFree(h->status); cudaFree(h->desc);
   cudaFree(h->cdesc); cudaFree(h->cpre); cudaFree(h->cp_desc); cudaFree(h->cp_ticket);
   cudaFree(h->magg); cudaFree(h->mpre); cudaFree(h->mp_desc); cudaFree(h->mp_status); cudaFree(h->mp_ticket);
@@ -411,6 +441,16 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
     CKD(cudaMemsetAsync(h->cnt[i], 0, (size_t)h->nb * sizeof(unsigned), h->st));
   }
   CKD(cudaMalloc(&h->split, (size_t)h->nb * sizeof(double)));
+  CKD(cudaMalloc(&h->split_alt, (size_t)h->nb * sizeof(double)));
+  {
+    const size_t nc = (size_t)h->nb / 8 + 8;  // cells of >= 8 buckets
+    CKD(cudaMalloc(&h->knot_sum, nc * sizeof(double)));
+    CKD(cudaMalloc(&h->knot_x, nc * sizeof(double)));
+    CKD(cudaMalloc(&h->knot_y, nc * sizeof(double)));
+    CKD(cudaMalloc(&h->knot_n, nc * sizeof(unsigned)));
+    CKD(cudaMemsetAsync(h->knot_sum, 0, nc * sizeof(double), h->st));
+    CKD(cudaMemsetAsync(h->knot_n, 0, nc * sizeof(unsigned), h->st));
+  }
   CKD(cudaMalloc(&h->tot, (size_t)n_segments * sizeof(double)));
   CKD(cudaMalloc(&h->ticket, 3 * sizeof(unsigned)));
   CKD(cudaMalloc(&h->status, (size_t)h->nb * sizeof(unsigned)));
@@ -519,6 +559,7 @@ int wendy_cuda_shard_substep(wendy_cuda_handle *h, double h_pre, double dt_kick,
       return 0;
     }
     h->n_fail++; h->n_sub--;
+    h->advect_on = advect_allowed();
     h->cur = cur0; h->ccur = ccur0; h->has_split = false;
     if (reset_flags(h)) return WENDY_E_CUDA;
   }
@@ -599,7 +640,7 @@ int wendy_cuda_shard_read(wendy_cuda_handle *h, double *x_host, double *v_host, 
   return 0;
 }
 
-// Enqueue sub-steps [k0, nleap) of one reference call (asynchronous apart from a layout rebuild).
+// Enqueue sub-steps [k0, nleap) of one reference call (asynchronous apart from layout rebuilds).
 static int enqueue_substeps(H *h, double dt, int nleap, int k0) {
   h->p_seq.clear(); h->p_cur.clear(); h->p_ccur.clear();
   h->p_dt = dt; h->p_nleap = nleap; h->p_k0 = k0;
@@ -613,22 +654,21 @@ static int enqueue_substeps(H *h, double dt, int nleap, int k0) {
     }
     h->last_dt = dt;
   }
-  if (h->mode != WENDY_SORT_RADIX) {
-    double need_h = (k0 == 0) ? dt / 2. : 0.;
-    if (h->dense || !h->has_split || h->bucket_h != need_h) {
-      int rc = rebucket(h, need_h);
+  for (int kk = k0; kk < nleap; kk++) {
+    const double h_pre = (kk == 0) ? dt / 2. : 0.;
+    const double dt_drift = (kk == nleap - 1) ? dt / 2. : dt;
+    const bool radix = h->mode == WENDY_SORT_RADIX || h->radix_left > 0;
+    if (!radix && (h->dense || !h->has_split || h->bucket_h != h_pre)) {
+      int rc = rebucket(h, h_pre);  // synchronous; only at start-up, after radix sub-steps or a dt change
       if (rc) return rc;
     }
-  }
-  for (int kk = k0; kk < nleap; kk++) {
     h->p_seq.push_back(h->seq);
     h->p_cur.push_back(h->cur);
     h->p_ccur.push_back(h->ccur);
-    double h_pre = (kk == 0) ? dt / 2. : 0.;
-    double dt_drift = (kk == nleap - 1) ? dt / 2. : dt;
-    if (h->mode == WENDY_SORT_RADIX) {
+    if (radix) {
       int rc = launch_radix_substep(h, h_pre, dt, dt_drift, nullptr, nullptr);
       if (rc) return rc;
+      if (h->radix_left > 0) h->radix_left--;
     } else {
       launch_bucket_substep(h, h_pre, dt, dt_drift, (kk == nleap - 1) ? dt / 2. : 0., nullptr, nullptr);
     }
@@ -651,6 +691,7 @@ static int finish_substeps(H *h) {
       if (h->p_seq[i] == f) kf = h->p_k0 + (int)i;
     if (kf < 0) return set_err(WENDY_E_CUDA, "internal: unknown failing launch");
     h->n_fail++;
+    if (h->nseg == 1 && advect_allowed()) h->advect_on = true;  // bucket edges could not keep up with the flow: let them move with it
     h->n_sub -= (nleap - kf);
     h->cur = h->p_cur[kf - h->p_k0];
     h->ccur = h->p_ccur[kf - h->p_k0];
@@ -667,6 +708,10 @@ static int finish_substeps(H *h) {
       if (rc) return rc;
       if (fetch_flags(h)) return WENDY_E_CUDA;
       h->n_radix_fallback++;
+      // violent phase (the density changes faster than the bucket head-room allows): stay on the
+      // radix path for a while before probing the bucket path again (exponential back-off)
+      h->radix_streak = h->radix_streak ? std::min(16, 2 * h->radix_streak) : 1;
+      h->radix_left = h->radix_streak;
       k++;
       attempts = 0;
       last_fail = -1;
@@ -674,6 +719,8 @@ static int finish_substeps(H *h) {
     int rc = enqueue_substeps(h, dt, nleap, k);
     if (rc) return rc;
   }
+  if (last_fail < 0 && h->radix_left == 0 && h->n_fail == h->fail_mark) h->radix_streak = 0;  // a clean call
+  h->fail_mark = h->n_fail;
   // adaptive layout: when most particles leave the 32-bucket window of the warp kernel every
   // sub-step (large N*dt), 2048-slot buckets with CTA-aggregated emission are faster
   if (h->adaptive && h->cap == 256 && !h->dense) {
@@ -781,6 +828,7 @@ int wendy_cuda_substep(wendy_cuda_handle *h, double dt_kick, double dt_drift, do
 
 int wendy_cuda_read_dev(wendy_cuda_handle *h, double *x_dev, double *v_dev) {
   if (!h) return set_err(WENDY_E_ARG, "null handle");
+  if (h->pending) return set_err(WENDY_E_ARG, "a call is in flight: wendy_cuda_step_end first");
   if (!h->xo) {
     CK(cudaMalloc(&h->xo, (size_t)h->n_cap * sizeof(double)));
     CK(cudaMalloc(&h->vo, (size_t)h->n_cap * sizeof(double)));
@@ -832,6 +880,7 @@ int wendy_cuda_read_end(wendy_cuda_handle *h) {
 
 int wendy_cuda_energy(wendy_cuda_handle *h, double out[4]) {
   if (!h || !out) return set_err(WENDY_E_ARG, "null argument");
+  if (h->pending) return set_err(WENDY_E_ARG, "a call is in flight: wendy_cuda_step_end first");
   // sort the synchronised positions (the layout may be keyed on x + h*v) and run the tile
   // kernel in diagnostic mode through the sorted permutation
   if (make_keys(h, 0., VAL_SLOT)) return WENDY_E_CUDA;

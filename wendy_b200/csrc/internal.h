@@ -42,7 +42,11 @@ struct TileParams {
   int *idout;
   unsigned *cnt_out;        // EMIT_SPLITTER: must be zero on entry; EMIT_RANK: written
   unsigned *cnt_zero;       // array this launch clears for the launch after next (or null)
-  const double *split;      // EMIT_SPLITTER: split[b] = lower edge of bucket b
+  const double *split;      // EMIT_SPLITTER: split[b] = lower edge of bucket b in the OUTPUT layout
+  const double *split_in;   // lower edges of the INPUT layout (differs from split when splitters are advected)
+  double *knot_sum;         // advection: per cell of knot_g buckets, sum of key displacements ... (or null)
+  unsigned *knot_n;         // ... and number of particles
+  int knot_g;
   // geometry
   int nb, nbps;             // buckets in total / per segment
   long long seg_len;        // particles per segment
@@ -85,6 +89,9 @@ void launch_wstep(cudaStream_t st, int cap, const TileParams &p);
 void launch_count_prefix(cudaStream_t st, const unsigned *cnt, int nb, unsigned *cpre,
                          unsigned long long *tile_desc, unsigned *ticket, unsigned epoch);
 int count_prefix_tiles(int nb);
+// Lagrangian splitters: move the bucket edges with the measured mean flow (monotone piecewise-linear map)
+void launch_advect_splitters(cudaStream_t st, const double *split_old, double *split_new, int nb, int G,
+                             double *knot_sum, unsigned *knot_n, double *knot_x, double *knot_y);
 // general masses: exact bucket masses (one read of m) and their exclusive 128-bit prefix
 void launch_mass_prefix(cudaStream_t st, const double *m, const unsigned *cnt, int cap, int nb, int fxE,
                         ulonglong2 *magg, ulonglong2 *mpre, Desc *desc, unsigned *status, unsigned *ticket,

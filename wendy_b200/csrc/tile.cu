@@ -193,8 +193,8 @@ tile_kernel(const TileParams p) {
   // otherwise (edge buckets, gathered tiles) reduce min / max over the block.
   double xmin = -CUDART_INF, xmax = CUDART_INF;
   if (LOAD == LOAD_BUCKET && EMIT == EMIT_SPLITTER) {
-    xmin = __ldg(p.split + b);
-    if (b + 1 < seg_hi) xmax = __ldg(p.split + b + 1);
+    xmin = __ldg(p.split_in + b);  // edges of the INPUT layout
+    if (b + 1 < seg_hi) xmax = __ldg(p.split_in + b + 1);
   }
   if (!(xmin > -CUDART_INF && xmax < CUDART_INF)) {  // uniform over the block
     double lmin = CUDART_INF, lmax = -CUDART_INF;
@@ -494,6 +494,25 @@ tile_kernel(const TileParams p) {
     return;
   }
   // EMIT_SPLITTER: append every particle to the bucket that contains its new key
+  if (p.knot_sum) {  // mean flow per cell of buckets, used to advect the splitters before the next sub-step
+    double dsum = 0.0;
+    unsigned dcount = 0;
+#pragma unroll
+    for (int k = 0; k < E; k++)
+      if (tid + k * THREADS < n) {
+        dsum += xb[k] - xk[k];
+        dcount++;
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      dsum += __shfl_xor_sync(WENDY_FULL_MASK, dsum, o);
+      dcount += __shfl_xor_sync(WENDY_FULL_MASK, dcount, o);
+    }
+    if (lane == 0 && dcount) {
+      atomicAdd(p.knot_sum + b / p.knot_g, dsum);
+      atomicAdd(p.knot_n + b / p.knot_g, dcount);
+    }
+  }
   int dest[E];
   unsigned lpos[E];
   unsigned outside = 0;

@@ -169,7 +169,8 @@ wstep_kernel(const TileParams p) {
   mbar_wait(bar, 0);
 
   // ---- keys: position at force time; key range -------------------------------------------------
-  double xmin = home_lo, xmax = home_hi;
+  // key range of THIS bucket in the input layout (its own edges may since have been advected)
+  double xmin = __ldg(p.split_in + b), xmax = (b + 1 < seg_hi) ? __ldg(p.split_in + b + 1) : CUDART_INF;
   if (p.h_pre != 0.0) {
 #pragma unroll
     for (int k = 0; k < E; k++) {
@@ -334,6 +335,8 @@ wstep_kernel(const TileParams p) {
   int dest[E];
   unsigned hoff[E];
   unsigned hc = 0, outside = 0;
+  double dsum = 0.0;  // advection statistic: total key displacement of this bucket's particles
+  unsigned dcount = 0;
   bool sh_overflow = false;
   const double sh_lo = SHARD ? __ldg(p.bounds + p.my_rank) : 0.0;
   const double sh_hi = SHARD ? __ldg(p.bounds + p.my_rank + 1) : 0.0;
@@ -367,6 +370,8 @@ wstep_kernel(const TileParams p) {
         S.sx[ps] = x2;
         S.sv[i] = v2;
         if (p.rank_out) p.rank_out[S.sid[i]] = (int)(Pc + (long long)WS_RANK(k));
+        dsum += key - xk;
+        dcount++;
         if (SHARD && (key < sh_lo || key >= sh_hi)) {
           // leaves this GPU's key range: append to the outbox of the rank that owns the key
           int peer = 0;
@@ -411,6 +416,17 @@ wstep_kernel(const TileParams p) {
       const unsigned home = __ballot_sync(WENDY_FULL_MASK, d == b);
       if (d == b) hoff[k] = hc + __popc(home & lt);
       hc += __popc(home);
+    }
+  }
+  if (p.knot_sum) {  // mean flow per cell of buckets, used to advect the splitters before the next sub-step
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      dsum += __shfl_xor_sync(WENDY_FULL_MASK, dsum, o);
+      dcount += __shfl_xor_sync(WENDY_FULL_MASK, dcount, o);
+    }
+    if (lane == 0 && dcount) {
+      atomicAdd(p.knot_sum + b / p.knot_g, dsum);
+      atomicAdd(p.knot_n + b / p.knot_g, dcount);
     }
   }
   // ---- slots: one global atomic per destination bucket of the window, all in one round trip ----------
@@ -493,6 +509,99 @@ count_prefix_kernel(const unsigned *__restrict__ cnt, int nb, unsigned *__restri
 }
 
 int count_prefix_tiles(int nb) { return (nb + CP_TILE - 1) / CP_TILE; }
+
+// ---- Lagrangian splitters ---------------------------------------------------------------------------------------
+// Coherent flows (cold collapse, bulk translation) carry whole regions across fixed bucket edges.  The step
+// kernels therefore measure the mean key displacement per cell of G buckets; before the next sub-step the
+// edges are moved by the piecewise-linear map through the cell-centre knots (X_j -> Y_j = cummax(X_j + D_j)),
+// which is monotone by construction.  The layout only affects speed, never results.
+__global__ void __launch_bounds__(1024)
+advect_knots_kernel(const double *__restrict__ split_old, int nb, int G, double *__restrict__ knot_sum,
+                    unsigned *__restrict__ knot_n, double *__restrict__ knot_x, double *__restrict__ knot_y,
+                    int ncell) {
+  __shared__ double wmax[32];
+  __shared__ double carry;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = -CUDART_INF;
+  __syncthreads();
+  for (int base = 0; base < ncell; base += 1024) {
+    const int j = base + threadIdx.x;
+    double y = -CUDART_INF;
+    if (j < ncell) {
+      const int c = min(j * G + G / 2, nb - 1);
+      const double X = split_old[c];
+      const unsigned n = knot_n[j];
+      const double D = n ? knot_sum[j] / (double)n : 0.0;
+      knot_sum[j] = 0.0;
+      knot_n[j] = 0u;
+      knot_x[j] = X;
+      y = (X > -CUDART_INF && X < CUDART_INF) ? X + D : X;
+    }
+    // inclusive running maximum over the cells
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double u = __shfl_up_sync(WENDY_FULL_MASK, y, o);
+      if (lane >= o) y = fmax(y, u);
+    }
+    if (lane == 31) wmax[wid] = y;
+    __syncthreads();
+    if (wid == 0) {
+      double t = wmax[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double u = __shfl_up_sync(WENDY_FULL_MASK, t, o);
+        if (lane >= o) t = fmax(t, u);
+      }
+      wmax[lane] = t;
+    }
+    __syncthreads();
+    double pre = carry;
+    if (wid > 0) pre = fmax(pre, wmax[wid - 1]);
+    y = fmax(y, pre);
+    if (j < ncell) knot_y[j] = y;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = y;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+advect_apply_kernel(const double *__restrict__ split_old, double *__restrict__ split_new, int nb, int G,
+                    const double *__restrict__ knot_x, const double *__restrict__ knot_y, int ncell) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  const double s = split_old[b];
+  double r = s;
+  if (s > -CUDART_INF && s < CUDART_INF) {
+    const int j = (b >= G / 2) ? (b - G / 2) / G : -1;  // knots sit at bucket jG + G/2
+    if (j < 0) {
+      const double X0 = knot_x[0], Y0 = knot_y[0];
+      if (X0 > -CUDART_INF && X0 < CUDART_INF) r = fmin(s + (Y0 - X0), Y0);
+    } else {
+      const double Xj = knot_x[j], Yj = knot_y[j];
+      const bool right_ok = (j + 1 < ncell) && knot_x[j + 1] < CUDART_INF;
+      if (!(Xj > -CUDART_INF && Xj < CUDART_INF)) {
+        r = s;
+      } else if (!right_ok) {
+        r = fmax(s + (Yj - Xj), Yj);
+      } else {
+        const double Xn = knot_x[j + 1], Yn = knot_y[j + 1];
+        double t = (Xn > Xj) ? (s - Xj) / (Xn - Xj) : 0.0;
+        t = fmin(1.0, fmax(0.0, t));
+        r = fmin(Yn, fmax(Yj, Yj + t * (Yn - Yj)));
+      }
+    }
+  }
+  split_new[b] = r;
+}
+
+void launch_advect_splitters(cudaStream_t st, const double *split_old, double *split_new, int nb, int G,
+                             double *knot_sum, unsigned *knot_n, double *knot_x, double *knot_y) {
+  if (nb <= 0) return;
+  const int ncell = (nb + G - 1) / G;
+  advect_knots_kernel<<<1, 1024, 0, st>>>(split_old, nb, G, knot_sum, knot_n, knot_x, knot_y, ncell);
+  advect_apply_kernel<<<(nb + 255) / 256, 256, 0, st>>>(split_old, split_new, nb, G, knot_x, knot_y, ncell);
+}
 
 // ---- general masses: exact 128-bit mass of every bucket, then its exclusive prefix ---------------------------
 // (one extra coalesced read of m per sub-step; replaces a decoupled look-back whose chains are long at
