@@ -140,6 +140,24 @@ def main():
     xc, vc, r = run_c(x, v, m, 0.05, 4, 5, sort='merge')
     cases['tracers'] = dict(x0=x, v0=v, m=m, dt=0.05, nleap=4, xs=xc, vs=vc)
 
+    # --- physics cross-check against the reference's EXACT event-driven solver ------------------
+    # (reference tests/test_approx.py:213-232: approx with nleap=2000 tracks the exact solution to 1e-5)
+    rs = numpy.random.RandomState(2)
+    N = 101
+    x = numpy.arctanh(2. * rs.uniform(size=N) - 1) * 2.
+    v = rs.normal(size=N)
+    v -= numpy.mean(v)
+    m = numpy.ones(N) / N * (1. + 0.1 * (2. * rs.uniform(size=N) - 1))
+    for name, om in (('exact_solver_101', None), ('exact_solver_101_harm', 1.1)):
+        g = wendy.nbody(x, v, m, 0.05, omega=om)  # approx=False: wendy/wendy.c:53-315 (out of scope here)
+        xs, vs = [], []
+        for _ in range(20):
+            tx, tv = next(g)
+            xs.append(tx.copy())
+            vs.append(tv.copy())
+        cases[name] = dict(x0=x, v0=v, m=m, dt=0.05, xs=numpy.array(xs), vs=numpy.array(vs),
+                           omega=numpy.nan if om is None else om)
+
     for name, d in cases.items():
         numpy.savez_compressed(os.path.join(OUT, name + '.npz'), **d)
         print('wrote', name, {k: numpy.shape(a) for k, a in d.items()})

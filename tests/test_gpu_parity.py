@@ -237,6 +237,21 @@ def test_energy_and_momentum_conservation():
     gen.close()
 
 
+# ---- physics cross-check against the reference's exact solver ------------------------------------
+@pytest.mark.parametrize('name', ['exact_solver_101', 'exact_solver_101_harm'])
+def test_tracks_the_reference_exact_solver(name):
+    """reference tests/test_approx.py:213-232 / tests/test_approx_harm.py:55-75, against a golden run of
+    the reference's event-driven solver (out of scope here, used only as a physics cross-check)."""
+    import wendy_b200
+    g = load_golden(name)
+    om = None if numpy.isnan(float(g['omega'])) else float(g['omega'])
+    gen = wendy_b200.nbody(g['x0'], g['v0'], g['m'], 0.05, approx=True, nleap=2000, omega=om)
+    for i in range(len(g['xs'])):
+        x, v = next(gen)
+        assert numpy.max(numpy.abs(x - g['xs'][i])) < 1e-5 and numpy.max(numpy.abs(v - g['vs'][i])) < 1e-5
+    gen.close()
+
+
 # ---- ensembles of independent realisations -------------------------------------------------------
 @pytest.mark.parametrize('sort', SORTS)
 def test_segments_equal_independent_runs(sort):

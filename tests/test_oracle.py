@@ -125,3 +125,16 @@ def test_exact_prefix_is_correctly_rounded():
     p = wo.exact_prefix(m)
     for i in (0, 1, 7, 100, 199):
         assert p[i] == math.fsum(m[:i])
+
+
+@pytest.mark.parametrize('name', ['exact_solver_101', 'exact_solver_101_harm'])
+def test_oracle_tracks_the_reference_exact_solver(name):
+    """Physics cross-check (reference tests/test_approx.py:213-232, tests/test_approx_harm.py:55-75): the
+    approximate integrator with nleap=2000 follows the reference's EXACT event-driven solver (golden
+    fixture generated by tests/golden/make_golden.py) to 1e-5."""
+    g = load_golden(name)
+    om = None if numpy.isnan(float(g['omega'])) else float(g['omega'])
+    o = wo.COracle(g['x0'], g['v0'], g['m'], 0.05, 2000, omega=om)
+    for i in range(len(g['xs'])):
+        x, v = o.step()
+        assert numpy.max(numpy.abs(x - g['xs'][i])) < 1e-5 and numpy.max(numpy.abs(v - g['vs'][i])) < 1e-5
