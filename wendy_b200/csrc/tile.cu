@@ -317,6 +317,7 @@ tile_kernel(const TileParams p) {
         const int ii = id[k];
 #if TK_TIE2
         unsigned eq = 0;
+#pragma unroll 1
         for (unsigned q = s0; q < s1; q++) {
           const double xj = S.sx[S.u.srt.slot[q]];
           rr += (xj < xi) ? 1u : 0u;
@@ -549,7 +550,9 @@ tile_kernel(const TileParams p) {
 #if TK_INTERP
         int lo = rel + (int)floor(fmax(-256.0, fmin(256.0, (key - home_lo) * inv_w)));
         lo = max(0, min(wn - 1, lo));
+#pragma unroll 1
         while (lo > 0 && S.ssplit[lo] > key) lo--;
+#pragma unroll 1
         while (lo < wn - 1 && S.ssplit[lo + 1] <= key) lo++;
 #else
         int lo = 0, hi = wn;

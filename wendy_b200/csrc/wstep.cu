@@ -72,7 +72,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 // largest d in [lo0, hi0) with split[d] <= key, starting from a guess (split[lo0] is -inf)
-__device__ __forceinline__ int gallop_search(const double *__restrict__ split, double key, int guess,
+__device__ __noinline__ int gallop_search(const double *__restrict__ split, double key, int guess,
                                              int lo0, int hi0) {
   int lo = min(max(guess, lo0), hi0 - 1), hi;
   int step = 1;
@@ -99,6 +99,24 @@ __device__ __forceinline__ int gallop_search(const double *__restrict__ split, d
     if (__ldg(split + mid) <= key) lo = mid; else hi = mid;
   }
   return lo;
+}
+
+// destination bucket of a key beyond the 32-bucket window: guess from the home bucket's width, then gallop
+__device__ __noinline__ int far_destination(const double *__restrict__ split, double key, double home_lo,
+                                            double inv_w, int b, int seg_lo, int seg_hi) {
+  double gq = (key - home_lo) * inv_w;
+  gq = fmax(-2.0e9, fmin(2.0e9, gq));
+  const int g = (int)max((long long)seg_lo, min((long long)seg_hi - 1, (long long)b + (long long)floor(gq)));
+  return gallop_search(split, key, g, seg_lo, seg_hi);
+}
+
+// rank correction for exact coincidences inside a sub-bucket: members with the same key and a smaller id
+template <typename SL>
+__device__ __noinline__ unsigned tie_rank(const SL &S, unsigned s0, unsigned s1, double xi, int ii) {
+  unsigned r = 0;
+  for (unsigned q = s0; q < s1; q++)
+    if (S.sx[q] == xi) r += (S.sid[S.slot[q]] < ii) ? 1u : 0u;
+  return r;
 }
 
 template <int WCAP, int WARPS, int EQM, int SHARD>
@@ -282,16 +300,14 @@ wstep_kernel(const TileParams p) {
         const double xi = xr[k];
 #if WS_TIE2
         unsigned eq = 0;
-        for (unsigned q = s0; q < s1; q++) {
+#pragma unroll 1
+        for (unsigned q = s0; q < s1; q++) {  // ~1.5 members on average: unrolling only bloats the code
           const double xj = S.sx[q];
           rr += (xj < xi) ? 1u : 0u;
           eq += (xj == xi) ? 1u : 0u;
         }
-        if (eq > 1u) {  // every particle ties with itself; real coincidences are ordered by particle index
-          const int ii = S.sid[i];
-          for (unsigned q = s0; q < s1; q++)
-            if (S.sx[q] == xi) rr += (S.sid[S.slot[q]] < ii) ? 1u : 0u;
-        }
+        // every particle ties with itself; real coincidences are ordered by particle index (rare path)
+        if (eq > 1u) rr += tie_rank(S, s0, s1, xi, S.sid[i]);
 #else
         for (unsigned q = s0; q < s1; q++) {
           const double xj = S.sx[q];
@@ -392,22 +408,14 @@ wstep_kernel(const TileParams p) {
           // interpolated guess from the home bucket's width, then a short walk to the exact bucket
           int lo = (b - wlo) + (int)floor(fmax(-64.0, fmin(64.0, (key - home_lo) * inv_w)));
           lo = max(0, min(31, lo));
+#pragma unroll 1
           while (lo > 0 && S.w.wsp[lo] > key) lo--;
+#pragma unroll 1
           while (lo < 31 && S.w.wsp[lo + 1] <= key) lo++;
           d = wlo + lo;
           hoff[k] = atomicAdd(&S.w.dcnt[lo], 1u);
-        } else {  // beyond the window: interpolated guess, probe 4 adjacent splitters, else gallop
-          double gq = (key - home_lo) * inv_w;
-          gq = fmax(-2.0e9, fmin(2.0e9, gq));
-          const int g = (int)max((long long)seg_lo + 1, min((long long)seg_hi - 3, (long long)b + (long long)floor(gq)));
-          if (WS_PROBE4 && g - 1 >= seg_lo && g + 2 < seg_hi) {
-            const double sA = __ldg(p.split + g - 1), sB = __ldg(p.split + g), sC = __ldg(p.split + g + 1),
-                         sD = __ldg(p.split + g + 2);
-            if (key >= sB && key < sC) d = g;
-            else if (key >= sC && key < sD) d = g + 1;
-            else if (key >= sA && key < sB) d = g - 1;
-          }
-          if (d < 0) d = gallop_search(p.split, key, g, seg_lo, seg_hi);
+        } else {  // beyond the window: interpolated guess, then galloping search (rare path, not inlined)
+          d = far_destination(p.split, key, home_lo, inv_w, b, seg_lo, seg_hi);
           hoff[k] = atomicAdd(&p.cnt_out[d], 1u);  // final slot
           outside++;
         }
