@@ -44,6 +44,7 @@ def parse():
     ap.add_argument('--skip-cpu-baseline', dest='no_cpu_baseline', action='store_true')
     ap.add_argument('--skip-e2e', dest='no_e2e', action='store_true')
     ap.add_argument('--cap', type=int, default=0, help='bucket capacity: 0/256 = warp kernel, 2048 = CTA kernel')
+    ap.add_argument('--fill', type=int, default=0, help='target particles per bucket (0 = library default)')
     ap.add_argument('--variants', action='store_true', help='also time other dt_leap / sort settings')
     ap.add_argument('--mode', default='auto', choices=['auto', 'ensemble', 'sharded'],
                     help='N>1: independent realisations per GPU, or ONE system of n*gpus particles '
@@ -163,7 +164,7 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
 
     def run(dt_leap, sort, steps, warmup, nleap):
-        st = wendy_b200.ApproxState(x, v, m, omega2=omega2, sort=sort, stream=stream, cap=a.cap)
+        st = wendy_b200.ApproxState(x, v, m, omega2=omega2, sort=sort, stream=stream, cap=a.cap, fill=a.fill)
         for _ in range(warmup):
             st.step(dt_leap, nleap)
         s0 = st.stats()

@@ -82,7 +82,6 @@ struct wendy_cuda_handle {
   int tcur = 0;
   unsigned *status = nullptr;
   Desc *desc = nullptr;
-  unsigned long long *cdesc = nullptr;
   unsigned *cpre = nullptr;            // exclusive prefix of the current bucket counts
   unsigned long long *cp_desc = nullptr;  // look-back words of the count_prefix kernel
   unsigned *cp_ticket = nullptr;
@@ -272,7 +271,7 @@ static void fill_tile_params(H *h, TileParams &p) {
   p.split = h->split; p.split_in = h->split;
   p.nb = h->nb; p.nbps = h->nbps; p.seg_len = h->seg_len;
   p.omega2 = h->omega2; p.tot = h->tot; p.fxE = h->fxE;
-  p.status = h->status; p.desc = h->desc; p.cdesc = h->cdesc;
+  p.status = h->status; p.desc = h->desc;
   p.eqm = h->eqm ? 1 : 0; p.m0 = h->m0;
   p.nranks = h->nranks; p.my_rank = h->my_rank; p.bounds = h->bounds;
   p.out_rec = h->out_rec; p.out_cnt = h->out_cnt;
@@ -364,7 +363,7 @@ void wendy_cuda_destroy(wendy_cuda_handle *h) {
   cudaFree(h->rs.table); cudaFree(h->rs.sums);
   cudaFree(h->split_alt); cudaFree(h->knot_sum); cudaFree(h->knot_x); cudaFree(h->knot_y); cudaFree(h->knot_n);
   cudaFree(h->split); cudaFree(h->tot); cudaFree(h->ticket); cudaFree(h->status); cudaFree(h->desc);
-  cudaFree(h->cdesc); cudaFree(h->cpre); cudaFree(h->cp_desc); cudaFree(h->cp_ticket);
+  cudaFree(h->cpre); cudaFree(h->cp_desc); cudaFree(h->cp_ticket);
   cudaFree(h->magg); cudaFree(h->mpre); cudaFree(h->mp_desc); cudaFree(h->mp_status); cudaFree(h->mp_ticket);
   cudaFree(h->flags); cudaFree(h->offs); cudaFree(h->xo); cudaFree(h->vo); cudaFree(h->epart);
   cudaFree(h->eout); cudaFree(h->rank);
@@ -455,8 +454,6 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
   CKD(cudaMalloc(&h->ticket, 3 * sizeof(unsigned)));
   CKD(cudaMalloc(&h->status, (size_t)h->nb * sizeof(unsigned)));
   CKD(cudaMalloc(&h->desc, (size_t)h->nb * sizeof(Desc)));
-  CKD(cudaMalloc(&h->cdesc, (size_t)h->nb * sizeof(unsigned long long)));
-  CKD(cudaMemsetAsync(h->cdesc, 0, (size_t)h->nb * sizeof(unsigned long long), h->st));
   CKD(cudaMalloc(&h->cpre, (size_t)h->nb * sizeof(unsigned)));
   CKD(cudaMalloc(&h->cp_desc, (size_t)(count_prefix_tiles(h->nb) + 1) * sizeof(unsigned long long)));
   CKD(cudaMemsetAsync(h->cp_desc, 0, (size_t)(count_prefix_tiles(h->nb) + 1) * sizeof(unsigned long long), h->st));

@@ -129,13 +129,7 @@ __device__ __forceinline__ unsigned warp_inclusive_scan_u32(unsigned v, int lane
   return v;
 }
 
-// bank-conflict-free index for "8 consecutive items per thread" access to shared arrays
-__device__ __forceinline__ int pad8(int r) { return r + (r >> 3); }
-
 // global loads that must not hit a stale L1 line (cross-CTA communication)
 __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) {
   return *(const volatile unsigned *)p;
-}
-__device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long *p) {
-  return __ldcg(p);
 }

@@ -59,7 +59,6 @@ struct TileParams {
   // cross-CTA machinery
   unsigned *status;         // per bucket: (epoch << 2) | state   (mass look-back)
   Desc *desc;
-  unsigned long long *cdesc;  // per bucket: packed count look-back word
   const unsigned *cpre;       // exclusive prefix of cnt_in over ALL buckets (count_prefix kernel)
   const ulonglong2 *mpre;     // general masses: exclusive 128-bit mass prefix over ALL buckets, or null
   unsigned epoch;
@@ -82,7 +81,6 @@ struct TileParams {
 };
 
 void launch_tile(cudaStream_t st, int cap, int load, int emit, int physics, const TileParams &p);
-size_t tile_smem_bytes(int cap);
 // wstep.cu: warp-per-bucket sub-step (cap 256)
 void launch_wstep(cudaStream_t st, int cap, const TileParams &p);
 // exclusive prefix sum of the bucket counts (single pass, decoupled look-back over CTA tiles)

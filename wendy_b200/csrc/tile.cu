@@ -32,9 +32,6 @@ namespace wendy {
 #ifndef TK_DW
 #define TK_DW 256
 #endif
-#ifndef TK_INTERP
-#define TK_INTERP 1
-#endif
 constexpr int DW = TK_DW;  // destination buckets tracked with shared-memory counters
 
 template <int CAP, int THREADS>
@@ -61,18 +58,6 @@ struct TileSmem {
   int bucket;
 };
 
-#ifndef TK_RANK2
-#define TK_RANK2 1
-#endif
-#ifndef TK_TIE2
-#define TK_TIE2 1
-#endif
-#ifndef TK_EARLY_V
-#define TK_EARLY_V 1
-#endif
-#ifndef TK_GALLOP
-#define TK_GALLOP 1
-#endif
 // largest d in [lo0, hi0) with split[d] <= key, starting from a guess (split[lo0] is -inf)
 __device__ __forceinline__ int gallop_search_tile(const double *__restrict__ split, double key, int guess,
                                                   int lo0, int hi0) {
@@ -184,8 +169,7 @@ tile_kernel(const TileParams p) {
   if (wid == 0) {
     unsigned pc;
     if (LOAD != LOAD_BUCKET) pc = (unsigned)kb * (unsigned)CAP;
-    else if (p.cpre) pc = p.cpre[b] - (unsigned)((long long)seg * p.seg_len);  // count_prefix kernel ran before
-    else pc = count_lookback(p.cdesc, p.epoch, b, seg_lo, n, lane);
+    else pc = p.cpre[b] - (unsigned)((long long)seg * p.seg_len);  // count_prefix kernel ran just before
     if (lane == 0) S.pre_cnt = (long long)pc;
   }
   // ---- 2. key range of the bucket ----------------------------------------------------------
@@ -289,14 +273,12 @@ tile_kernel(const TileParams p) {
   // ---- 6. exact rank under the (x, id) order; masses are fetched meanwhile ---------------
   double m[E];
   unsigned r[E];
-#if TK_EARLY_V
   double vreg[E];  // velocities are fetched now so that the load overlaps the ranking
 #pragma unroll
   for (int k = 0; k < E; k++) {
     vreg[k] = 0.0;
     if (tid + k * THREADS < n) vreg[k] = p.vin[g[k]];
   }
-#endif
   if (!EQM) {
 #pragma unroll
     for (int k = 0; k < E; k++) {
@@ -315,7 +297,6 @@ tile_kernel(const TileParams p) {
       if (s1 - s0 > 1u) {  // shared sub-bucket: count the members that sort before this one
         const double xi = xk[k];
         const int ii = id[k];
-#if TK_TIE2
         unsigned eq = 0;
 #pragma unroll 1
         for (unsigned q = s0; q < s1; q++) {
@@ -331,18 +312,6 @@ tile_kernel(const TileParams p) {
             if (S.sx[j] == xi) rr += (S.sid[j] < ii) ? 1u : 0u;
           }
         }
-#else
-        for (unsigned q = s0; q < s1; q++) {
-          unsigned j = S.u.srt.slot[q];
-          double xj = S.sx[j];
-#if TK_RANK2
-          rr += (xj < xi) ? 1u : 0u;
-          if (xj == xi) rr += (S.sid[j] < ii) ? 1u : 0u;  // exact coincidence: ties by particle index
-#else
-          rr += (xj < xi || (xj == xi && S.sid[j] < ii)) ? 1u : 0u;
-#endif
-        }
-#endif
       }
       r[k] = rr;
     }
@@ -428,11 +397,7 @@ tile_kernel(const TileParams p) {
         mk = m[k];
         c = S.u.mcum[r[k] + r[k] / E];
       }
-#if TK_EARLY_V
       const double v = vreg[k];
-#else
-      const double v = p.vin[g[k]];
-#endif
       double grav = __dsub_rn(__dsub_rn(tot, __dmul_rn(2.0, c)), mk);
       if (PHYS) {
         double acc = grav;
@@ -547,35 +512,18 @@ tile_kernel(const TileParams p) {
       } else if (key >= home_lo && key < home_hi) {
         d = b;
       } else if (key >= S.ssplit[0] && key < S.ssplit[wn]) {
-#if TK_INTERP
         int lo = rel + (int)floor(fmax(-256.0, fmin(256.0, (key - home_lo) * inv_w)));
         lo = max(0, min(wn - 1, lo));
 #pragma unroll 1
         while (lo > 0 && S.ssplit[lo] > key) lo--;
 #pragma unroll 1
         while (lo < wn - 1 && S.ssplit[lo + 1] <= key) lo++;
-#else
-        int lo = 0, hi = wn;
-        while (hi - lo > 1) {
-          int mid = (lo + hi) >> 1;
-          if (S.ssplit[mid] <= key) lo = mid; else hi = mid;
-        }
-#endif
         d = wlo + lo;
       } else {  // far move (split[seg_lo] is -inf)
-#if TK_GALLOP
         // interpolated guess from the home bucket's width, then a galloping search around it
         double gq = fmax(-2.0e9, fmin(2.0e9, (key - home_lo) * inv_w));
         const int g = (int)max((long long)seg_lo, min((long long)seg_hi - 1, (long long)b + (long long)floor(gq)));
         d = gallop_search_tile(p.split, key, g, seg_lo, seg_hi);
-#else
-        int lo = seg_lo, hi = seg_hi;
-        while (hi - lo > 1) {
-          int mid = (lo + hi) >> 1;
-          if (__ldg(p.split + mid) <= key) lo = mid; else hi = mid;
-        }
-        d = lo;
-#endif
       }
     }
     dest[k] = d;
@@ -652,10 +600,6 @@ static void launch_tile_cap(cudaStream_t st, int load, int emit, int physics, co
 }
 
 bool tile_cap_supported(int cap) { return cap == 2048 || cap == 256; }
-
-size_t tile_smem_bytes(int cap) {
-  return cap == 2048 ? sizeof(TileSmem<2048, 512>) : sizeof(TileSmem<256, 64>);
-}
 
 void launch_tile(cudaStream_t st, int cap, int load, int emit, int physics, const TileParams &p) {
   if (p.nb <= 0) return;

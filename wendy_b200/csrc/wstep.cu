@@ -21,17 +21,8 @@
 #include "internal.h"
 #include "lookback.cuh"
 
-#ifndef WS_RANK2
-#define WS_RANK2 1
-#endif
-#ifndef WS_TIE2
-#define WS_TIE2 1
-#endif
-#ifndef WS_NEIGH
-#define WS_NEIGH 0
-#endif
-#ifndef WS_PROBE4
-#define WS_PROBE4 0
+#ifndef WS_WARPS
+#define WS_WARPS 8
 #endif
 
 namespace wendy {
@@ -298,7 +289,6 @@ wstep_kernel(const TileParams p) {
       unsigned rr = s0;
       if (s1 - s0 > 1u) {
         const double xi = xr[k];
-#if WS_TIE2
         unsigned eq = 0;
 #pragma unroll 1
         for (unsigned q = s0; q < s1; q++) {  // ~1.5 members on average: unrolling only bloats the code
@@ -308,13 +298,6 @@ wstep_kernel(const TileParams p) {
         }
         // every particle ties with itself; real coincidences are ordered by particle index (rare path)
         if (eq > 1u) rr += tie_rank(S, s0, s1, xi, S.sid[i]);
-#else
-        for (unsigned q = s0; q < s1; q++) {
-          const double xj = S.sx[q];
-          rr += (xj < xi) ? 1u : 0u;
-          if (xj == xi) rr += (S.sid[S.slot[q]] < S.sid[i]) ? 1u : 0u;  // coincidence: ties by particle index
-        }
-#endif
       }
       pk[k] |= rr << 16;
     }
@@ -715,9 +698,9 @@ bool wstep_cap_supported(int cap) { return cap == 256; }
 
 void launch_wstep(cudaStream_t st, int cap, const TileParams &p) {
   if (p.nb <= 0) return;
-  if (p.bounds) launch_wstep_t<256, 8, 1, 1>(st, p);  // sharded mode: equal masses only
-  else if (p.eqm) launch_wstep_t<256, 8, 1, 0>(st, p);
-  else launch_wstep_t<256, 8, 0, 0>(st, p);
+  if (p.bounds) launch_wstep_t<256, WS_WARPS, 1, 1>(st, p);  // sharded mode: equal masses only
+  else if (p.eqm) launch_wstep_t<256, WS_WARPS, 1, 0>(st, p);
+  else launch_wstep_t<256, WS_WARPS, 0, 0>(st, p);
 }
 
 }  // namespace wendy
