@@ -206,6 +206,63 @@ def test_nleap_call_pattern_matters_like_the_reference():
     assert numpy.array_equal(x10, xo) and numpy.array_equal(v10, vo)
 
 
+@pytest.mark.parametrize('n', [1, 2, 127, 128, 129, 255, 256, 257, 1535, 1536, 1537, 2047, 2048, 2049, 4097])
+def test_sizes_around_bucket_boundaries(n):
+    import wendy_b200
+    x, v, m = wo.sech2_ic(max(n, 2), seed=n, mass_jitter=0.1)
+    x, v, m = x[:n], v[:n], m[:n]
+    for cap in CAPS:
+        gen = wendy_b200.nbody(x, v, m, 0.04, approx=True, nleap=2, omega=0.7, _cap=cap)
+        xo, vo = x, v
+        for _ in range(2):
+            xg, vg = next(gen)
+            xo, vo, _, _ = wo.numpy_onestep(xo, vo, m, numpy.sum(m), 0.02, 2, 0.7 ** 2., exact_scan=True)
+        gen.close()
+        assert numpy.array_equal(xg, xo) and numpy.array_equal(vg, vo), (n, cap)
+
+
+def test_resume_from_a_yielded_state_is_bit_identical():
+    """The reference's de-facto checkpoint/resume (examples/AdiabaticVsNonAdiabatic.ipynb:6791-6802): build a
+    new generator from a yielded (x, v).  The yielded state is complete, and results do not depend on
+    the internal bucket layout, so the continuation must be bit-identical."""
+    import wendy_b200
+    x, v, m = wo.sech2_ic(60000, seed=21, mass_jitter=0.05)
+    g1 = wendy_b200.nbody(x, v, m, 0.05, approx=True, nleap=5)
+    for _ in range(3):
+        xa, va = next(g1)
+    g2 = wendy_b200.nbody(xa.copy(), va.copy(), m, 0.05, approx=True, nleap=5, sort='gpu-radix')
+    for _ in range(2):
+        xa, va = next(g1)
+        xb, vb = next(g2)
+    assert numpy.array_equal(xa, xb) and numpy.array_equal(va, vb)
+    g1.close(); g2.close()
+
+
+def test_interleaved_generators_are_independent():
+    import wendy_b200
+    ics = [wo.sech2_ic(5000, seed=s) for s in (1, 2)]
+    gens = [wendy_b200.nbody(x, v, m, 0.05, approx=True, nleap=3) for x, v, m in ics]
+    outs = [None, None]
+    for _ in range(3):
+        for i, g in enumerate(gens):
+            outs[i] = [a.copy() for a in next(g)]
+    for i, (x, v, m) in enumerate(ics):
+        xo, vo = x, v
+        for _ in range(3):
+            xo, vo, _, _ = wo.numpy_onestep(xo, vo, m, numpy.sum(m), 0.05 / 3, 3, exact_scan=True)
+        assert numpy.array_equal(outs[i][0], xo) and numpy.array_equal(outs[i][1], vo)
+    [g.close() for g in gens]
+
+
+def test_omega_zero_equals_no_harmonic_term():
+    """reference wendy/wendy.py:363-366: omega=0.0 takes the harmonic branch with omega^2 = 0."""
+    import wendy_b200
+    x, v, m = wo.sech2_ic(3000, seed=3)
+    a = next(wendy_b200.nbody(x, v, m, 0.05, approx=True, nleap=4, omega=0.0))
+    b = next(wendy_b200.nbody(x, v, m, 0.05, approx=True, nleap=4, omega=None))
+    assert numpy.array_equal(a[0], b[0]) and numpy.array_equal(a[1], b[1])
+
+
 # ---- energy / momentum -------------------------------------------------------------------------
 @pytest.mark.parametrize('omega', [None, 1.1])
 @pytest.mark.parametrize('n', [3, 1000, 100000])
