@@ -194,8 +194,6 @@ static int make_keys(H *h, double hkey, int val_mode) {
   return 0;
 }
 
-// (Re)build the bucket layout for key = x + hkey*v: exact quantile splitters from a radix
-// sort of the keys, then one streaming scatter of the state into the other buffer.
 // WENDY_B200_ADVECT=0 disables the Lagrangian splitters (A/B experiments)
 static bool advect_allowed() {
   const char *e = getenv("WENDY_B200_ADVECT");
@@ -207,6 +205,9 @@ static int default_fill(const H *h, int cap) {
   return cap == 256 ? 128 : cap * 3 / 4;
 }
 
+// (Re)build the bucket layout for key = x + hkey*v: exact quantile splitters from a radix
+// sort of the keys, then one streaming scatter of the state into the other buffer (optionally
+// together with `n_extra` packed migrant records: shard inject).
 static int rebucket(H *h, double hkey, const double *extra = nullptr, long long n_extra = 0) {
   // target geometry (may differ from the geometry the state is currently stored in)
   const int ncap = h->want_cap ? h->want_cap : h->cap;
@@ -410,22 +411,38 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
   CKD(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev));
   double sum_abs = 0.;
   {
-    // x*0 is 0 for finite x and NaN otherwise: one vectorisable pass instead of 3N isfinite calls
+    // one multi-threaded pass over the inputs: finiteness (x*0 is 0 for finite x, NaN otherwise),
+    // per-segment sum of |m| for the fixed-point exponent, and the equal-mass test
     double probe = 0.;
-    for (long long i = 0; i < N; i++) probe += x[i] * 0. + v[i] * 0. + m[i] * 0.;
+    long long n_diff = 0;
+    const double m_first = m[0];
+    const long long L = h->seg_len;
+#pragma omp parallel for reduction(+ : probe, n_diff) reduction(max : sum_abs) schedule(static) if (n_segments > 1)
+    for (int s = 0; s < (n_segments > 1 ? n_segments : 0); s++) {
+      double a = 0.;
+      for (long long i = s * L; i < (s + 1) * L; i++) {
+        probe += x[i] * 0. + v[i] * 0. + m[i] * 0.;
+        a += fabs(m[i]);
+        n_diff += (m[i] != m_first);
+      }
+      if (a > sum_abs) sum_abs = a;
+    }
+    if (n_segments == 1) {  // a single segment: parallelise over chunks instead
+      probe = 0.; n_diff = 0; sum_abs = 0.;
+#pragma omp parallel for reduction(+ : probe, n_diff, sum_abs) schedule(static)
+      for (long long i = 0; i < N; i++) {
+        probe += x[i] * 0. + v[i] * 0. + m[i] * 0.;
+        sum_abs += fabs(m[i]);
+        n_diff += (m[i] != m_first);
+      }
+    }
     if (!(probe == 0.)) {
       wendy_cuda_destroy(h);
       return set_err(WENDY_E_ARG, "x, v, m must be finite (NaN keys are undefined in the reference sort too)");
     }
-  }
-  for (int s = 0; s < n_segments; s++) {
-    double a = 0.;
-    for (long long i = s * h->seg_len; i < (s + 1) * h->seg_len; i++) a += fabs(m[i]);
-    if (a > sum_abs) sum_abs = a;
+    h->eqm = !(flags & WENDY_FLAG_GENERAL_MASSES) && n_diff == 0;
   }
   h->fxE = choose_fx_exponent(sum_abs);
-  h->eqm = !(flags & WENDY_FLAG_GENERAL_MASSES);
-  for (long long i = 1; i < N && h->eqm; i++) h->eqm = (m[i] == m[0]);
   h->m0 = m[0];
   for (int i = 0; i < 2; i++) {
     CKD(cudaMalloc(&h->x[i], h->slots * sizeof(double)));
@@ -510,7 +527,6 @@ int wendy_cuda_create_shard(wendy_cuda_handle **out, long long n_local, long lon
   if (rc) return rc;
   H *h = *out;
   h->nranks = nranks; h->my_rank = rank; h->ocap = outbox_capacity;
-  // nranks == 1 still runs the sharded kernel variant when asked to (tests): force it with nranks >= 1
   cudaError_t e = cudaSuccess;
   if (e == cudaSuccess) e = cudaMalloc(&h->bounds, (size_t)(nranks + 1) * sizeof(double));
   if (e == cudaSuccess) e = cudaMemcpy(h->bounds, bounds, (size_t)(nranks + 1) * sizeof(double), cudaMemcpyHostToDevice);

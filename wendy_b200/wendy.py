@@ -198,7 +198,10 @@ def _nbody_approx(x, v, m, dt, nleap, t0=0., omega=None, ext_force=None, sort='g
     omega2 = -1. if omega is None else omega ** 2.
     x = numpy.require(numpy.array(x, dtype=numpy.float64), requirements=['C', 'W'])
     v = numpy.require(numpy.array(v, dtype=numpy.float64), requirements=['C', 'W'])
-    ms = numpy.require(twopiG * numpy.array(m, dtype=numpy.float64), requirements=['C', 'W'])
+    # masses are only read by the library: scale (reference wendy/wendy.py:371) but do not copy needlessly
+    ms = numpy.ascontiguousarray(m, dtype=numpy.float64)
+    if twopiG != 1.:
+        ms = twopiG * ms
     # the yielded buffers are re-used for every D2H copy: page-lock them (best effort)
     lib = _lib.load()
     pinned = [a for a in (x, v) if a.nbytes >= (1 << 20) and lib.wendy_cuda_pin(a.ctypes.data, a.nbytes) == 0]
