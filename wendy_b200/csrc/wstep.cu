@@ -290,11 +290,24 @@ wstep_kernel(const TileParams p) {
       if (s1 - s0 > 1u) {
         const double xi = xr[k];
         unsigned eq = 0;
+        const unsigned c = s1 - s0;
+        // sub-buckets hold ~1.5 members on average: the first four are handled by predicated
+        // straight-line code, a loop only runs for crowded sub-buckets
+#pragma unroll
+        for (unsigned j = 0; j < 4; j++) {
+          if (j < c) {
+            const double xj = S.sx[s0 + j];
+            rr += (xj < xi) ? 1u : 0u;
+            eq += (xj == xi) ? 1u : 0u;
+          }
+        }
+        if (c > 4u) {
 #pragma unroll 1
-        for (unsigned q = s0; q < s1; q++) {  // ~1.5 members on average: unrolling only bloats the code
-          const double xj = S.sx[q];
-          rr += (xj < xi) ? 1u : 0u;
-          eq += (xj == xi) ? 1u : 0u;
+          for (unsigned q = s0 + 4; q < s1; q++) {
+            const double xj = S.sx[q];
+            rr += (xj < xi) ? 1u : 0u;
+            eq += (xj == xi) ? 1u : 0u;
+          }
         }
         // every particle ties with itself; real coincidences are ordered by particle index (rare path)
         if (eq > 1u) rr += tie_rank(S, s0, s1, xi, S.sid[i]);
