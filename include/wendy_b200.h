@@ -69,6 +69,11 @@ int wendy_cuda_create(wendy_cuda_handle **h, long long N, const double *x, const
                       const double *m, const double *totmass, double omega2, int n_segments,
                       int flags, int cap, int fill, void *cuda_stream);
 
+/* Same, from DEVICE arrays (no host staging).  m_dev may be NULL: all particles have mass m0. */
+int wendy_cuda_create_dev(wendy_cuda_handle **h, long long N, const double *x_dev, const double *v_dev,
+                          const double *m_dev, double m0, const double *totmass, double omega2,
+                          int n_segments, int flags, int cap, int fill, void *cuda_stream);
+
 /* One call of the reference entry point: drift dt/2, nleap x [force, kick, drift], with the
  * last drift dt/2 (wendy/wendy.c:398-411).  Synchronous; *time_elapsed (may be NULL) gets the
  * wall seconds of the call (wendy/wendy.c:396,416-417).  No external force. */

@@ -428,6 +428,37 @@ def test_ext_force_on_an_ensemble_matches_separate_runs():
         assert relerr(Xg[s * L:(s + 1) * L], xo) < 1e-12 and relerr(Vg[s * L:(s + 1) * L], vo) < 1e-12
 
 
+def test_device_constructor_and_ic_generators_match_host_path():
+    """from_device (no host staging) must give exactly what the host constructor gives for the same data."""
+    import torch
+    import wendy_b200
+    from wendy_b200 import ic
+    for gen_ic in (ic.sech2_disk, ic.cold_slab, ic.exponential_disk):
+        x, v, m0 = gen_ic(50000, seed=5)
+        a = wendy_b200.ApproxState.from_device(x, v, m0, omega2=0.25)
+        xh, vh = x.cpu().numpy(), v.cpu().numpy()
+        b = wendy_b200.ApproxState(xh, vh, numpy.full(len(xh), m0), omega2=0.25)
+        b_tot = numpy.sum(numpy.full(len(xh), m0))
+        for st in (a, b):
+            st.step(0.01, 5)
+        xa, va = a.read(); xb, vb = b.read()
+        a.close(); b.close()
+        if b_tot == m0 * len(xh):  # identical total mass -> identical results
+            assert numpy.array_equal(xa, xb) and numpy.array_equal(va, vb)
+        else:
+            assert relerr(xa, xb) < 1e-13 and relerr(va, vb) < 1e-13
+    # general masses from a device tensor
+    x, v, m0 = ic.sech2_disk(20000, seed=6)
+    m = torch.full_like(x, m0) * (1. + 0.1 * torch.sin(torch.arange(len(x), device=x.device, dtype=torch.float64)))
+    a = wendy_b200.ApproxState.from_device(x, v, m)
+    b = wendy_b200.ApproxState(x.cpu().numpy(), v.cpu().numpy(), m.cpu().numpy())
+    for st in (a, b):
+        st.step(0.01, 3)
+    xa, va = a.read(); xb, vb = b.read()
+    a.close(); b.close()
+    assert relerr(xa, xb) < 1e-13 and relerr(va, vb) < 1e-13
+
+
 # ---- robustness ------------------------------------------------------------------------------------
 def test_overflow_recovery_by_rebalancing():
     """A violently collapsing cold slab changes the density by orders of magnitude: buckets

@@ -44,6 +44,9 @@ def load():
     lib.wendy_cuda_create.argtypes = [ctypes.POINTER(vp), ctypes.c_longlong, _nd('f8'), _nd('f8'),
                                       _nd('f8'), _nd('f8'), ctypes.c_double, ctypes.c_int,
                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
+    lib.wendy_cuda_create_dev.restype = ctypes.c_int
+    lib.wendy_cuda_create_dev.argtypes = [ctypes.POINTER(vp), ctypes.c_longlong, vp, vp, vp, ctypes.c_double, _nd('f8'),
+                                          ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
     lib.wendy_cuda_step.restype = ctypes.c_int
     lib.wendy_cuda_step.argtypes = [vp, ctypes.c_double, ctypes.c_int, c_double_p]
     lib.wendy_cuda_step_begin.restype = ctypes.c_int
@@ -103,7 +106,7 @@ def load():
 
 
 #: every symbol include/wendy_b200.h declares (checked by tests/test_abi.py)
-EXPORTED = ['wendy_cuda_create', 'wendy_cuda_step', 'wendy_cuda_step_begin', 'wendy_cuda_step_end',
+EXPORTED = ['wendy_cuda_create', 'wendy_cuda_create_dev', 'wendy_cuda_step', 'wendy_cuda_step_begin', 'wendy_cuda_step_end',
             'wendy_cuda_read_begin', 'wendy_cuda_read_end', 'wendy_cuda_force_positions',
             'wendy_cuda_substep', 'wendy_cuda_read', 'wendy_cuda_read_dev', 'wendy_cuda_energy',
             'wendy_cuda_stats', 'wendy_cuda_create_shard', 'wendy_cuda_shard_substep', 'wendy_cuda_shard_outbox',

@@ -37,6 +37,7 @@ namespace wendy {
 void launch_iota(cudaStream_t st, int *id, long long n);
 void launch_gather_by_id(cudaStream_t st, const double *a_by_id, const int *id, const unsigned *cnt,
                          int cap, int nb, double *a_slots);
+void launch_validate(cudaStream_t st, const double *x, const double *v, const double *m, long long n, double *out3);
 void launch_make_keys_packed(cudaStream_t st, const double *packed, double h, long long n, uint64_t *keys,
                              uint32_t *vals);
 void launch_make_keys_by_id(cudaStream_t st, const double *x, const double *v, const int *id, const unsigned *cnt,
@@ -378,10 +379,12 @@ void wendy_cuda_destroy(wendy_cuda_handle *h) {
   delete h;
 }
 
+// dev_inputs: x, v (and m unless null: then all masses equal m0_dev) are DEVICE arrays
 static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, const double *x, const double *v,
                        const double *m, const int *ids, const double *totmass, double omega2, int n_segments,
-                       int flags, int cap, int fill, void *cuda_stream) {
-  if (!out || !x || !v || !m || !totmass) return set_err(WENDY_E_ARG, "null argument");
+                       int flags, int cap, int fill, void *cuda_stream, bool dev_inputs = false,
+                       double m0_dev = 0.) {
+  if (!out || !x || !v || (!m && !dev_inputs) || !totmass) return set_err(WENDY_E_ARG, "null argument");
   if (N <= 0 || N >= (1ll << 31) || n_cap < N || n_cap >= (1ll << 31))
     return set_err(WENDY_E_ARG, "N must be in [1, 2^31) and not exceed the capacity");
   if (n_segments < 1 || N % n_segments) return set_err(WENDY_E_ARG, "N must be a multiple of n_segments");
@@ -410,7 +413,23 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
   CKD(cudaGetDevice(&dev));
   CKD(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev));
   double sum_abs = 0.;
-  {
+  if (dev_inputs) {
+    // device inputs: one validation kernel (finiteness, sum |m|, equal-mass test)
+    double *d_out = nullptr;
+    double h_out[3] = {0., 0., 0.};
+    CKD(cudaMalloc(&d_out, 3 * sizeof(double)));
+    CKD(cudaMemsetAsync(d_out, 0, 3 * sizeof(double), h->st));
+    launch_validate(h->st, x, v, m, N, d_out);
+    CKD(cudaMemcpyAsync(h_out, d_out, sizeof(h_out), cudaMemcpyDeviceToHost, h->st));
+    CKD(cudaStreamSynchronize(h->st));
+    cudaFree(d_out);
+    if (!(h_out[0] == 0.)) {
+      wendy_cuda_destroy(h);
+      return set_err(WENDY_E_ARG, "x, v, m must be finite (NaN keys are undefined in the reference sort too)");
+    }
+    sum_abs = m ? h_out[1] : fabs(m0_dev) * (double)h->seg_len;  // an upper bound per segment suffices
+    h->eqm = !m || (!(flags & WENDY_FLAG_GENERAL_MASSES) && h_out[2] == 0.);
+  } else {
     // one multi-threaded pass over the inputs: finiteness (x*0 is 0 for finite x, NaN otherwise),
     // per-segment sum of |m| for the fixed-point exponent, and the equal-mass test
     double probe = 0.;
@@ -443,7 +462,12 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
     h->eqm = !(flags & WENDY_FLAG_GENERAL_MASSES) && n_diff == 0;
   }
   h->fxE = choose_fx_exponent(sum_abs);
-  h->m0 = m[0];
+  if (dev_inputs) {
+    h->m0 = m0_dev;
+    if (m) CKD(cudaMemcpy(&h->m0, m, sizeof(double), cudaMemcpyDeviceToHost));
+  } else {
+    h->m0 = m[0];
+  }
   for (int i = 0; i < 2; i++) {
     CKD(cudaMalloc(&h->x[i], h->slots * sizeof(double)));
     CKD(cudaMalloc(&h->v[i], h->slots * sizeof(double)));
@@ -495,9 +519,10 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
   CKD(cudaMallocHost(&h->h_eout, 4 * sizeof(double)));
   memset(h->h_flags, 0, 136 * sizeof(unsigned));
   CKD(cudaMemsetAsync(h->status, 0, (size_t)h->nb * sizeof(unsigned), h->st));
-  CKD(cudaMemcpyAsync(h->x[0], x, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->st));
-  CKD(cudaMemcpyAsync(h->v[0], v, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->st));
-  if (!h->eqm) CKD(cudaMemcpyAsync(h->m[0], m, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  const cudaMemcpyKind kind = dev_inputs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  CKD(cudaMemcpyAsync(h->x[0], x, (size_t)N * sizeof(double), kind, h->st));
+  CKD(cudaMemcpyAsync(h->v[0], v, (size_t)N * sizeof(double), kind, h->st));
+  if (!h->eqm) CKD(cudaMemcpyAsync(h->m[0], m, (size_t)N * sizeof(double), kind, h->st));
   CKD(cudaMemcpyAsync(h->tot, totmass, (size_t)n_segments * sizeof(double), cudaMemcpyHostToDevice, h->st));
   if (ids) CKD(cudaMemcpyAsync(h->id[0], ids, (size_t)N * sizeof(int), cudaMemcpyHostToDevice, h->st));
   else launch_iota(h->st, h->id[0], N);
@@ -513,6 +538,15 @@ int wendy_cuda_create(wendy_cuda_handle **out, long long N, const double *x, con
                       const double *m, const double *totmass, double omega2, int n_segments, int flags,
                       int cap, int fill, void *cuda_stream) {
   return create_impl(out, N, N, x, v, m, nullptr, totmass, omega2, n_segments, flags, cap, fill, cuda_stream);
+}
+
+// Same as wendy_cuda_create, from DEVICE arrays (no host staging).  m_dev may be
+// NULL: every particle then has mass m0.
+int wendy_cuda_create_dev(wendy_cuda_handle **out, long long N, const double *x_dev, const double *v_dev,
+                          const double *m_dev, double m0, const double *totmass, double omega2, int n_segments,
+                          int flags, int cap, int fill, void *cuda_stream) {
+  return create_impl(out, N, N, x_dev, v_dev, m_dev, nullptr, totmass, omega2, n_segments, flags, cap, fill,
+                     cuda_stream, true, m0);
 }
 
 // ---- sharded single system: this GPU owns the key range [bounds[rank], bounds[rank+1]) ------------------

@@ -879,6 +879,40 @@ void launch_unsort(cudaStream_t st, const double *x, const double *v, const int 
   unsort_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, v, id, cnt, cap, total, xo, vo);
 }
 
+// validation of device inputs: out3[0] += x*0 + v*0 + m*0 (non-zero/NaN iff something is not finite),
+// out3[1] += |m|, out3[2] += (m != m[0])
+__global__ void __launch_bounds__(256)
+validate_kernel(const double *__restrict__ x, const double *__restrict__ v, const double *__restrict__ m,
+                long long n, double *__restrict__ out3) {
+  double probe = 0., sabs = 0., ndiff = 0.;
+  const double m_first = m ? m[0] : 0.;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    probe += x[i] * 0. + v[i] * 0.;
+    if (m) {
+      probe += m[i] * 0.;
+      sabs += fabs(m[i]);
+      ndiff += (m[i] != m_first) ? 1. : 0.;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    probe += __shfl_xor_sync(WENDY_FULL_MASK, probe, o);
+    sabs += __shfl_xor_sync(WENDY_FULL_MASK, sabs, o);
+    ndiff += __shfl_xor_sync(WENDY_FULL_MASK, ndiff, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out3, probe);
+    atomicAdd(out3 + 1, sabs);
+    atomicAdd(out3 + 2, ndiff);
+  }
+}
+void launch_validate(cudaStream_t st, const double *x, const double *v, const double *m, long long n, double *out3) {
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (n > 0) validate_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, v, m, n, out3);
+}
+
 __global__ void iota_kernel(int *__restrict__ id, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)

@@ -64,6 +64,38 @@ class ApproxState(object):
                                                ctypes.c_void_p(stream) if stream else None))
         self.time_elapsed = 0.
 
+    @classmethod
+    def from_device(cls, x, v, m, omega2=-1., n_segments=1, sort='gpu', cap=0, fill=0):
+        """Build the state from CUDA torch tensors without host staging.
+
+        ``m`` is a float (equal masses, already times twopiG) or a CUDA tensor.  ``totmass`` per
+        segment is ``m * seg_len`` for equal masses and a device sum otherwise (there is no
+        host-side numpy.sum to mirror for device-generated initial conditions)."""
+        import torch
+        self = cls.__new__(cls)
+        self._lib = _lib.load()
+        x = x.detach().to(dtype=torch.float64).contiguous()
+        v = v.detach().to(dtype=torch.float64).contiguous()
+        self.N = x.numel()
+        self.n_segments = int(n_segments)
+        if torch.is_tensor(m):
+            m = m.detach().to(dtype=torch.float64).contiguous()
+            tot = m.reshape(self.n_segments, -1).sum(dim=1).cpu().numpy()
+            mptr, m0 = ctypes.c_void_p(m.data_ptr()), 0.
+        else:
+            tot = numpy.full(self.n_segments, float(m) * (self.N // self.n_segments))
+            mptr, m0 = None, float(m)
+        if sort in _REFERENCE_SORTS:
+            sort = 'gpu'
+        self._h = ctypes.c_void_p()
+        torch.cuda.current_stream().synchronize()
+        _lib.check(self._lib.wendy_cuda_create_dev(
+            ctypes.byref(self._h), self.N, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(v.data_ptr()), mptr, m0,
+            numpy.ascontiguousarray(tot, dtype=numpy.float64), float(omega2), self.n_segments,
+            _lib.SORT_FLAGS[sort], int(cap), int(fill), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        self.time_elapsed = 0.
+        return self
+
     def close(self):
         if getattr(self, '_h', None) is not None and self._h:
             self._lib.wendy_cuda_destroy(self._h)
