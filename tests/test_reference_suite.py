@@ -30,7 +30,8 @@ def _conserves(gen, m, E, n_out, tol, **ekw):
 def test_three_body_energy(m):  # tests/test_approx.py:6-32
     import wendy_b200
     x, v, m = numpy.array([-1.1, 0.1, 1.3]), numpy.array([3., 2., -5.]), numpy.array(m)
-    _conserves(wendy_b200.nbody(x, v, m, 0.05, approx=True, nleap=20000), m, wo.energy(x, v, m), 10, 1e-6)
+    # nleap as in the reference (the leapfrog error across collisions is first order in dt_leap); 3 outputs
+    _conserves(wendy_b200.nbody(x, v, m, 0.05, approx=True, nleap=100000), m, wo.energy(x, v, m), 3, 1e-6)
 
 
 @pytest.mark.parametrize('sort', ['quick', 'merge', 'tim', 'qsort', 'parallel', 'gpu-radix'])
