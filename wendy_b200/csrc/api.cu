@@ -62,6 +62,7 @@ struct wendy_cuda_handle {
   int cur = 0;
   unsigned *cnt[3] = {nullptr, nullptr, nullptr};
   int ccur = 0;
+  bool small_ok = false;   // systems of <= 1024 particles: resident kernel while the state is dense
   bool adaptive = false;   // cap chosen by the library: 256 (warp kernel) <-> 2048 (CTA kernel)
   int want_cap = 0;        // geometry to switch to at the next layout rebuild (0: keep)
   bool rebuild_pending = false;  // shard: rebuild at the start of the next sub-step (state complete)
@@ -379,6 +380,8 @@ void wendy_cuda_destroy(wendy_cuda_handle *h) {
   delete h;
 }
 
+static inline bool dev_inputs_shard(const int *ids) { return ids != nullptr; }  // shard handles carry global ids
+
 // dev_inputs: x, v (and m unless null: then all masses equal m0_dev) are DEVICE arrays
 static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, const double *x, const double *v,
                        const double *m, const int *ids, const double *totmass, double omega2, int n_segments,
@@ -403,6 +406,7 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
   h->N = N; h->n_cap = n_cap; h->nseg = n_segments; h->seg_len = N / n_segments; h->omega2 = omega2;
   h->mode = flags & 0xf; h->cap = cap; h->fill = fill;
   h->adaptive = adaptive && h->mode != WENDY_SORT_RADIX;
+  h->small_ok = h->adaptive && !dev_inputs_shard(ids) && (N / n_segments) <= small_max_particles();
   h->nbps = (int)(((n_cap / n_segments) + fill - 1) / fill);
   long long nb = (long long)h->nbps * n_segments;
   if (nb * cap >= (1ll << 32)) { delete h; return set_err(WENDY_E_ARG, "too many storage slots for u32 indices"); }
@@ -691,6 +695,15 @@ int wendy_cuda_shard_read(wendy_cuda_handle *h, double *x_host, double *v_host, 
 static int enqueue_substeps(H *h, double dt, int nleap, int k0) {
   h->p_seq.clear(); h->p_cur.clear(); h->p_ccur.clear();
   h->p_dt = dt; h->p_nleap = nleap; h->p_k0 = k0;
+  if (h->small_ok && h->dense && k0 == 0) {
+    // small systems: the whole call is ONE launch of the resident kernel (state stays dense, in id order)
+    launch_small(h->st, h->x[h->cur], h->v[h->cur], h->m[h->cur], h->seg_len, h->nseg, h->tot, h->eqm ? 1 : 0,
+                 h->m0, h->omega2, h->fxE, dt, nleap);
+    h->n_launch++;
+    h->n_sub += nleap;
+    h->last_dt = dt;
+    return 0;
+  }
   if (k0 == 0) {
     h->n_outside += outside_total(h);
     memset(h->h_flags + 8, 0, 128 * sizeof(unsigned));

@@ -81,6 +81,10 @@ struct TileParams {
 };
 
 void launch_tile(cudaStream_t st, int cap, int load, int emit, int physics, const TileParams &p);
+// small.cu: resident kernel, one CTA per small system, all nleap sub-steps of a call in one launch
+void launch_small(cudaStream_t st, double *x, double *v, const double *m, long long seg_len, int nseg,
+                  const double *tot_seg, int eqm, double m0, double omega2, int fxE, double dt, int nleap);
+int small_max_particles();
 // wstep.cu: warp-per-bucket sub-step (cap 256)
 void launch_wstep(cudaStream_t st, int cap, const TileParams &p);
 // exclusive prefix sum of the bucket counts (single pass, decoupled look-back over CTA tiles)
