@@ -210,6 +210,29 @@ def main():
         s.close()
         return ms, d
 
+    def e2e_sharded(dt_leap, steps_e, nleap):
+        """Public multi-GPU API with host buffers: construction (key sample, all-to-all partition, H2D) +
+        steps, each followed by read_local() (compaction + D2H of the particles this rank owns)."""
+        from wendy_b200 import multi
+        barrier()
+        t0 = time.perf_counter()
+        comm = multi.TorchComm(device='cuda')
+        ids = (numpy.arange(n, dtype=numpy.int64) + rank * n).astype(numpy.int32)
+        m0 = 1. / (n * world)
+        s = multi.ShardedSystem(x, v, ids, m0, m0 * n * world, comm, omega=a.omega)
+        got = 0
+        for _ in range(steps_e):
+            s.step(dt_leap, nleap)
+            il, xl, vl = s.read_local()
+            got = len(il)
+        torch.cuda.synchronize()
+        el = max_over_ranks(time.perf_counter() - t0)
+        s.close()
+        return {'value': float(n) * world * nleap * steps_e / el, 'unit': 'particle-steps/s',
+                'h2d_bytes_per_step': 20. * n / steps_e, 'd2h_bytes_per_step': 20. * got,
+                'note': 'multi.ShardedSystem from host arrays (sample-sort partition + H2D, amortised over %d steps) '
+                        '+ step() + read_local() (D2H of x, v, id of the owned particles) each step' % steps_e}
+
     sharded = world > 1 and a.mode in ('auto', 'sharded')
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -295,6 +318,8 @@ def main():
         out['variants'] = var
 
     # ---- end to end through the public generator API, host buffers --------------------------
+    if not a.no_e2e and sharded:
+        out['e2e'] = e2e_sharded(a.dt_leap, max(2, min(a.steps, 10)), a.nleap)
     if not a.no_e2e and not sharded:
         steps_e = max(2, min(a.steps, 10))
         barrier()
