@@ -134,6 +134,11 @@ int wendy_cuda_create_shard(wendy_cuda_handle **h, long long n_local, long long 
                             const double *x, const double *v, const int *ids, double m0,
                             double totmass, double omega2, int nranks, int rank,
                             const double *bounds, long long outbox_capacity, void *cuda_stream);
+/* create_shard from DEVICE arrays (x_dev, v_dev, ids_dev), for a partition done on the GPU. */
+int wendy_cuda_create_shard_dev(wendy_cuda_handle **h, long long n_local, long long n_capacity,
+                                const double *x_dev, const double *v_dev, const int *ids_dev,
+                                double m0, double totmass, double omega2, int nranks, int rank,
+                                const double *bounds, long long outbox_capacity, void *cuda_stream);
 int wendy_cuda_shard_substep(wendy_cuda_handle *h, double h_pre, double dt_kick, double dt_drift,
                              double h_next, long long pc_offset, unsigned *out_counts);
 int wendy_cuda_shard_outbox(wendy_cuda_handle *h, double **records, long long *ocap);

@@ -528,7 +528,7 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
   CKD(cudaMemcpyAsync(h->v[0], v, (size_t)N * sizeof(double), kind, h->st));
   if (!h->eqm) CKD(cudaMemcpyAsync(h->m[0], m, (size_t)N * sizeof(double), kind, h->st));
   CKD(cudaMemcpyAsync(h->tot, totmass, (size_t)n_segments * sizeof(double), cudaMemcpyHostToDevice, h->st));
-  if (ids) CKD(cudaMemcpyAsync(h->id[0], ids, (size_t)N * sizeof(int), cudaMemcpyHostToDevice, h->st));
+  if (ids) CKD(cudaMemcpyAsync(h->id[0], ids, (size_t)N * sizeof(int), cudaMemcpyDefault, h->st));
   else launch_iota(h->st, h->id[0], N);
   if (reset_flags(h)) { std::string s = g_err; wendy_cuda_destroy(h); return set_err(WENDY_E_CUDA, s); }
   CKD(cudaGetLastError());
@@ -554,14 +554,43 @@ int wendy_cuda_create_dev(wendy_cuda_handle **out, long long N, const double *x_
 }
 
 // ---- sharded single system: this GPU owns the key range [bounds[rank], bounds[rank+1]) ------------------
+static int create_shard_impl(wendy_cuda_handle **out, long long n_local, long long n_capacity, const double *x,
+                             const double *v, const int *ids, double m0, double totmass, double omega2,
+                             int nranks, int rank, const double *bounds, long long outbox_capacity,
+                             void *cuda_stream, bool dev);
 int wendy_cuda_create_shard(wendy_cuda_handle **out, long long n_local, long long n_capacity, const double *x,
                             const double *v, const int *ids, double m0, double totmass, double omega2,
                             int nranks, int rank, const double *bounds, long long outbox_capacity,
                             void *cuda_stream) {
   if (!ids || !bounds || nranks < 1 || rank < 0 || rank >= nranks || outbox_capacity < 1)
     return set_err(WENDY_E_ARG, "bad shard argument");
-  std::vector<double> m((size_t)n_local, m0);
-  int rc = create_impl(out, n_local, n_capacity, x, v, m.data(), ids, &totmass, omega2, 1, 0, 0, 0, cuda_stream);
+  return create_shard_impl(out, n_local, n_capacity, x, v, ids, m0, totmass, omega2, nranks, rank, bounds,
+                           outbox_capacity, cuda_stream, false);
+}
+
+// Same, from DEVICE arrays (the partition of multi.py runs on the GPU and hands its result over in place).
+int wendy_cuda_create_shard_dev(wendy_cuda_handle **out, long long n_local, long long n_capacity,
+                                const double *x_dev, const double *v_dev, const int *ids_dev, double m0,
+                                double totmass, double omega2, int nranks, int rank, const double *bounds,
+                                long long outbox_capacity, void *cuda_stream) {
+  return create_shard_impl(out, n_local, n_capacity, x_dev, v_dev, ids_dev, m0, totmass, omega2, nranks, rank,
+                           bounds, outbox_capacity, cuda_stream, true);
+}
+
+static int create_shard_impl(wendy_cuda_handle **out, long long n_local, long long n_capacity, const double *x,
+                             const double *v, const int *ids, double m0, double totmass, double omega2,
+                             int nranks, int rank, const double *bounds, long long outbox_capacity,
+                             void *cuda_stream, bool dev) {
+  if (!ids || !bounds || nranks < 1 || rank < 0 || rank >= nranks || outbox_capacity < 1)
+    return set_err(WENDY_E_ARG, "bad shard argument");
+  int rc;
+  if (dev) {
+    rc = create_impl(out, n_local, n_capacity, x, v, nullptr, ids, &totmass, omega2, 1, 0, 0, 0, cuda_stream,
+                     true, m0);
+  } else {
+    std::vector<double> m((size_t)n_local, m0);
+    rc = create_impl(out, n_local, n_capacity, x, v, m.data(), ids, &totmass, omega2, 1, 0, 0, 0, cuda_stream);
+  }
   if (rc) return rc;
   H *h = *out;
   h->nranks = nranks; h->my_rank = rank; h->ocap = outbox_capacity;

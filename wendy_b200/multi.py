@@ -105,15 +105,26 @@ class CudaShardEngine(object):
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else device
         self.nranks, self.rank = nranks, rank
         self._h = ctypes.c_void_p()
-        x = numpy.ascontiguousarray(x, dtype=numpy.float64)
-        v = numpy.ascontiguousarray(v, dtype=numpy.float64)
-        ids = numpy.ascontiguousarray(ids, dtype=numpy.int32)
         bounds = numpy.ascontiguousarray(bounds, dtype=numpy.float64)
         self.capacity = int(capacity)
-        _lib.check(self._lib.wendy_cuda_create_shard(
-            ctypes.byref(self._h), len(x), self.capacity, x, v, ids, float(m0), float(totmass),
-            float(omega2), nranks, rank, bounds, int(outbox_capacity),
-            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        if torch.is_tensor(x):
+            # the partition ran on this GPU: hand the device arrays over in place
+            x = x.to(device=self.device, dtype=torch.float64).contiguous()
+            v = v.to(device=self.device, dtype=torch.float64).contiguous()
+            ids = ids.to(device=self.device, dtype=torch.int32).contiguous()
+            _lib.check(self._lib.wendy_cuda_create_shard_dev(
+                ctypes.byref(self._h), x.shape[0], self.capacity, x.data_ptr(), v.data_ptr(), ids.data_ptr(),
+                float(m0), float(totmass), float(omega2), nranks, rank, bounds, int(outbox_capacity), st))
+            torch.cuda.current_stream().synchronize()
+        else:
+            x = numpy.ascontiguousarray(x, dtype=numpy.float64)
+            v = numpy.ascontiguousarray(v, dtype=numpy.float64)
+            ids = numpy.ascontiguousarray(ids, dtype=numpy.int32)
+            _lib.check(self._lib.wendy_cuda_create_shard(
+                ctypes.byref(self._h), len(x), self.capacity, x, v, ids, float(m0), float(totmass),
+                float(omega2), nranks, rank, bounds, int(outbox_capacity), st))
+        self._pinned = None
         pr, oc = ctypes.c_void_p(), ctypes.c_longlong()
         _lib.check(self._lib.wendy_cuda_shard_outbox(self._h, ctypes.byref(pr), ctypes.byref(oc)))
         self._ocap = oc.value
@@ -151,9 +162,13 @@ class CudaShardEngine(object):
         return n.value
 
     def read(self):
-        x = numpy.empty(self.capacity)
-        v = numpy.empty(self.capacity)
-        ids = numpy.empty(self.capacity, dtype=numpy.int32)
+        """(ids, x, v) of the local particles: views of page-locked buffers this engine re-uses on
+        every call (copy them to keep a snapshot across reads)."""
+        if self._pinned is None:
+            t = self.torch
+            self._pinned = tuple(t.empty(self.capacity, dtype=d, pin_memory=True).numpy()
+                                 for d in (t.float64, t.float64, t.int32))
+        x, v, ids = self._pinned
         n = ctypes.c_longlong()
         _lib.check(self._lib.wendy_cuda_shard_read(self._h, x, v, ids, ctypes.byref(n)))
         return ids[:n.value], x[:n.value], v[:n.value]
@@ -211,8 +226,10 @@ class ShardedSystem(object):
         sample = numpy.full(self.n_sample, numpy.nan)
         sample[:len(take)] = key[take] if len(key) else []  # a strided subset is an unbiased key sample
         self.bounds = choose_bounds(comm.allgather_vec(sample), comm.size)
-        owner = route(key, self.bounds)
         cap = int(self.capacity_factor * n_tot / comm.size) + 1024
+        if str(comm.device).startswith('cuda') and self.engine_factory is CudaShardEngine:
+            return self._partition_device(dt_leap, cap)
+        owner = route(key, self.bounds)
         # the engine's tensors decide where the exchange buffers live (cuda for NCCL, cpu for gloo)
         import torch
         send = [torch.as_tensor(numpy.stack((x[owner == p], v[owner == p], ids[owner == p].astype(numpy.float64)),
@@ -222,6 +239,35 @@ class ShardedSystem(object):
         self.engine = self.engine_factory(mine[:, 0].copy(), mine[:, 1].copy(), mine[:, 2].astype(numpy.int32),
                                           self.m0, self.totmass, self.omega2, comm.size, comm.rank,
                                           self.bounds, cap, max(1024, int(self.outbox_fraction * cap)))
+        self._raw = None
+        self.dt_leap = dt_leap
+        self._update_offset()
+
+    def _partition_device(self, dt_leap, cap):
+        """The same partition with the bulk work on the GPU: one H2D of the raw arrays, owner by
+        binary search in the bounds, grouping by owner with one sort, NCCL all-to-all, and the engine
+        takes the device arrays as they are."""
+        import torch
+        x, v, ids = self._raw
+        comm = self.comm
+        dev = comm.device
+        xd, vd = torch.as_tensor(x, device=dev), torch.as_tensor(v, device=dev)
+        key = xd + (dt_leap / 2.) * vd
+        inner = torch.as_tensor(self.bounds[1:-1], device=dev)
+        owner = torch.bucketize(key, inner, right=True)  # == route(): largest p with bounds[p] <= key
+        del key
+        n_to = torch.bincount(owner, minlength=comm.size).cpu().numpy()
+        order = torch.argsort(owner)
+        del owner
+        packed = torch.stack((xd, vd, torch.as_tensor(ids, device=dev).to(torch.float64)), dim=1)[order]
+        del order, xd, vd
+        send = list(torch.split(packed, [int(c) for c in n_to], dim=0))
+        mine = torch.cat((send[comm.rank], comm.exchange(send)), dim=0)
+        del send, packed
+        self.engine = CudaShardEngine(mine[:, 0], mine[:, 1], mine[:, 2].to(torch.int32),
+                                      self.m0, self.totmass, self.omega2, comm.size, comm.rank,
+                                      self.bounds, cap, max(1024, int(self.outbox_fraction * cap)))
+        del mine
         self._raw = None
         self.dt_leap = dt_leap
         self._update_offset()
