@@ -147,6 +147,18 @@ int wendy_cuda_shard_count(wendy_cuda_handle *h, long long *n_local);
 int wendy_cuda_shard_read(wendy_cuda_handle *h, double *x_host, double *v_host, int *id_host,
                           long long *n);
 
+/* Diagnostics on arbitrary particle arrays (each pointer may be HOST or DEVICE memory); m is the
+ * unscaled mass, twopiG multiplies the sums as in the reference; omega2 < 0: no harmonic term.
+ *   potential          out[j] = omega2 y_j^2/2 + twopiG sum_i m_i |x_i - y_j|      (wendy/wendy.py:494-517)
+ *   energy_individual  out[i] = m_i (omega2 x_i^2/2 + v_i^2/2 + twopiG sum_k m_k |x_k - x_i|)
+ *                                                                                  (wendy/wendy.py:466-470)
+ * O((N + Y) log N): one radix sort + prefix sums + a binary search per point, instead of the
+ * reference's O(N Y) broadcast. */
+int wendy_cuda_potential(const double *y, long long Y, const double *x, const double *m, long long N,
+                         double twopiG, double omega2, double *out, void *cuda_stream);
+int wendy_cuda_energy_individual(const double *x, const double *v, const double *m, long long N,
+                                 double twopiG, double omega2, double *out, void *cuda_stream);
+
 /* Page-lock (cudaHostRegister) / release a HOST buffer the caller passes repeatedly to
  * wendy_cuda_read, so the per-yield D2H copy runs at full PCIe speed.  Optional. */
 int wendy_cuda_pin(void *host_ptr, unsigned long long bytes);

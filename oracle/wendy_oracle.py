@@ -234,6 +234,30 @@ def energy(x, v, m, twopiG=1., omega=None):
     return harm + twopiG * numpy.sum(m[s] * (below * x[s] - xbelow)) + numpy.sum(m * v ** 2. / 2.)
 
 
+def potential(y, x, v, m, twopiG=1., omega=None, chunk=256):
+    """reference wendy/wendy.py:494-517: omega^2 y^2/2 + twopiG * sum_i m_i |x_i - y_j| (O(N*Y) broadcast,
+    evaluated in chunks of y so large N fits in memory; the row sums are numpy's pairwise sums as there)."""
+    y = numpy.atleast_1d(numpy.asarray(y, dtype='f8'))
+    x = numpy.asarray(x, dtype='f8')
+    m = numpy.asarray(m, dtype='f8')
+    out = numpy.empty(len(y))
+    for s in range(0, len(y), chunk):
+        yy = y[s:s + chunk]
+        out[s:s + chunk] = twopiG * numpy.sum(m * numpy.fabs(x - numpy.atleast_2d(yy).T), axis=1)
+    if omega is not None:
+        out = omega ** 2. * y ** 2. / 2. + out
+    return out
+
+
+def energy_individual(x, v, m, twopiG=1., omega=None):
+    """reference wendy/wendy.py:466-470 (individual=True branch)."""
+    x = numpy.asarray(x, dtype='f8')
+    v = numpy.asarray(v, dtype='f8')
+    m = numpy.asarray(m, dtype='f8')
+    out = 0. if omega is None else m * omega ** 2. * x ** 2. / 2.
+    return out + m * potential(x, x, v, m, twopiG=twopiG) + m * v ** 2. / 2.
+
+
 def momentum(v, m):
     """reference wendy/wendy.py:491"""
     return numpy.sum(numpy.asarray(m) * numpy.asarray(v))

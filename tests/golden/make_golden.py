@@ -158,7 +158,24 @@ def main():
         cases[name] = dict(x0=x, v0=v, m=m, dt=0.05, xs=numpy.array(xs), vs=numpy.array(vs),
                            omega=numpy.nan if om is None else om)
 
+    # --- diagnostics: potential(y) and per-particle energies (wendy/wendy.py:494-517, 466-470) -----------
+    rs = numpy.random.RandomState(7)
+    N = 1000
+    x = numpy.arctanh(2. * rs.uniform(size=N) - 1) * 2.
+    x[100:110] = x[100]  # coincident particles
+    v = rs.normal(size=N)
+    m = numpy.ones(N) / N * (1. + 0.5 * (2. * rs.uniform(size=N) - 1))
+    y = numpy.concatenate((numpy.linspace(-12., 12., 201), x[::50], [x.min(), x.max(), -50., 50.]))
+    cases['potential_1000'] = dict(
+        x=x, v=v, m=m, y=y, twopiG=1.7, omega=1.1,
+        pot=wendy.potential(y, x, v, m, twopiG=1.7), pot_harm=wendy.potential(y, x, v, m, twopiG=1.7, omega=1.1),
+        eind=wendy.energy(x, v, m, twopiG=1.7, individual=True),
+        eind_harm=wendy.energy(x, v, m, twopiG=1.7, individual=True, omega=1.1))
+
+    only = sys.argv[1:]
     for name, d in cases.items():
+        if only and name not in only:
+            continue
         numpy.savez_compressed(os.path.join(OUT, name + '.npz'), **d)
         print('wrote', name, {k: numpy.shape(a) for k, a in d.items()})
     import hashlib

@@ -294,6 +294,54 @@ def test_energy_and_momentum_conservation():
     gen.close()
 
 
+# ---- potential(y) and per-particle energies (reference wendy/wendy.py:494-517, 466-470) ----------------
+def test_potential_and_individual_energies_vs_reference_golden():
+    """fp64 tolerance: 1e-13 of the largest potential (different, fixed summation order)."""
+    import wendy_b200
+    g = load_golden('potential_1000')
+    tg, om = float(g['twopiG']), float(g['omega'])
+    for omega, kp, ke in ((None, 'pot', 'eind'), (om, 'pot_harm', 'eind_harm')):
+        p = wendy_b200.potential(g['y'], g['x'], g['v'], g['m'], twopiG=tg, omega=omega)
+        assert numpy.max(numpy.abs(p - g[kp])) <= 1e-13 * numpy.max(numpy.abs(g[kp]))
+        e = wendy_b200.energy(g['x'], g['v'], g['m'], twopiG=tg, individual=True, omega=omega)
+        assert numpy.max(numpy.abs(e - g[ke])) <= 1e-13 * numpy.max(numpy.abs(g[ke]))
+
+
+@pytest.mark.parametrize('n', [1, 2, 2047, 2048, 2049, 300000])
+def test_potential_vs_oracle_sizes(n):
+    import wendy_b200
+    x, v, m = wo.sech2_ic(n, seed=11, mass_jitter=0.3)
+    y = numpy.concatenate((numpy.linspace(-9., 9., 57), x[:: max(1, n // 13)], [-1e3, 1e3]))
+    ref = wo.potential(y, x, v, m, twopiG=2., omega=0.7)
+    got = wendy_b200.potential(y, x, v, m, twopiG=2., omega=0.7)
+    assert numpy.max(numpy.abs(got - ref)) <= 1e-12 * numpy.max(numpy.abs(ref))
+    assert wendy_b200.potential(numpy.empty(0), x, v, m).shape == (0,)
+
+
+def test_individual_energies_sum_rule_large_n_device_tensors():
+    """sum_i E_i = kinetic + harmonic + 2 * pair energy, so sum_i E_i - energy() is the pair energy; torch
+    CUDA tensors in, CUDA tensor out (nothing staged through the host)."""
+    import torch
+    import wendy_b200
+    n = 2000000
+    x, v, m = wo.sech2_ic(n, seed=5, mass_jitter=0.2)
+    xd, vd, md = (torch.as_tensor(a, device='cuda') for a in (x, v, m))
+    e = wendy_b200.energy(xd, vd, md, twopiG=1.3, individual=True, omega=0.9)
+    assert e.is_cuda and e.shape == (n,)
+    E = wo.energy(x, v, m, twopiG=1.3, omega=0.9)
+    one_body = numpy.sum(m * v ** 2. / 2.) + numpy.sum(m * 0.81 * x ** 2. / 2.)
+    pair = E - one_body
+    assert abs(float(e.sum()) - (one_body + 2. * pair)) <= 1e-11 * abs(E)
+    yd = torch.linspace(-5., 5., 1001, dtype=torch.float64, device='cuda')
+    p = wendy_b200.potential(yd, xd, vd, md, twopiG=1.3)
+    assert p.is_cuda
+    ref = wo.potential(yd.cpu().numpy()[::100], x, v, m, twopiG=1.3)
+    assert numpy.max(numpy.abs(p.cpu().numpy()[::100] - ref)) <= 1e-12 * numpy.max(numpy.abs(ref))
+    # the potential is convex with slope -> +-twopiG*M outside the system
+    pp = p.cpu().numpy()
+    assert numpy.all(numpy.diff(pp, 2) >= -1e-12)
+
+
 # ---- physics cross-check against the reference's exact solver ------------------------------------
 @pytest.mark.parametrize('name', ['exact_solver_101', 'exact_solver_101_harm'])
 def test_tracks_the_reference_exact_solver(name):

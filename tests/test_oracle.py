@@ -138,3 +138,15 @@ def test_oracle_tracks_the_reference_exact_solver(name):
     for i in range(len(g['xs'])):
         x, v = o.step()
         assert numpy.max(numpy.abs(x - g['xs'][i])) < 1e-5 and numpy.max(numpy.abs(v - g['vs'][i])) < 1e-5
+
+
+def test_potential_restatement_vs_reference_golden():
+    """oracle potential / individual energies against wendy.potential / wendy.energy(individual=True)
+    run in the dev container (tests/golden/make_golden.py)."""
+    g = load_golden('potential_1000')
+    tg, om = float(g['twopiG']), float(g['omega'])
+    assert numpy.array_equal(wo.potential(g['y'], g['x'], g['v'], g['m'], twopiG=tg), g['pot'])
+    assert numpy.array_equal(wo.potential(g['y'], g['x'], g['v'], g['m'], twopiG=tg, omega=om), g['pot_harm'])
+    assert numpy.allclose(wo.energy_individual(g['x'], g['v'], g['m'], twopiG=tg), g['eind'], rtol=1e-14, atol=0)
+    assert numpy.allclose(wo.energy_individual(g['x'], g['v'], g['m'], twopiG=tg, omega=om), g['eind_harm'],
+                          rtol=1e-14, atol=0)

@@ -80,6 +80,12 @@ def load():
                                                 vp, vp, vp, ctypes.c_double,
                                                 ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int,
                                                 _nd('f8'), ctypes.c_longlong, vp]
+    lib.wendy_cuda_potential.restype = ctypes.c_int
+    lib.wendy_cuda_potential.argtypes = [vp, ctypes.c_longlong, vp, vp, ctypes.c_longlong, ctypes.c_double,
+                                         ctypes.c_double, vp, vp]
+    lib.wendy_cuda_energy_individual.restype = ctypes.c_int
+    lib.wendy_cuda_energy_individual.argtypes = [vp, vp, vp, ctypes.c_longlong, ctypes.c_double,
+                                                 ctypes.c_double, vp, vp]
     lib.wendy_cuda_shard_substep.restype = ctypes.c_int
     lib.wendy_cuda_shard_substep.argtypes = [vp, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                              ctypes.c_double, ctypes.c_longlong, _nd('u4')]
@@ -115,7 +121,7 @@ EXPORTED = ['wendy_cuda_create', 'wendy_cuda_create_dev', 'wendy_cuda_step', 'we
             'wendy_cuda_read_begin', 'wendy_cuda_read_end', 'wendy_cuda_force_positions',
             'wendy_cuda_substep', 'wendy_cuda_read', 'wendy_cuda_read_dev', 'wendy_cuda_energy',
             'wendy_cuda_stats', 'wendy_cuda_create_shard', 'wendy_cuda_create_shard_dev', 'wendy_cuda_shard_substep', 'wendy_cuda_shard_outbox',
-            'wendy_cuda_shard_inject', 'wendy_cuda_shard_count', 'wendy_cuda_shard_read', 'wendy_cuda_pin', 'wendy_cuda_unpin', 'wendy_cuda_debug_layout', 'wendy_cuda_destroy', 'wendy_cuda_last_error',
+            'wendy_cuda_shard_inject', 'wendy_cuda_shard_count', 'wendy_cuda_shard_read', 'wendy_cuda_potential', 'wendy_cuda_energy_individual', 'wendy_cuda_pin', 'wendy_cuda_unpin', 'wendy_cuda_debug_layout', 'wendy_cuda_destroy', 'wendy_cuda_last_error',
             'wendy_cuda_argsort', '_wendy_nbody_approx_onestep']
 
 

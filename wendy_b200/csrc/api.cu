@@ -1045,6 +1045,28 @@ int wendy_cuda_argsort(const double *x_host, long long N, int *perm_out) {
   return rc;
 }
 
+// ---- diagnostics on arbitrary (x, v, m): potential(y) and per-particle energies ------------------------------
+// Reference wendy/wendy.py:494-517 (potential) and :466-470 (energy(individual=True)); every array may be a
+// host or a device pointer, m is the UNSCALED mass and twopiG multiplies the sum as in the reference.
+int wendy_cuda_potential(const double *y, long long Y, const double *x, const double *m, long long N,
+                         double twopiG, double omega2, double *out, void *cuda_stream) {
+  if (Y < 0 || N < 1 || N >= (1ll << 31) || !x || !m || (Y > 0 && (!y || !out)))
+    return set_err(WENDY_E_ARG, "bad argument");
+  std::string err;
+  if (wendy::potential_eval((cudaStream_t)cuda_stream, x, nullptr, m, N, y, Y, twopiG, omega2, out, 0, err))
+    return set_err(WENDY_E_CUDA, err);
+  return 0;
+}
+
+int wendy_cuda_energy_individual(const double *x, const double *v, const double *m, long long N, double twopiG,
+                                 double omega2, double *out, void *cuda_stream) {
+  if (N < 1 || N >= (1ll << 31) || !x || !v || !m || !out) return set_err(WENDY_E_ARG, "bad argument");
+  std::string err;
+  if (wendy::potential_eval((cudaStream_t)cuda_stream, x, v, m, N, nullptr, 0, twopiG, omega2, out, 1, err))
+    return set_err(WENDY_E_CUDA, err);
+  return 0;
+}
+
 // ---- compat export -------------------------------------------------------------------------------------
 // The reference's own entry point (wendy/wendy.c:385-393) on host pointers.  State does not
 // survive the call (the reference C side is stateless as well); use the resident API for

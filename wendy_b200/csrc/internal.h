@@ -5,6 +5,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <string>
+
 namespace wendy {
 
 // ---- radix.cu -----------------------------------------------------------------------
@@ -138,5 +140,10 @@ void launch_reduce_energy(cudaStream_t st, const double *part, int nb, double *o
 // compact (x, v, id) of the live slots into dense arrays (order: bucket-major, arbitrary inside)
 void launch_compact(cudaStream_t st, const double *x, const double *v, const int *id, const unsigned *cnt,
                     const unsigned *cpre, int cap, int nb, double *xo, double *vo, int *ido);
+
+// ---- potential.cu ----------------------------------------------------------------------------------
+int potential_eval(cudaStream_t st, const double *x, const double *v, const double *m, long long N,
+                   const double *y, long long Y, double twopiG, double omega2, double *out, int individual,
+                   std::string &err);
 
 }  // namespace wendy

@@ -273,9 +273,10 @@ def _nbody_approx(x, v, m, dt, nleap, t0=0., omega=None, ext_force=None, sort='g
 def energy(x, v, m, twopiG=1., individual=False, omega=None, n_segments=1):
     """System energy by the formula of reference wendy/wendy.py:458-475 (individual=False),
     evaluated on the GPU: one radix sort + the exact mass scan + a fixed-order reduction.
-    With n_segments > 1 the sum over all segments is returned."""
+    With n_segments > 1 the sum over all segments is returned.  individual=True gives the
+    reference's per-particle energies (wendy/wendy.py:466-470) in O(N log N)."""
     if individual:
-        raise NotImplementedError('individual=True is an O(N^2) diagnostic outside the hot path')
+        return _diagnostic(None, x, v, m, twopiG, omega)
     x = numpy.asarray(x, dtype=numpy.float64)
     ms = twopiG * numpy.asarray(m, dtype=numpy.float64)
     st = ApproxState(x, v, ms, omega2=-1. if omega is None else omega ** 2., n_segments=n_segments)
@@ -286,6 +287,65 @@ def energy(x, v, m, twopiG=1., individual=False, omega=None, n_segments=1):
     if twopiG == 0.:
         return numpy.sum(numpy.asarray(m) * numpy.asarray(v) ** 2. / 2.)
     return (he + pe + ke) / twopiG
+
+
+def _as_f8(a):
+    """(pointer, keep-alive object, is_cuda_tensor) of a float64 array: numpy-like or a torch CUDA tensor."""
+    if hasattr(a, 'is_cuda') and a.is_cuda:
+        import torch
+        a = a.to(torch.float64).contiguous()
+        return a.data_ptr(), a, True
+    a = numpy.require(numpy.atleast_1d(a), dtype=numpy.float64, requirements=['C'])
+    return a.ctypes.data, a, False
+
+
+def _diagnostic(y, x, v, m, twopiG, omega):
+    lib = _lib.load()
+    om2 = -1. if omega is None else float(omega) ** 2.
+    px, kx, cx = _as_f8(x)
+    n = kx.shape[0]
+    if not hasattr(m, 'is_cuda') and numpy.ndim(m) == 0:  # one common mass, as numpy broadcasting allows
+        if cx:
+            import torch
+            m = torch.full((n,), float(m), dtype=torch.float64, device=kx.device)
+        else:
+            m = numpy.full(n, float(m))
+    pm, km, _ = _as_f8(m)
+    if km.shape[0] != n:
+        raise ValueError('x and m must have the same length')
+    stream = None
+    if cx:
+        import torch
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if y is None:
+        pv, kv, _ = _as_f8(v)
+        if cx:
+            out = torch.empty(n, dtype=torch.float64, device=kx.device)
+            po = out.data_ptr()
+        else:
+            out = numpy.empty(n)
+            po = out.ctypes.data
+        _lib.check(lib.wendy_cuda_energy_individual(px, pv, pm, n, float(twopiG), om2, po, stream))
+        return out
+    py, ky, cy = _as_f8(y)
+    ny = ky.shape[0]
+    if cy:
+        import torch
+        out = torch.empty(ny, dtype=torch.float64, device=ky.device)
+        po = out.data_ptr()
+    else:
+        out = numpy.empty(ny)
+        po = out.ctypes.data
+    _lib.check(lib.wendy_cuda_potential(py, ny, px, pm, n, float(twopiG), om2, po, stream))
+    return out
+
+
+def potential(y, x, v, m, twopiG=1., omega=None):
+    """Gravitational (+ harmonic) potential at the points y -- reference wendy/wendy.py:494-517, same
+    arguments (v is unused there too).  O((N + Y) log N) on the GPU instead of the reference's O(N Y)
+    broadcast: radix sort, prefix sums of m and m x, one binary search per point.  Arrays may be
+    numpy-like (result: numpy) or torch CUDA tensors (result: CUDA tensor, nothing crosses PCIe)."""
+    return _diagnostic(y, x, v, m, twopiG, omega)
 
 
 def momentum(v, m):
