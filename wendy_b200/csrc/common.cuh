@@ -130,6 +130,14 @@ __device__ __forceinline__ unsigned warp_inclusive_scan_u32(unsigned v, int lane
 }
 
 // global loads that must not hit a stale L1 line (cross-CTA communication)
+// ~20-bit reciprocal (one MUFU + fix-up) for quantities that only steer a monotone binning or a search
+// guess -- never for anything that reaches the particle state.
+__device__ __forceinline__ double rcp_approx(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return r;
+}
+
 __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) {
   return *(const volatile unsigned *)p;
 }

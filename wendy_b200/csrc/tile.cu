@@ -38,12 +38,11 @@ template <int CAP, int THREADS>
 struct TileSmem {
   static constexpr int E = CAP / THREADS;
   static constexpr int PADN = CAP + CAP / E + 4;
-  double sx[CAP];  // sort keys (positions at force time), indexed by load slot
-  int sid[CAP];    // particle ids, indexed by load slot
+  double sx[CAP];  // sort keys (positions at force time), grouped by sub-bucket
+  int sid[CAP];    // particle ids, same order
   union {
     struct {
       unsigned cnt[PADN];        // interpolation sub-bucket counters -> start offsets
-      unsigned short slot[CAP];  // load slots grouped by sub-bucket
     } srt;
     double mcum[PADN];  // masses in sorted order -> cumulative mass below
   } u;
@@ -106,7 +105,11 @@ tile_kernel(const TileParams p) {
   if (ld_volatile_u32(p.fail_seq) < p.seq) return;
 
   if (tid == 0) S.bucket = (int)atomicAdd(p.ticket, 1u);
-  for (int i = tid; i < SM::PADN; i += THREADS) S.u.srt.cnt[i] = 0;
+  {
+    static_assert(SM::PADN % 4 == 0, "counters are cleared 16 bytes at a time");
+    uint4 *c4 = reinterpret_cast<uint4 *>(S.u.srt.cnt);
+    for (int i = tid; i < SM::PADN / 4; i += THREADS) c4[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
   for (int i = tid; i < DW; i += THREADS) S.dcnt[i] = 0;
   __syncthreads();
   const int b = S.bucket;
@@ -216,7 +219,7 @@ tile_kernel(const TileParams p) {
     xmax = S.dred[2][1];
   }
   const double range = xmax - xmin;
-  const double scale = (range > 0.0 && range < CUDART_INF) ? (double)(BK - 1) / range : 0.0;
+  const double scale = (range > 0.0 && range < CUDART_INF) ? (double)(BK - 1) * rcp_approx(range) : 0.0;
 
   // ---- 3. interpolation sub-bucket of every key (monotone in x), arrival slot -----------
   unsigned pk[E];  // sub-bucket | arrival order << 16
@@ -264,9 +267,8 @@ tile_kernel(const TileParams p) {
     if (i < n) {
       unsigned sub = pk[k] & 0xffffu;
       unsigned pos = S.u.srt.cnt[sub + sub / E] + (pk[k] >> 16);
-      S.u.srt.slot[pos] = (unsigned short)i;
-      S.sx[i] = xk[k];
-      S.sid[i] = id[k];
+      S.sx[pos] = xk[k];
+      S.sid[pos] = id[k];
     }
   }
   __syncthreads();
@@ -300,7 +302,7 @@ tile_kernel(const TileParams p) {
         unsigned eq = 0;
 #pragma unroll 1
         for (unsigned q = s0; q < s1; q++) {
-          const double xj = S.sx[S.u.srt.slot[q]];
+          const double xj = S.sx[q];
           rr += (xj < xi) ? 1u : 0u;
           eq += (xj == xi) ? 1u : 0u;
         }
@@ -308,8 +310,7 @@ tile_kernel(const TileParams p) {
         // ordered by particle index in a second (rare) pass
         if (eq > 1u) {
           for (unsigned q = s0; q < s1; q++) {
-            const unsigned j = S.u.srt.slot[q];
-            if (S.sx[j] == xi) rr += (S.sid[j] < ii) ? 1u : 0u;
+            if (S.sx[q] == xi) rr += (S.sid[q] < ii) ? 1u : 0u;
           }
         }
       }
@@ -383,6 +384,7 @@ tile_kernel(const TileParams p) {
   }
   // ---- 11. force, kick, drift (or diagnostics) ----------------------------------------------------
   const double tot = p.tot[seg];
+  const double PcD = (double)(Pc + p.pc_offset);  // pc_offset: particles of the lower ranks (sharded)
   double x2[E], v2[E], xb[E];
   double e_ke = 0.0, e_he = 0.0, e_pe = 0.0, e_mom = 0.0;
 #pragma unroll
@@ -392,7 +394,7 @@ tile_kernel(const TileParams p) {
       double c, mk;
       if (EQM) {
         mk = p.m0;
-        c = __dmul_rn((double)(Pc + p.pc_offset + (long long)r[k]), p.m0);  // pc_offset: lower ranks (sharded)
+        c = __dmul_rn(__dadd_rn(PcD, (double)r[k]), p.m0);  // exact integer sum below 2^53
       } else {
         mk = m[k];
         c = S.u.mcum[r[k] + r[k] / E];
@@ -486,7 +488,7 @@ tile_kernel(const TileParams p) {
   const double home_lo = S.ssplit[rel], home_hi = S.ssplit[rel + 1];
   bool sh_overflow = false;
   const double wdt = home_hi - home_lo;
-  const double inv_w = (wdt > 0.0 && wdt < CUDART_INF) ? 1.0 / wdt : 0.0;
+  const double inv_w = (wdt > 0.0 && wdt < CUDART_INF) ? rcp_approx(wdt) : 0.0;
   const double sh_lo = p.bounds ? __ldg(p.bounds + p.my_rank) : 0.0;
   const double sh_hi = p.bounds ? __ldg(p.bounds + p.my_rank + 1) : 0.0;
 #pragma unroll

@@ -206,7 +206,7 @@ wstep_kernel(const TileParams p) {
     xmax = lmax;
   }
   const double range = xmax - xmin;
-  const double scale = (range > 0.0 && range < CUDART_INF) ? (double)(BK - 1) / range : 0.0;
+  const double scale = (range > 0.0 && range < CUDART_INF) ? (double)(BK - 1) * rcp_approx(range) : 0.0;
 
   // general masses: the bucket's mass does not depend on the order -> publish it now and
   // resolve the prefix while the sort runs on the other warps
@@ -353,7 +353,7 @@ wstep_kernel(const TileParams p) {
   const double sh_lo = SHARD ? __ldg(p.bounds + p.my_rank) : 0.0;
   const double sh_hi = SHARD ? __ldg(p.bounds + p.my_rank + 1) : 0.0;
   const double wdt = home_hi - home_lo;
-  const double inv_w = (wdt > 0.0 && wdt < CUDART_INF) ? 1.0 / wdt : 0.0;
+  const double inv_w = (wdt > 0.0 && wdt < CUDART_INF) ? rcp_approx(wdt) : 0.0;
 #pragma unroll
   for (int k = 0; k < E; k++) {
     dest[k] = -1;
