@@ -34,10 +34,16 @@ namespace wendy {
 #endif
 constexpr int DW = TK_DW;  // destination buckets tracked with shared-memory counters
 
-template <int CAP, int THREADS>
+template <int CAP, int THREADS, int PERSIST = 0>
 struct TileSmem {
   static constexpr int E = CAP / THREADS;
   static constexpr int PADN = CAP + CAP / E + 4;
+  // PERSIST: landing zone of the TMA bulk copies of the NEXT bucket (x, v, id by load slot)
+  double stx[PERSIST ? CAP : 2];
+  double stv[PERSIST ? CAP : 2];
+  int stid[PERSIST ? CAP : 4];
+  unsigned long long mbar;
+  unsigned long long pad_;
   double sx[CAP];  // sort keys (positions at force time), grouped by sub-bucket
   int sid[CAP];    // particle ids, same order
   union {
@@ -46,7 +52,8 @@ struct TileSmem {
     } srt;
     double mcum[PADN];  // masses in sorted order -> cumulative mass below
   } u;
-  double ssplit[DW + 2];
+  double ssplit[(PERSIST ? 2 : 1) * (DW + 2)];  // destination window (PERSIST: current / next, alternating)
+  double nx_lo[2], nx_hi[2];                    // PERSIST: key range of the current / next bucket
   unsigned dcnt[DW], dbase[DW];
   unsigned long long wlo[32], whi[32];
   unsigned uw[32];
@@ -87,10 +94,14 @@ __device__ __forceinline__ int gallop_search_tile(const double *__restrict__ spl
   return lo;
 }
 
-template <int CAP, int THREADS, int LOAD, int EMIT, int PHYS, int EQM>
+// PERSIST = 1 (LOAD_BUCKET only): the grid is a fixed number of resident CTAs; each walks the buckets
+// blockIdx.x, blockIdx.x + gridDim.x, ... and the (x, v, id) of its NEXT bucket arrive by TMA bulk copy
+// (cp.async.bulk + mbarrier) while the current bucket is ranked, kicked and emitted.
+template <int CAP, int THREADS, int LOAD, int EMIT, int PHYS, int EQM, int PERSIST = 0>
 __global__ void __launch_bounds__(THREADS, (CAP * 48 <= 100 * 1024) ? 2 : 1)
 tile_kernel(const TileParams p) {
-  using SM = TileSmem<CAP, THREADS>;
+  using SM = TileSmem<CAP, THREADS, PERSIST>;
+  static_assert(!PERSIST || (LOAD == LOAD_BUCKET && EQM), "the persistent variant stages x, v, id only");
   constexpr int E = SM::E;
   constexpr int NW = THREADS / 32;
   constexpr int BK = CAP;  // interpolation sub-buckets
@@ -104,7 +115,48 @@ tile_kernel(const TileParams p) {
   // A launch queued behind a failed one must not touch anything (host re-runs from there).
   if (ld_volatile_u32(p.fail_seq) < p.seq) return;
 
-  if (tid == 0) S.bucket = (int)atomicAdd(p.ticket, 1u);
+  // stage one bucket: three bulk copies of the live part (sizes rounded up to 16 bytes, inside the bucket's slots)
+  const uint32_t bar = smem_u32(&S.mbar);
+  auto stage_issue = [&](int bb, unsigned nn) {
+    nn = min(nn, (unsigned)CAP);
+    const uint32_t b8 = (nn * 8u + 15u) & ~15u, b4 = (nn * 4u + 15u) & ~15u;
+    const size_t base = (size_t)bb * CAP;
+    mbar_expect_tx(bar, 2u * b8 + b4);
+    tma_load_1d(S.stx, p.xin + base, b8, bar);
+    tma_load_1d(S.stv, p.vin + base, b8, bar);
+    tma_load_1d(S.stid, p.idin + base, b4, bar);
+  };
+  // destination window of bucket bb: DW buckets around it, clipped to its segment
+  auto window_of = [&](int bb, int &w_lo, int &w_n, int &s_hi) {
+    const int sg = (p.nbps == p.nb) ? 0 : bb / p.nbps;
+    const int s_lo = sg * p.nbps;
+    s_hi = s_lo + p.nbps;
+    w_lo = bb - DW / 2;
+    if (w_lo > s_hi - DW) w_lo = s_hi - DW;
+    if (w_lo < s_lo) w_lo = s_lo;
+    w_n = min(DW, s_hi - w_lo);
+  };
+  uint32_t phase = 0;
+  int b_it = blockIdx.x;  // PERSIST: the launch guarantees gridDim.x <= p.nb
+  unsigned n_it = 0;
+  int cur = 0;            // PERSIST: which half of ssplit / nx_* belongs to the current bucket
+  if (PERSIST) {
+    static_assert(!PERSIST || THREADS >= DW + 1, "one thread per window splitter");
+    n_it = p.cnt_in[b_it];
+    if (tid == 0) {
+      mbar_init(bar, 1);
+      if (n_it) stage_issue(b_it, n_it);
+    }
+    int w_lo, w_n, s_hi;
+    window_of(b_it, w_lo, w_n, s_hi);
+    if (tid <= w_n) S.ssplit[tid] = (w_lo + tid < s_hi) ? p.split[w_lo + tid] : CUDART_INF;
+    if (tid == 0) {
+      S.nx_lo[0] = __ldg(p.split_in + b_it);
+      S.nx_hi[0] = (b_it + 1 < s_hi) ? __ldg(p.split_in + b_it + 1) : CUDART_INF;
+    }
+  }
+  for (;;) {  // one bucket per iteration (a single iteration unless PERSIST)
+  if (!PERSIST && tid == 0) S.bucket = (int)atomicAdd(p.ticket, 1u);
   {
     static_assert(SM::PADN % 4 == 0, "counters are cleared 16 bytes at a time");
     uint4 *c4 = reinterpret_cast<uint4 *>(S.u.srt.cnt);
@@ -112,13 +164,26 @@ tile_kernel(const TileParams p) {
   }
   for (int i = tid; i < DW; i += THREADS) S.dcnt[i] = 0;
   __syncthreads();
-  const int b = S.bucket;
+  const int b = PERSIST ? b_it : S.bucket;
   const int seg = (p.nbps == p.nb) ? 0 : b / p.nbps;
   const int kb = b - seg * p.nbps;
   const int seg_lo = seg * p.nbps, seg_hi = seg_lo + p.nbps;
+  // PERSIST: what the next iteration needs to know early (loads complete long before they are used)
+  const int b_nx = b + (int)gridDim.x;
+  unsigned n_nx = 0, pc_reg = 0;
+  if (PERSIST) {
+    if (b_nx < p.nb) n_nx = p.cnt_in[b_nx];
+    pc_reg = p.cpre[b] - (unsigned)((long long)seg * p.seg_len);
+  }
 
   unsigned n;
-  if (LOAD == LOAD_BUCKET) {
+  if (PERSIST) {
+    n = n_it;
+    if (n > (unsigned)CAP) {
+      n = CAP;
+      if (tid == 0) atomicMin(p.fail_seq, p.seq);
+    }
+  } else if (LOAD == LOAD_BUCKET) {
     n = p.cnt_in[b];
     if (n > (unsigned)CAP) {  // cannot happen for a state produced by a successful launch
       n = CAP;
@@ -137,39 +202,55 @@ tile_kernel(const TileParams p) {
 
   // destination window of splitters (EMIT_SPLITTER)
   int wlo = 0, wn = 0;
+  const int sbase = PERSIST ? cur * (DW + 2) : 0;
   if (EMIT == EMIT_SPLITTER) {
     wlo = b - DW / 2;
     if (wlo > seg_hi - DW) wlo = seg_hi - DW;
     if (wlo < seg_lo) wlo = seg_lo;
     wn = min(DW, seg_hi - wlo);
-    for (int i = tid; i <= wn; i += THREADS)
-      S.ssplit[i] = (wlo + i < seg_hi) ? p.split[wlo + i] : CUDART_INF;
+    if (!PERSIST)  // (PERSIST: written during the previous iteration)
+      for (int i = tid; i <= wn; i += THREADS)
+        S.ssplit[sbase + i] = (wlo + i < seg_hi) ? p.split[wlo + i] : CUDART_INF;
   }
 
   // ---- 1. load positions and ids; key = position at force time -----------------------
   unsigned g[E];
   double xk[E];
   int id[E];
+  double vreg[E];
+  if (PERSIST && n) {  // this bucket's bulk copies were issued one iteration ago
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+  }
 #pragma unroll
   for (int k = 0; k < E; k++) {
     unsigned i = tid + k * THREADS;
     xk[k] = 0.0;
     id[k] = 0;
     g[k] = 0;
+    vreg[k] = 0.0;
     if (i < n) {
       if (LOAD == LOAD_BUCKET)
         g[k] = (unsigned)b * (unsigned)CAP + i;
       else
         g[k] = p.perm[(size_t)seg * p.seg_len + (size_t)kb * CAP + i];
-      double x = p.xin[g[k]];
-      id[k] = p.idin[g[k]];
-      if (p.h_pre != 0.0) x = __dadd_rn(x, __dmul_rn(p.h_pre, p.vin[g[k]]));
-      xk[k] = x;
+      if (PERSIST) {
+        double x = S.stx[i];
+        id[k] = S.stid[i];
+        vreg[k] = S.stv[i];
+        if (p.h_pre != 0.0) x = __dadd_rn(x, __dmul_rn(p.h_pre, vreg[k]));
+        xk[k] = x;
+      } else {
+        double x = p.xin[g[k]];
+        id[k] = p.idin[g[k]];
+        if (p.h_pre != 0.0) x = __dadd_rn(x, __dmul_rn(p.h_pre, p.vin[g[k]]));
+        xk[k] = x;
+      }
     }
   }
   // ---- 1b. number of particles in the preceding buckets of the segment -------------------
   // (known at entry: published and resolved while the loads above are in flight)
-  if (wid == 0) {
+  if (!PERSIST && wid == 0) {
     unsigned pc;
     if (LOAD != LOAD_BUCKET) pc = (unsigned)kb * (unsigned)CAP;
     else pc = p.cpre[b] - (unsigned)((long long)seg * p.seg_len);  // count_prefix kernel ran just before
@@ -179,7 +260,10 @@ tile_kernel(const TileParams p) {
   // Interior buckets of a splitter layout know their range [split[b], split[b+1]) a priori;
   // otherwise (edge buckets, gathered tiles) reduce min / max over the block.
   double xmin = -CUDART_INF, xmax = CUDART_INF;
-  if (LOAD == LOAD_BUCKET && EMIT == EMIT_SPLITTER) {
+  if (PERSIST) {
+    xmin = S.nx_lo[cur];
+    xmax = S.nx_hi[cur];
+  } else if (LOAD == LOAD_BUCKET && EMIT == EMIT_SPLITTER) {
     xmin = __ldg(p.split_in + b);  // edges of the INPUT layout
     if (b + 1 < seg_hi) xmax = __ldg(p.split_in + b + 1);
   }
@@ -234,6 +318,25 @@ tile_kernel(const TileParams p) {
     }
   }
   __syncthreads();
+  // everyone has taken its share of the staged bucket into registers: fetch the next one
+  if (PERSIST && tid == 0 && n_nx) stage_issue(b_nx, n_nx);
+  // ... and its splitter window and key range: per-thread asynchronous copies (cp.async, no registers
+  // held), waited for at the end of this iteration
+  if (PERSIST && b_nx < p.nb) {
+    int w_lo, w_n, s_hi;
+    window_of(b_nx, w_lo, w_n, s_hi);
+    const int nb_ = (cur ^ 1) * (DW + 2);
+    if (tid <= w_n) {
+      if (w_lo + tid < s_hi) cp_async_8(&S.ssplit[nb_ + tid], p.split + w_lo + tid);
+      else S.ssplit[nb_ + tid] = CUDART_INF;
+    }
+    if (tid == THREADS - 1) {
+      cp_async_8(&S.nx_lo[cur ^ 1], p.split_in + b_nx);
+      if (b_nx + 1 < s_hi) cp_async_8(&S.nx_hi[cur ^ 1], p.split_in + b_nx + 1);
+      else S.nx_hi[cur ^ 1] = CUDART_INF;
+    }
+    cp_async_commit();
+  }
   // ---- 4. exclusive scan of the sub-bucket counters ------------------------------------
   {
     unsigned c[E], run = 0;
@@ -275,11 +378,10 @@ tile_kernel(const TileParams p) {
   // ---- 6. exact rank under the (x, id) order; masses are fetched meanwhile ---------------
   double m[E];
   unsigned r[E];
-  double vreg[E];  // velocities are fetched now so that the load overlaps the ranking
+  if (!PERSIST) {  // velocities are fetched now so that the load overlaps the ranking
 #pragma unroll
-  for (int k = 0; k < E; k++) {
-    vreg[k] = 0.0;
-    if (tid + k * THREADS < n) vreg[k] = p.vin[g[k]];
+    for (int k = 0; k < E; k++)
+      if (tid + k * THREADS < n) vreg[k] = p.vin[g[k]];
   }
   if (!EQM) {
 #pragma unroll
@@ -321,8 +423,12 @@ tile_kernel(const TileParams p) {
   if (EQM) {
     // Equal masses: the exact prefix sum below sorted position k is k*m0, so its correctly
     // rounded value is one fp64 multiply -- bit-identical to the general path below.
-    __syncthreads();  // S.pre_cnt (written by warp 0 long ago) is visible to everyone
-    Pc = S.pre_cnt;
+    if (PERSIST) {
+      Pc = (long long)pc_reg;
+    } else {
+      __syncthreads();  // S.pre_cnt (written by warp 0 long ago) is visible to everyone
+      Pc = S.pre_cnt;
+    }
   } else {
     __syncthreads();  // counters and slots are dead from here on; mcum aliases them
     // ---- 7. masses into sorted order --------------------------------------------------------
@@ -485,7 +591,7 @@ tile_kernel(const TileParams p) {
   unsigned lpos[E];
   unsigned outside = 0;
   const int rel = b - wlo;
-  const double home_lo = S.ssplit[rel], home_hi = S.ssplit[rel + 1];
+  const double home_lo = S.ssplit[sbase + rel], home_hi = S.ssplit[sbase + rel + 1];
   bool sh_overflow = false;
   const double wdt = home_hi - home_lo;
   const double inv_w = (wdt > 0.0 && wdt < CUDART_INF) ? rcp_approx(wdt) : 0.0;
@@ -513,13 +619,13 @@ tile_kernel(const TileParams p) {
         d = -3;
       } else if (key >= home_lo && key < home_hi) {
         d = b;
-      } else if (key >= S.ssplit[0] && key < S.ssplit[wn]) {
+      } else if (key >= S.ssplit[sbase] && key < S.ssplit[sbase + wn]) {
         int lo = rel + (int)floor(fmax(-256.0, fmin(256.0, (key - home_lo) * inv_w)));
         lo = max(0, min(wn - 1, lo));
 #pragma unroll 1
-        while (lo > 0 && S.ssplit[lo] > key) lo--;
+        while (lo > 0 && S.ssplit[sbase + lo] > key) lo--;
 #pragma unroll 1
-        while (lo < wn - 1 && S.ssplit[lo + 1] <= key) lo++;
+        while (lo < wn - 1 && S.ssplit[sbase + lo + 1] <= key) lo++;
         d = wlo + lo;
       } else {  // far move (split[seg_lo] is -inf)
         // interpolated guess from the home bucket's width, then a galloping search around it
@@ -579,9 +685,28 @@ tile_kernel(const TileParams p) {
     }
   }
   if (overflow || sh_overflow) atomicMin(p.fail_seq, p.seq);
+  // no barrier needed here: what the next iteration overwrites first (counters, window counts, splitters)
+  // was last read before the two barriers of the emission
+  if (!PERSIST) break;
+  cp_async_wait_all();  // window / key range of the next bucket (visible to all after its first barrier)
+  b_it = b_nx;
+  n_it = n_nx;
+  cur ^= 1;
+  if (b_it >= p.nb) break;
+  }
 }
 
 // ---- dispatch -------------------------------------------------------------------------------------------
+// WENDY_B200_PERSIST=0 falls back to one CTA per bucket (A/B experiments)
+static bool persist_allowed() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("WENDY_B200_PERSIST");
+    v = !(e && e[0] == '0');
+  }
+  return v != 0;
+}
+
 template <int CAP, int THREADS, int EQM>
 static void launch_tile_cap(cudaStream_t st, int load, int emit, int physics, const TileParams &p) {
   size_t sm = sizeof(TileSmem<CAP, THREADS>);
@@ -595,7 +720,24 @@ static void launch_tile_cap(cudaStream_t st, int load, int emit, int physics, co
     }                                                                                               \
     tile_kernel<CAP, THREADS, L, EM, PH, EQM><<<p.nb, THREADS, sm, st>>>(p);                        \
   } while (0)
-  if (load == LOAD_BUCKET && emit == EMIT_SPLITTER && physics) WENDY_LAUNCH(LOAD_BUCKET, EMIT_SPLITTER, 1);
+  if (load == LOAD_BUCKET && emit == EMIT_SPLITTER && physics && EQM && CAP == 2048 && persist_allowed()) {
+    // persistent CTAs, two per SM, next bucket prefetched by TMA
+    constexpr int PE = (EQM && CAP == 2048) ? 1 : 0;  // (keeps the other instantiations out of the binary)
+    constexpr int PQ = PE ? EQM : 1;
+    static int grid = 0;
+    const size_t smp = sizeof(TileSmem<CAP, THREADS, PE>);
+    if (!grid) {
+      int dev = 0, sms = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaFuncSetAttribute(tile_kernel<CAP, THREADS, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, PE>,
+                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp);
+      cudaFuncSetAttribute(tile_kernel<CAP, THREADS, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, PE>,
+                           cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+      grid = 2 * sms;
+    }
+    tile_kernel<CAP, THREADS, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, PE><<<min(grid, p.nb), THREADS, smp, st>>>(p);
+  } else if (load == LOAD_BUCKET && emit == EMIT_SPLITTER && physics) WENDY_LAUNCH(LOAD_BUCKET, EMIT_SPLITTER, 1);
   else if (load == LOAD_GATHER && emit == EMIT_RANK && physics) WENDY_LAUNCH(LOAD_GATHER, EMIT_RANK, 1);
   else if (load == LOAD_GATHER && emit == EMIT_NONE && !physics) WENDY_LAUNCH(LOAD_GATHER, EMIT_NONE, 0);
 #undef WENDY_LAUNCH

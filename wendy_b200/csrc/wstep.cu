@@ -47,21 +47,6 @@ struct __align__(16) WarpSlab {
   unsigned long long mbar;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  } while (!ok);
-}
-
 // largest d in [lo0, hi0) with split[d] <= key, starting from a guess (split[lo0] is -inf)
 __device__ __noinline__ int gallop_search(const double *__restrict__ split, double key, int guess,
                                              int lo0, int hi0) {
