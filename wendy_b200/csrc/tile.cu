@@ -102,6 +102,8 @@ __global__ void __launch_bounds__(THREADS, (CAP * 48 <= 100 * 1024) ? 2 : 1)
 tile_kernel(const TileParams p) {
   using SM = TileSmem<CAP, THREADS, PERSIST>;
   static_assert(!PERSIST || (LOAD == LOAD_BUCKET && EQM), "the persistent variant stages x, v, id only");
+  // PERSIST == 2: additionally specialised for the plain case (no external force, no rank output, one GPU)
+  constexpr bool PLAIN = (PERSIST == 2);
   constexpr int E = SM::E;
   constexpr int NW = THREADS / 32;
   constexpr int BK = CAP;  // interpolation sub-buckets
@@ -510,7 +512,7 @@ tile_kernel(const TileParams p) {
       if (PHYS) {
         double acc = grav;
         if (p.omega2 >= 0.0) acc = __dsub_rn(acc, __dmul_rn(p.omega2, xk[k]));
-        if (p.aext) acc = __dadd_rn(p.aext[g[k]], acc);
+        if (!PLAIN && p.aext) acc = __dadd_rn(p.aext[g[k]], acc);
         v2[k] = __dadd_rn(v, __dmul_rn(p.dt_kick, acc));
         x2[k] = __dadd_rn(xk[k], __dmul_rn(p.dt_drift, v2[k]));
         xb[k] = (p.h_next != 0.0) ? __dadd_rn(x2[k], __dmul_rn(p.h_next, v2[k])) : x2[k];
@@ -525,7 +527,7 @@ tile_kernel(const TileParams p) {
         e_pe -= mk * xk[k] * grav;
         e_mom += mk * v;
       }
-      if (p.rank_out) p.rank_out[id[k]] = (int)(Pc + (long long)r[k]);
+      if (!PLAIN && p.rank_out) p.rank_out[id[k]] = (int)(Pc + (long long)r[k]);
       if (!EQM) m[k] = mk;
     }
   }
@@ -595,15 +597,17 @@ tile_kernel(const TileParams p) {
   bool sh_overflow = false;
   const double wdt = home_hi - home_lo;
   const double inv_w = (wdt > 0.0 && wdt < CUDART_INF) ? rcp_approx(wdt) : 0.0;
-  const double sh_lo = p.bounds ? __ldg(p.bounds + p.my_rank) : 0.0;
-  const double sh_hi = p.bounds ? __ldg(p.bounds + p.my_rank + 1) : 0.0;
+  const float inv_wf = (float)fmin(inv_w, 3.0e38);
+  const double win_lo = S.ssplit[sbase], win_hi = S.ssplit[sbase + wn];
+  const double sh_lo = (!PLAIN && p.bounds) ? __ldg(p.bounds + p.my_rank) : 0.0;
+  const double sh_hi = (!PLAIN && p.bounds) ? __ldg(p.bounds + p.my_rank + 1) : 0.0;
 #pragma unroll
   for (int k = 0; k < E; k++) {
     int d = -1;
     const bool ok = tid + k * THREADS < n;
     if (ok) {
       const double key = xb[k];
-      if (p.bounds && (key < sh_lo || key >= sh_hi)) {
+      if (!PLAIN && p.bounds && (key < sh_lo || key >= sh_hi)) {
         // sharded system: the key leaves this GPU's range -> outbox of the owning rank
         int peer = 0;
         while (peer + 1 < p.nranks && key >= __ldg(p.bounds + peer + 1)) peer++;
@@ -619,8 +623,9 @@ tile_kernel(const TileParams p) {
         d = -3;
       } else if (key >= home_lo && key < home_hi) {
         d = b;
-      } else if (key >= S.ssplit[sbase] && key < S.ssplit[sbase + wn]) {
-        int lo = rel + (int)floor(fmax(-256.0, fmin(256.0, (key - home_lo) * inv_w)));
+      } else if (key >= win_lo && key < win_hi) {
+        // guess from the home bucket's width (single precision is plenty: the loops below settle it)
+        int lo = rel + __float2int_rd(fmaxf(-256.f, fminf(256.f, (float)(key - home_lo) * inv_wf)));
         lo = max(0, min(wn - 1, lo));
 #pragma unroll 1
         while (lo > 0 && S.ssplit[sbase + lo] > key) lo--;
@@ -635,28 +640,34 @@ tile_kernel(const TileParams p) {
       }
     }
     dest[k] = d;
-    // slot allocation, aggregated per warp and destination
-    unsigned basel = 0, mask;
-    int leader;
+  }
+  // slot allocation, aggregated per warp and destination; the E requests are issued back to back and
+  // their results consumed afterwards, so the atomics' latencies overlap
+  unsigned amask[E];
+#pragma unroll
+  for (int k = 0; k < E; k++) {
+    const int d = dest[k];
+    const bool ok = tid + k * THREADS < n;
+    unsigned mask;
     const unsigned valid = __ballot_sync(WENDY_FULL_MASK, ok);
-    if (__all_sync(WENDY_FULL_MASK, d == b || !ok)) {  // whole warp stays home (the common case)
-      mask = ok ? valid : 0u;
-      leader = __ffs(valid) - 1;
-    } else {
-      mask = __match_any_sync(WENDY_FULL_MASK, d);
-      leader = __ffs(mask) - 1;
-    }
-    const bool inwin = (d >= wlo && d < wlo + wn);
-    if (ok && d >= 0 && lane == leader) {
-      if (inwin) {
-        basel = atomicAdd(&S.dcnt[d - wlo], (unsigned)__popc(mask));
+    if (__all_sync(WENDY_FULL_MASK, d == b || !ok)) mask = ok ? valid : 0u;  // whole warp stays home (common)
+    else mask = __match_any_sync(WENDY_FULL_MASK, d);
+    amask[k] = mask;
+    lpos[k] = 0;
+    if (ok && d >= 0 && lane == __ffs(mask) - 1) {
+      if (d >= wlo && d < wlo + wn) {
+        lpos[k] = atomicAdd(&S.dcnt[d - wlo], (unsigned)__popc(mask));
       } else {
-        basel = atomicAdd(&p.cnt_out[d], (unsigned)__popc(mask));
+        lpos[k] = atomicAdd(&p.cnt_out[d], (unsigned)__popc(mask));
         outside += __popc(mask);
       }
     }
-    basel = __shfl_sync(WENDY_FULL_MASK, basel, leader < 0 ? 0 : leader);
-    lpos[k] = basel + __popc(mask & lt);
+  }
+#pragma unroll
+  for (int k = 0; k < E; k++) {
+    const int leader = __ffs(amask[k]) - 1;
+    const unsigned basel = __shfl_sync(WENDY_FULL_MASK, lpos[k], leader < 0 ? 0 : leader);
+    lpos[k] = basel + __popc(amask[k] & lt);
   }
   __syncthreads();
   for (int i = tid; i < wn; i += THREADS)
@@ -736,7 +747,19 @@ static void launch_tile_cap(cudaStream_t st, int load, int emit, int physics, co
                            cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
       grid = 2 * sms;
     }
-    tile_kernel<CAP, THREADS, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, PE><<<min(grid, p.nb), THREADS, smp, st>>>(p);
+    if (!p.aext && !p.rank_out && !p.bounds) {
+      static bool set2 = false;
+      if (!set2) {
+        cudaFuncSetAttribute(tile_kernel<CAP, THREADS, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 2 * PE>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp);
+        cudaFuncSetAttribute(tile_kernel<CAP, THREADS, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 2 * PE>,
+                             cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        set2 = true;
+      }
+      tile_kernel<CAP, THREADS, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 2 * PE><<<min(grid, p.nb), THREADS, smp, st>>>(p);
+    } else {
+      tile_kernel<CAP, THREADS, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, PE><<<min(grid, p.nb), THREADS, smp, st>>>(p);
+    }
   } else if (load == LOAD_BUCKET && emit == EMIT_SPLITTER && physics) WENDY_LAUNCH(LOAD_BUCKET, EMIT_SPLITTER, 1);
   else if (load == LOAD_GATHER && emit == EMIT_RANK && physics) WENDY_LAUNCH(LOAD_GATHER, EMIT_RANK, 1);
   else if (load == LOAD_GATHER && emit == EMIT_NONE && !physics) WENDY_LAUNCH(LOAD_GATHER, EMIT_NONE, 0);
