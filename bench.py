@@ -272,11 +272,11 @@ def main():
                      'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback', 'unit': 'GB/s',
                      'frac': achieved / peak,
                      # dram__bytes_read+write per launch from the ncu --set full captures under profiles/r01
-                     # (wstep: 40.2 B/particle, CTA kernel: 40.6 B/particle), scaled to this N
-                     'traffic': (40.2 if getattr(run, 'cap', 256) == 256 else 40.6) * n if a.sort == 'gpu' else None,
+                     # (wstep: 40.2 B/particle, persistent CTA kernel: 39.9 B/particle), scaled to this N
+                     'traffic': (40.2 if getattr(run, 'cap', 256) == 256 else 39.9) * n if a.sort == 'gpu' else None,
                      'kernel': ('radix passes + tile_kernel<LOAD_GATHER>' if a.sort != 'gpu' else
                                 'wstep_kernel<256,8,EQM> (one warp per bucket)' if getattr(run, 'cap', 256) == 256 else
-                                'tile_kernel<2048,512,LOAD_BUCKET,EMIT_SPLITTER,EQM> (one CTA per bucket; layout chosen adaptively)'),
+                                'tile_kernel<2048,512,LOAD_BUCKET,EMIT_SPLITTER,EQM,PERSIST> (persistent CTAs, two per SM; next bucket prefetched by TMA)'),
                      'ms_per_launch': ms_per_launch},
         'clocks': clocks,
     }

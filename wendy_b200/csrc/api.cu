@@ -65,6 +65,7 @@ struct wendy_cuda_handle {
   bool small_ok = false;   // systems of <= 1024 particles: resident kernel while the state is dense
   bool adaptive = false;   // cap chosen by the library: 256 (warp kernel) <-> 2048 (CTA kernel)
   int want_cap = 0;        // geometry to switch to at the next layout rebuild (0: keep)
+  bool coarse_default = false;  // large equal-mass systems start (and stay) on 2048-slot buckets
   bool rebuild_pending = false;  // shard: rebuild at the start of the next sub-step (state complete)
   int user_fill = 0, user_cap = 0;
   double last_dt = 0.;
@@ -466,6 +467,14 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
     h->eqm = !(flags & WENDY_FLAG_GENERAL_MASSES) && n_diff == 0;
   }
   h->fxE = choose_fx_exponent(sum_abs);
+  // Geometry chosen by the library: the persistent CTA kernel (2048-slot buckets, next bucket prefetched by
+  // TMA) is the fastest step for large equal-mass systems at every dt measured; small
+  // systems and general masses start on 256-slot buckets (warp kernel) and switch when the window statistic
+  // says so.
+  if (h->adaptive && h->eqm && N >= (1ll << 20)) {
+    h->want_cap = 2048;
+    h->coarse_default = true;
+  }
   if (dev_inputs) {
     h->m0 = m0_dev;
     if (m) CKD(cudaMemcpy(&h->m0, m, sizeof(double), cudaMemcpyDeviceToHost));
@@ -737,7 +746,7 @@ static int enqueue_substeps(H *h, double dt, int nleap, int k0) {
     h->n_outside += outside_total(h);
     memset(h->h_flags + 8, 0, 128 * sizeof(unsigned));
     CK(cudaMemsetAsync(h->flags + 8, 0, 128 * sizeof(unsigned), h->st));  // per-call window statistic
-    if (h->adaptive && h->last_dt != 0. && dt != h->last_dt && h->cap != 256) {
+    if (h->adaptive && !h->coarse_default && h->last_dt != 0. && dt != h->last_dt && h->cap != 256) {
       h->want_cap = 256;  // a new time step: start again from the fine layout and re-measure
       h->has_split = false;
     }
