@@ -48,7 +48,7 @@ struct TileSmem {
   int sid[CAP];    // particle ids, same order
   union {
     struct {
-      unsigned cnt[PADN];        // interpolation sub-bucket counters -> start offsets
+      unsigned cnt[(PERSIST ? 2 : 1) * PADN];  // interpolation sub-bucket counters -> start offsets (PERSIST: two sets)
     } srt;
     double mcum[PADN];  // masses in sorted order -> cumulative mass below
   } u;
@@ -157,15 +157,22 @@ tile_kernel(const TileParams p) {
       S.nx_hi[0] = (b_it + 1 < s_hi) ? __ldg(p.split_in + b_it + 1) : CUDART_INF;
     }
   }
+  static_assert(SM::PADN % 4 == 0, "counters are cleared 16 bytes at a time");
+  if (PERSIST) {  // both counter sets start clean; inside the loop each is cleared while the other is in use
+    uint4 *c4 = reinterpret_cast<uint4 *>(S.u.srt.cnt);
+    for (int i = tid; i < 2 * SM::PADN / 4; i += THREADS) c4[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < DW; i += THREADS) S.dcnt[i] = 0;
+    __syncthreads();
+  }
   for (;;) {  // one bucket per iteration (a single iteration unless PERSIST)
-  if (!PERSIST && tid == 0) S.bucket = (int)atomicAdd(p.ticket, 1u);
-  {
-    static_assert(SM::PADN % 4 == 0, "counters are cleared 16 bytes at a time");
+  if (!PERSIST) {
+    if (tid == 0) S.bucket = (int)atomicAdd(p.ticket, 1u);
     uint4 *c4 = reinterpret_cast<uint4 *>(S.u.srt.cnt);
     for (int i = tid; i < SM::PADN / 4; i += THREADS) c4[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < DW; i += THREADS) S.dcnt[i] = 0;
+    __syncthreads();
   }
-  for (int i = tid; i < DW; i += THREADS) S.dcnt[i] = 0;
-  __syncthreads();
+  const int cbase = PERSIST ? cur * SM::PADN : 0;  // this bucket's counter set
   const int b = PERSIST ? b_it : S.bucket;
   const int seg = (p.nbps == p.nb) ? 0 : b / p.nbps;
   const int kb = b - seg * p.nbps;
@@ -315,7 +322,7 @@ tile_kernel(const TileParams p) {
     if (tid + k * THREADS < n) {
       int sub = (int)((xk[k] - xmin) * scale);
       sub = max(0, min(BK - 1, sub));
-      unsigned o = atomicAdd(&S.u.srt.cnt[sub + sub / E], 1u);
+      unsigned o = atomicAdd(&S.u.srt.cnt[cbase + sub + sub / E], 1u);
       pk[k] = (unsigned)sub | (o << 16);
     }
   }
@@ -342,7 +349,7 @@ tile_kernel(const TileParams p) {
   // ---- 4. exclusive scan of the sub-bucket counters ------------------------------------
   {
     unsigned c[E], run = 0;
-    unsigned *cp = &S.u.srt.cnt[tid * (E + 1)];
+    unsigned *cp = &S.u.srt.cnt[cbase + tid * (E + 1)];
 #pragma unroll
     for (int q = 0; q < E; q++) {
       c[q] = cp[q];
@@ -351,13 +358,10 @@ tile_kernel(const TileParams p) {
     unsigned inc = warp_inclusive_scan_u32(run, lane);
     if (lane == 31) S.uw[wid] = inc;
     __syncthreads();
-    if (wid == 0) {
-      unsigned t = lane < NW ? S.uw[lane] : 0u;
-      unsigned ti = warp_inclusive_scan_u32(t, lane);
-      if (lane < NW) S.uw[lane] = ti - t;
-    }
-    __syncthreads();
-    unsigned ex = inc - run + S.uw[wid];
+    // every warp scans the (<= 32) warp totals itself: cheaper than a second block-wide barrier
+    const unsigned t = lane < NW ? S.uw[lane] : 0u;
+    const unsigned ti = warp_inclusive_scan_u32(t, lane);
+    unsigned ex = inc - run + __shfl_sync(WENDY_FULL_MASK, ti - t, wid);
 #pragma unroll
     for (int q = 0; q < E; q++) {
       cp[q] = ex;
@@ -371,7 +375,7 @@ tile_kernel(const TileParams p) {
     unsigned i = tid + k * THREADS;
     if (i < n) {
       unsigned sub = pk[k] & 0xffffu;
-      unsigned pos = S.u.srt.cnt[sub + sub / E] + (pk[k] >> 16);
+      unsigned pos = S.u.srt.cnt[cbase + sub + sub / E] + (pk[k] >> 16);
       S.sx[pos] = xk[k];
       S.sid[pos] = id[k];
     }
@@ -397,8 +401,8 @@ tile_kernel(const TileParams p) {
     r[k] = 0;
     if (tid + k * THREADS < n) {
       unsigned sub = pk[k] & 0xffffu;
-      unsigned s0 = S.u.srt.cnt[sub + sub / E];
-      unsigned s1 = (sub + 1 < (unsigned)BK) ? S.u.srt.cnt[(sub + 1) + (sub + 1) / E] : n;
+      unsigned s0 = S.u.srt.cnt[cbase + sub + sub / E];
+      unsigned s1 = (sub + 1 < (unsigned)BK) ? S.u.srt.cnt[cbase + (sub + 1) + (sub + 1) / E] : n;
       unsigned rr = s0;
       if (s1 - s0 > 1u) {  // shared sub-bucket: count the members that sort before this one
         const double xi = xk[k];
@@ -676,7 +680,16 @@ tile_kernel(const TileParams p) {
     const unsigned wsum = __reduce_add_sync(WENDY_FULL_MASK, outside);
     if (lane == 0 && wsum) atomicAdd(p.outside + (b & 63), (unsigned long long)wsum);
   }
+  if (PERSIST) {
+    // prepare the next iteration in the shadow of this barrier pair: its counter set (last read during the
+    // previous bucket's ranking) is cleared, its splitter window / key range (cp.async) have landed
+    uint4 *c4 = reinterpret_cast<uint4 *>(S.u.srt.cnt + (cur ^ 1) * SM::PADN);
+    for (int i = tid; i < SM::PADN / 4; i += THREADS) c4[i] = make_uint4(0u, 0u, 0u, 0u);
+    cp_async_wait_all();
+  }
   __syncthreads();
+  if (PERSIST)  // the window counts were last read before the barrier above
+    for (int i = tid; i < DW; i += THREADS) S.dcnt[i] = 0;
   bool overflow = false;
 #pragma unroll
   for (int k = 0; k < E; k++) {
@@ -696,10 +709,9 @@ tile_kernel(const TileParams p) {
     }
   }
   if (overflow || sh_overflow) atomicMin(p.fail_seq, p.seq);
-  // no barrier needed here: what the next iteration overwrites first (counters, window counts, splitters)
-  // was last read before the two barriers of the emission
+  // no barrier needed here: everything the next iteration touches before its first barrier was prepared
+  // before the last barrier of the emission
   if (!PERSIST) break;
-  cp_async_wait_all();  // window / key range of the next bucket (visible to all after its first barrier)
   b_it = b_nx;
   n_it = n_nx;
   cur ^= 1;
