@@ -543,6 +543,32 @@ def test_adaptive_layout_switches_to_coarse_buckets_and_stays_exact():
     assert numpy.array_equal(xg, xo) and numpy.array_equal(vg, vo)
 
 
+@pytest.mark.parametrize('grid', ['1', '3'])
+@pytest.mark.parametrize('ext', [False, True])
+def test_persistent_kernel_many_buckets_per_cta(monkeypatch, grid, ext):
+    """The persistent CTA kernel walks several buckets per CTA with TMA prefetch, double-buffered counters
+    and splitter windows; a tiny grid makes every CTA iterate ~10-30 times on a small system.  Bit-exact
+    against the exact-scan oracle (plain instance and the instance with an external-force array)."""
+    import wendy_b200
+    monkeypatch.setenv('WENDY_B200_PERSIST_GRID', grid)
+    x, v, m = wo.sech2_ic(50000, seed=21)
+    kw = dict(omega=1.1)
+    if ext:
+        kw = dict(ext_force=lambda xx, t: -1.21 * xx + 0.1 * t, t0=0.5)
+    g = wendy_b200.nbody(x, v, m, 0.02, approx=True, nleap=4, _cap=2048, **kw)
+    xo, vo = x, v
+    t0 = 0.5
+    for _ in range(3):
+        xg, vg = next(g)
+        if ext:
+            xo, vo, t0, _ = wo.numpy_onestep(xo, vo, m, numpy.sum(m), 0.005, 4, -1., exact_scan=True,
+                                             ext_force=lambda xx, t: -1.21 * xx + 0.1 * t, t0=t0)
+        else:
+            xo, vo, _, _ = wo.numpy_onestep(xo, vo, m, numpy.sum(m), 0.005, 4, 1.1 ** 2., exact_scan=True)
+        assert numpy.array_equal(xg, xo) and numpy.array_equal(vg, vo)
+    g.close()
+
+
 def test_rejects_non_finite_input():
     import wendy_b200
     with pytest.raises(RuntimeError):

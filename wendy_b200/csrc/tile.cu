@@ -759,6 +759,9 @@ static void launch_tile_cap(cudaStream_t st, int load, int emit, int physics, co
                            cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
       grid = 2 * sms;
     }
+    // WENDY_B200_PERSIST_GRID=<n> shrinks the grid (tests: many buckets per CTA even for small systems)
+    int g_use = min(grid, p.nb);
+    if (const char *ge = getenv("WENDY_B200_PERSIST_GRID")) g_use = max(1, min(g_use, atoi(ge)));
     if (!p.aext && !p.rank_out && !p.bounds) {
       static bool set2 = false;
       if (!set2) {
@@ -768,9 +771,9 @@ static void launch_tile_cap(cudaStream_t st, int load, int emit, int physics, co
                              cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
         set2 = true;
       }
-      tile_kernel<CAP, THREADS, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 2 * PE><<<min(grid, p.nb), THREADS, smp, st>>>(p);
+        tile_kernel<CAP, THREADS, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 2 * PE><<<g_use, THREADS, smp, st>>>(p);
     } else {
-      tile_kernel<CAP, THREADS, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, PE><<<min(grid, p.nb), THREADS, smp, st>>>(p);
+      tile_kernel<CAP, THREADS, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, PE><<<g_use, THREADS, smp, st>>>(p);
     }
   } else if (load == LOAD_BUCKET && emit == EMIT_SPLITTER && physics) WENDY_LAUNCH(LOAD_BUCKET, EMIT_SPLITTER, 1);
   else if (load == LOAD_GATHER && emit == EMIT_RANK && physics) WENDY_LAUNCH(LOAD_GATHER, EMIT_RANK, 1);
