@@ -215,7 +215,12 @@ static int rebucket(H *h, double hkey, const double *extra = nullptr, long long 
   // target geometry (may differ from the geometry the state is currently stored in)
   const int ncap = h->want_cap ? h->want_cap : h->cap;
   const int nfill = (ncap == h->cap) ? h->fill : default_fill(h, ncap);
-  const int nnbps = (int)(((h->n_cap / h->nseg) + nfill - 1) / nfill);
+  // buckets for the particles actually present: a shard is allocated for n_cap > N particles (migrants may
+  // accumulate), but a layout sized for n_cap would run every bucket under-filled (more buckets, same
+  // per-bucket overheads).  2 % head-room; if the shard outgrows it the overflow protocol rebuilds.
+  long long n_target = h->n_cap / h->nseg;
+  if (h->bounds) n_target = std::min(n_target, (long long)((double)(h->N + n_extra) * 1.02) + 1);
+  const int nnbps = (int)((n_target + nfill - 1) / nfill);
   const int nnb = nnbps * h->nseg;
   if (alloc_radix(h, (size_t)(h->N + n_extra))) return WENDY_E_CUDA;
   if (make_keys(h, hkey, VAL_SEGMENT)) return WENDY_E_CUDA;
@@ -383,6 +388,59 @@ void wendy_cuda_destroy(wendy_cuda_handle *h) {
 
 static inline bool dev_inputs_shard(const int *ids) { return ids != nullptr; }  // shard handles carry global ids
 
+// Host -> device upload of large arrays.  Page-locked sources go straight to cudaMemcpyAsync; pageable ones
+// (what a numpy caller normally has) are staged: all host threads copy 32 MB chunks into two page-locked
+// bounce buffers while the previous chunk is in flight, which beats the driver's single-threaded staging
+// several times over on many-core hosts.
+static int upload_host_arrays(cudaStream_t st, const double *const *src, double *const *dst, int narr, size_t n,
+                              std::string &err) {
+  const size_t CH = (size_t)4 << 20;  // doubles per chunk
+  double *stage[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  bool used[2] = {false, false};
+  int rc = 0, turn = 0;
+  auto fail = [&](cudaError_t e, const char *what) { err = std::string(what) + ": " + cudaGetErrorString(e); rc = -1; };
+  for (int a = 0; a < narr && !rc; a++) {
+    if (!src[a] || !dst[a]) continue;
+    cudaPointerAttributes at;
+    const bool pinned = cudaPointerGetAttributes(&at, src[a]) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned || n < CH) {
+      cudaError_t e = cudaMemcpyAsync(dst[a], src[a], n * sizeof(double), cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) fail(e, "cudaMemcpyAsync");
+      continue;
+    }
+    for (size_t off = 0; off < n && !rc; off += CH) {
+      const size_t len = std::min(CH, n - off);
+      const int bsel = turn & 1;
+      turn++;
+      if (!stage[bsel]) {
+        cudaError_t e = cudaMallocHost(&stage[bsel], CH * sizeof(double));
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev[bsel], cudaEventDisableTiming);
+        if (e != cudaSuccess) { fail(e, "cudaMallocHost"); break; }
+      }
+      if (used[bsel]) cudaEventSynchronize(ev[bsel]);  // the copy that last read this bounce buffer
+      const double *sp = src[a] + off;
+      double *bp = stage[bsel];
+#pragma omp parallel for schedule(static)
+      for (long long blk = 0; blk < (long long)((len + 65535) / 65536); blk++) {
+        const size_t b0 = (size_t)blk * 65536, bl = std::min((size_t)65536, len - b0);
+        memcpy(bp + b0, sp + b0, bl * sizeof(double));
+      }
+      cudaError_t e = cudaMemcpyAsync(dst[a] + off, bp, len * sizeof(double), cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess) e = cudaEventRecord(ev[bsel], st);
+      if (e != cudaSuccess) { fail(e, "cudaMemcpyAsync"); break; }
+      used[bsel] = true;
+    }
+  }
+  for (int i = 0; i < 2; i++) {
+    if (used[i]) cudaEventSynchronize(ev[i]);
+    if (ev[i]) cudaEventDestroy(ev[i]);
+    if (stage[i]) cudaFreeHost(stage[i]);
+  }
+  return rc;
+}
+
 // dev_inputs: x, v (and m unless null: then all masses equal m0_dev) are DEVICE arrays
 static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, const double *x, const double *v,
                        const double *m, const int *ids, const double *totmass, double omega2, int n_segments,
@@ -532,10 +590,16 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
   CKD(cudaMallocHost(&h->h_eout, 4 * sizeof(double)));
   memset(h->h_flags, 0, 136 * sizeof(unsigned));
   CKD(cudaMemsetAsync(h->status, 0, (size_t)h->nb * sizeof(unsigned), h->st));
-  const cudaMemcpyKind kind = dev_inputs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  CKD(cudaMemcpyAsync(h->x[0], x, (size_t)N * sizeof(double), kind, h->st));
-  CKD(cudaMemcpyAsync(h->v[0], v, (size_t)N * sizeof(double), kind, h->st));
-  if (!h->eqm) CKD(cudaMemcpyAsync(h->m[0], m, (size_t)N * sizeof(double), kind, h->st));
+  if (dev_inputs) {
+    CKD(cudaMemcpyAsync(h->x[0], x, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    CKD(cudaMemcpyAsync(h->v[0], v, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    if (!h->eqm) CKD(cudaMemcpyAsync(h->m[0], m, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+  } else {
+    const double *src[3] = {x, v, h->eqm ? nullptr : m};
+    double *dst[3] = {h->x[0], h->v[0], h->eqm ? nullptr : h->m[0]};
+    std::string uerr;
+    if (upload_host_arrays(h->st, src, dst, 3, (size_t)N, uerr)) { wendy_cuda_destroy(h); return set_err(WENDY_E_CUDA, uerr); }
+  }
   CKD(cudaMemcpyAsync(h->tot, totmass, (size_t)n_segments * sizeof(double), cudaMemcpyHostToDevice, h->st));
   if (ids) CKD(cudaMemcpyAsync(h->id[0], ids, (size_t)N * sizeof(int), cudaMemcpyDefault, h->st));
   else launch_iota(h->st, h->id[0], N);

@@ -228,24 +228,46 @@ def _nbody_approx(x, v, m, dt, nleap, t0=0., omega=None, ext_force=None, sort='g
                   twopiG=1., full_output=False, n_segments=1, _cap=0, _fill=0, _general_masses=False):
     """Setup follows reference wendy/wendy.py:363-387,422; loop follows :424-437."""
     omega2 = -1. if omega is None else omega ** 2.
-    x = numpy.require(numpy.array(x, dtype=numpy.float64), requirements=['C', 'W'])
-    v = numpy.require(numpy.array(v, dtype=numpy.float64), requirements=['C', 'W'])
+    # The inputs are only read (the reference copies them, wendy/wendy.py:369-370; here the "copy" is the
+    # upload); the arrays that are yielded -- the same two every time, as in the reference -- are separate
+    # page-locked buffers, so that the per-output D2H copy runs at full PCIe speed.
+    xin = numpy.ascontiguousarray(x, dtype=numpy.float64)
+    vin = numpy.ascontiguousarray(v, dtype=numpy.float64)
     # masses are only read by the library: scale (reference wendy/wendy.py:371) but do not copy needlessly
     ms = numpy.ascontiguousarray(m, dtype=numpy.float64)
     if twopiG != 1.:
         ms = twopiG * ms
-    # the yielded buffers are re-used for every D2H copy: page-lock them (best effort)
+    n = xin.shape[0]
+    out = {}
     lib = _lib.load()
-    pinned = [a for a in (x, v) if a.nbytes >= (1 << 20) and lib.wendy_cuda_pin(a.ctypes.data, a.nbytes) == 0]
+
+    def alloc_outputs():
+        # page-locking 16 bytes/particle takes a few hundred ms at N=1e8: done on a helper thread while
+        # the main thread validates, uploads and builds the first layout
+        # (cudaHostRegister of untouched numpy memory: faster than cudaHostAlloc, and the arrays stay valid
+        # ordinary memory after the generator has been closed and the registration dropped)
+        out['x'], out['v'] = numpy.empty(n), numpy.empty(n)
+        if n * 8 >= (1 << 20):
+            out['pinned'] = [a for a in (out['x'], out['v']) if lib.wendy_cuda_pin(a.ctypes.data, a.nbytes) == 0]
+
+    import threading
+    helper = threading.Thread(target=alloc_outputs)
+    helper.start()
     state = None
     dt_leap = dt / nleap
     try:
-        state = ApproxState(x, v, ms, omega2=omega2, n_segments=n_segments, sort=sort, cap=_cap,
-                            fill=_fill, general_masses=_general_masses)
+        try:
+            state = ApproxState(xin, vin, ms, omega2=omega2, n_segments=n_segments, sort=sort, cap=_cap,
+                                fill=_fill, general_masses=_general_masses)
+            if ext_force is None:
+                state.step_begin(dt_leap, nleap)
+        finally:
+            helper.join()
+        x, v = out['x'], out['v']
+        del xin, vin
         if ext_force is None:
             # The generator is infinite (reference wendy/wendy.py:424), so the call after this
             # one is always needed: enqueue it before the D2H copy of this one has finished.
-            state.step_begin(dt_leap, nleap)
             while True:
                 state.step_end()
                 te = state.time_elapsed
@@ -266,7 +288,7 @@ def _nbody_approx(x, v, m, dt, nleap, t0=0., omega=None, ext_force=None, sort='g
     finally:
         if state is not None:
             state.close()
-        for a in pinned:
+        for a in out.get('pinned', []):
             lib.wendy_cuda_unpin(a.ctypes.data)
 
 
