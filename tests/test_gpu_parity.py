@@ -525,6 +525,28 @@ def test_overflow_recovery_by_rebalancing():
     assert numpy.array_equal(xg, xo) and numpy.array_equal(vg, vo)
 
 
+def test_optimistic_fill_backs_off_after_an_overflow():
+    """Large equal-mass systems start on 2048-slot buckets filled to 13/16; the first overflow (here: a
+    collapsing cold slab) moves the handle back to 3/4 for good.  Results equal the radix path bit for bit."""
+    import wendy_b200
+    n = 1 << 20
+    x, v, m = wo.slab_ic(n, seed=8)
+    a = wendy_b200.ApproxState(x, v, m)
+    b = wendy_b200.ApproxState(x, v, m, sort='gpu-radix')
+    a.step(0.001, 2)
+    b.step(0.001, 2)
+    s0 = a.stats()
+    assert s0['cap'] == 2048 and s0['buckets'] == -(-n // 1664), s0
+    for _ in range(6):
+        a.step(0.05, 5)
+        b.step(0.05, 5)
+    s1 = a.stats()
+    xa, va = a.read(); xb, vb = b.read()
+    a.close(); b.close()
+    assert s1['failed_substeps'] > 0 and s1['buckets'] == -(-n // 1536), s1
+    assert numpy.array_equal(xa, xb) and numpy.array_equal(va, vb)
+
+
 def test_adaptive_layout_switches_to_coarse_buckets_and_stays_exact():
     """With a large N*dt most particles leave the 32-bucket window of the warp kernel; the library
     then rebuilds the layout with 2048-slot buckets (CTA kernel).  Results must not change."""

@@ -66,6 +66,7 @@ struct wendy_cuda_handle {
   bool adaptive = false;   // cap chosen by the library: 256 (warp kernel) <-> 2048 (CTA kernel)
   int want_cap = 0;        // geometry to switch to at the next layout rebuild (0: keep)
   bool coarse_default = false;  // large equal-mass systems start (and stay) on 2048-slot buckets
+  bool fill_backoff = false;    // a library-chosen coarse layout overflowed at the optimistic fill: use 3/4 from now on
   bool rebuild_pending = false;  // shard: rebuild at the start of the next sub-step (state complete)
   int user_fill = 0, user_cap = 0;
   double last_dt = 0.;
@@ -203,9 +204,27 @@ static bool advect_allowed() {
   return !(e && e[0] == '0');
 }
 
+// Target particles per bucket.  Coarse buckets chosen by the library are filled to 13/16 (1664 of 2048 slots:
+// per-bucket overheads amortise over more particles, +2 % at N=1e8); the head-room is then 6.7 sigma of the
+// steady-state count noise (sqrt(2*fill)) instead of 9, so the first overflow or
+// nearly-full bucket of a handle -- a system whose density evolves -- moves it back to 3/4 for good.
+#ifndef WENDY_COARSE_FILL_16THS
+#define WENDY_COARSE_FILL_16THS 13
+#endif
 static int default_fill(const H *h, int cap) {
   if (h->user_fill > 0 && cap == h->user_cap) return h->user_fill;
-  return cap == 256 ? 128 : cap * 3 / 4;
+  if (cap == 256) return 128;
+  // (shards keep 3/4: their edge buckets also take the migrants of the neighbouring ranks)
+  return (h->adaptive && !h->fill_backoff && !h->bounds) ? cap * WENDY_COARSE_FILL_16THS / 16 : cap * 3 / 4;
+}
+
+// called when a bucket of the current layout overflowed or came close: give up the optimistic fill
+static void fill_back_off(H *h) {
+  if (h->adaptive && !h->fill_backoff && h->cap != 256 && h->fill > h->cap * 3 / 4 &&
+      !(h->user_fill > 0 && h->cap == h->user_cap)) {
+    h->fill_backoff = true;
+    h->fill = h->cap * 3 / 4;
+  }
 }
 
 // (Re)build the bucket layout for key = x + hkey*v: exact quantile splitters from a radix
@@ -452,7 +471,7 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
   if (n_segments < 1 || N % n_segments) return set_err(WENDY_E_ARG, "N must be a multiple of n_segments");
   const bool adaptive = (cap == 0);
   if (cap == 0) cap = 256;
-  if (!tile_cap_supported(cap)) return set_err(WENDY_E_ARG, "cap must be 2048 or 256");
+  if (!tile_cap_supported(cap)) return set_err(WENDY_E_ARG, "cap must be 2048 or 256");  // (2048: tile_coarse_cap())
   // Splitters are exact quantiles of ONE random sample, so bucket widths carry their own
   // 1/sqrt(fill) noise and the steady-state count variance is 2*fill (measured: DESIGN.md).
   // Defaults leave >= 8 sigma of head-room: 128 + 8*sqrt(256) = 256, 1536 + 9*sqrt(3072) < 2048.
@@ -530,7 +549,7 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
   // systems and general masses start on 256-slot buckets (warp kernel) and switch when the window statistic
   // says so.
   if (h->adaptive && h->eqm && N >= (1ll << 20)) {
-    h->want_cap = 2048;
+    h->want_cap = tile_coarse_cap();
     h->coarse_default = true;
   }
   if (dev_inputs) {
@@ -703,7 +722,7 @@ int wendy_cuda_shard_substep(wendy_cuda_handle *h, double h_pre, double dt_kick,
       if (h->adaptive && h->cap == 256 && (double)outside_total(h) > 0.5 * (double)h->N) {
         // switch to coarse buckets, but only once the incoming migrants have been injected: a
         // layout built now would see a boundary region depleted of the particles in flight
-        h->want_cap = 2048;
+        h->want_cap = tile_coarse_cap();
         h->rebuild_pending = true;
       }
       h->n_outside += outside_total(h);
@@ -712,6 +731,7 @@ int wendy_cuda_shard_substep(wendy_cuda_handle *h, double h_pre, double dt_kick,
       return 0;
     }
     h->n_fail++; h->n_sub--;
+    fill_back_off(h);
     h->advect_on = advect_allowed();
     h->cur = cur0; h->ccur = ccur0; h->has_split = false;
     if (reset_flags(h)) return WENDY_E_CUDA;
@@ -853,6 +873,7 @@ static int finish_substeps(H *h) {
       if (h->p_seq[i] == f) kf = h->p_k0 + (int)i;
     if (kf < 0) return set_err(WENDY_E_CUDA, "internal: unknown failing launch");
     h->n_fail++;
+    fill_back_off(h);
     if (h->nseg == 1 && advect_allowed()) h->advect_on = true;  // bucket edges could not keep up with the flow: let them move with it
     h->n_sub -= (nleap - kf);
     h->cur = h->p_cur[kf - h->p_k0];
@@ -888,7 +909,7 @@ static int finish_substeps(H *h) {
   if (h->adaptive && h->cap == 256 && !h->dense) {
     const double moved = (double)outside_total(h);
     if (moved > 0.5 * (double)h->N * (double)nleap) {
-      h->want_cap = 2048;
+      h->want_cap = tile_coarse_cap();
       int rc = rebucket(h, h->bucket_h);
       if (rc) return rc;
       return 0;
@@ -896,6 +917,7 @@ static int finish_substeps(H *h) {
   }
   // cheap insurance: re-balance between calls when some bucket is nearly full
   if (h->mode != WENDY_SORT_RADIX && h->h_flags[1] > (unsigned)(h->cap - (h->cap - h->fill) / 16)) {
+    fill_back_off(h);
     int rc = rebucket(h, h->bucket_h);
     if (rc) return rc;
   }
@@ -974,6 +996,7 @@ int wendy_cuda_substep(wendy_cuda_handle *h, double dt_kick, double dt_drift, do
   if (fetch_flags(h)) return WENDY_E_CUDA;
   if (h->h_flags[0] != 0xffffffffu) {
     h->n_fail++; h->n_sub--;
+    fill_back_off(h);
     h->cur = cur0; h->ccur = ccur0;
     if (reset_flags(h)) return WENDY_E_CUDA;
     int rc = rebucket(h, 0.);
@@ -982,6 +1005,7 @@ int wendy_cuda_substep(wendy_cuda_handle *h, double dt_kick, double dt_drift, do
   }
   if (h->h_flags[1] > (unsigned)(h->cap - (h->cap - h->fill) / 16)) {
     // nearly full bucket: re-balance now; the caller's next force_positions sees the new slots
+    fill_back_off(h);
     int rc = rebucket(h, h_next);
     if (rc) return rc;
   }

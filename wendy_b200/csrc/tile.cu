@@ -23,6 +23,8 @@
 // reference's association order (no FMA contraction): SURVEY.md H2.
 #include <math_constants.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "internal.h"
 #include "lookback.cuh"
@@ -31,6 +33,13 @@ namespace wendy {
 
 #ifndef TK_DW
 #define TK_DW 256
+#endif
+// Tunables kept as macros for A/B builds (scripts/ab_variants.py; measured values in DESIGN.md section 3.0)
+#ifndef TK_RANK_STRAIGHT
+#define TK_RANK_STRAIGHT 4  // members of a shared sub-bucket compared by straight-line code before a loop takes over
+#endif
+#ifndef TK_COARSE_CAP
+#define TK_COARSE_CAP 2048  // slots per bucket of the CTA kernel (E = 4 particles per thread: 512 threads at 2048)
 #endif
 constexpr int DW = TK_DW;  // destination buckets tracked with shared-memory counters
 
@@ -98,7 +107,7 @@ __device__ __forceinline__ int gallop_search_tile(const double *__restrict__ spl
 // blockIdx.x, blockIdx.x + gridDim.x, ... and the (x, v, id) of its NEXT bucket arrive by TMA bulk copy
 // (cp.async.bulk + mbarrier) while the current bucket is ranked, kicked and emitted.
 template <int CAP, int THREADS, int LOAD, int EMIT, int PHYS, int EQM, int PERSIST = 0>
-__global__ void __launch_bounds__(THREADS, (CAP * 48 <= 100 * 1024) ? 2 : 1)
+__global__ void __launch_bounds__(THREADS, (CAP * 48 <= 50 * 1024) ? 4 : (CAP * 48 <= 74 * 1024) ? 3 : (CAP * 48 <= 100 * 1024) ? 2 : 1)
 tile_kernel(const TileParams p) {
   using SM = TileSmem<CAP, THREADS, PERSIST>;
   static_assert(!PERSIST || (LOAD == LOAD_BUCKET && EQM), "the persistent variant stages x, v, id only");
@@ -143,7 +152,6 @@ tile_kernel(const TileParams p) {
   unsigned n_it = 0;
   int cur = 0;            // PERSIST: which half of ssplit / nx_* belongs to the current bucket
   if (PERSIST) {
-    static_assert(!PERSIST || THREADS >= DW + 1, "one thread per window splitter");
     n_it = p.cnt_in[b_it];
     if (tid == 0) {
       mbar_init(bar, 1);
@@ -151,7 +159,7 @@ tile_kernel(const TileParams p) {
     }
     int w_lo, w_n, s_hi;
     window_of(b_it, w_lo, w_n, s_hi);
-    if (tid <= w_n) S.ssplit[tid] = (w_lo + tid < s_hi) ? p.split[w_lo + tid] : CUDART_INF;
+    for (int i = tid; i <= w_n; i += THREADS) S.ssplit[i] = (w_lo + i < s_hi) ? p.split[w_lo + i] : CUDART_INF;
     if (tid == 0) {
       S.nx_lo[0] = __ldg(p.split_in + b_it);
       S.nx_hi[0] = (b_it + 1 < s_hi) ? __ldg(p.split_in + b_it + 1) : CUDART_INF;
@@ -335,9 +343,12 @@ tile_kernel(const TileParams p) {
     int w_lo, w_n, s_hi;
     window_of(b_nx, w_lo, w_n, s_hi);
     const int nb_ = (cur ^ 1) * (DW + 2);
-    if (tid <= w_n) {
-      if (w_lo + tid < s_hi) cp_async_8(&S.ssplit[nb_ + tid], p.split + w_lo + tid);
-      else S.ssplit[nb_ + tid] = CUDART_INF;
+#pragma unroll
+    for (int i = tid; i <= DW; i += THREADS) {
+      if (i <= w_n) {
+        if (w_lo + i < s_hi) cp_async_8(&S.ssplit[nb_ + i], p.split + w_lo + i);
+        else S.ssplit[nb_ + i] = CUDART_INF;
+      }
     }
     if (tid == THREADS - 1) {
       cp_async_8(&S.nx_lo[cur ^ 1], p.split_in + b_nx);
@@ -396,30 +407,49 @@ tile_kernel(const TileParams p) {
       if (tid + k * THREADS < n) m[k] = p.min[g[k]];
     }
   }
+  // The sub-bucket bounds of all E particles are fetched first (independent shared-memory loads in flight
+  // together); sub-buckets hold 1.75 members on average, so the first TK_RANK_STRAIGHT members are compared
+  // by predicated straight-line code and a loop only runs for crowded sub-buckets.
 #pragma unroll
   for (int k = 0; k < E; k++) {
     r[k] = 0;
     if (tid + k * THREADS < n) {
-      unsigned sub = pk[k] & 0xffffu;
-      unsigned s0 = S.u.srt.cnt[cbase + sub + sub / E];
-      unsigned s1 = (sub + 1 < (unsigned)BK) ? S.u.srt.cnt[cbase + (sub + 1) + (sub + 1) / E] : n;
-      unsigned rr = s0;
-      if (s1 - s0 > 1u) {  // shared sub-bucket: count the members that sort before this one
-        const double xi = xk[k];
-        const int ii = id[k];
-        unsigned eq = 0;
+      const unsigned sub = pk[k] & 0xffffu;
+      const unsigned s0 = S.u.srt.cnt[cbase + sub + sub / E];
+      const unsigned s1 = (sub + 1 < (unsigned)BK) ? S.u.srt.cnt[cbase + (sub + 1) + (sub + 1) / E] : n;
+      r[k] = s0;
+      pk[k] = s1 - s0;  // the sub-bucket index is not needed any more
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < E; k++) {
+    if (tid + k * THREADS < n && pk[k] > 1u) {  // shared sub-bucket: count the members that sort before this one
+      const unsigned s0 = r[k], c = pk[k];
+      const double xi = xk[k];
+      unsigned rr = s0, eq = 0;
+#pragma unroll
+      for (unsigned j = 0; j < (unsigned)TK_RANK_STRAIGHT; j++) {
+        if (j < c) {
+          const double xj = S.sx[s0 + j];
+          rr += (xj < xi) ? 1u : 0u;
+          eq += (xj == xi) ? 1u : 0u;
+        }
+      }
+      if (c > (unsigned)TK_RANK_STRAIGHT) {
 #pragma unroll 1
-        for (unsigned q = s0; q < s1; q++) {
+        for (unsigned q = s0 + TK_RANK_STRAIGHT; q < s0 + c; q++) {
           const double xj = S.sx[q];
           rr += (xj < xi) ? 1u : 0u;
           eq += (xj == xi) ? 1u : 0u;
         }
-        // every particle ties with itself once; anything beyond that is an exact coincidence,
-        // ordered by particle index in a second (rare) pass
-        if (eq > 1u) {
-          for (unsigned q = s0; q < s1; q++) {
-            if (S.sx[q] == xi) rr += (S.sid[q] < ii) ? 1u : 0u;
-          }
+      }
+      // every particle ties with itself once; anything beyond that is an exact coincidence,
+      // ordered by particle index in a second (rare) pass
+      if (eq > 1u) {
+        const int ii = id[k];
+#pragma unroll 1
+        for (unsigned q = s0; q < s0 + c; q++) {
+          if (S.sx[q] == xi) rr += (S.sid[q] < ii) ? 1u : 0u;
         }
       }
       r[k] = rr;
@@ -499,6 +529,36 @@ tile_kernel(const TileParams p) {
   const double PcD = (double)(Pc + p.pc_offset);  // pc_offset: particles of the lower ranks (sharded)
   double x2[E], v2[E], xb[E];
   double e_ke = 0.0, e_he = 0.0, e_pe = 0.0, e_mom = 0.0;
+  if (PLAIN) {
+    // Plain instance: unguarded straight-line arithmetic.  Per-particle `if (i < n)` blocks compile to separate
+    // branched regions, i.e. E dependent chains of eleven fp64 operations one after the other; without the
+    // guards the chains interleave (slots beyond n compute on zeros; nothing of theirs is ever stored).  The
+    // last round, which most warps of a bucket filled to about 3/4 do not have, sits behind a warp-uniform branch.
+    auto phys_rounds = [&](auto k0c, auto k1c) {
+      constexpr int k0 = decltype(k0c)::value, k1 = decltype(k1c)::value;
+      double acc[E];
+#pragma unroll
+      for (int k = k0; k < k1; k++) {
+        const double c = __dmul_rn(__dadd_rn(PcD, (double)r[k]), p.m0);  // exact integer sum below 2^53
+        acc[k] = __dsub_rn(__dsub_rn(tot, __dmul_rn(2.0, c)), p.m0);
+      }
+#pragma unroll
+      for (int k = k0; k < k1; k++)
+        if (p.omega2 >= 0.0) acc[k] = __dsub_rn(acc[k], __dmul_rn(p.omega2, xk[k]));
+#pragma unroll
+      for (int k = k0; k < k1; k++) {
+        v2[k] = __dadd_rn(vreg[k], __dmul_rn(p.dt_kick, acc[k]));
+        x2[k] = __dadd_rn(xk[k], __dmul_rn(p.dt_drift, v2[k]));
+      }
+#pragma unroll
+      for (int k = k0; k < k1; k++)
+        xb[k] = (p.h_next != 0.0) ? __dadd_rn(x2[k], __dmul_rn(p.h_next, v2[k])) : x2[k];
+    };
+    phys_rounds(std::integral_constant<int, 0>(), std::integral_constant<int, E - 1>());
+    x2[E - 1] = v2[E - 1] = xb[E - 1] = 0.0;
+    if ((unsigned)((E - 1) * THREADS + (tid & ~31)) < n)
+      phys_rounds(std::integral_constant<int, E - 1>(), std::integral_constant<int, E>());
+  } else
 #pragma unroll
   for (int k = 0; k < E; k++) {
     x2[k] = v2[k] = xb[k] = 0.0;
@@ -630,11 +690,23 @@ tile_kernel(const TileParams p) {
       } else if (key >= win_lo && key < win_hi) {
         // guess from the home bucket's width (single precision is plenty: the loops below settle it)
         int lo = rel + __float2int_rd(fmaxf(-256.f, fminf(256.f, (float)(key - home_lo) * inv_wf)));
-        lo = max(0, min(wn - 1, lo));
+        // The guess is nearly always within one bucket of the answer: fetch the four splitters around it
+        // (independent loads), correct by at most one, and verify; the search loops only run if that fails.
+        bool settled = false;
+        if (wn >= 3) {
+          lo = max(1, min(wn - 2, lo));
+          const double *sp = &S.ssplit[sbase + lo];
+          const double sm1 = sp[-1], s0 = sp[0], s1 = sp[1], s2 = sp[2];
+          lo += (key >= s1 ? 1 : 0) - (key < s0 ? 1 : 0);
+          settled = (key >= sm1) && (key < s2);
+        }
+        if (!settled) {
+          lo = max(0, min(wn - 1, lo));
 #pragma unroll 1
-        while (lo > 0 && S.ssplit[sbase + lo] > key) lo--;
+          while (lo > 0 && S.ssplit[sbase + lo] > key) lo--;
 #pragma unroll 1
-        while (lo < wn - 1 && S.ssplit[sbase + lo + 1] <= key) lo++;
+          while (lo < wn - 1 && S.ssplit[sbase + lo + 1] <= key) lo++;
+        }
         d = wlo + lo;
       } else {  // far move (split[seg_lo] is -inf)
         // interpolated guess from the home bucket's width, then a galloping search around it
@@ -743,9 +815,9 @@ static void launch_tile_cap(cudaStream_t st, int load, int emit, int physics, co
     }                                                                                               \
     tile_kernel<CAP, THREADS, L, EM, PH, EQM><<<p.nb, THREADS, sm, st>>>(p);                        \
   } while (0)
-  if (load == LOAD_BUCKET && emit == EMIT_SPLITTER && physics && EQM && CAP == 2048 && persist_allowed()) {
-    // persistent CTAs, two per SM, next bucket prefetched by TMA
-    constexpr int PE = (EQM && CAP == 2048) ? 1 : 0;  // (keeps the other instantiations out of the binary)
+  if (load == LOAD_BUCKET && emit == EMIT_SPLITTER && physics && EQM && CAP >= 1024 && persist_allowed()) {
+    // persistent CTAs (as many as fit an SM: two at 2048 slots), next bucket prefetched by TMA
+    constexpr int PE = (EQM && CAP >= 1024) ? 1 : 0;  // (keeps the other instantiations out of the binary)
     constexpr int PQ = PE ? EQM : 1;
     static int grid = 0;
     const size_t smp = sizeof(TileSmem<CAP, THREADS, PE>);
@@ -757,7 +829,10 @@ static void launch_tile_cap(cudaStream_t st, int load, int emit, int physics, co
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp);
       cudaFuncSetAttribute(tile_kernel<CAP, THREADS, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, PE>,
                            cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-      grid = 2 * sms;
+      int per_sm = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &per_sm, tile_kernel<CAP, THREADS, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, PE>, THREADS, smp);
+      grid = max(1, per_sm) * sms;
     }
     // WENDY_B200_PERSIST_GRID=<n> shrinks the grid (tests: many buckets per CTA even for small systems)
     int g_use = min(grid, p.nb);
@@ -781,13 +856,14 @@ static void launch_tile_cap(cudaStream_t st, int load, int emit, int physics, co
 #undef WENDY_LAUNCH
 }
 
-bool tile_cap_supported(int cap) { return cap == 2048 || cap == 256; }
+bool tile_cap_supported(int cap) { return cap == TK_COARSE_CAP || cap == 256; }
+int tile_coarse_cap() { return TK_COARSE_CAP; }
 
 void launch_tile(cudaStream_t st, int cap, int load, int emit, int physics, const TileParams &p) {
   if (p.nb <= 0) return;
-  if (cap == 2048) {
-    if (p.eqm) launch_tile_cap<2048, 512, 1>(st, load, emit, physics, p);
-    else launch_tile_cap<2048, 512, 0>(st, load, emit, physics, p);
+  if (cap == TK_COARSE_CAP) {
+    if (p.eqm) launch_tile_cap<TK_COARSE_CAP, TK_COARSE_CAP / 4, 1>(st, load, emit, physics, p);
+    else launch_tile_cap<TK_COARSE_CAP, TK_COARSE_CAP / 4, 0>(st, load, emit, physics, p);
   } else {
     if (p.eqm) launch_tile_cap<256, 64, 1>(st, load, emit, physics, p);
     else launch_tile_cap<256, 64, 0>(st, load, emit, physics, p);
