@@ -161,6 +161,11 @@ int wendy_cuda_energy_individual(const double *x, const double *v, const double 
 
 /* Page-lock (cudaHostRegister) / release a HOST buffer the caller passes repeatedly to
  * wendy_cuda_read, so the per-yield D2H copy runs at full PCIe speed.  Optional. */
+/* Device blocks of >= 32 MB released by wendy_cuda_destroy are cached for the next handle of the same size
+ * (cudaMalloc of the multi-GB state is a visible part of the set-up time; bounded by WENDY_B200_ALLOC_CACHE_GB,
+ * default 48, 0 = off; emptied automatically when an allocation fails).  wendy_cuda_trim returns them to the
+ * driver.  No reference counterpart: the reference keeps its state in numpy arrays (wendy/wendy.py:369-387). */
+void wendy_cuda_trim(void);
 int wendy_cuda_pin(void *host_ptr, unsigned long long bytes);
 int wendy_cuda_unpin(void *host_ptr);
 

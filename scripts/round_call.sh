@@ -35,6 +35,9 @@ timeout 240 compute-sanitizer --tool memcheck python scripts/sanitize_small.py >
 echo "memcheck exit $? $(tail -2 $O/memcheck.log | head -1)"
 timeout 120 python scripts/e2e_phases.py > $O/e2e_phases.log 2>&1
 cat $O/e2e_phases.log
+WENDY_B200_TRACE=1 timeout 120 python scripts/e2e_phases.py > $O/e2e_phases_trace.log 2>&1
+WENDY_B200_PIN_CHUNK_MB=65536 WENDY_B200_TRACE=1 timeout 120 python scripts/e2e_phases.py > $O/e2e_phases_trace_unchunked.log 2>&1
+grep "generator" $O/e2e_phases_trace.log $O/e2e_phases_trace_unchunked.log
 # A/B of whatever variant builds are present (never installed here: the stages above test the default build)
 cp wendy_b200/libwendy_b200.so wendy_b200/variants/lib_base.so
 VARS="wendy_b200/variants/lib_base.so"

@@ -6,12 +6,15 @@
 // with the leading half drift folded into the first sub-step's key computation (h_pre) and
 // the de-sort deferred to wendy_cuda_read().
 #include <math.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 #include <chrono>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -123,6 +126,148 @@ struct wendy_cuda_handle {
 };
 typedef wendy_cuda_handle H;
 
+// ---- device block cache -----------------------------------------------------------------------------------
+// cudaMalloc / cudaFree of the multi-GB state arrays cost 30-100 ms per GB on this platform (measured:
+// profiles/r01/e2e_phases_N1e8.txt), which dominates the set-up of a generator.  Blocks of >= 32 MB released
+// by wendy_cuda_destroy are therefore kept and handed to the next handle that asks for exactly the same size
+// on the same device (a new generator over the same N: the usual notebook pattern).  The cache is bounded
+// (WENDY_B200_ALLOC_CACHE_GB, default 48; 0 disables it), emptied when a cudaMalloc fails, and can be
+// emptied by the caller with wendy_cuda_trim().
+namespace {
+struct BlockCache {
+  std::mutex mu;
+  std::multimap<std::pair<int, size_t>, void *> idle;
+  std::map<void *, std::pair<int, size_t>> live;
+  size_t idle_bytes = 0;
+};
+BlockCache g_blocks;
+constexpr size_t kCacheMinBlock = (size_t)32 << 20;
+size_t cache_limit_bytes() {
+  static long long v = -1;
+  if (v < 0) {
+    const char *e = getenv("WENDY_B200_ALLOC_CACHE_GB");
+    v = (long long)((e ? atof(e) : 48.) * 1073741824.);
+    if (v < 0) v = 0;
+  }
+  return (size_t)v;
+}
+void cache_trim() {
+  std::vector<void *> drop;
+  {
+    std::lock_guard<std::mutex> lk(g_blocks.mu);
+    for (auto &kv : g_blocks.idle) drop.push_back(kv.second);
+    g_blocks.idle.clear();
+    g_blocks.idle_bytes = 0;
+  }
+  for (void *q : drop) cudaFree(q);
+}
+cudaError_t dev_alloc_bytes(void **out, size_t bytes) {
+  *out = nullptr;
+  const bool big = bytes >= kCacheMinBlock && cache_limit_bytes() > 0;
+  int dev = 0;
+  if (big) {
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_blocks.mu);
+    auto it = g_blocks.idle.find(std::make_pair(dev, bytes));
+    if (it != g_blocks.idle.end()) {
+      *out = it->second;
+      g_blocks.idle.erase(it);
+      g_blocks.idle_bytes -= bytes;
+      g_blocks.live[*out] = std::make_pair(dev, bytes);
+      return cudaSuccess;
+    }
+  }
+  cudaError_t e = cudaMalloc(out, bytes);
+  if (e != cudaSuccess) {  // give the idle blocks back to the driver and try once more
+    cudaGetLastError();
+    cache_trim();
+    e = cudaMalloc(out, bytes);
+  }
+  if (e == cudaSuccess && big) {
+    std::lock_guard<std::mutex> lk(g_blocks.mu);
+    g_blocks.live[*out] = std::make_pair(dev, bytes);
+  }
+  return e;
+}
+}  // namespace
+
+template <class T>
+static cudaError_t dev_alloc(T **out, size_t bytes) {
+  return dev_alloc_bytes(reinterpret_cast<void **>(out), bytes);
+}
+// the caller guarantees that no work using the block is still in flight (wendy_cuda_destroy synchronises)
+static void dev_free(void *q) {
+  if (!q) return;
+  {
+    std::lock_guard<std::mutex> lk(g_blocks.mu);
+    auto it = g_blocks.live.find(q);
+    if (it != g_blocks.live.end()) {
+      const std::pair<int, size_t> key = it->second;
+      g_blocks.live.erase(it);
+      if (g_blocks.idle_bytes + key.second <= cache_limit_bytes()) {
+        g_blocks.idle.insert(std::make_pair(key, q));
+        g_blocks.idle_bytes += key.second;
+        return;
+      }
+    }
+  }
+  cudaFree(q);
+}
+
+void wendy_cuda_trim(void) { cache_trim(); }
+
+// ---- page-locked host ranges ------------------------------------------------------------------------------
+// cudaHostRegister of a GB-sized range holds a driver lock for hundreds of milliseconds, during which every
+// other CUDA call of the process waits (measured: the allocations of a handle being created on another thread
+// took 495 ms instead of 90).  wendy_cuda_pin therefore registers a range piecewise, in chunks that end on
+// absolute 16 MB address boundaries, and every large host<->device copy of this library is split at the same
+// boundaries, so that each piece lies inside one registration and runs as a page-locked copy.
+namespace {
+uintptr_t pin_chunk() {  // WENDY_B200_PIN_CHUNK_MB overrides the piece size (A/B runs)
+  static uintptr_t v = 0;
+  if (!v) {
+    const char *e = getenv("WENDY_B200_PIN_CHUNK_MB");
+    const long mb = e ? atol(e) : 16;
+    v = (uintptr_t)(mb > 0 ? mb : 16) << 20;
+  }
+  return v;
+}
+std::mutex g_pin_mu;
+std::map<void *, std::vector<std::pair<void *, size_t>>> g_pins;
+inline size_t pin_piece(const void *host, size_t left) {
+  const uintptr_t a = (uintptr_t)host;
+  const uintptr_t to_edge = pin_chunk() - (a % pin_chunk());
+  return left < to_edge ? left : (size_t)to_edge;
+}
+cudaError_t copy_split(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st) {
+  char *d = (char *)dst;
+  const char *s = (const char *)src;
+  while (bytes) {
+    const size_t piece = pin_piece(kind == cudaMemcpyDeviceToHost ? (const void *)d : (const void *)s, bytes);
+    cudaError_t e = cudaMemcpyAsync(d, s, piece, kind, st);
+    if (e != cudaSuccess) return e;
+    d += piece; s += piece; bytes -= piece;
+  }
+  return cudaSuccess;
+}
+}  // namespace
+
+// WENDY_B200_TRACE=1: host-side phase timings of set-up, layout builds and read-outs on stderr (each mark
+// synchronises the stream, so the numbers are only meaningful for finding where the time goes)
+static bool trace_on() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("WENDY_B200_TRACE"); v = (e && e[0] && e[0] != '0') ? 1 : 0; }
+  return v != 0;
+}
+static void trace_mark(cudaStream_t st, const char *label) {
+  if (!trace_on()) return;
+  static std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+  cudaStreamSynchronize(st);
+  const auto now = std::chrono::steady_clock::now();
+  fprintf(stderr, "[wendy_b200 trace] %-44s %9.2f ms\n", label, 1e3 * std::chrono::duration<double>(now - last).count());
+  last = now;
+}
+
 static int choose_fx_exponent(double sum_abs) {
   if (!(sum_abs > 0.) || !std::isfinite(sum_abs)) return 0;
   int e;
@@ -133,17 +278,17 @@ static int choose_fx_exponent(double sum_abs) {
 static int alloc_radix(H *h, size_t n) {
   if (h->rs.n_alloc >= n) return 0;
   for (int i = 0; i < 2; i++) {
-    if (h->rs.key[i]) cudaFree(h->rs.key[i]);
-    if (h->rs.val[i]) cudaFree(h->rs.val[i]);
+    if (h->rs.key[i]) dev_free(h->rs.key[i]);
+    if (h->rs.val[i]) dev_free(h->rs.val[i]);
   }
-  if (h->rs.table) cudaFree(h->rs.table);
-  if (h->rs.sums) cudaFree(h->rs.sums);
+  if (h->rs.table) dev_free(h->rs.table);
+  if (h->rs.sums) dev_free(h->rs.sums);
   for (int i = 0; i < 2; i++) {
-    CK(cudaMalloc(&h->rs.key[i], n * sizeof(uint64_t)));
-    CK(cudaMalloc(&h->rs.val[i], n * sizeof(uint32_t)));
+    CK(dev_alloc(&h->rs.key[i], n * sizeof(uint64_t)));
+    CK(dev_alloc(&h->rs.val[i], n * sizeof(uint32_t)));
   }
-  CK(cudaMalloc(&h->rs.table, radix_table_entries(n) * sizeof(uint32_t)));
-  CK(cudaMalloc(&h->rs.sums, (radix_sums_entries(n) + 1) * sizeof(uint32_t)));
+  CK(dev_alloc(&h->rs.table, radix_table_entries(n) * sizeof(uint32_t)));
+  CK(dev_alloc(&h->rs.sums, (radix_sums_entries(n) + 1) * sizeof(uint32_t)));
   h->rs.n_alloc = n;
   return 0;
 }
@@ -241,7 +386,9 @@ static int rebucket(H *h, double hkey, const double *extra = nullptr, long long 
   if (h->bounds) n_target = std::min(n_target, (long long)((double)(h->N + n_extra) * 1.02) + 1);
   const int nnbps = (int)((n_target + nfill - 1) / nfill);
   const int nnb = nnbps * h->nseg;
+  trace_mark(h->st, "(rebucket: start)");
   if (alloc_radix(h, (size_t)(h->N + n_extra))) return WENDY_E_CUDA;
+  trace_mark(h->st, "rebucket: radix scratch");
   if (make_keys(h, hkey, VAL_SEGMENT)) return WENDY_E_CUDA;
   if (n_extra > 0)  // shard inject: the layout is built from the union of local state and inbox
     launch_make_keys_packed(h->st, extra, hkey, n_extra, h->rs.key[0] + h->N, h->rs.val[0] + h->N);
@@ -249,6 +396,7 @@ static int rebucket(H *h, double hkey, const double *extra = nullptr, long long 
   int res = radix_sort_pairs(h->st, h->rs, (size_t)n_all, seg_bits(h), 1u);
   h->n_launch += 5 * (8 + (seg_bits(h) + 7) / 8);
   launch_pick_splitters(h->st, h->rs.key[res], n_extra > 0 ? n_all : h->seg_len, nfill, nnbps, nnb, h->split);
+  trace_mark(h->st, "rebucket: keys + radix sort + splitters");
   int c1 = (h->ccur + 1) % 3, c2 = (h->ccur + 2) % 3;
   CK(cudaMemsetAsync(h->cnt[c1], 0, (size_t)h->nb_alloc * sizeof(unsigned), h->st));
   CK(cudaMemsetAsync(h->cnt[c2], 0, (size_t)h->nb_alloc * sizeof(unsigned), h->st));
@@ -276,6 +424,7 @@ static int rebucket(H *h, double hkey, const double *extra = nullptr, long long 
                                      "coincident particles for one bucket");
   }
   h->cur = o; h->ccur = c1; h->dense = false; h->has_split = true; h->bucket_h = hkey;
+  trace_mark(h->st, "rebucket: scatter");
   h->cap = ncap; h->fill = nfill; h->nbps = nnbps; h->nb = nnb; h->want_cap = 0;
   {
     const size_t nc = (size_t)h->nb_alloc / 8 + 8;  // flow statistics belong to the old layout
@@ -383,20 +532,23 @@ const char *wendy_cuda_last_error(void) { return g_err.c_str(); }
 
 void wendy_cuda_destroy(wendy_cuda_handle *h) {
   if (!h) return;
+  // released blocks may be handed to another handle at once: nothing of this one may still be running
+  if (h->st_copy) cudaStreamSynchronize(h->st_copy);
+  cudaStreamSynchronize(h->st);
   for (int i = 0; i < 2; i++) {
-    cudaFree(h->x[i]); cudaFree(h->v[i]); cudaFree(h->m[i]); cudaFree(h->id[i]);
-    cudaFree(h->rs.key[i]); cudaFree(h->rs.val[i]);
+    dev_free(h->x[i]); dev_free(h->v[i]); dev_free(h->m[i]); dev_free(h->id[i]);
+    dev_free(h->rs.key[i]); dev_free(h->rs.val[i]);
   }
-  for (int i = 0; i < 3; i++) cudaFree(h->cnt[i]);
-  cudaFree(h->rs.table); cudaFree(h->rs.sums);
-  cudaFree(h->split_alt); cudaFree(h->knot_sum); cudaFree(h->knot_x); cudaFree(h->knot_y); cudaFree(h->knot_n);
-  cudaFree(h->split); cudaFree(h->tot); cudaFree(h->ticket); cudaFree(h->status); cudaFree(h->desc);
-  cudaFree(h->cpre); cudaFree(h->cp_desc); cudaFree(h->cp_ticket);
-  cudaFree(h->magg); cudaFree(h->mpre); cudaFree(h->mp_desc); cudaFree(h->mp_status); cudaFree(h->mp_ticket);
-  cudaFree(h->flags); cudaFree(h->offs); cudaFree(h->xo); cudaFree(h->vo); cudaFree(h->epart);
-  cudaFree(h->eout); cudaFree(h->rank);
-  cudaFree(h->bounds); cudaFree(h->out_rec); cudaFree(h->out_cnt);
-  cudaFree(h->cid);
+  for (int i = 0; i < 3; i++) dev_free(h->cnt[i]);
+  dev_free(h->rs.table); dev_free(h->rs.sums);
+  dev_free(h->split_alt); dev_free(h->knot_sum); dev_free(h->knot_x); dev_free(h->knot_y); dev_free(h->knot_n);
+  dev_free(h->split); dev_free(h->tot); dev_free(h->ticket); dev_free(h->status); dev_free(h->desc);
+  dev_free(h->cpre); dev_free(h->cp_desc); dev_free(h->cp_ticket);
+  dev_free(h->magg); dev_free(h->mpre); dev_free(h->mp_desc); dev_free(h->mp_status); dev_free(h->mp_ticket);
+  dev_free(h->flags); dev_free(h->offs); dev_free(h->xo); dev_free(h->vo); dev_free(h->epart);
+  dev_free(h->eout); dev_free(h->rank);
+  dev_free(h->bounds); dev_free(h->out_rec); dev_free(h->out_cnt);
+  dev_free(h->cid);
   if (h->h_out_cnt) cudaFreeHost(h->h_out_cnt);
   if (h->st_copy) cudaStreamDestroy(h->st_copy);
   if (h->ev_unsort) cudaEventDestroy(h->ev_unsort);
@@ -425,7 +577,7 @@ static int upload_host_arrays(cudaStream_t st, const double *const *src, double 
     const bool pinned = cudaPointerGetAttributes(&at, src[a]) == cudaSuccess && at.type == cudaMemoryTypeHost;
     cudaGetLastError();
     if (pinned || n < CH) {
-      cudaError_t e = cudaMemcpyAsync(dst[a], src[a], n * sizeof(double), cudaMemcpyHostToDevice, st);
+      cudaError_t e = copy_split(dst[a], src[a], n * sizeof(double), cudaMemcpyHostToDevice, st);
       if (e != cudaSuccess) fail(e, "cudaMemcpyAsync");
       continue;
     }
@@ -471,6 +623,7 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
   if (n_segments < 1 || N % n_segments) return set_err(WENDY_E_ARG, "N must be a multiple of n_segments");
   const bool adaptive = (cap == 0);
   if (cap == 0) cap = 256;
+  trace_mark((cudaStream_t)cuda_stream, "(create: start)");
   if (!tile_cap_supported(cap)) return set_err(WENDY_E_ARG, "cap must be 2048 or 256");  // (2048: tile_coarse_cap())
   // Splitters are exact quantiles of ONE random sample, so bucket widths carry their own
   // 1/sqrt(fill) noise and the steady-state count variance is 2*fill (measured: DESIGN.md).
@@ -499,12 +652,12 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
     // device inputs: one validation kernel (finiteness, sum |m|, equal-mass test)
     double *d_out = nullptr;
     double h_out[3] = {0., 0., 0.};
-    CKD(cudaMalloc(&d_out, 3 * sizeof(double)));
+    CKD(dev_alloc(&d_out, 3 * sizeof(double)));
     CKD(cudaMemsetAsync(d_out, 0, 3 * sizeof(double), h->st));
     launch_validate(h->st, x, v, m, N, d_out);
     CKD(cudaMemcpyAsync(h_out, d_out, sizeof(h_out), cudaMemcpyDeviceToHost, h->st));
     CKD(cudaStreamSynchronize(h->st));
-    cudaFree(d_out);
+    dev_free(d_out);
     if (!(h_out[0] == 0.)) {
       wendy_cuda_destroy(h);
       return set_err(WENDY_E_ARG, "x, v, m must be finite (NaN keys are undefined in the reference sort too)");
@@ -544,13 +697,23 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
     h->eqm = !(flags & WENDY_FLAG_GENERAL_MASSES) && n_diff == 0;
   }
   h->fxE = choose_fx_exponent(sum_abs);
+  trace_mark(h->st, "create: validation pass");
   // Geometry chosen by the library: the persistent CTA kernel (2048-slot buckets, next bucket prefetched by
   // TMA) is the fastest step for large equal-mass systems at every dt measured; small
   // systems and general masses start on 256-slot buckets (warp kernel) and switch when the window statistic
   // says so.
   if (h->adaptive && h->eqm && N >= (1ll << 20)) {
-    h->want_cap = tile_coarse_cap();
+    // ... and stay there, so the storage is sized for that geometry: n/(3/4) slots per particle array instead
+    // of the 2n of the fine layout (less to allocate -- cudaMalloc is a visible part of the set-up time --
+    // and N=1e9 needs 75 GB instead of 106 GB).  Bucket arrays are sized for the conservative fill, which
+    // the handle falls back to after an overflow (fill_back_off).
     h->coarse_default = true;
+    h->cap = tile_coarse_cap();
+    h->fill = default_fill(h, h->cap);
+    h->nbps = (int)(((n_cap / n_segments) + (h->cap * 3 / 4) - 1) / (h->cap * 3 / 4));
+    h->nb = h->nbps * n_segments;
+    h->nb_alloc = h->nb;
+    h->slots = (size_t)h->nb * h->cap;
   }
   if (dev_inputs) {
     h->m0 = m0_dev;
@@ -559,54 +722,55 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
     h->m0 = m[0];
   }
   for (int i = 0; i < 2; i++) {
-    CKD(cudaMalloc(&h->x[i], h->slots * sizeof(double)));
-    CKD(cudaMalloc(&h->v[i], h->slots * sizeof(double)));
-    if (!h->eqm) CKD(cudaMalloc(&h->m[i], h->slots * sizeof(double)));
-    CKD(cudaMalloc(&h->id[i], h->slots * sizeof(int)));
+    CKD(dev_alloc(&h->x[i], h->slots * sizeof(double)));
+    CKD(dev_alloc(&h->v[i], h->slots * sizeof(double)));
+    if (!h->eqm) CKD(dev_alloc(&h->m[i], h->slots * sizeof(double)));
+    CKD(dev_alloc(&h->id[i], h->slots * sizeof(int)));
     CKD(cudaMemsetAsync(h->x[i], 0, h->slots * sizeof(double), h->st));
     CKD(cudaMemsetAsync(h->v[i], 0, h->slots * sizeof(double), h->st));
   }
   for (int i = 0; i < 3; i++) {
-    CKD(cudaMalloc(&h->cnt[i], (size_t)h->nb * sizeof(unsigned)));
+    CKD(dev_alloc(&h->cnt[i], (size_t)h->nb * sizeof(unsigned)));
     CKD(cudaMemsetAsync(h->cnt[i], 0, (size_t)h->nb * sizeof(unsigned), h->st));
   }
-  CKD(cudaMalloc(&h->split, (size_t)h->nb * sizeof(double)));
-  CKD(cudaMalloc(&h->split_alt, (size_t)h->nb * sizeof(double)));
+  CKD(dev_alloc(&h->split, (size_t)h->nb * sizeof(double)));
+  CKD(dev_alloc(&h->split_alt, (size_t)h->nb * sizeof(double)));
   {
     const size_t nc = (size_t)h->nb / 8 + 8;  // cells of >= 8 buckets
-    CKD(cudaMalloc(&h->knot_sum, nc * sizeof(double)));
-    CKD(cudaMalloc(&h->knot_x, nc * sizeof(double)));
-    CKD(cudaMalloc(&h->knot_y, nc * sizeof(double)));
-    CKD(cudaMalloc(&h->knot_n, nc * sizeof(unsigned)));
+    CKD(dev_alloc(&h->knot_sum, nc * sizeof(double)));
+    CKD(dev_alloc(&h->knot_x, nc * sizeof(double)));
+    CKD(dev_alloc(&h->knot_y, nc * sizeof(double)));
+    CKD(dev_alloc(&h->knot_n, nc * sizeof(unsigned)));
     CKD(cudaMemsetAsync(h->knot_sum, 0, nc * sizeof(double), h->st));
     CKD(cudaMemsetAsync(h->knot_n, 0, nc * sizeof(unsigned), h->st));
   }
-  CKD(cudaMalloc(&h->tot, (size_t)n_segments * sizeof(double)));
-  CKD(cudaMalloc(&h->ticket, 3 * sizeof(unsigned)));
-  CKD(cudaMalloc(&h->status, (size_t)h->nb * sizeof(unsigned)));
-  CKD(cudaMalloc(&h->desc, (size_t)h->nb * sizeof(Desc)));
-  CKD(cudaMalloc(&h->cpre, (size_t)h->nb * sizeof(unsigned)));
-  CKD(cudaMalloc(&h->cp_desc, (size_t)(count_prefix_tiles(h->nb) + 1) * sizeof(unsigned long long)));
+  CKD(dev_alloc(&h->tot, (size_t)n_segments * sizeof(double)));
+  CKD(dev_alloc(&h->ticket, 3 * sizeof(unsigned)));
+  CKD(dev_alloc(&h->status, (size_t)h->nb * sizeof(unsigned)));
+  CKD(dev_alloc(&h->desc, (size_t)h->nb * sizeof(Desc)));
+  CKD(dev_alloc(&h->cpre, (size_t)h->nb * sizeof(unsigned)));
+  CKD(dev_alloc(&h->cp_desc, (size_t)(count_prefix_tiles(h->nb) + 1) * sizeof(unsigned long long)));
   CKD(cudaMemsetAsync(h->cp_desc, 0, (size_t)(count_prefix_tiles(h->nb) + 1) * sizeof(unsigned long long), h->st));
-  CKD(cudaMalloc(&h->cp_ticket, sizeof(unsigned)));
+  CKD(dev_alloc(&h->cp_ticket, sizeof(unsigned)));
   CKD(cudaMemsetAsync(h->cp_ticket, 0, sizeof(unsigned), h->st));
   if (!h->eqm) {
     const size_t mt = (size_t)mass_prefix_tiles(h->nb) + 1;
-    CKD(cudaMalloc(&h->magg, (size_t)h->nb * sizeof(ulonglong2)));
-    CKD(cudaMalloc(&h->mpre, (size_t)h->nb * sizeof(ulonglong2)));
-    CKD(cudaMalloc(&h->mp_desc, mt * sizeof(Desc)));
-    CKD(cudaMalloc(&h->mp_status, mt * sizeof(unsigned)));
+    CKD(dev_alloc(&h->magg, (size_t)h->nb * sizeof(ulonglong2)));
+    CKD(dev_alloc(&h->mpre, (size_t)h->nb * sizeof(ulonglong2)));
+    CKD(dev_alloc(&h->mp_desc, mt * sizeof(Desc)));
+    CKD(dev_alloc(&h->mp_status, mt * sizeof(unsigned)));
     CKD(cudaMemsetAsync(h->mp_status, 0, mt * sizeof(unsigned), h->st));
-    CKD(cudaMalloc(&h->mp_ticket, sizeof(unsigned)));
+    CKD(dev_alloc(&h->mp_ticket, sizeof(unsigned)));
     CKD(cudaMemsetAsync(h->mp_ticket, 0, sizeof(unsigned), h->st));
   }
-  CKD(cudaMalloc(&h->flags, 136 * sizeof(unsigned)));
+  CKD(dev_alloc(&h->flags, 136 * sizeof(unsigned)));
   CKD(cudaMemsetAsync(h->flags, 0, 136 * sizeof(unsigned), h->st));
-  CKD(cudaMalloc(&h->offs, (size_t)h->nb * sizeof(unsigned long long)));
-  CKD(cudaMalloc(&h->epart, (size_t)h->nb * 4 * sizeof(double)));
-  CKD(cudaMalloc(&h->eout, 4 * sizeof(double)));
+  CKD(dev_alloc(&h->offs, (size_t)h->nb * sizeof(unsigned long long)));
+  CKD(dev_alloc(&h->epart, (size_t)h->nb * 4 * sizeof(double)));
+  CKD(dev_alloc(&h->eout, 4 * sizeof(double)));
   CKD(cudaMallocHost(&h->h_flags, 136 * sizeof(unsigned)));
   CKD(cudaMallocHost(&h->h_eout, 4 * sizeof(double)));
+  trace_mark(h->st, "create: device allocations");
   memset(h->h_flags, 0, 136 * sizeof(unsigned));
   CKD(cudaMemsetAsync(h->status, 0, (size_t)h->nb * sizeof(unsigned), h->st));
   if (dev_inputs) {
@@ -622,6 +786,7 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
   CKD(cudaMemcpyAsync(h->tot, totmass, (size_t)n_segments * sizeof(double), cudaMemcpyHostToDevice, h->st));
   if (ids) CKD(cudaMemcpyAsync(h->id[0], ids, (size_t)N * sizeof(int), cudaMemcpyDefault, h->st));
   else launch_iota(h->st, h->id[0], N);
+  trace_mark(h->st, "create: upload");
   if (reset_flags(h)) { std::string s = g_err; wendy_cuda_destroy(h); return set_err(WENDY_E_CUDA, s); }
   CKD(cudaGetLastError());
 #undef CKD
@@ -687,14 +852,15 @@ static int create_shard_impl(wendy_cuda_handle **out, long long n_local, long lo
   H *h = *out;
   h->nranks = nranks; h->my_rank = rank; h->ocap = outbox_capacity;
   cudaError_t e = cudaSuccess;
-  if (e == cudaSuccess) e = cudaMalloc(&h->bounds, (size_t)(nranks + 1) * sizeof(double));
+  if (e == cudaSuccess) e = dev_alloc(&h->bounds, (size_t)(nranks + 1) * sizeof(double));
   if (e == cudaSuccess) e = cudaMemcpy(h->bounds, bounds, (size_t)(nranks + 1) * sizeof(double), cudaMemcpyHostToDevice);
   size_t ob = (size_t)nranks * (size_t)outbox_capacity;
-  if (e == cudaSuccess) e = cudaMalloc(&h->out_rec, ob * 3 * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc(&h->out_cnt, (size_t)nranks * sizeof(unsigned));
+  if (e == cudaSuccess) e = dev_alloc(&h->out_rec, ob * 3 * sizeof(double));
+  if (e == cudaSuccess) e = dev_alloc(&h->out_cnt, (size_t)nranks * sizeof(unsigned));
   if (e == cudaSuccess) e = cudaMallocHost(&h->h_out_cnt, (size_t)nranks * sizeof(unsigned));
-  if (e == cudaSuccess) e = cudaMalloc(&h->cid, (size_t)n_capacity * sizeof(int));
+  if (e == cudaSuccess) e = dev_alloc(&h->cid, (size_t)n_capacity * sizeof(int));
   if (e != cudaSuccess) { std::string msg = cudaGetErrorString(e); wendy_cuda_destroy(h); *out = nullptr; return set_err(WENDY_E_CUDA, msg); }
+  if (h->cap != 256) h->fill = default_fill(h, h->cap);  // shards keep the conservative fill (bounds is known now)
   return 0;
 }
 
@@ -791,21 +957,23 @@ int wendy_cuda_shard_count(wendy_cuda_handle *h, long long *n_local) {
 int wendy_cuda_shard_read(wendy_cuda_handle *h, double *x_host, double *v_host, int *id_host, long long *n) {
   if (!h || !h->bounds || !x_host || !v_host || !id_host || !n) return set_err(WENDY_E_ARG, "bad argument");
   if (!h->xo) {
-    CK(cudaMalloc(&h->xo, (size_t)h->n_cap * sizeof(double)));
-    CK(cudaMalloc(&h->vo, (size_t)h->n_cap * sizeof(double)));
+    trace_mark(h->st, "(read: start)");
+    CK(dev_alloc(&h->xo, (size_t)h->n_cap * sizeof(double)));
+    CK(dev_alloc(&h->vo, (size_t)h->n_cap * sizeof(double)));
+    trace_mark(h->st, "read: staging allocation");
   }
   if (h->dense) {
-    CK(cudaMemcpyAsync(x_host, h->x[h->cur], (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
-    CK(cudaMemcpyAsync(v_host, h->v[h->cur], (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
-    CK(cudaMemcpyAsync(id_host, h->id[h->cur], (size_t)h->N * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(copy_split(x_host, h->x[h->cur], (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CK(copy_split(v_host, h->v[h->cur], (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CK(copy_split(id_host, h->id[h->cur], (size_t)h->N * sizeof(int), cudaMemcpyDeviceToHost, h->st));
   } else {
     launch_count_prefix(h->st, h->cnt[h->ccur], h->nb, h->cpre, h->cp_desc, h->cp_ticket, h->seq++);
     launch_compact(h->st, h->x[h->cur], h->v[h->cur], h->id[h->cur], h->cnt[h->ccur], h->cpre, h->cap, h->nb,
                    h->xo, h->vo, h->cid);
     h->n_launch += 2;
-    CK(cudaMemcpyAsync(x_host, h->xo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
-    CK(cudaMemcpyAsync(v_host, h->vo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
-    CK(cudaMemcpyAsync(id_host, h->cid, (size_t)h->N * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(copy_split(x_host, h->xo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CK(copy_split(v_host, h->vo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CK(copy_split(id_host, h->cid, (size_t)h->N * sizeof(int), cudaMemcpyDeviceToHost, h->st));
   }
   CK(cudaStreamSynchronize(h->st));
   CK(cudaGetLastError());
@@ -1016,8 +1184,10 @@ int wendy_cuda_read_dev(wendy_cuda_handle *h, double *x_dev, double *v_dev) {
   if (!h) return set_err(WENDY_E_ARG, "null handle");
   if (h->pending) return set_err(WENDY_E_ARG, "a call is in flight: wendy_cuda_step_end first");
   if (!h->xo) {
-    CK(cudaMalloc(&h->xo, (size_t)h->n_cap * sizeof(double)));
-    CK(cudaMalloc(&h->vo, (size_t)h->n_cap * sizeof(double)));
+    trace_mark(h->st, "(read: start)");
+    CK(dev_alloc(&h->xo, (size_t)h->n_cap * sizeof(double)));
+    CK(dev_alloc(&h->vo, (size_t)h->n_cap * sizeof(double)));
+    trace_mark(h->st, "read: staging allocation");
   }
   double *xd = x_dev ? x_dev : h->xo, *vd = v_dev ? v_dev : h->vo;
   if (h->dense) {
@@ -1034,8 +1204,8 @@ int wendy_cuda_read_dev(wendy_cuda_handle *h, double *x_dev, double *v_dev) {
 int wendy_cuda_read(wendy_cuda_handle *h, double *x_host, double *v_host) {
   int rc = wendy_cuda_read_dev(h, nullptr, nullptr);
   if (rc) return rc;
-  if (x_host) CK(cudaMemcpyAsync(x_host, h->xo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
-  if (v_host) CK(cudaMemcpyAsync(v_host, h->vo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  if (x_host) CK(copy_split(x_host, h->xo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  if (v_host) CK(copy_split(v_host, h->vo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
   return 0;
 }
@@ -1053,14 +1223,15 @@ int wendy_cuda_read_begin(wendy_cuda_handle *h, double *x_host, double *v_host) 
   if (rc) return rc;
   CK(cudaEventRecord(h->ev_unsort, h->st));
   CK(cudaStreamWaitEvent(h->st_copy, h->ev_unsort, 0));
-  if (x_host) CK(cudaMemcpyAsync(x_host, h->xo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st_copy));
-  if (v_host) CK(cudaMemcpyAsync(v_host, h->vo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st_copy));
+  if (x_host) CK(copy_split(x_host, h->xo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st_copy));
+  if (v_host) CK(copy_split(v_host, h->vo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st_copy));
   return 0;
 }
 
 int wendy_cuda_read_end(wendy_cuda_handle *h) {
   if (!h) return set_err(WENDY_E_ARG, "null handle");
   if (h->st_copy) CK(cudaStreamSynchronize(h->st_copy));
+  trace_mark(h->st, "read_end: D2H done");
   return 0;
 }
 
@@ -1099,13 +1270,36 @@ int wendy_cuda_stats(wendy_cuda_handle *h, long long *out, int n) {
 
 int wendy_cuda_pin(void *host_ptr, unsigned long long bytes) {
   if (!host_ptr || !bytes) return set_err(WENDY_E_ARG, "null argument");
-  CK(cudaHostRegister(host_ptr, (size_t)bytes, cudaHostRegisterDefault));
+  std::vector<std::pair<void *, size_t>> done;
+  char *q = (char *)host_ptr;
+  size_t left = (size_t)bytes;
+  while (left) {
+    const size_t piece = pin_piece(q, left);
+    cudaError_t e = cudaHostRegister(q, piece, cudaHostRegisterDefault);
+    if (e != cudaSuccess) {
+      for (auto &d : done) cudaHostUnregister(d.first);
+      cudaGetLastError();
+      return set_err(WENDY_E_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e));
+    }
+    done.push_back(std::make_pair((void *)q, piece));
+    q += piece; left -= piece;
+  }
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  g_pins[host_ptr] = done;
   return 0;
 }
 
 int wendy_cuda_unpin(void *host_ptr) {
   if (!host_ptr) return set_err(WENDY_E_ARG, "null argument");
-  CK(cudaHostUnregister(host_ptr));
+  std::vector<std::pair<void *, size_t>> pieces;
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    auto it = g_pins.find(host_ptr);
+    if (it == g_pins.end()) return set_err(WENDY_E_ARG, "not a range registered by wendy_cuda_pin");
+    pieces = it->second;
+    g_pins.erase(it);
+  }
+  for (auto &d : pieces) CK(cudaHostUnregister(d.first));
   return 0;
 }
 
@@ -1127,7 +1321,7 @@ int wendy_cuda_argsort(const double *x_host, long long N, int *perm_out) {
   if (alloc_radix(&tmp, (size_t)N)) return WENDY_E_CUDA;
   int rc = 0;
   do {
-    if (cudaMalloc(&dx, (size_t)N * sizeof(double)) != cudaSuccess) { rc = set_err(WENDY_E_CUDA, "cudaMalloc"); break; }
+    if (dev_alloc(&dx, (size_t)N * sizeof(double)) != cudaSuccess) { rc = set_err(WENDY_E_CUDA, "cudaMalloc"); break; }
     cudaMemcpy(dx, x_host, (size_t)N * sizeof(double), cudaMemcpyHostToDevice);
     launch_make_keys(nullptr, dx, nullptr, 0., nullptr, nullptr, 0, 0, N, tmp.rs.key[0], tmp.rs.val[0],
                      VAL_INDEX, N, 0);
@@ -1136,9 +1330,9 @@ int wendy_cuda_argsort(const double *x_host, long long N, int *perm_out) {
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) rc = set_err(WENDY_E_CUDA, cudaGetErrorString(e));
   } while (0);
-  cudaFree(dx);
-  for (int i = 0; i < 2; i++) { cudaFree(tmp.rs.key[i]); cudaFree(tmp.rs.val[i]); }
-  cudaFree(tmp.rs.table); cudaFree(tmp.rs.sums);
+  dev_free(dx);
+  for (int i = 0; i < 2; i++) { dev_free(tmp.rs.key[i]); dev_free(tmp.rs.val[i]); }
+  dev_free(tmp.rs.table); dev_free(tmp.rs.sums);
   return rc;
 }
 
@@ -1186,7 +1380,7 @@ void _wendy_nbody_approx_onestep(int N, struct wendy_array_w_index *xi, double *
   H *h = nullptr;
   int rc = wendy_cuda_create(&h, N, xs.data(), v, m, &totmass, omega2, 1, flags, ecap ? atoi(ecap) : 0, 0, nullptr);
   std::vector<int> rank((size_t)N);
-  if (!rc) rc = (cudaMalloc(&h->rank, (size_t)N * sizeof(int)) == cudaSuccess) ? 0 : WENDY_E_CUDA;
+  if (!rc) rc = (dev_alloc(&h->rank, (size_t)N * sizeof(int)) == cudaSuccess) ? 0 : WENDY_E_CUDA;
   if (!rc && !ext_force) {
     // sub-step by sub-step so that the sort order of the LAST force evaluation is recorded
     for (int k = 0; k < nleap && !rc; k++) {
@@ -1214,14 +1408,14 @@ void _wendy_nbody_approx_onestep(int N, struct wendy_array_w_index *xi, double *
   } else if (!rc) {
     std::vector<double> xh((size_t)N), ah((size_t)N);
     double *a_id = nullptr, *a_slot = nullptr;
-    if (cudaMalloc(&a_id, (size_t)N * sizeof(double)) != cudaSuccess) rc = WENDY_E_CUDA;
+    if (dev_alloc(&a_id, (size_t)N * sizeof(double)) != cudaSuccess) rc = WENDY_E_CUDA;
     for (int k = 0; k < nleap && !rc; k++) {
       int tries = 0;
       do {
         double *xd; long long ns;
         rc = wendy_cuda_force_positions(h, dt, k == 0, &xd, &ns);
         if (rc) break;
-        if (!a_slot && cudaMalloc(&a_slot, (size_t)ns * sizeof(double)) != cudaSuccess) { rc = WENDY_E_CUDA; break; }
+        if (!a_slot && dev_alloc(&a_slot, (size_t)ns * sizeof(double)) != cudaSuccess) { rc = WENDY_E_CUDA; break; }
         rc = wendy_cuda_read(h, xh.data(), nullptr);  // positions at force time, particle order
         if (rc) break;
         if (N > 10) {  // EXTERNAL_SWITCH, wendy/wendy.h:9-11 and wendy/wendy.c:362-370
@@ -1248,7 +1442,7 @@ void _wendy_nbody_approx_onestep(int N, struct wendy_array_w_index *xi, double *
       } while (rc == WENDY_RETRY && ++tries < 3);
       if (!rc) *t0 += dt;  // wendy/wendy.c:403-404,409-410
     }
-    cudaFree(a_id); cudaFree(a_slot);
+    dev_free(a_id); dev_free(a_slot);
   }
   if (!rc) rc = wendy_cuda_read(h, x, v);
   if (!rc) {

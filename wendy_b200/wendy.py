@@ -241,18 +241,24 @@ def _nbody_approx(x, v, m, dt, nleap, t0=0., omega=None, ext_force=None, sort='g
     out = {}
     lib = _lib.load()
 
+    out['pinned'] = []
+
     def alloc_outputs():
-        # page-locking 16 bytes/particle takes a few hundred ms at N=1e8: done on a helper thread while
-        # the main thread validates, uploads and builds the first layout
+        # page-locking 16 bytes/particle takes a few hundred ms at N=1e8: done on a helper thread while the
+        # main thread validates, uploads and builds the first layout (the library registers the range
+        # piecewise, so the CUDA calls of the main thread are not held up behind one long registration)
         # (cudaHostRegister of untouched numpy memory: faster than cudaHostAlloc, and the arrays stay valid
         # ordinary memory after the generator has been closed and the registration dropped)
-        out['x'], out['v'] = numpy.empty(n), numpy.empty(n)
-        if n * 8 >= (1 << 20):
-            out['pinned'] = [a for a in (out['x'], out['v']) if lib.wendy_cuda_pin(a.ctypes.data, a.nbytes) == 0]
+        for name in ('x', 'v'):
+            a = numpy.empty(n)
+            out[name] = a
+            if a.nbytes >= (1 << 20) and lib.wendy_cuda_pin(a.ctypes.data, a.nbytes) == 0:
+                out['pinned'].append(a)
 
     import threading
-    helper = threading.Thread(target=alloc_outputs)
-    helper.start()
+    helpers = [threading.Thread(target=alloc_outputs)]
+    for t in helpers:
+        t.start()
     state = None
     dt_leap = dt / nleap
     try:
@@ -262,7 +268,8 @@ def _nbody_approx(x, v, m, dt, nleap, t0=0., omega=None, ext_force=None, sort='g
             if ext_force is None:
                 state.step_begin(dt_leap, nleap)
         finally:
-            helper.join()
+            for t in helpers:
+                t.join()
         x, v = out['x'], out['v']
         del xin, vin
         if ext_force is None:
@@ -368,6 +375,11 @@ def potential(y, x, v, m, twopiG=1., omega=None):
     broadcast: radix sort, prefix sums of m and m x, one binary search per point.  Arrays may be
     numpy-like (result: numpy) or torch CUDA tensors (result: CUDA tensor, nothing crosses PCIe)."""
     return _diagnostic(y, x, v, m, twopiG, omega)
+
+
+def trim():
+    """Return the device blocks cached from closed generators to the CUDA driver (wendy_cuda_trim)."""
+    _lib.load().wendy_cuda_trim()
 
 
 def momentum(v, m):
