@@ -16,6 +16,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/wendy_b200.h"
@@ -48,6 +49,7 @@ void launch_make_keys_by_id(cudaStream_t st, const double *x, const double *v, c
                             uint32_t *vals);
 }
 
+struct BounceRing;
 struct wendy_cuda_handle {
   long long N = 0, seg_len = 0;
   int nseg = 1, mode = 0, fxE = 0;
@@ -120,6 +122,10 @@ struct wendy_cuda_handle {
   std::vector<int> p_cur, p_ccur;
   cudaStream_t st_copy = nullptr;
   cudaEvent_t ev_unsort = nullptr;
+  int device = 0;               // CUDA device of the handle (worker threads select it)
+  std::thread reader;           // bounce-buffered read-out in flight (wendy_cuda_read_begin / _end)
+  int reader_rc = 0;
+  struct BounceRing *ring = nullptr;
   // counters
   long long n_sub = 0, n_rebuild = 0, n_fail = 0, max_cnt = 0, n_outside = 0, n_launch = 0;
   long long n_radix_fallback = 0;
@@ -251,6 +257,103 @@ cudaError_t copy_split(void *dst, const void *src, size_t bytes, cudaMemcpyKind 
   return cudaSuccess;
 }
 }  // namespace
+
+// ---- bounce-buffered device -> host copies -------------------------------------------------------------------
+// Page-locking the arrays a generator yields costs 350-450 ms per 1.6 GB on this platform (cudaHostRegister,
+// profiles/r01/pcie_probe.txt) -- more than everything else in the set-up together.  A destination that is NOT
+// page-locked is therefore filled through a small ring of page-locked bounce buffers: the copy engine writes
+// piece i+1.. while all host threads copy piece i into the caller's array (the mirror image of
+// upload_host_arrays).  Rings are pooled per process; a handle borrows one for its lifetime.
+struct BounceRing {
+  static constexpr int NB = 4;
+  static constexpr size_t BYTES = (size_t)16 << 20;
+  void *buf[NB] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[NB] = {nullptr, nullptr, nullptr, nullptr};
+  int device = 0;
+};
+namespace {
+std::mutex g_ring_mu;
+std::vector<BounceRing *> g_rings;
+BounceRing *ring_acquire(int device) {
+  {
+    std::lock_guard<std::mutex> lk(g_ring_mu);
+    for (size_t i = 0; i < g_rings.size(); i++)
+      if (g_rings[i]->device == device) {
+        BounceRing *r = g_rings[i];
+        g_rings.erase(g_rings.begin() + i);
+        return r;
+      }
+  }
+  BounceRing *r = new BounceRing;
+  r->device = device;
+  for (int i = 0; i < BounceRing::NB; i++) {
+    if (cudaMallocHost(&r->buf[i], BounceRing::BYTES) != cudaSuccess ||
+        cudaEventCreateWithFlags(&r->ev[i], cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      for (int j = 0; j <= i; j++) {
+        if (r->buf[j]) cudaFreeHost(r->buf[j]);
+        if (r->ev[j]) cudaEventDestroy(r->ev[j]);
+      }
+      delete r;
+      return nullptr;
+    }
+  }
+  return r;
+}
+void ring_release(BounceRing *r) {
+  if (!r) return;
+  std::lock_guard<std::mutex> lk(g_ring_mu);
+  g_rings.push_back(r);
+}
+bool host_range_is_pinned(const void *q) {
+  cudaPointerAttributes at;
+  const bool pinned = cudaPointerGetAttributes(&at, q) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  return pinned;
+}
+// dst (pageable host) <- src (device), through the ring, on stream st; returns when the data is in dst
+int bounce_d2h(BounceRing *r, cudaStream_t st, void *const *dst, const void *const *src, const size_t *bytes, int narr) {
+  struct Piece { char *d; const char *s; size_t n; };
+  std::vector<Piece> pieces;
+  for (int a = 0; a < narr; a++) {
+    if (!dst[a]) continue;
+    for (size_t off = 0; off < bytes[a]; off += BounceRing::BYTES)
+      pieces.push_back({(char *)dst[a] + off, (const char *)src[a] + off, std::min(BounceRing::BYTES, bytes[a] - off)});
+  }
+  const int np = (int)pieces.size();
+  int issued = 0;
+  auto issue = [&](int i) -> cudaError_t {
+    const int sl = i % BounceRing::NB;
+    cudaError_t e = cudaMemcpyAsync(r->buf[sl], pieces[i].s, pieces[i].n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaEventRecord(r->ev[sl], st);
+    return e;
+  };
+  for (; issued < np && issued < BounceRing::NB - 1; issued++)
+    if (issue(issued) != cudaSuccess) return -1;
+  for (int i = 0; i < np; i++) {
+    // keep the copy engine NB-1 pieces ahead; the slot of piece i-1 was drained in the previous iteration
+    if (issued < np) { if (issue(issued) != cudaSuccess) return -1; issued++; }
+    const int sl = i % BounceRing::NB;
+    if (cudaEventSynchronize(r->ev[sl]) != cudaSuccess) return -1;
+    const char *bp = (const char *)r->buf[sl];
+    char *dp = pieces[i].d;
+    const long long nblk = (long long)((pieces[i].n + 262143) / 262144);
+#pragma omp parallel for schedule(static)
+    for (long long blk = 0; blk < nblk; blk++) {
+      const size_t b0 = (size_t)blk * 262144, bl = std::min((size_t)262144, pieces[i].n - b0);
+      memcpy(dp + b0, bp + b0, bl);
+    }
+  }
+  return 0;
+}
+}  // namespace
+
+// WENDY_B200_D2H=pinned keeps pageable destinations on the driver's own staging path (A/B runs)
+static bool bounce_allowed() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("WENDY_B200_D2H"); v = !(e && e[0] == 'p'); }
+  return v != 0;
+}
 
 // WENDY_B200_TRACE=1: host-side phase timings of set-up, layout builds and read-outs on stderr (each mark
 // synchronises the stream, so the numbers are only meaningful for finding where the time goes)
@@ -533,8 +636,11 @@ const char *wendy_cuda_last_error(void) { return g_err.c_str(); }
 void wendy_cuda_destroy(wendy_cuda_handle *h) {
   if (!h) return;
   // released blocks may be handed to another handle at once: nothing of this one may still be running
+  if (h->reader.joinable()) h->reader.join();
   if (h->st_copy) cudaStreamSynchronize(h->st_copy);
   cudaStreamSynchronize(h->st);
+  ring_release(h->ring);
+  h->ring = nullptr;
   for (int i = 0; i < 2; i++) {
     dev_free(h->x[i]); dev_free(h->v[i]); dev_free(h->m[i]); dev_free(h->id[i]);
     dev_free(h->rs.key[i]); dev_free(h->rs.val[i]);
@@ -646,6 +752,7 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
   int dev = 0;
 #define CKD(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { std::string s__ = std::string(#call) + ": " + cudaGetErrorString(e__); wendy_cuda_destroy(h); return set_err(WENDY_E_CUDA, s__); } } while (0)
   CKD(cudaGetDevice(&dev));
+  h->device = dev;
   CKD(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev));
   double sum_abs = 0.;
   if (dev_inputs) {
@@ -1201,13 +1308,56 @@ int wendy_cuda_read_dev(wendy_cuda_handle *h, double *x_dev, double *v_dev) {
   return 0;
 }
 
+// Start the device -> host copy of the de-sorted staging arrays on stream st: page-locked destinations get
+// plain (split) copies; large pageable ones are filled through the bounce ring by a worker thread, so that
+// the caller can go on enqueueing work.  finish_read() waits for both.
+static int start_read(H *h, double *x_host, double *v_host, cudaStream_t st) {
+  if (h->reader.joinable()) return set_err(WENDY_E_ARG, "a read-out is in flight: wendy_cuda_read_end first");
+  const size_t bytes = (size_t)h->N * sizeof(double);
+  void *dst[2] = {nullptr, nullptr};
+  const void *src[2] = {h->xo, h->vo};
+  double *host[2] = {x_host, v_host};
+  int nb = 0;
+  for (int a = 0; a < 2; a++) {
+    if (!host[a]) continue;
+    if (bytes >= ((size_t)4 << 20) && bounce_allowed() && !host_range_is_pinned(host[a])) { dst[a] = host[a]; nb++; }
+    else CK(copy_split(host[a], src[a], bytes, cudaMemcpyDeviceToHost, st));
+  }
+  if (!nb) return 0;
+  if (!h->ring) h->ring = ring_acquire(h->device);
+  if (!h->ring) {  // no page-locked memory to be had: let the driver stage the copies
+    for (int a = 0; a < 2; a++)
+      if (dst[a]) CK(copy_split(dst[a], src[a], bytes, cudaMemcpyDeviceToHost, st));
+    return 0;
+  }
+  h->reader_rc = 0;
+  H *hh = h;
+  void *d0 = dst[0], *d1 = dst[1];
+  h->reader = std::thread([hh, d0, d1, bytes, st]() {
+    cudaSetDevice(hh->device);
+    void *const d[2] = {d0, d1};
+    const void *const sr[2] = {hh->xo, hh->vo};
+    const size_t nby[2] = {bytes, bytes};
+    hh->reader_rc = bounce_d2h(hh->ring, st, d, sr, nby, 2);
+  });
+  return 0;
+}
+
+static int finish_read(H *h, cudaStream_t st) {
+  if (h->reader.joinable()) {
+    h->reader.join();
+    if (h->reader_rc) return set_err(WENDY_E_CUDA, "device -> host copy through the bounce buffers failed");
+  }
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
 int wendy_cuda_read(wendy_cuda_handle *h, double *x_host, double *v_host) {
   int rc = wendy_cuda_read_dev(h, nullptr, nullptr);
   if (rc) return rc;
-  if (x_host) CK(copy_split(x_host, h->xo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
-  if (v_host) CK(copy_split(v_host, h->vo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
-  CK(cudaStreamSynchronize(h->st));
-  return 0;
+  rc = start_read(h, x_host, v_host, h->st);
+  if (rc) return rc;
+  return finish_read(h, h->st);
 }
 
 // Overlapped read-out: de-sort into staging on the compute stream, D2H on a private copy stream.
@@ -1215,6 +1365,7 @@ int wendy_cuda_read(wendy_cuda_handle *h, double *x_host, double *v_host) {
 int wendy_cuda_read_begin(wendy_cuda_handle *h, double *x_host, double *v_host) {
   if (!h) return set_err(WENDY_E_ARG, "null handle");
   if (h->pending) return set_err(WENDY_E_ARG, "finish the call in flight first");
+  if (h->reader.joinable()) return set_err(WENDY_E_ARG, "a read-out is in flight: wendy_cuda_read_end first");
   if (!h->st_copy) {
     CK(cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->ev_unsort, cudaEventDisableTiming));
@@ -1223,14 +1374,15 @@ int wendy_cuda_read_begin(wendy_cuda_handle *h, double *x_host, double *v_host) 
   if (rc) return rc;
   CK(cudaEventRecord(h->ev_unsort, h->st));
   CK(cudaStreamWaitEvent(h->st_copy, h->ev_unsort, 0));
-  if (x_host) CK(copy_split(x_host, h->xo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st_copy));
-  if (v_host) CK(copy_split(v_host, h->vo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st_copy));
-  return 0;
+  return start_read(h, x_host, v_host, h->st_copy);
 }
 
 int wendy_cuda_read_end(wendy_cuda_handle *h) {
   if (!h) return set_err(WENDY_E_ARG, "null handle");
-  if (h->st_copy) CK(cudaStreamSynchronize(h->st_copy));
+  if (h->st_copy) {
+    int rc = finish_read(h, h->st_copy);
+    if (rc) return rc;
+  }
   trace_mark(h->st, "read_end: D2H done");
   return 0;
 }

@@ -19,6 +19,7 @@ Differences a user can observe:
     can run).
 """
 import ctypes
+import os
 
 import numpy
 
@@ -242,17 +243,20 @@ def _nbody_approx(x, v, m, dt, nleap, t0=0., omega=None, ext_force=None, sort='g
     lib = _lib.load()
 
     out['pinned'] = []
+    # The yielded arrays are ordinary numpy memory: the library fills pageable destinations through its own
+    # page-locked bounce buffers at PCIe speed (all host threads copy piece i while the copy engine delivers
+    # piece i+1), which avoids page-locking 16 bytes/particle per generator -- 350-450 ms at N=1e8, more than
+    # the rest of the set-up together.  WENDY_B200_D2H=pinned restores the page-locked yield buffers.
+    pin_outputs = os.environ.get('WENDY_B200_D2H', 'bounce').startswith('p')
 
     def alloc_outputs():
-        # page-locking 16 bytes/particle takes a few hundred ms at N=1e8: done on a helper thread while the
-        # main thread validates, uploads and builds the first layout (the library registers the range
-        # piecewise, so the CUDA calls of the main thread are not held up behind one long registration)
         # (cudaHostRegister of untouched numpy memory: faster than cudaHostAlloc, and the arrays stay valid
-        # ordinary memory after the generator has been closed and the registration dropped)
+        # ordinary memory after the generator has been closed and the registration dropped; done on a helper
+        # thread while the main thread validates, uploads and builds the first layout)
         for name in ('x', 'v'):
             a = numpy.empty(n)
             out[name] = a
-            if a.nbytes >= (1 << 20) and lib.wendy_cuda_pin(a.ctypes.data, a.nbytes) == 0:
+            if pin_outputs and a.nbytes >= (1 << 20) and lib.wendy_cuda_pin(a.ctypes.data, a.nbytes) == 0:
                 out['pinned'].append(a)
 
     import threading
