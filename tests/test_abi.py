@@ -73,3 +73,23 @@ def test_nbody_argument_errors():
     assert 'nleap' in str(e.value)
     with pytest.raises(NotImplementedError):
         next(wendy_b200.nbody([0.], [0.], [1.], 0.1))
+
+
+def test_host_stream_copy_is_exact_for_every_alignment_and_size():
+    """The non-temporal host copy behind the bounce-buffered read-out (csrc/api.cu stream_copy): heads and
+    tails that are not multiples of 16 / 64 bytes, sizes across the 256 KB block size.  Pure host code."""
+    import ctypes
+    import numpy
+    from wendy_b200 import _lib
+    lib = _lib.load()
+    lib.wendy_host_stream_copy.restype = None
+    lib.wendy_host_stream_copy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_ulonglong]
+    rs = numpy.random.RandomState(1)
+    src = rs.randint(0, 256, size=3 * 262144 + 977, dtype=numpy.uint8)
+    for n in (0, 1, 15, 16, 17, 63, 64, 65, 1000, 262143, 262144, 262145, 3 * 262144 + 900):
+        for so in (0, 1, 8, 13):
+            for do in (0, 3, 8, 16, 29):
+                dst = numpy.full(n + do + 64, 7, dtype=numpy.uint8)
+                lib.wendy_host_stream_copy(dst.ctypes.data + do, src.ctypes.data + so, n)
+                assert numpy.array_equal(dst[do:do + n], src[so:so + n]), (n, so, do)
+                assert numpy.all(dst[:do] == 7) and numpy.all(dst[do + n:] == 7), (n, so, do)

@@ -7,6 +7,9 @@
 // the de-sort deferred to wendy_cuda_read().
 #include <math.h>
 #include <stdint.h>
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#endif
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -311,6 +314,31 @@ bool host_range_is_pinned(const void *q) {
   cudaGetLastError();
   return pinned;
 }
+// Copy out of a bounce buffer with non-temporal stores: the destination is written once and not read back
+// soon, so ordinary stores would first read every destination line into the cache (one third more memory
+// traffic on the path that bounds the read-out).
+inline void stream_copy(char *d, const char *s, size_t n) {
+#if defined(__x86_64__) || defined(_M_X64)
+  size_t head = (size_t)((16 - ((uintptr_t)d & 15)) & 15);
+  if (head > n) head = n;
+  memcpy(d, s, head);
+  d += head; s += head; n -= head;
+  const size_t nv = n / 64;
+  for (size_t i = 0; i < nv; i++) {
+    const __m128i a = _mm_loadu_si128((const __m128i *)s), b = _mm_loadu_si128((const __m128i *)(s + 16));
+    const __m128i c = _mm_loadu_si128((const __m128i *)(s + 32)), e = _mm_loadu_si128((const __m128i *)(s + 48));
+    _mm_stream_si128((__m128i *)d, a);
+    _mm_stream_si128((__m128i *)(d + 16), b);
+    _mm_stream_si128((__m128i *)(d + 32), c);
+    _mm_stream_si128((__m128i *)(d + 48), e);
+    s += 64; d += 64;
+  }
+  memcpy(d, s, n - nv * 64);
+  _mm_sfence();
+#else
+  memcpy(d, s, n);
+#endif
+}
 // dst (pageable host) <- src (device), through the ring, on stream st; returns when the data is in dst
 int bounce_d2h(BounceRing *r, cudaStream_t st, void *const *dst, const void *const *src, const size_t *bytes, int narr) {
   struct Piece { char *d; const char *s; size_t n; };
@@ -341,12 +369,22 @@ int bounce_d2h(BounceRing *r, cudaStream_t st, void *const *dst, const void *con
 #pragma omp parallel for schedule(static)
     for (long long blk = 0; blk < nblk; blk++) {
       const size_t b0 = (size_t)blk * 262144, bl = std::min((size_t)262144, pieces[i].n - b0);
-      memcpy(dp + b0, bp + b0, bl);
+      stream_copy(dp + b0, bp + b0, bl);
     }
   }
   return 0;
 }
 }  // namespace
+
+// test hook (tests/test_abi.py): the host-side copy used by the bounce-buffered read-out, multi-threaded
+extern "C" void wendy_host_stream_copy(void *dst, const void *src, unsigned long long bytes) {
+  const long long nblk = (long long)((bytes + 262143) / 262144);
+#pragma omp parallel for schedule(static)
+  for (long long blk = 0; blk < nblk; blk++) {
+    const size_t b0 = (size_t)blk * 262144, bl = std::min((size_t)262144, (size_t)bytes - b0);
+    stream_copy((char *)dst + b0, (const char *)src + b0, bl);
+  }
+}
 
 // WENDY_B200_D2H=pinned keeps pageable destinations on the driver's own staging path (A/B runs)
 static bool bounce_allowed() {
