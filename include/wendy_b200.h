@@ -166,6 +166,9 @@ int wendy_cuda_energy_individual(const double *x, const double *v, const double 
  * default 48, 0 = off; emptied automatically when an allocation fails).  wendy_cuda_trim returns them to the
  * driver.  No reference counterpart: the reference keeps its state in numpy arrays (wendy/wendy.py:369-387). */
 void wendy_cuda_trim(void);
+/* Touch every page of a freshly allocated host array (contents kept) with a few threads, so that the first
+ * read-out into it does not pay the page faults.  Host-only; no CUDA call. */
+void wendy_host_prefault(void *host_ptr, unsigned long long bytes);
 int wendy_cuda_pin(void *host_ptr, unsigned long long bytes);
 int wendy_cuda_unpin(void *host_ptr);
 

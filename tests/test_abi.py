@@ -93,3 +93,18 @@ def test_host_stream_copy_is_exact_for_every_alignment_and_size():
                 lib.wendy_host_stream_copy(dst.ctypes.data + do, src.ctypes.data + so, n)
                 assert numpy.array_equal(dst[do:do + n], src[so:so + n]), (n, so, do)
                 assert numpy.all(dst[:do] == 7) and numpy.all(dst[do + n:] == 7), (n, so, do)
+
+
+def test_host_prefault_keeps_contents():
+    import numpy
+    from wendy_b200 import _lib
+    lib = _lib.load()
+    a = numpy.arange(300001, dtype=numpy.float64)
+    b = a.copy()
+    lib.wendy_host_prefault(a.ctypes.data + 8, a.nbytes - 8)
+    lib.wendy_host_prefault(None, 0)
+    assert numpy.array_equal(a, b)
+    c = numpy.empty(5000000)
+    lib.wendy_host_prefault(c.ctypes.data, c.nbytes)
+    c[:] = 1.
+    assert c.sum() == 5000000.

@@ -256,8 +256,13 @@ def _nbody_approx(x, v, m, dt, nleap, t0=0., omega=None, ext_force=None, sort='g
         for name in ('x', 'v'):
             a = numpy.empty(n)
             out[name] = a
-            if pin_outputs and a.nbytes >= (1 << 20) and lib.wendy_cuda_pin(a.ctypes.data, a.nbytes) == 0:
-                out['pinned'].append(a)
+            if a.nbytes < (1 << 20):
+                continue
+            if pin_outputs:
+                if lib.wendy_cuda_pin(a.ctypes.data, a.nbytes) == 0:
+                    out['pinned'].append(a)
+            else:
+                lib.wendy_host_prefault(a.ctypes.data, a.nbytes)  # page faults now, not inside the first read-out
 
     import threading
     helpers = [threading.Thread(target=alloc_outputs)]
