@@ -9,9 +9,10 @@ self-gravitating disk with a harmonic term (omega=1.1), N=1e8 per GPU, fp64, see
   python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path
   python bench.py --impl reference ...                          the reference's own C path on the host
 
-N>1 is launched by torchrun (one rank per GPU).  Until the NCCL sample-sort mode lands, ranks run
-independent realisations (BASELINE.json configs[4]-style ensemble, no data-path collective), so
-scaling is "weak".
+N>1 is launched by torchrun (one rank per GPU).  By default the ranks then hold ONE system of N*gpus
+particles, range-partitioned by position (wendy_b200/multi.py: all-to-all of migrants + all-gather of
+counts per sub-step; BASELINE.json configs[3]); --mode ensemble runs independent realisations instead
+(configs[4], no data-path collective).  Per-GPU work is fixed either way, so scaling is "weak".
 """
 import argparse
 import json
@@ -272,7 +273,8 @@ def main():
                      'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback', 'unit': 'GB/s',
                      'frac': achieved / peak,
                      # dram__bytes_read+write per launch from the ncu --set full captures under profiles/r01
-                     # (wstep: 40.2 B/particle, persistent CTA kernel: 39.9 B/particle), scaled to this N
+                     # (wstep: 40.2 B/particle, persistent CTA kernel: 39.9 B/particle -- 2.027 GB read + 1.963 GB
+                     # written at N=1e8, tile_1e8_dt1e-3_summary.txt), scaled to this N
                      'traffic': (40.2 if getattr(run, 'cap', 256) == 256 else 39.9) * n if a.sort == 'gpu' else None,
                      'kernel': ('radix passes + tile_kernel<LOAD_GATHER>' if a.sort != 'gpu' else
                                 'wstep_kernel<256,8,EQM> (one warp per bucket)' if getattr(run, 'cap', 256) == 256 else

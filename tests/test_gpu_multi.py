@@ -69,6 +69,19 @@ def test_sharded_large_dt_switches_geometry_and_recovers_inject_overflow():
         assert numpy.array_equal(X, Xs) and numpy.array_equal(V, Vs)
 
 
+def test_sharded_ranks_of_more_than_2_20_particles_use_the_coarse_layout():
+    """Shards of >= 2^20 equal-mass particles are created directly on 2048-slot buckets with storage sized for
+    that geometry (the shape of the multi-GPU bench at 1e8 particles per rank); bit-identical to one GPU."""
+    n = 2400000
+    x, v, m = wo.sech2_ic(n, seed=6)
+    Xs, Vs = _single_gpu(x, v, m, 0.001, 4, 2, 1.1)
+    res = run_threads(2, lambda comm: _run_rank(comm, n, 1.1, 0.001, 4, 2), device='cuda')
+    for X, V, mig, counts in res:
+        assert numpy.array_equal(X, Xs) and numpy.array_equal(V, Vs)
+        assert int(counts.sum()) == n
+    assert sum(r[2] for r in res) > 0
+
+
 def _nccl_worker(rank, world, port, n, out_path):
     import torch
     import torch.distributed as dist
