@@ -38,6 +38,16 @@ namespace wendy {
 #ifndef TK_RANK_STRAIGHT
 #define TK_RANK_STRAIGHT 4  // members of a shared sub-bucket compared by straight-line code before a loop takes over
 #endif
+// candidates prepared for the next A/B run (not measured yet; 0 = the measured default)
+#ifndef TK_SLOT_WARPPATH
+#define TK_SLOT_WARPPATH 0  // one all-home / general decision per warp and bucket instead of two votes per particle round
+#endif
+#ifndef TK_DEST_NOWIN
+#define TK_DEST_NOWIN 0     // no window-range test before the four-splitter check (the verification covers it)
+#endif
+#ifndef TK_STORE32
+#define TK_STORE32 0        // 32-bit slot arithmetic in the emission stores (slot numbers fit: checked at creation)
+#endif
 #ifndef TK_COARSE_CAP
 #define TK_COARSE_CAP 2048  // slots per bucket of the CTA kernel (E = 4 particles per thread: 512 threads at 2048)
 #endif
@@ -687,7 +697,7 @@ tile_kernel(const TileParams p) {
         d = -3;
       } else if (key >= home_lo && key < home_hi) {
         d = b;
-      } else if (key >= win_lo && key < win_hi) {
+      } else if (TK_DEST_NOWIN || (key >= win_lo && key < win_hi)) {
         // guess from the home bucket's width (single precision is plenty: the loops below settle it)
         int lo = rel + __float2int_rd(fmaxf(-256.f, fminf(256.f, (float)(key - home_lo) * inv_wf)));
         // The guess is nearly always within one bucket of the answer: fetch the four splitters around it
@@ -700,6 +710,14 @@ tile_kernel(const TileParams p) {
           lo += (key >= s1 ? 1 : 0) - (key < s0 ? 1 : 0);
           settled = (key >= sm1) && (key < s2);
         }
+#if TK_DEST_NOWIN
+        if (!settled && !(key >= win_lo && key < win_hi)) {  // far move after all
+          double gq = fmax(-2.0e9, fmin(2.0e9, (key - home_lo) * inv_w));
+          const int g = (int)max((long long)seg_lo, min((long long)seg_hi - 1, (long long)b + (long long)floor(gq)));
+          lo = gallop_search_tile(p.split, key, g, seg_lo, seg_hi) - wlo;
+          settled = true;
+        }
+#endif
         if (!settled) {
           lo = max(0, min(wn - 1, lo));
 #pragma unroll 1
@@ -720,6 +738,37 @@ tile_kernel(const TileParams p) {
   // slot allocation, aggregated per warp and destination; the E requests are issued back to back and
   // their results consumed afterwards, so the atomics' latencies overlap
   unsigned amask[E];
+#if TK_SLOT_WARPPATH
+  bool leaves = false;
+#pragma unroll
+  for (int k = 0; k < E; k++) leaves |= (tid + k * THREADS < n) && dest[k] != b;
+  if (!__any_sync(WENDY_FULL_MASK, leaves)) {  // the whole warp stays home (common at small dt): ballots only
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+      const bool ok = tid + k * THREADS < n;
+      const unsigned valid = __ballot_sync(WENDY_FULL_MASK, ok);
+      amask[k] = ok ? valid : 0u;
+      lpos[k] = 0;
+      if (ok && lane == __ffs(valid) - 1) lpos[k] = atomicAdd(&S.dcnt[rel], (unsigned)__popc(valid));
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+      const int d = dest[k];  // -1: no particle, -3: went to an outbox
+      const unsigned mask = __match_any_sync(WENDY_FULL_MASK, d);
+      amask[k] = mask;
+      lpos[k] = 0;
+      if (d >= 0 && lane == __ffs(mask) - 1) {
+        if (d >= wlo && d < wlo + wn) {
+          lpos[k] = atomicAdd(&S.dcnt[d - wlo], (unsigned)__popc(mask));
+        } else {
+          lpos[k] = atomicAdd(&p.cnt_out[d], (unsigned)__popc(mask));
+          outside += __popc(mask);
+        }
+      }
+    }
+  }
+#else
 #pragma unroll
   for (int k = 0; k < E; k++) {
     const int d = dest[k];
@@ -739,6 +788,7 @@ tile_kernel(const TileParams p) {
       }
     }
   }
+#endif
 #pragma unroll
   for (int k = 0; k < E; k++) {
     const int leader = __ffs(amask[k]) - 1;
@@ -770,7 +820,11 @@ tile_kernel(const TileParams p) {
       unsigned pos = lpos[k];
       if (d >= wlo && d < wlo + wn) pos += S.dbase[d - wlo];
       if (pos < (unsigned)CAP) {
+#if TK_STORE32
+        const unsigned o = (unsigned)d * (unsigned)CAP + pos;
+#else
         size_t o = (size_t)d * CAP + pos;
+#endif
         p.xout[o] = x2[k];
         p.vout[o] = v2[k];
         if (!EQM) p.mout[o] = m[k];
