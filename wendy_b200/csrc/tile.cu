@@ -48,6 +48,9 @@ namespace wendy {
 #ifndef TK_STORE32
 #define TK_STORE32 0        // 32-bit slot arithmetic in the emission stores (slot numbers fit: checked at creation)
 #endif
+#ifndef TK_PERSIST_E
+#define TK_PERSIST_E 4      // particles per thread of the PERSISTENT instances (threads = CAP / TK_PERSIST_E).  2: 1024
+#endif                      // threads, 32 registers, 64 warps per SM (compiles with 24 bytes of spills); not measured yet
 #ifndef TK_COARSE_CAP
 #define TK_COARSE_CAP 2048  // slots per bucket of the CTA kernel (E = 4 particles per thread: 512 threads at 2048)
 #endif
@@ -873,19 +876,20 @@ static void launch_tile_cap(cudaStream_t st, int load, int emit, int physics, co
     // persistent CTAs (as many as fit an SM: two at 2048 slots), next bucket prefetched by TMA
     constexpr int PE = (EQM && CAP >= 1024) ? 1 : 0;  // (keeps the other instantiations out of the binary)
     constexpr int PQ = PE ? EQM : 1;
+    constexpr int PT = PE ? CAP / TK_PERSIST_E : THREADS;  // threads of the persistent instances
     static int grid = 0;
-    const size_t smp = sizeof(TileSmem<CAP, THREADS, PE>);
+    const size_t smp = sizeof(TileSmem<CAP, PT, PE>);
     if (!grid) {
       int dev = 0, sms = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      cudaFuncSetAttribute(tile_kernel<CAP, THREADS, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, PE>,
+      cudaFuncSetAttribute(tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, PE>,
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp);
-      cudaFuncSetAttribute(tile_kernel<CAP, THREADS, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, PE>,
+      cudaFuncSetAttribute(tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, PE>,
                            cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
       int per_sm = 0;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          &per_sm, tile_kernel<CAP, THREADS, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, PE>, THREADS, smp);
+          &per_sm, tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, PE>, PT, smp);
       grid = max(1, per_sm) * sms;
     }
     // WENDY_B200_PERSIST_GRID=<n> shrinks the grid (tests: many buckets per CTA even for small systems)
@@ -894,15 +898,15 @@ static void launch_tile_cap(cudaStream_t st, int load, int emit, int physics, co
     if (!p.aext && !p.rank_out && !p.bounds) {
       static bool set2 = false;
       if (!set2) {
-        cudaFuncSetAttribute(tile_kernel<CAP, THREADS, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 2 * PE>,
+        cudaFuncSetAttribute(tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 2 * PE>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp);
-        cudaFuncSetAttribute(tile_kernel<CAP, THREADS, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 2 * PE>,
+        cudaFuncSetAttribute(tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 2 * PE>,
                              cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
         set2 = true;
       }
-        tile_kernel<CAP, THREADS, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 2 * PE><<<g_use, THREADS, smp, st>>>(p);
+        tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 2 * PE><<<g_use, PT, smp, st>>>(p);
     } else {
-      tile_kernel<CAP, THREADS, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, PE><<<g_use, THREADS, smp, st>>>(p);
+      tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, PE><<<g_use, PT, smp, st>>>(p);
     }
   } else if (load == LOAD_BUCKET && emit == EMIT_SPLITTER && physics) WENDY_LAUNCH(LOAD_BUCKET, EMIT_SPLITTER, 1);
   else if (load == LOAD_GATHER && emit == EMIT_RANK && physics) WENDY_LAUNCH(LOAD_GATHER, EMIT_RANK, 1);
