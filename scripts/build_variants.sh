@@ -8,9 +8,7 @@ mkdir -p ../variants
 B="nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC -Xcompiler -fopenmp"
 if [ $# -eq 0 ]; then
   set -- "base:" "wp:-DTK_SLOT_WARPPATH=1" "nw:-DTK_DEST_NOWIN=1" "s32:-DTK_STORE32=1" \
-         "all3:-DTK_SLOT_WARPPATH=1 -DTK_DEST_NOWIN=1 -DTK_STORE32=1" "c1024:-DTK_COARSE_CAP=1024" \
-         "pe2:-DTK_PERSIST_E=2" "pe2c1024:-DTK_PERSIST_E=2 -DTK_COARSE_CAP=1024" \
-         "pe2all3:-DTK_PERSIST_E=2 -DTK_SLOT_WARPPATH=1 -DTK_DEST_NOWIN=1 -DTK_STORE32=1"
+         "all3:-DTK_SLOT_WARPPATH=1 -DTK_DEST_NOWIN=1 -DTK_STORE32=1" "c1024:-DTK_COARSE_CAP=1024"
 fi
 for v in "$@"; do
   n=${v%%:*}; f=${v#*:}
