@@ -1087,7 +1087,7 @@ static int start_read(H *h, double *x_host, double *v_host, cudaStream_t st) {
   int nb = 0;
   for (int a = 0; a < 2; a++) {
     if (!host[a]) continue;
-    if (bytes >= ((size_t)4 << 20) && bounce_allowed() && !host_range_is_pinned(host[a])) { dst[a] = host[a]; nb++; }
+    if (bytes >= ((size_t)4 << 20) && bounce_allowed() && !host_range_is_pinned(host[a], bytes)) { dst[a] = host[a]; nb++; }
     else CK(copy_split(host[a], src[a], bytes, cudaMemcpyDeviceToHost, st));
   }
   if (!nb) return 0;

@@ -201,11 +201,16 @@ void ring_release(BounceRing *r) {
   std::lock_guard<std::mutex> lk(g_ring_mu);
   g_rings.push_back(r);
 }
-bool host_range_is_pinned(const void *q) {
+bool host_byte_is_pinned(const void *q) {
   cudaPointerAttributes at;
   const bool pinned = cudaPointerGetAttributes(&at, q) == cudaSuccess && at.type == cudaMemoryTypeHost;
   cudaGetLastError();
   return pinned;
+}
+// first and last byte: wendy_cuda_pin registers a range piecewise in address order, possibly on another thread
+// while read-outs go on, so a range counts as page-locked only once its last piece is
+bool host_range_is_pinned(const void *q, size_t bytes) {
+  return host_byte_is_pinned(q) && (bytes < 2 || host_byte_is_pinned((const char *)q + bytes - 1));
 }
 // Copy out of a bounce buffer with non-temporal stores: the destination is written once and not read back
 // soon, so ordinary stores would first read every destination line into the cache (one third more memory

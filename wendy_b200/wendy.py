@@ -247,7 +247,12 @@ def _nbody_approx(x, v, m, dt, nleap, t0=0., omega=None, ext_force=None, sort='g
     # page-locked bounce buffers at PCIe speed (all host threads copy piece i while the copy engine delivers
     # piece i+1), which avoids page-locking 16 bytes/particle per generator -- 350-450 ms at N=1e8, more than
     # the rest of the set-up together.  WENDY_B200_D2H=pinned restores the page-locked yield buffers.
-    pin_outputs = os.environ.get('WENDY_B200_D2H', 'bounce').startswith('p')
+    d2h_mode = os.environ.get('WENDY_B200_D2H', 'bounce')
+    pin_outputs = d2h_mode.startswith('p')
+    # 'hybrid' (opt-in, not measured yet): start as above, page-lock the arrays in the background after the
+    # second output; the library switches to direct copies (37 instead of 42 ms per output at N=1e8) by
+    # itself once a whole array is registered
+    pin_later = d2h_mode.startswith('h')
 
     def alloc_outputs():
         # (cudaHostRegister of untouched numpy memory: faster than cudaHostAlloc, and the arrays stay valid
@@ -284,12 +289,21 @@ def _nbody_approx(x, v, m, dt, nleap, t0=0., omega=None, ext_force=None, sort='g
         if ext_force is None:
             # The generator is infinite (reference wendy/wendy.py:424), so the call after this
             # one is always needed: enqueue it before the D2H copy of this one has finished.
+            n_out = 0
             while True:
                 state.step_end()
                 te = state.time_elapsed
                 state.read_begin(x, v)
                 state.step_begin(dt_leap, nleap)
                 state.read_end()
+                n_out += 1
+                if pin_later and n_out == 2 and x.nbytes >= (1 << 20):
+                    def pin_in_background():
+                        for a in (x, v):
+                            if lib.wendy_cuda_pin(a.ctypes.data, a.nbytes) == 0:
+                                out['pinned'].append(a)
+                    out['pin_thread'] = threading.Thread(target=pin_in_background, daemon=True)
+                    out['pin_thread'].start()
                 if full_output:
                     yield (x, v, te)
                 else:
@@ -304,6 +318,8 @@ def _nbody_approx(x, v, m, dt, nleap, t0=0., omega=None, ext_force=None, sort='g
     finally:
         if state is not None:
             state.close()
+        if out.get('pin_thread') is not None:
+            out['pin_thread'].join()
         for a in out.get('pinned', []):
             lib.wendy_cuda_unpin(a.ctypes.data)
 
