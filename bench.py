@@ -121,6 +121,9 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', 0))
     n = int(a.n)
     cores = os.cpu_count()
+    # both arms may use every host thread (reference: its OpenMP loops; ours: input validation, staging of
+    # pageable uploads and the bounce-buffered read-out); libgomp reads this when the libraries are loaded
+    os.environ.pop('OMP_NUM_THREADS', None)
 
     if a.impl == 'reference':
         if rank != 0:
