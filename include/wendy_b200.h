@@ -83,7 +83,9 @@ int wendy_cuda_step(wendy_cuda_handle *h, double dt_leap, int nleap, double *tim
  * checks for bucket overflow and (rarely) re-runs.  wendy_cuda_read_begin / _end is the
  * overlapped read-out: the de-sort runs on the compute stream, the D2H copies on a private copy
  * stream, so   step_end(k); read_begin; step_begin(k+1); read_end   hides the copy behind the
- * next call's kernels.  Host buffers should be page-locked (wendy_cuda_pin). */
+ * next call's kernels.  Host buffers may be page-locked (wendy_cuda_pin: direct copies) or ordinary
+ * pageable memory (filled through the library's page-locked bounce buffers by a worker thread that
+ * wendy_cuda_read_end joins); the same holds for wendy_cuda_read. */
 int wendy_cuda_step_begin(wendy_cuda_handle *h, double dt_leap, int nleap);
 int wendy_cuda_step_end(wendy_cuda_handle *h);
 int wendy_cuda_read_begin(wendy_cuda_handle *h, double *x_host, double *v_host);
@@ -159,18 +161,23 @@ int wendy_cuda_potential(const double *y, long long Y, const double *x, const do
 int wendy_cuda_energy_individual(const double *x, const double *v, const double *m, long long N,
                                  double twopiG, double omega2, double *out, void *cuda_stream);
 
-/* Page-lock (cudaHostRegister) / release a HOST buffer the caller passes repeatedly to
- * wendy_cuda_read, so the per-yield D2H copy runs at full PCIe speed.  Optional. */
+/* Page-lock (cudaHostRegister) / release a HOST buffer the caller passes repeatedly to wendy_cuda_read, so
+ * that the per-yield D2H copy is a direct DMA (37 instead of 42 ms per output at N=1e8; registering costs
+ * about 0.2 s per GB, which is why wendy_b200.nbody does not do it by default).  The range is registered
+ * piecewise (16 MB pieces ending on absolute address boundaries) so that other CUDA calls of the process are
+ * not held up behind one long registration; wendy_cuda_unpin takes the pointer given to wendy_cuda_pin. */
+int wendy_cuda_pin(void *host_ptr, unsigned long long bytes);
+int wendy_cuda_unpin(void *host_ptr);
+
 /* Device blocks of >= 32 MB released by wendy_cuda_destroy are cached for the next handle of the same size
- * (cudaMalloc of the multi-GB state is a visible part of the set-up time; bounded by WENDY_B200_ALLOC_CACHE_GB,
- * default 48, 0 = off; emptied automatically when an allocation fails).  wendy_cuda_trim returns them to the
- * driver.  No reference counterpart: the reference keeps its state in numpy arrays (wendy/wendy.py:369-387). */
+ * (bounded by WENDY_B200_ALLOC_CACHE_GB, default 48, 0 = off; emptied automatically when an allocation
+ * fails).  wendy_cuda_trim returns them to the driver.  No reference counterpart: the reference keeps its
+ * state in numpy arrays (wendy/wendy.py:369-387). */
 void wendy_cuda_trim(void);
+
 /* Touch every page of a freshly allocated host array (contents kept) with a few threads, so that the first
  * read-out into it does not pay the page faults.  Host-only; no CUDA call. */
 void wendy_host_prefault(void *host_ptr, unsigned long long bytes);
-int wendy_cuda_pin(void *host_ptr, unsigned long long bytes);
-int wendy_cuda_unpin(void *host_ptr);
 
 /* Test/diagnostic hook: copies the per-bucket particle counts and lower splitters of the current
  * layout to HOST arrays of nb_max entries; returns the number of buckets (0: no layout yet). */
