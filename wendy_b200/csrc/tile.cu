@@ -51,6 +51,9 @@ namespace wendy {
 #ifndef TK_PERSIST_E
 #define TK_PERSIST_E 4      // particles per thread of the PERSISTENT instances (threads = CAP / TK_PERSIST_E).  2: 1024
 #endif                      // threads, 32 registers, 64 warps per SM -- measured 16 % slower
+#ifndef TK_OWNER_SORT
+#define TK_OWNER_SORT 0     // plain persistent instance: the thread that scanned a sub-bucket sorts its members in place,
+#endif                      // ranks are then positions (prepared candidate, not measured; see "owner sort" below)
 #ifndef TK_COARSE_CAP
 #define TK_COARSE_CAP 2048  // slots per bucket of the CTA kernel (E = 4 particles per thread: 512 threads at 2048)
 #endif
@@ -68,6 +71,9 @@ struct TileSmem {
   unsigned long long pad_;
   double sx[CAP];  // sort keys (positions at force time), grouped by sub-bucket
   int sid[CAP];    // particle ids, same order
+#if TK_OWNER_SORT
+  double sv[PERSIST ? CAP : 2];  // owner sort: velocities, same order
+#endif
   union {
     struct {
       unsigned cnt[(PERSIST ? 2 : 1) * PADN];  // interpolation sub-bucket counters -> start offsets (PERSIST: two sets)
@@ -371,6 +377,18 @@ tile_kernel(const TileParams p) {
     cp_async_commit();
   }
   // ---- 4. exclusive scan of the sub-bucket counters ------------------------------------
+#if TK_OWNER_SORT
+  // Owner sort (plain instance): the thread that scans sub-buckets [E*tid, E*tid + E) knows their sizes and
+  // where they start; after the grouping it sorts the members of every shared sub-bucket in place (x, v, id
+  // move together), so that the particle at position p has rank p and the per-particle comparison loops of
+  // step 6 disappear: the work is done once per sub-bucket instead of once per member, and particles alone
+  // in their sub-bucket cost nothing.  The CTA then continues position-wise.  A sub-bucket with more than
+  // OWNER_SORT_MAX members (a pathological clump; quadratic for one thread) sends the whole bucket down the
+  // member-wise path of step 6 instead -- the verdict rides on the barrier that follows the scan.
+  constexpr int OWNER_SORT_MAX = 12;
+  unsigned own_c[E], own_o = 0;
+  int crowded = 0;
+#endif
   {
     unsigned c[E], run = 0;
     unsigned *cp = &S.u.srt.cnt[cbase + tid * (E + 1)];
@@ -386,13 +404,28 @@ tile_kernel(const TileParams p) {
     const unsigned t = lane < NW ? S.uw[lane] : 0u;
     const unsigned ti = warp_inclusive_scan_u32(t, lane);
     unsigned ex = inc - run + __shfl_sync(WENDY_FULL_MASK, ti - t, wid);
+#if TK_OWNER_SORT
+    if (PLAIN) {
+      own_o = ex;
+#pragma unroll
+      for (int q = 0; q < E; q++) {
+        own_c[q] = c[q];
+        crowded |= c[q] > (unsigned)OWNER_SORT_MAX;
+      }
+    }
+#endif
 #pragma unroll
     for (int q = 0; q < E; q++) {
       cp[q] = ex;
       ex += c[q];
     }
   }
+#if TK_OWNER_SORT
+  if (PLAIN) crowded = __syncthreads_or(crowded);  // (the barrier after the scan, with the verdict on the side)
+  else __syncthreads();
+#else
   __syncthreads();
+#endif
   // ---- 5. group load slots by sub-bucket -------------------------------------------------
 #pragma unroll
   for (int k = 0; k < E; k++) {
@@ -402,6 +435,9 @@ tile_kernel(const TileParams p) {
       unsigned pos = S.u.srt.cnt[cbase + sub + sub / E] + (pk[k] >> 16);
       S.sx[pos] = xk[k];
       S.sid[pos] = id[k];
+#if TK_OWNER_SORT
+      if (PLAIN) S.sv[pos] = vreg[k];
+#endif
     }
   }
   __syncthreads();
@@ -420,6 +456,53 @@ tile_kernel(const TileParams p) {
       if (tid + k * THREADS < n) m[k] = p.min[g[k]];
     }
   }
+#if TK_OWNER_SORT
+  if (PLAIN && !crowded) {
+    unsigned o = own_o;
+#pragma unroll
+    for (int q = 0; q < E; q++) {
+      const unsigned c = own_c[q];
+      if (c > 1u) {  // insertion sort of positions [o, o + c) under (x, id)
+#pragma unroll 1
+        for (unsigned i = o + 1; i < o + c; i++) {
+          const double xi = S.sx[i];
+          const int idi = S.sid[i];
+          unsigned j = i;
+#pragma unroll 1
+          while (j > o) {
+            const double xj = S.sx[j - 1];
+            if (xj < xi || (xj == xi && S.sid[j - 1] < idi)) break;
+            j--;
+          }
+          if (j != i) {
+            const double vi = S.sv[i];
+#pragma unroll 1
+            for (unsigned t = i; t > j; t--) {
+              S.sx[t] = S.sx[t - 1];
+              S.sv[t] = S.sv[t - 1];
+              S.sid[t] = S.sid[t - 1];
+            }
+            S.sx[j] = xi;
+            S.sv[j] = vi;
+            S.sid[j] = idi;
+          }
+        }
+      }
+      o += c;
+    }
+    __syncthreads();
+    // from here on a thread works on the particles at positions tid, tid + THREADS, ...: rank = position
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+      const unsigned pp = tid + k * THREADS;
+      const bool ok = pp < n;
+      xk[k] = ok ? S.sx[ok ? pp : 0u] : 0.0;
+      vreg[k] = ok ? S.sv[ok ? pp : 0u] : 0.0;
+      id[k] = ok ? S.sid[ok ? pp : 0u] : 0;
+      r[k] = ok ? pp : 0u;
+    }
+  } else {
+#endif
   // The sub-bucket bounds of all E particles are fetched first (independent shared-memory loads in flight
   // together); sub-buckets hold 1.75 members on average, so the first TK_RANK_STRAIGHT members are compared
   // by predicated straight-line code and a loop only runs for crowded sub-buckets.
@@ -468,6 +551,9 @@ tile_kernel(const TileParams p) {
       r[k] = rr;
     }
   }
+#if TK_OWNER_SORT
+  }
+#endif
   long long Pc;
   if (EQM) {
     // Equal masses: the exact prefix sum below sorted position k is k*m0, so its correctly
