@@ -69,6 +69,10 @@ int wendy_cuda_create(wendy_cuda_handle **h, long long N, const double *x, const
                       const double *m, const double *totmass, double omega2, int n_segments,
                       int flags, int cap, int fill, void *cuda_stream);
 
+/* Replace the total mass per segment given at creation (n_segments values).  Lets the caller compute
+ * numpy.sum(m) (wendy/wendy.py:383) concurrently with wendy_cuda_create; call before the first step. */
+int wendy_cuda_set_totmass(wendy_cuda_handle *h, const double *totmass);
+
 /* Same, from DEVICE arrays (no host staging).  m_dev may be NULL: all particles have mass m0. */
 int wendy_cuda_create_dev(wendy_cuda_handle **h, long long N, const double *x_dev, const double *v_dev,
                           const double *m_dev, double m0, const double *totmass, double omega2,

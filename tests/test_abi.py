@@ -43,6 +43,7 @@ def test_argument_validation_needs_no_device(lib):
     assert rc == -2 and b'multiple' in lib.wendy_cuda_last_error()
     rc = lib.wendy_cuda_create(ctypes.byref(h), 4, x, x, x, tot, -1., 1, 0, 100, 0, None)
     assert rc == -2 and b'cap' in lib.wendy_cuda_last_error()
+    assert lib.wendy_cuda_set_totmass(None, tot) == -2
 
 
 def test_record_layout_matches_reference_struct():

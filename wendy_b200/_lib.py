@@ -44,6 +44,8 @@ def load():
     lib.wendy_cuda_create.argtypes = [ctypes.POINTER(vp), ctypes.c_longlong, _nd('f8'), _nd('f8'),
                                       _nd('f8'), _nd('f8'), ctypes.c_double, ctypes.c_int,
                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
+    lib.wendy_cuda_set_totmass.restype = ctypes.c_int
+    lib.wendy_cuda_set_totmass.argtypes = [vp, _nd('f8')]
     lib.wendy_cuda_create_dev.restype = ctypes.c_int
     lib.wendy_cuda_create_dev.argtypes = [ctypes.POINTER(vp), ctypes.c_longlong, vp, vp, vp, ctypes.c_double, _nd('f8'),
                                           ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
@@ -125,7 +127,7 @@ EXPORTED = ['wendy_cuda_create', 'wendy_cuda_create_dev', 'wendy_cuda_step', 'we
             'wendy_cuda_read_begin', 'wendy_cuda_read_end', 'wendy_cuda_force_positions',
             'wendy_cuda_substep', 'wendy_cuda_read', 'wendy_cuda_read_dev', 'wendy_cuda_energy',
             'wendy_cuda_stats', 'wendy_cuda_create_shard', 'wendy_cuda_create_shard_dev', 'wendy_cuda_shard_substep', 'wendy_cuda_shard_outbox',
-            'wendy_cuda_shard_inject', 'wendy_cuda_shard_count', 'wendy_cuda_shard_read', 'wendy_cuda_potential', 'wendy_cuda_energy_individual', 'wendy_cuda_trim', 'wendy_host_prefault', 'wendy_cuda_pin', 'wendy_cuda_unpin', 'wendy_cuda_debug_layout', 'wendy_cuda_destroy', 'wendy_cuda_last_error',
+            'wendy_cuda_shard_inject', 'wendy_cuda_shard_count', 'wendy_cuda_shard_read', 'wendy_cuda_potential', 'wendy_cuda_energy_individual', 'wendy_cuda_set_totmass', 'wendy_cuda_trim', 'wendy_host_prefault', 'wendy_cuda_pin', 'wendy_cuda_unpin', 'wendy_cuda_debug_layout', 'wendy_cuda_destroy', 'wendy_cuda_last_error',
             'wendy_cuda_argsort', '_wendy_nbody_approx_onestep']
 
 

@@ -669,6 +669,17 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
   return 0;
 }
 
+// Replace the total mass per segment given at creation.  Lets a host language compute it (the reference's
+// numpy.sum over all masses, wendy/wendy.py:383: tens of milliseconds at N=1e8) while wendy_cuda_create
+// validates and uploads; must be called before the first step.
+int wendy_cuda_set_totmass(wendy_cuda_handle *h, const double *totmass) {
+  if (!h || !totmass) return set_err(WENDY_E_ARG, "null argument");
+  if (h->pending) return set_err(WENDY_E_ARG, "a call is in flight: wendy_cuda_step_end first");
+  CK(cudaMemcpyAsync(h->tot, totmass, (size_t)h->nseg * sizeof(double), cudaMemcpyHostToDevice, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
 int wendy_cuda_create(wendy_cuda_handle **out, long long N, const double *x, const double *v,
                       const double *m, const double *totmass, double omega2, int n_segments, int flags,
                       int cap, int fill, void *cuda_stream) {

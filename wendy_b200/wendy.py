@@ -50,19 +50,36 @@ class ApproxState(object):
             raise ValueError('x, v, m must be 1-D arrays of the same length')
         self.N = len(x)
         self.n_segments = int(n_segments)
-        # totmass exactly as the reference computes it: numpy's pairwise sum
-        # (wendy/wendy.py:383), one value per independent segment
-        tot = numpy.ascontiguousarray(numpy.sum(m.reshape(self.n_segments, -1), axis=1))
         if sort in _REFERENCE_SORTS:
             sort = 'gpu'
         if sort not in _lib.SORT_FLAGS:
             raise KeyError(sort)
+
+        # totmass exactly as the reference computes it: numpy's pairwise sum
+        # (wendy/wendy.py:383), one value per independent segment
+        def total_mass():
+            return numpy.ascontiguousarray(numpy.sum(m.reshape(self.n_segments, -1), axis=1))
+
         self._h = ctypes.c_void_p()
-        _lib.check(self._lib.wendy_cuda_create(ctypes.byref(self._h), self.N, x, v, m, tot,
-                                               float(omega2), self.n_segments,
-                                               _lib.SORT_FLAGS[sort] | (0x10 if general_masses else 0),
-                                               int(cap), int(fill),
-                                               ctypes.c_void_p(stream) if stream else None))
+        flags = _lib.SORT_FLAGS[sort] | (0x10 if general_masses else 0)
+        st = ctypes.c_void_p(stream) if stream else None
+        if self.N < (1 << 22) or self.N % self.n_segments:
+            _lib.check(self._lib.wendy_cuda_create(ctypes.byref(self._h), self.N, x, v, m, total_mass(),
+                                                   float(omega2), self.n_segments, flags, int(cap), int(fill), st))
+        else:
+            # the sum takes tens of milliseconds at N=1e8: a helper thread forms it while the library validates
+            # and uploads (numpy and ctypes both release the GIL), then it replaces the placeholder
+            import threading
+            box = {}
+            th = threading.Thread(target=lambda: box.__setitem__('tot', total_mass()))
+            th.start()
+            try:
+                _lib.check(self._lib.wendy_cuda_create(ctypes.byref(self._h), self.N, x, v, m,
+                                                       numpy.zeros(self.n_segments), float(omega2),
+                                                       self.n_segments, flags, int(cap), int(fill), st))
+            finally:
+                th.join()
+            _lib.check(self._lib.wendy_cuda_set_totmass(self._h, box['tot']))
         self.time_elapsed = 0.
 
     @classmethod
