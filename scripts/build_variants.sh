@@ -9,7 +9,8 @@ B="nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=f
 if [ $# -eq 0 ]; then
   set -- "base:" "wp:-DTK_SLOT_WARPPATH=1" "nw:-DTK_DEST_NOWIN=1" "s32:-DTK_STORE32=1" \
          "all3:-DTK_SLOT_WARPPATH=1 -DTK_DEST_NOWIN=1 -DTK_STORE32=1" "c1024:-DTK_COARSE_CAP=1024" \
-         "pe8:-DTK_PERSIST_E=8" "os:-DTK_OWNER_SORT=1" "os8:-DTK_OWNER_SORT=1 -DTK_PERSIST_E=8"
+         "pe8:-DTK_PERSIST_E=8" "os:-DTK_OWNER_SORT=1" "os8:-DTK_OWNER_SORT=1 -DTK_PERSIST_E=8" \
+         "rd:-DTK_ROUNDS=1" "rdos:-DTK_ROUNDS=1 -DTK_OWNER_SORT=1"
 fi
 for v in "$@"; do
   n=${v%%:*}; f=${v#*:}

@@ -51,6 +51,9 @@ namespace wendy {
 #ifndef TK_PERSIST_E
 #define TK_PERSIST_E 4      // particles per thread of the PERSISTENT instances (threads = CAP / TK_PERSIST_E).  2: 1024
 #endif                      // threads, 32 registers, 64 warps per SM -- measured 16 % slower
+#ifndef TK_ROUNDS
+#define TK_ROUNDS 0         // persistent instances: load / sub-bucket / grouping / sub-bucket bounds run unguarded for the
+#endif                      // rounds that are (nearly) always full, the last round behind a warp-uniform branch (candidate)
 #ifndef TK_OWNER_SORT
 #define TK_OWNER_SORT 0     // plain persistent instance: the thread that scanned a sub-bucket sorts its members in place,
 #endif                      // ranks are then positions (prepared candidate, not measured; see "owner sort" below)
@@ -258,6 +261,29 @@ tile_kernel(const TileParams p) {
     mbar_wait(bar, phase);
     phase ^= 1u;
   }
+#if TK_ROUNDS
+  // rounds 0 .. E-2 are full in all but the emptiest buckets: their code carries no guards (values of slots
+  // beyond n are replaced by zeros, side effects are predicated); the last round, which most warps of a bucket
+  // filled to 13/16 do not have, is skipped by a warp-uniform branch
+  const bool last_round = (unsigned)((E - 1) * THREADS + (tid & ~31)) < n;
+  if (PERSIST) {
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+      xk[k] = 0.0; id[k] = 0; g[k] = 0; vreg[k] = 0.0;
+      if (k == E - 1 && !last_round) continue;
+      const unsigned i = tid + k * THREADS;
+      const bool ok = i < n;
+      double x = S.stx[i];
+      const double vv = S.stv[i];
+      const int ii = S.stid[i];
+      if (p.h_pre != 0.0) x = __dadd_rn(x, __dmul_rn(p.h_pre, vv));
+      xk[k] = ok ? x : 0.0;
+      vreg[k] = ok ? vv : 0.0;
+      id[k] = ok ? ii : 0;
+      g[k] = ok ? (unsigned)b * (unsigned)CAP + i : 0u;
+    }
+  } else
+#endif
 #pragma unroll
   for (int k = 0; k < E; k++) {
     unsigned i = tid + k * THREADS;
@@ -343,6 +369,21 @@ tile_kernel(const TileParams p) {
 
   // ---- 3. interpolation sub-bucket of every key (monotone in x), arrival slot -----------
   unsigned pk[E];  // sub-bucket | arrival order << 16
+#if TK_ROUNDS
+  if (PERSIST) {
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+      pk[k] = 0;
+      if (k == E - 1 && !last_round) continue;
+      const bool ok = tid + k * THREADS < n;
+      int sub = (int)((xk[k] - xmin) * scale);
+      sub = max(0, min(BK - 1, sub));
+      unsigned o = 0;
+      if (ok) o = atomicAdd(&S.u.srt.cnt[cbase + sub + sub / E], 1u);
+      pk[k] = ok ? ((unsigned)sub | (o << 16)) : 0u;
+    }
+  } else
+#endif
 #pragma unroll
   for (int k = 0; k < E; k++) {
     pk[k] = 0;
@@ -427,6 +468,24 @@ tile_kernel(const TileParams p) {
   __syncthreads();
 #endif
   // ---- 5. group load slots by sub-bucket -------------------------------------------------
+#if TK_ROUNDS
+  if (PERSIST) {
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+      if (k == E - 1 && !last_round) continue;
+      const bool ok = tid + k * THREADS < n;
+      const unsigned sub = pk[k] & 0xffffu;
+      const unsigned pos = S.u.srt.cnt[cbase + sub + sub / E] + (pk[k] >> 16);
+      if (ok) {
+        S.sx[pos] = xk[k];
+        S.sid[pos] = id[k];
+#if TK_OWNER_SORT
+        if (PLAIN) S.sv[pos] = vreg[k];
+#endif
+      }
+    }
+  } else
+#endif
 #pragma unroll
   for (int k = 0; k < E; k++) {
     unsigned i = tid + k * THREADS;
@@ -506,6 +565,21 @@ tile_kernel(const TileParams p) {
   // The sub-bucket bounds of all E particles are fetched first (independent shared-memory loads in flight
   // together); sub-buckets hold 1.75 members on average, so the first TK_RANK_STRAIGHT members are compared
   // by predicated straight-line code and a loop only runs for crowded sub-buckets.
+#if TK_ROUNDS
+  if (PERSIST) {
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+      r[k] = 0;
+      if (k == E - 1 && !last_round) { pk[k] = 0; continue; }
+      const bool ok = tid + k * THREADS < n;
+      const unsigned sub = pk[k] & 0xffffu;
+      const unsigned s0 = S.u.srt.cnt[cbase + sub + sub / E];
+      const unsigned s1 = (sub + 1 < (unsigned)BK) ? S.u.srt.cnt[cbase + (sub + 1) + (sub + 1) / E] : n;
+      r[k] = ok ? s0 : 0u;
+      pk[k] = ok ? s1 - s0 : 0u;  // the sub-bucket index is not needed any more
+    }
+  } else
+#endif
 #pragma unroll
   for (int k = 0; k < E; k++) {
     r[k] = 0;
