@@ -42,9 +42,16 @@ typedef struct wendy_cuda_handle wendy_cuda_handle;
 /* sort modes (flags & 0xf) */
 #define WENDY_SORT_AUTO 0    /* bucket fast path, radix sort to (re)build the layout */
 #define WENDY_SORT_RADIX 1   /* full LSD radix sort every sub-step (A/B and fallback) */
-/* When all masses are bit-identical the library uses cum = RN(rank * m0), which equals the
- * correctly rounded exact prefix sum of the general path; this flag forces the general path. */
+/* Cumulative mass (reference wendy/wendy.c:359-360, a SERIAL fp64 running sum over the sorted order):
+ *  - all masses bit-identical (the usual case): the library evaluates the reference's own serial sum in
+ *    closed form (it depends only on the sorted position), so x and v are bit-identical to the reference
+ *    C path at any N.  WENDY_FLAG_EXACT_SCAN selects the correctly rounded exact sum RN(rank * m0) instead
+ *    (what the general path below computes; differs from the reference by the reference's own accumulated
+ *    rounding, ~N * 2^-54 relative).
+ *  - general masses: correctly rounded exact prefix sum (128-bit fixed point); WENDY_FLAG_GENERAL_MASSES
+ *    forces this path (and its mass arrays) even when the masses are equal. */
 #define WENDY_FLAG_GENERAL_MASSES 0x10
+#define WENDY_FLAG_EXACT_SCAN 0x20
 
 /* Mirror of the reference record, wendy/wendy.h:12-16 (int idx; 4 bytes pad; double val). */
 struct wendy_array_w_index {
@@ -117,6 +124,11 @@ int wendy_cuda_read_dev(wendy_cuda_handle *h, double *x_dev, double *v_dev);
  * the stored (twopiG-scaled) masses: out[0] kinetic, out[1] harmonic, out[2] potential,
  * out[3] momentum, each summed over all segments.  E_reference = (out0+out1+out2)/twopiG. */
 int wendy_cuda_energy(wendy_cuda_handle *h, double out[4]);
+
+/* Closed form of the reference's serial cumulative-mass sum for N equal masses (wendy/wendy.c:359-360:
+ * cumulmass[0] = 0, cumulmass[i+1] = cumulmass[i] + m0 in fp64): out[i] = cumulmass[k0 + i], i < n.  Host only
+ * (no GPU): this is the table the equal-mass kernels evaluate.  Returns the number of linear pieces (> 0). */
+int wendy_serial_cum(double m0, long long k0, long long n, double *out);
 
 /* Counters: out[0] sub-steps, [1] layout rebuilds, [2] failed (re-run) sub-steps,
  * [3] max bucket count seen, [4] particles that left the 32-bucket window,

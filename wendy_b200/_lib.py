@@ -70,6 +70,8 @@ def load():
     lib.wendy_cuda_read_dev.argtypes = [vp, vp, vp]
     lib.wendy_cuda_energy.restype = ctypes.c_int
     lib.wendy_cuda_energy.argtypes = [vp, _nd('f8')]
+    lib.wendy_serial_cum.restype = ctypes.c_int
+    lib.wendy_serial_cum.argtypes = [ctypes.c_double, ctypes.c_longlong, ctypes.c_longlong, _nd('f8')]
     lib.wendy_cuda_stats.restype = ctypes.c_int
     lib.wendy_cuda_stats.argtypes = [vp, _nd('i8'), ctypes.c_int]
     lib.wendy_cuda_create_shard.restype = ctypes.c_int
@@ -126,7 +128,7 @@ def load():
 EXPORTED = ['wendy_cuda_create', 'wendy_cuda_create_dev', 'wendy_cuda_step', 'wendy_cuda_step_begin', 'wendy_cuda_step_end',
             'wendy_cuda_read_begin', 'wendy_cuda_read_end', 'wendy_cuda_force_positions',
             'wendy_cuda_substep', 'wendy_cuda_read', 'wendy_cuda_read_dev', 'wendy_cuda_energy',
-            'wendy_cuda_stats', 'wendy_cuda_create_shard', 'wendy_cuda_create_shard_dev', 'wendy_cuda_shard_substep', 'wendy_cuda_shard_outbox',
+            'wendy_cuda_stats', 'wendy_serial_cum', 'wendy_cuda_create_shard', 'wendy_cuda_create_shard_dev', 'wendy_cuda_shard_substep', 'wendy_cuda_shard_outbox',
             'wendy_cuda_shard_inject', 'wendy_cuda_shard_count', 'wendy_cuda_shard_read', 'wendy_cuda_potential', 'wendy_cuda_energy_individual', 'wendy_cuda_set_totmass', 'wendy_cuda_trim', 'wendy_host_prefault', 'wendy_cuda_pin', 'wendy_cuda_unpin', 'wendy_cuda_debug_layout', 'wendy_cuda_destroy', 'wendy_cuda_last_error',
             'wendy_cuda_argsort', '_wendy_nbody_approx_onestep']
 

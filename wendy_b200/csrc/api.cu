@@ -58,8 +58,9 @@ struct wendy_cuda_handle {
   long long N = 0, seg_len = 0;
   int nseg = 1, mode = 0, fxE = 0;
   int nb_alloc = 0;
-  bool eqm = false;        // all masses identical: no mass arrays, cum = rank * m0
+  bool eqm = false;        // all masses identical: no mass arrays
   double m0 = 0.;
+  SerialTab *stab = nullptr;  // equal masses: closed form of the reference's serial running sum (serialsum.cuh)
   double omega2 = -1.;
   int cap = 0, fill = 0, nb = 0, nbps = 0;
   size_t slots = 0;
@@ -77,6 +78,7 @@ struct wendy_cuda_handle {
   bool coarse_default = false;  // large equal-mass systems start (and stay) on 2048-slot buckets
   bool fill_backoff = false;    // a library-chosen coarse layout overflowed at the optimistic fill: use 3/4 from now on
   bool rebuild_pending = false;  // shard: rebuild at the start of the next sub-step (state complete)
+  bool ext_half_done = false;    // ext-force stepping: the leading half drift of the call is already in x
   int user_fill = 0, user_cap = 0;
   double last_dt = 0.;
   bool dense = true;       // state is the dense upload in buffer `cur` (no layout yet)
@@ -319,7 +321,7 @@ static void fill_tile_params(H *h, TileParams &p) {
   p.nb = h->nb; p.nbps = h->nbps; p.seg_len = h->seg_len;
   p.omega2 = h->omega2; p.tot = h->tot; p.fxE = h->fxE;
   p.status = h->status; p.desc = h->desc;
-  p.eqm = h->eqm ? 1 : 0; p.m0 = h->m0;
+  p.eqm = h->eqm ? 1 : 0; p.m0 = h->m0; p.stab = h->stab;
   p.nranks = h->nranks; p.my_rank = h->my_rank; p.bounds = h->bounds;
   p.out_rec = h->out_rec; p.out_cnt = h->out_cnt;
   p.ocap = (unsigned)h->ocap; p.pc_offset = h->pc_offset;
@@ -421,7 +423,7 @@ void wendy_cuda_destroy(wendy_cuda_handle *h) {
   dev_free(h->flags); dev_free(h->offs); dev_free(h->xo); dev_free(h->vo); dev_free(h->epart);
   dev_free(h->eout); dev_free(h->rank);
   dev_free(h->bounds); dev_free(h->out_rec); dev_free(h->out_cnt);
-  dev_free(h->cid);
+  dev_free(h->cid); dev_free(h->stab);
   if (h->h_out_cnt) cudaFreeHost(h->h_out_cnt);
   if (h->st_copy) cudaStreamDestroy(h->st_copy);
   if (h->ev_unsort) cudaEventDestroy(h->ev_unsort);
@@ -594,6 +596,19 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
     if (m) CKD(cudaMemcpy(&h->m0, m, sizeof(double), cudaMemcpyDeviceToHost));
   } else {
     h->m0 = m[0];
+  }
+  if (h->eqm && !(flags & WENDY_FLAG_EXACT_SCAN) && h->m0 != 0. && std::isfinite(h->m0)) {
+    // Equal masses: reproduce the reference's serial fp64 running sum (wendy/wendy.c:359-360) bit for bit
+    // through its closed form, for every sorted position a system (or a sharded system's global rank) can
+    // have.  WENDY_FLAG_EXACT_SCAN keeps the correctly rounded exact sum RN(rank*m0) of the general path.
+    SerialTab *T = new SerialTab;
+    if (serial_tab_build(*T, h->m0, 1ll << 31) == 0) {
+      cudaError_t e = dev_alloc(&h->stab, sizeof(SerialTab));
+      if (e == cudaSuccess) e = cudaMemcpyAsync(h->stab, T, sizeof(SerialTab), cudaMemcpyHostToDevice, h->st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+      if (e != cudaSuccess) { delete T; std::string s__ = cudaGetErrorString(e); wendy_cuda_destroy(h); return set_err(WENDY_E_CUDA, s__); }
+    }
+    delete T;
   }
   for (int i = 0; i < 2; i++) {
     CKD(dev_alloc(&h->x[i], h->slots * sizeof(double)));
@@ -873,7 +888,7 @@ static int enqueue_substeps(H *h, double dt, int nleap, int k0) {
   if (h->small_ok && h->dense && k0 == 0) {
     // small systems: the whole call is ONE launch of the resident kernel (state stays dense, in id order)
     launch_small(h->st, h->x[h->cur], h->v[h->cur], h->m[h->cur], h->seg_len, h->nseg, h->tot, h->eqm ? 1 : 0,
-                 h->m0, h->omega2, h->fxE, dt, nleap);
+                 h->m0, h->stab, h->omega2, h->fxE, dt, nleap);
     h->n_launch++;
     h->n_sub += nleap;
     h->last_dt = dt;
@@ -1014,7 +1029,9 @@ int wendy_cuda_step(wendy_cuda_handle *h, double dt_leap, int nleap, double *tim
 int wendy_cuda_force_positions(wendy_cuda_handle *h, double dt_leap, int first_substep, double **x_dev,
                                long long *n_slots) {
   if (!h || !x_dev || !n_slots) return set_err(WENDY_E_ARG, "null argument");
-  double need_h = first_substep ? dt_leap / 2. : 0.;
+  // The leading half drift is materialised in the stored positions below; a caller that comes back for the same
+  // sub-step after WENDY_RETRY (the layout overflowed and was rebuilt) must not have it applied a second time.
+  double need_h = (first_substep && !h->ext_half_done) ? dt_leap / 2. : 0.;
   if (h->mode == WENDY_SORT_RADIX) {
     // radix mode keeps no splitters; give it a (compact or bucketed) layout to expose
     if (h->dense) { int rc = rebucket(h, need_h); if (rc) return rc; }
@@ -1026,6 +1043,7 @@ int wendy_cuda_force_positions(wendy_cuda_handle *h, double dt_leap, int first_s
     launch_apply_drift(h->st, h->x[h->cur], h->v[h->cur], need_h, h->cnt[h->ccur], h->cap, h->nb);
     h->n_launch++;
     h->bucket_h = 0.;
+    h->ext_half_done = true;
   }
   *x_dev = h->x[h->cur];
   *n_slots = (long long)h->slots;
@@ -1042,6 +1060,7 @@ int wendy_cuda_substep(wendy_cuda_handle *h, double dt_kick, double dt_drift, do
     if (rc) return rc;
     // radix mode applies no trailing re-bucket key: the next call's half drift goes via h_pre
     if (fetch_flags(h)) return WENDY_E_CUDA;
+    h->ext_half_done = false;
     return 0;
   }
   if (!h->has_split || h->bucket_h != 0.) return set_err(WENDY_E_ARG, "layout is not keyed on the stored positions");
@@ -1056,6 +1075,7 @@ int wendy_cuda_substep(wendy_cuda_handle *h, double dt_kick, double dt_drift, do
     if (rc) return rc;
     return WENDY_RETRY;
   }
+  h->ext_half_done = false;
   if (h->h_flags[1] > (unsigned)(h->cap - (h->cap - h->fill) / 16)) {
     // nearly full bucket: re-balance now; the caller's next force_positions sees the new slots
     fill_back_off(h);
@@ -1188,6 +1208,25 @@ int wendy_cuda_energy(wendy_cuda_handle *h, double out[4]) {
   CK(cudaGetLastError());
   for (int i = 0; i < 4; i++) out[i] = h->h_eout[i];
   return 0;
+}
+
+// Host evaluation of the closed-form serial sum the equal-mass kernels use (serialsum.cuh): out[i] = cum below
+// sorted position k0 + i, i.e. the reference's cumulmass[k0 + i] (wendy/wendy.c:359-360) for N equal masses m0.
+// No GPU involved; lets a caller (and the CPU test-suite) check the table against a plain serial loop.
+int wendy_serial_cum(double m0, long long k0, long long n, double *out) {
+  if (k0 < 0 || n < 0 || k0 + n > (1ll << 31) || (n > 0 && !out)) return set_err(WENDY_E_ARG, "bad argument");
+  SerialTab *T = new SerialTab;
+  if (serial_tab_build(*T, m0, 1ll << 31)) { delete T; return set_err(WENDY_E_ARG, "no closed form for this m0"); }
+  int s = 0;
+  for (long long i = 0; i < n; i++) {
+    const long long k = k0 + i;
+    while (k >= T->i0[s + 1]) s++;
+    volatile double prod = (double)(k - T->i0[s]) * T->inc[s];
+    out[i] = T->c0[s] + prod;
+  }
+  const int pieces = T->nseg;
+  delete T;
+  return pieces;
 }
 
 int wendy_cuda_stats(wendy_cuda_handle *h, long long *out, int n) {
@@ -1334,6 +1373,7 @@ void _wendy_nbody_approx_onestep(int N, struct wendy_array_w_index *xi, double *
           }
         }
       } while (rc == WENDY_RETRY && ++tries < 3);
+      h->ext_half_done = false;
     }
   } else if (!rc) {
     std::vector<double> xh((size_t)N), ah((size_t)N);
@@ -1370,6 +1410,7 @@ void _wendy_nbody_approx_onestep(int N, struct wendy_array_w_index *xi, double *
           }
         }
       } while (rc == WENDY_RETRY && ++tries < 3);
+      h->ext_half_done = false;
       if (!rc) *t0 += dt;  // wendy/wendy.c:403-404,409-410
     }
     dev_free(a_id); dev_free(a_slot);

@@ -7,6 +7,8 @@
 
 #include <string>
 
+#include "serialsum.cuh"
+
 namespace wendy {
 
 // ---- radix.cu -----------------------------------------------------------------------
@@ -56,8 +58,10 @@ struct TileParams {
   double h_pre, dt_kick, dt_drift, h_next, omega2;
   const double *tot;        // total mass per segment
   int fxE;                  // fixed-point exponent
-  int eqm;                  // all masses equal m0: cumulative mass = rank * m0 (no mass arrays)
+  int eqm;                  // all masses equal m0 (no mass arrays)
   double m0;
+  const SerialTab *stab;    // equal masses: the reference's serial sum in closed form (serialsum.cuh);
+                            // null: correctly rounded exact sum RN(rank * m0)
   // cross-CTA machinery
   unsigned *status;         // per bucket: (epoch << 2) | state   (mass look-back)
   Desc *desc;
@@ -85,7 +89,8 @@ struct TileParams {
 void launch_tile(cudaStream_t st, int cap, int load, int emit, int physics, const TileParams &p);
 // small.cu: resident kernel, one CTA per small system, all nleap sub-steps of a call in one launch
 void launch_small(cudaStream_t st, double *x, double *v, const double *m, long long seg_len, int nseg,
-                  const double *tot_seg, int eqm, double m0, double omega2, int fxE, double dt, int nleap);
+                  const double *tot_seg, int eqm, double m0, const SerialTab *stab, double omega2, int fxE,
+                  double dt, int nleap);
 int small_max_particles();
 // wstep.cu: warp-per-bucket sub-step (cap 256)
 void launch_wstep(cudaStream_t st, int cap, const TileParams &p);

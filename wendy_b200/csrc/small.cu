@@ -33,7 +33,8 @@ struct SmallSmem {
 template <int SCAP, int THREADS, int EQM>
 __global__ void __launch_bounds__(THREADS)
 small_kernel(double *__restrict__ x, double *__restrict__ v, const double *__restrict__ m, long long seg_len,
-             const double *__restrict__ tot_seg, double m0, double omega2, int fxE, double dt, int nleap) {
+             const double *__restrict__ tot_seg, double m0, const SerialTab *__restrict__ stab, double omega2,
+             int fxE, double dt, int nleap) {
   using SM = SmallSmem<SCAP, THREADS, EQM>;
   constexpr int E = SM::E;
   constexpr int NW = THREADS / 32;
@@ -160,7 +161,8 @@ small_kernel(double *__restrict__ x, double *__restrict__ v, const double *__res
     double cum[E];
     if (EQM) {
 #pragma unroll
-      for (int k = 0; k < E; k++) cum[k] = __dmul_rn((double)r[k], m0);
+      for (int k = 0; k < E; k++)  // serial table: the reference's own running sum, bit for bit (serialsum.cuh)
+        cum[k] = stab ? serial_cum_at(stab, (long long)r[k]) : __dmul_rn((double)r[k], m0);
     } else {
 #pragma unroll
       for (int k = 0; k < E; k++) {
@@ -226,7 +228,8 @@ small_kernel(double *__restrict__ x, double *__restrict__ v, const double *__res
 int small_max_particles() { return 1024; }
 
 void launch_small(cudaStream_t st, double *x, double *v, const double *m, long long seg_len, int nseg,
-                  const double *tot_seg, int eqm, double m0, double omega2, int fxE, double dt, int nleap) {
+                  const double *tot_seg, int eqm, double m0, const SerialTab *stab, double omega2, int fxE,
+                  double dt, int nleap) {
   if (nseg <= 0 || seg_len <= 0) return;
   if (eqm) {
     const size_t sm = sizeof(SmallSmem<1024, 256, 1>);
@@ -235,7 +238,7 @@ void launch_small(cudaStream_t st, double *x, double *v, const double *m, long l
       cudaFuncSetAttribute(small_kernel<1024, 256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
       set1 = true;
     }
-    small_kernel<1024, 256, 1><<<nseg, 256, sm, st>>>(x, v, m, seg_len, tot_seg, m0, omega2, fxE, dt, nleap);
+    small_kernel<1024, 256, 1><<<nseg, 256, sm, st>>>(x, v, m, seg_len, tot_seg, m0, stab, omega2, fxE, dt, nleap);
   } else {
     const size_t sm = sizeof(SmallSmem<1024, 256, 0>);
     static bool set0 = false;
@@ -243,7 +246,7 @@ void launch_small(cudaStream_t st, double *x, double *v, const double *m, long l
       cudaFuncSetAttribute(small_kernel<1024, 256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
       set0 = true;
     }
-    small_kernel<1024, 256, 0><<<nseg, 256, sm, st>>>(x, v, m, seg_len, tot_seg, m0, omega2, fxE, dt, nleap);
+    small_kernel<1024, 256, 0><<<nseg, 256, sm, st>>>(x, v, m, seg_len, tot_seg, m0, nullptr, omega2, fxE, dt, nleap);
   }
 }
 

@@ -700,6 +700,18 @@ tile_kernel(const TileParams p) {
   // ---- 11. force, kick, drift (or diagnostics) ----------------------------------------------------
   const double tot = p.tot[seg];
   const double PcD = (double)(Pc + p.pc_offset);  // pc_offset: particles of the lower ranks (sharded)
+  // Equal masses: cumulative mass below sorted position K0 + r.  With the serial table it is the reference's own
+  // running sum (wendy/wendy.c:359-360) bit for bit; a bucket nearly always lies inside one linear piece.
+  SerialRun SR;
+  SR.c0 = 0.0; SR.inc = 0.0; SR.j0 = 0u; SR.uniform = true;
+  if (EQM && p.stab) SR = serial_run(p.stab, Pc + p.pc_offset, n);
+  auto cum_eqm = [&](unsigned rk) -> double {
+    if (p.stab) {
+      if (SR.uniform) return serial_cum_run(SR, rk);
+      return serial_cum_at(p.stab, Pc + p.pc_offset + (long long)rk);
+    }
+    return __dmul_rn(__dadd_rn(PcD, (double)rk), p.m0);  // exact integer sum below 2^53, one rounding
+  };
   double x2[E], v2[E], xb[E];
   double e_ke = 0.0, e_he = 0.0, e_pe = 0.0, e_mom = 0.0;
   if (PLAIN) {
@@ -707,14 +719,20 @@ tile_kernel(const TileParams p) {
     // branched regions, i.e. E dependent chains of eleven fp64 operations one after the other; without the
     // guards the chains interleave (slots beyond n compute on zeros; nothing of theirs is ever stored).  The
     // last round, which most warps of a bucket filled to about 3/4 do not have, sits behind a warp-uniform branch.
+    double cm[E];
+    if (p.stab && SR.uniform) {
+#pragma unroll
+      for (int k = 0; k < E; k++) cm[k] = serial_cum_run(SR, r[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < E; k++) cm[k] = cum_eqm(r[k]);
+    }
     auto phys_rounds = [&](auto k0c, auto k1c) {
       constexpr int k0 = decltype(k0c)::value, k1 = decltype(k1c)::value;
       double acc[E];
 #pragma unroll
-      for (int k = k0; k < k1; k++) {
-        const double c = __dmul_rn(__dadd_rn(PcD, (double)r[k]), p.m0);  // exact integer sum below 2^53
-        acc[k] = __dsub_rn(__dsub_rn(tot, __dmul_rn(2.0, c)), p.m0);
-      }
+      for (int k = k0; k < k1; k++)
+        acc[k] = __dsub_rn(__dsub_rn(tot, __dmul_rn(2.0, cm[k])), p.m0);
 #pragma unroll
       for (int k = k0; k < k1; k++)
         if (p.omega2 >= 0.0) acc[k] = __dsub_rn(acc[k], __dmul_rn(p.omega2, xk[k]));
@@ -739,7 +757,7 @@ tile_kernel(const TileParams p) {
       double c, mk;
       if (EQM) {
         mk = p.m0;
-        c = __dmul_rn(__dadd_rn(PcD, (double)r[k]), p.m0);  // exact integer sum below 2^53
+        c = cum_eqm(r[k]);
       } else {
         mk = m[k];
         c = S.u.mcum[r[k] + r[k] / E];

@@ -143,6 +143,9 @@ wstep_kernel(const TileParams p) {
   for (int i = lane; i < SL::PADN; i += 32) S.cnt[i] = 0;
   // particles in the preceding buckets of the segment (count_prefix kernel ran just before)
   const long long Pc = (long long)p.cpre[b] - (long long)seg * p.seg_len + (SHARD ? p.pc_offset : 0ll);
+  SerialRun SR;
+  SR.c0 = 0.0; SR.inc = 0.0; SR.j0 = 0u; SR.uniform = true;
+  if (EQM && p.stab) SR = serial_run(p.stab, Pc, n);
   // lower splitters of the 32 buckets around b, in shared memory (only leaving lanes search)
   int wlo = b - 15;
   if (wlo > seg_hi - 32) wlo = seg_hi - 32;
@@ -353,7 +356,9 @@ wstep_kernel(const TileParams p) {
         double c, mk;
         if (EQM) {
           mk = p.m0;
-          c = __dmul_rn((double)(Pc + (long long)WS_RANK(k)), p.m0);  // Pc includes the lower ranks' particles
+          // Pc includes the lower ranks' particles; serial table: the reference's own running sum (serialsum.cuh)
+          if (p.stab) c = SR.uniform ? serial_cum_run(SR, WS_RANK(k)) : serial_cum_at(p.stab, Pc + (long long)WS_RANK(k));
+          else c = __dmul_rn((double)(Pc + (long long)WS_RANK(k)), p.m0);
         } else {
           mk = S.sm[i];
           c = S.so[WS_RANK(k) + WS_RANK(k) / E];

@@ -14,9 +14,12 @@ Differences a user can observe:
     F must be element-wise.
   * ``sort=`` accepts the reference's names (all map to the GPU default) plus
     ``'gpu'``/``'gpu-bucket'`` and ``'gpu-radix'``.
-  * the cumulative mass is the correctly rounded exact prefix sum rather than a serial fp64
-    running sum (agrees with the reference to ~1e-16 relative at the sizes the reference
-    can run).
+  * cumulative mass (reference wendy/wendy.c:359-360, a serial fp64 running sum): for equal
+    masses the library evaluates that serial sum in closed form, so x and v are BIT-IDENTICAL
+    to the reference C path at any N (tests: 1e4 ... 1e8 against the compiled reference);
+    for unequal masses it is the correctly rounded exact prefix sum, which differs from the
+    reference by the reference's own accumulated rounding (about N * 1e-16 relative in the
+    cumulative mass; measured differences in x, v are in DESIGN.md section 4).
 """
 import ctypes
 import os
@@ -41,7 +44,7 @@ class ApproxState(object):
     """Device-resident particle state + the step driver (one per generator)."""
 
     def __init__(self, x, v, m, omega2=-1., n_segments=1, sort='gpu', cap=0, fill=0, stream=None,
-                 general_masses=False):
+                 general_masses=False, exact_scan=False):
         self._lib = _lib.load()
         x = numpy.require(x, dtype=numpy.float64, requirements=['C'])
         v = numpy.require(v, dtype=numpy.float64, requirements=['C'])
@@ -61,7 +64,7 @@ class ApproxState(object):
             return numpy.ascontiguousarray(numpy.sum(m.reshape(self.n_segments, -1), axis=1))
 
         self._h = ctypes.c_void_p()
-        flags = _lib.SORT_FLAGS[sort] | (0x10 if general_masses else 0)
+        flags = _lib.SORT_FLAGS[sort] | (0x10 if general_masses else 0) | (0x20 if exact_scan else 0)
         st = ctypes.c_void_p(stream) if stream else None
         if self.N < (1 << 22) or self.N % self.n_segments:
             _lib.check(self._lib.wendy_cuda_create(ctypes.byref(self._h), self.N, x, v, m, total_mass(),
@@ -83,7 +86,7 @@ class ApproxState(object):
         self.time_elapsed = 0.
 
     @classmethod
-    def from_device(cls, x, v, m, omega2=-1., n_segments=1, sort='gpu', cap=0, fill=0):
+    def from_device(cls, x, v, m, omega2=-1., n_segments=1, sort='gpu', cap=0, fill=0, exact_scan=False):
         """Build the state from CUDA torch tensors without host staging.
 
         ``m`` is a float (equal masses, already times twopiG) or a CUDA tensor.  ``totmass`` per
@@ -110,7 +113,8 @@ class ApproxState(object):
         _lib.check(self._lib.wendy_cuda_create_dev(
             ctypes.byref(self._h), self.N, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(v.data_ptr()), mptr, m0,
             numpy.ascontiguousarray(tot, dtype=numpy.float64), float(omega2), self.n_segments,
-            _lib.SORT_FLAGS[sort], int(cap), int(fill), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            _lib.SORT_FLAGS[sort] | (0x20 if exact_scan else 0), int(cap), int(fill),
+            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
         self.time_elapsed = 0.
         return self
 
@@ -208,7 +212,7 @@ class ApproxState(object):
 def nbody(x, v, m, dt, t0=0., twopiG=1., omega=None, ext_force=None,
           approx=False, nleap=None, sort='gpu',
           maxcoll=100000, warn_maxcoll=False,
-          full_output=False, n_segments=1, _cap=0, _fill=0, _general_masses=False):
+          full_output=False, n_segments=1, _cap=0, _fill=0, _general_masses=False, _exact_scan=False):
     """
     NAME:
        nbody
@@ -238,12 +242,13 @@ def nbody(x, v, m, dt, t0=0., twopiG=1., omega=None, ext_force=None,
     for item in _nbody_approx(x, v, m, dt, nleap, t0=t0, sort=sort, omega=omega,
                               ext_force=ext_force, twopiG=twopiG, full_output=full_output,
                               n_segments=n_segments, _cap=_cap, _fill=_fill,
-                              _general_masses=_general_masses):
+                              _general_masses=_general_masses, _exact_scan=_exact_scan):
         yield item
 
 
 def _nbody_approx(x, v, m, dt, nleap, t0=0., omega=None, ext_force=None, sort='gpu',
-                  twopiG=1., full_output=False, n_segments=1, _cap=0, _fill=0, _general_masses=False):
+                  twopiG=1., full_output=False, n_segments=1, _cap=0, _fill=0, _general_masses=False,
+                  _exact_scan=False):
     """Setup follows reference wendy/wendy.py:363-387,422; loop follows :424-437."""
     omega2 = -1. if omega is None else omega ** 2.
     # The inputs are only read (the reference copies them, wendy/wendy.py:369-370; here the "copy" is the
@@ -295,7 +300,7 @@ def _nbody_approx(x, v, m, dt, nleap, t0=0., omega=None, ext_force=None, sort='g
     try:
         try:
             state = ApproxState(xin, vin, ms, omega2=omega2, n_segments=n_segments, sort=sort, cap=_cap,
-                                fill=_fill, general_masses=_general_masses)
+                                fill=_fill, general_masses=_general_masses, exact_scan=_exact_scan)
             if ext_force is None:
                 state.step_begin(dt_leap, nleap)
         finally:
