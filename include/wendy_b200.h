@@ -165,6 +165,29 @@ int wendy_cuda_shard_count(wendy_cuda_handle *h, long long *n_local);
 int wendy_cuda_shard_read(wendy_cuda_handle *h, double *x_host, double *v_host, int *id_host,
                           long long *n);
 
+/* ---- sharded single system, device-driven exchange over peer memory (NVLink) ---------------------
+ * With these entry points a sub-step needs NO host round trip and no host-side collective: the step kernel
+ * stores migrants straight into the owner's inbox (peer memory), an inject kernel appends them, and the ranks
+ * hand each other counts through flag words in each other's comm buffers (wendy_b200/csrc/peer.cuh).  One
+ * process per GPU (CUDA IPC) or several ranks in one process (raw pointers).  Equal masses, <= 16 ranks.
+ *   comm_export   allocate this rank's comm buffer; *ptr / *bytes describe it, ipc_handle64 receives the 64-byte
+ *                 CUDA IPC handle (returns 1 instead of 0 when IPC is unavailable: raw pointers only)
+ *   comm_open     map every peer's buffer: raw_ptrs[r] != 0 (same process) or ipc_handles + 64 r
+ *   seed_counts   counts[r] = particles rank r owns; once after the partition and after every rollback
+ *   step_begin    enqueue sub-steps [k0, nleap) of one call (wendy/wendy.c:398-411) on this rank's stream
+ *   step_end      wait; *k_fail = first sub-step that did not complete here (nleap: none), *n_local = particles
+ *                 owned now, *migrated_in = records received during the call.  The ranks agree on min(k_fail)
+ *                 with ONE host collective per call; if it is < nleap every rank calls
+ *   rollback      back to the input of sub-step k (then: all-gather the counts, seed_counts, step_begin(k0 = k)) */
+int wendy_cuda_shard_comm_export(wendy_cuda_handle *h, unsigned long long *ptr, unsigned long long *bytes,
+                                 unsigned char *ipc_handle64);
+int wendy_cuda_shard_comm_open(wendy_cuda_handle *h, const unsigned char *ipc_handles,
+                               const unsigned long long *raw_ptrs);
+int wendy_cuda_shard_seed_counts(wendy_cuda_handle *h, const long long *counts);
+int wendy_cuda_shard_step_begin(wendy_cuda_handle *h, double dt_leap, int nleap, int k0);
+int wendy_cuda_shard_step_end(wendy_cuda_handle *h, int *k_fail, long long *n_local, long long *migrated_in);
+int wendy_cuda_shard_rollback(wendy_cuda_handle *h, int k, long long *n_local);
+
 /* Diagnostics on arbitrary particle arrays (each pointer may be HOST or DEVICE memory); m is the
  * unscaled mass, twopiG multiplies the sums as in the reference; omega2 < 0: no harmonic term.
  *   potential          out[j] = omega2 y_j^2/2 + twopiG sum_i m_i |x_i - y_j|      (wendy/wendy.py:494-517)

@@ -7,7 +7,7 @@ cd "$(dirname "$0")/../wendy_b200/csrc" || exit 1
 mkdir -p ../variants
 B="nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC -Xcompiler -fopenmp"
 if [ $# -eq 0 ]; then
-  set -- "base:" "wp:-DTK_SLOT_WARPPATH=1" "nw:-DTK_DEST_NOWIN=1" "s32:-DTK_STORE32=1" \
+  set -- "base:" "exact:-DWENDY_FORCE_EXACT_SCAN=1" "wp:-DTK_SLOT_WARPPATH=1" "nw:-DTK_DEST_NOWIN=1" "s32:-DTK_STORE32=1" \
          "all3:-DTK_SLOT_WARPPATH=1 -DTK_DEST_NOWIN=1 -DTK_STORE32=1" "c1024:-DTK_COARSE_CAP=1024" \
          "pe8:-DTK_PERSIST_E=8" "os:-DTK_OWNER_SORT=1" "os8:-DTK_OWNER_SORT=1 -DTK_PERSIST_E=8" \
          "rd:-DTK_ROUNDS=1" "rdos:-DTK_ROUNDS=1 -DTK_OWNER_SORT=1"

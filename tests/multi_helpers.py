@@ -10,7 +10,7 @@ from wendy_b200.multi import route
 
 class NumpyShardEngine(object):
     """CPU stand-in for CudaShardEngine with identical semantics; arithmetic follows the oracle
-    restatement (oracle/wendy_oracle.py::numpy_onestep with the exact scan, equal masses)."""
+    restatement (oracle/wendy_oracle.py::numpy_onestep, serial scan, equal masses)."""
 
     def __init__(self, x, v, ids, m0, totmass, omega2, nranks, rank, bounds, capacity, outbox_capacity):
         self.x, self.v, self.ids = numpy.array(x), numpy.array(v), numpy.array(ids, dtype=numpy.int32)
@@ -22,7 +22,8 @@ class NumpyShardEngine(object):
         x = self.x + h_pre * self.v if h_pre != 0. else self.x
         order = numpy.lexsort((self.ids, x))
         xs, vs, ids = x[order], self.v[order], self.ids[order]
-        cum = (pc_offset + numpy.arange(len(xs))).astype(numpy.float64) * self.m0
+        # the reference's serial running sum (wendy.c:359-360) at the GLOBAL sorted position, as the CUDA engine
+        cum = numpy.concatenate(([0.], numpy.cumsum(numpy.full(pc_offset + len(xs), self.m0))))[pc_offset:pc_offset + len(xs)]
         g = (self.tot - 2. * cum) - self.m0
         if self.omega2 >= 0:
             g = g - self.omega2 * xs

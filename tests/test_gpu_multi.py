@@ -36,9 +36,20 @@ def _run_rank(comm, n, omega, dt_leap, nleap, calls):
     return X, V, mig, counts
 
 
+@pytest.fixture(params=['peer', 'host'])
+def exchange(request, monkeypatch):
+    """Both exchange paths: 'peer' = device-driven over peer memory (here: raw pointers between ranks that are
+    threads of one process; their persistent kernels wait for each other, so all of them must be resident on the
+    one GPU at the same time -- small grids), 'host' = all-gather + all-to-all per sub-step."""
+    monkeypatch.setenv('WENDY_B200_SHARD_PEER', '1' if request.param == 'peer' else '0')
+    if request.param == 'peer':
+        monkeypatch.setenv('WENDY_B200_PERSIST_GRID', '12')
+    return request.param
+
+
 @pytest.mark.parametrize('ranks', [2, 3])
 @pytest.mark.parametrize('n,dt_leap', [(40000, 0.01), (200000, 0.002)])
-def test_sharded_threads_one_gpu_equals_single_gpu(ranks, n, dt_leap):
+def test_sharded_threads_one_gpu_equals_single_gpu(ranks, n, dt_leap, exchange):
     x, v, m = wo.sech2_ic(n, seed=6)
     Xs, Vs = _single_gpu(x, v, m, dt_leap, 5, 2, 1.1)
     res = run_threads(ranks, lambda comm: _run_rank(comm, n, 1.1, dt_leap, 5, 2), device='cuda')
@@ -48,17 +59,17 @@ def test_sharded_threads_one_gpu_equals_single_gpu(ranks, n, dt_leap):
     assert sum(r[2] for r in res) > 0
 
 
-def test_sharded_matches_oracle():
+def test_sharded_matches_oracle(exchange):
     n = 30000
     x, v, m = wo.sech2_ic(n, seed=6)
     xo, vo = x, v
     for _ in range(2):
-        xo, vo, _, _ = wo.numpy_onestep(xo, vo, m, numpy.sum(m), 0.01, 3, -1., exact_scan=True)
+        xo, vo, _, _ = wo.numpy_onestep(xo, vo, m, numpy.sum(m), 0.01, 3, -1.)  # equal masses: serial scan
     res = run_threads(2, lambda comm: _run_rank(comm, n, None, 0.01, 3, 2), device='cuda')
     assert numpy.array_equal(res[0][0], xo) and numpy.array_equal(res[0][1], vo)
 
 
-def test_sharded_large_dt_switches_geometry_and_recovers_inject_overflow():
+def test_sharded_large_dt_switches_geometry_and_recovers_inject_overflow(exchange):
     """Large N*dt: every rank switches to coarse buckets (deferred to the next sub-step) and heavy
     migration hits the range edges; the result must still equal the single-GPU path bit for bit."""
     n = 300000
@@ -69,7 +80,7 @@ def test_sharded_large_dt_switches_geometry_and_recovers_inject_overflow():
         assert numpy.array_equal(X, Xs) and numpy.array_equal(V, Vs)
 
 
-def test_sharded_ranks_of_more_than_2_20_particles_use_the_coarse_layout():
+def test_sharded_ranks_of_more_than_2_20_particles_use_the_coarse_layout(exchange):
     """Shards of >= 2^20 equal-mass particles are created directly on 2048-slot buckets with storage sized for
     that geometry (the shape of the multi-GPU bench at 1e8 particles per rank); bit-identical to one GPU."""
     n = 2400000
@@ -79,6 +90,55 @@ def test_sharded_ranks_of_more_than_2_20_particles_use_the_coarse_layout():
     for X, V, mig, counts in res:
         assert numpy.array_equal(X, Xs) and numpy.array_equal(V, Vs)
         assert int(counts.sum()) == n
+    assert sum(r[2] for r in res) > 0
+
+
+def test_sharded_four_ranks_and_a_changed_time_step(exchange):
+    """Four ranks; the second call uses another dt (re-partition on the key of the new first force evaluation)."""
+    import wendy_b200
+    n = 120000
+    x, v, m = wo.sech2_ic(n, seed=6)
+    st = wendy_b200.ApproxState(x, v, m, omega2=1.21)
+    st.step(0.004, 4)
+    st.step(0.009, 3)
+    Xs, Vs = st.read()
+    st.close()
+
+    def run(comm):
+        from wendy_b200 import multi
+        mine = numpy.arange(n) % comm.size == comm.rank
+        s = multi.ShardedSystem(x[mine], v[mine], numpy.arange(n)[mine], m[0], numpy.sum(m), comm, omega=1.1)
+        s.step(0.004, 4)
+        s.step(0.009, 3)
+        X, V = s.gather(n)
+        s.close()
+        return X, V
+    for X, V in run_threads(4, run, device='cuda'):
+        assert numpy.array_equal(X, Xs) and numpy.array_equal(V, Vs)
+
+
+def test_sharded_peer_exchange_rolls_back_after_an_overflow(monkeypatch):
+    """A collapsing cold slab overflows buckets in the middle of a call: the failing rank's flag words stop every
+    rank within one exchange, all roll back to the input of that sub-step, rebuild, and finish the call."""
+    monkeypatch.setenv('WENDY_B200_SHARD_PEER', '1')
+    monkeypatch.setenv('WENDY_B200_PERSIST_GRID', '12')
+    n = 60000
+    x, v, m = wo.slab_ic(n, seed=5)
+    Xs, Vs = _single_gpu(x, v, m, 0.05, 5, 4, None)
+
+    def run(comm):
+        from wendy_b200 import multi
+        mine = numpy.arange(n) % comm.size == comm.rank
+        s = multi.ShardedSystem(x[mine], v[mine], numpy.arange(n)[mine], m[0], numpy.sum(m), comm)
+        for _ in range(4):
+            s.step(0.05, 5)
+        X, V = s.gather(n)
+        fails = s.engine.stats()['failed_substeps']
+        s.close()
+        return X, V, fails
+    res = run_threads(2, run, device='cuda')
+    for X, V, fails in res:
+        assert numpy.array_equal(X, Xs) and numpy.array_equal(V, Vs)
     assert sum(r[2] for r in res) > 0
 
 

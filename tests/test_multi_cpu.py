@@ -23,7 +23,7 @@ def _problem(n=3000, seed=4):
 def _oracle(x, v, m, dt_leap, nleap, calls, omega):
     om2 = -1. if omega is None else omega ** 2
     for _ in range(calls):
-        x, v, _, _ = wo.numpy_onestep(x, v, m, numpy.sum(m), dt_leap, nleap, om2, exact_scan=True)
+        x, v, _, _ = wo.numpy_onestep(x, v, m, numpy.sum(m), dt_leap, nleap, om2)
     return x, v
 
 

@@ -120,6 +120,19 @@ struct wendy_cuda_handle {
   int *cid = nullptr;
   unsigned *out_cnt = nullptr, *h_out_cnt = nullptr;
   long long ocap = 0, pc_offset = 0;
+  // ... device-driven exchange over peer memory (peer.cuh): comm buffer (peers write into it), mapped peers
+  void *comm = nullptr;
+  size_t comm_bytes = 0;
+  void *peer_map[PEER_MAX] = {nullptr};   // cudaIpcOpenMemHandle results (closed on destroy)
+  PeerComm *peer_dev = nullptr;           // device copy of the pointer table
+  PeerComm peer_host;
+  unsigned *peer_scratch = nullptr;       // out_cnt[PEER_MAX] | cta_done[2] | peer_stat[1]
+  long long *peer_n = nullptr;            // n_local | n_hist[PEER_NHIST]
+  long long *h_peer_n = nullptr;          // pinned mirror
+  unsigned pepoch = 1, peer_mig_seen = 0;
+  bool peer_on = false;
+  std::vector<unsigned> p_seq_inj;
+  std::vector<long long> p_nstart;
   // asynchronous call in flight (wendy_cuda_step_begin / _end) and overlapped read-out
   bool pending = false;
   double p_dt = 0.;
@@ -325,6 +338,7 @@ static void fill_tile_params(H *h, TileParams &p) {
   p.nranks = h->nranks; p.my_rank = h->my_rank; p.bounds = h->bounds;
   p.out_rec = h->out_rec; p.out_cnt = h->out_cnt;
   p.ocap = (unsigned)h->ocap; p.pc_offset = h->pc_offset;
+  p.peer = h->peer_on ? h->peer_dev : nullptr; p.pepoch = h->pepoch;
   p.ticket = h->ticket + h->tcur; p.ticket_zero = h->ticket + (h->tcur + 2) % 3;
   p.fail_seq = h->flags; p.stats = h->flags + 1; p.outside = (unsigned long long *)(h->flags + 8);
   p.seq = h->seq; p.epoch = h->seq;
@@ -424,6 +438,11 @@ void wendy_cuda_destroy(wendy_cuda_handle *h) {
   dev_free(h->eout); dev_free(h->rank);
   dev_free(h->bounds); dev_free(h->out_rec); dev_free(h->out_cnt);
   dev_free(h->cid); dev_free(h->stab);
+  for (int r = 0; r < PEER_MAX; r++)
+    if (h->peer_map[r]) cudaIpcCloseMemHandle(h->peer_map[r]);
+  if (h->comm) cudaFree(h->comm);
+  dev_free(h->peer_dev); dev_free(h->peer_scratch); dev_free(h->peer_n);
+  if (h->h_peer_n) cudaFreeHost(h->h_peer_n);
   if (h->h_out_cnt) cudaFreeHost(h->h_out_cnt);
   if (h->st_copy) cudaStreamDestroy(h->st_copy);
   if (h->ev_unsort) cudaEventDestroy(h->ev_unsort);
@@ -597,6 +616,9 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
   } else {
     h->m0 = m[0];
   }
+#ifdef WENDY_FORCE_EXACT_SCAN  // A/B builds: what the serial table costs
+  flags |= WENDY_FLAG_EXACT_SCAN;
+#endif
   if (h->eqm && !(flags & WENDY_FLAG_EXACT_SCAN) && h->m0 != 0. && std::isfinite(h->m0)) {
     // Equal masses: reproduce the reference's serial fp64 running sum (wendy/wendy.c:359-360) bit for bit
     // through its closed form, for every sorted position a system (or a sharded system's global rank) can
@@ -878,6 +900,222 @@ int wendy_cuda_shard_read(wendy_cuda_handle *h, double *x_host, double *v_host, 
   CK(cudaStreamSynchronize(h->st));
   CK(cudaGetLastError());
   *n = h->N;
+  return 0;
+}
+
+// ---- sharded system: device-driven exchange over peer memory (peer.cuh) -------------------------------------
+constexpr int PEER_NHIST = 4096;  // sub-steps per call whose particle counts are recorded (nleap limit in this mode)
+static size_t comm_flag_bytes() { return (size_t)4 * PEER_MAX * sizeof(unsigned long long); }
+static size_t comm_inbox_bytes(const H *h) { return (size_t)2 * h->nranks * (size_t)h->ocap * 3 * sizeof(double); }
+
+// Allocate this rank's comm buffer (flags + inboxes; plain cudaMalloc so that it can be exported) and describe
+// it: raw device pointer, size, and the 64-byte CUDA IPC handle another PROCESS on this node opens it with.
+int wendy_cuda_shard_comm_export(wendy_cuda_handle *h, unsigned long long *ptr, unsigned long long *bytes,
+                                 unsigned char *ipc_handle64) {
+  if (!h || !h->bounds || !ptr || !bytes || !ipc_handle64) return set_err(WENDY_E_ARG, "not a shard handle");
+  if (h->nranks > PEER_MAX) return set_err(WENDY_E_ARG, "peer exchange supports at most 16 ranks");
+  if (!h->eqm) return set_err(WENDY_E_ARG, "peer exchange: equal masses only");
+  if (!h->comm) {
+    h->comm_bytes = 256 + comm_flag_bytes() + comm_inbox_bytes(h);
+    CK(cudaMalloc(&h->comm, h->comm_bytes));
+    CK(cudaMemset(h->comm, 0, h->comm_bytes));
+  }
+  *ptr = (unsigned long long)(uintptr_t)h->comm;
+  *bytes = (unsigned long long)h->comm_bytes;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t ih;
+  memset(&ih, 0, sizeof(ih));
+  cudaError_t e = cudaIpcGetMemHandle(&ih, h->comm);
+  if (e != cudaSuccess) cudaGetLastError();  // no IPC on this platform: ranks in one process can still use raw pointers
+  memcpy(ipc_handle64, &ih, 64);
+  return e == cudaSuccess ? 0 : 1;
+}
+
+// Map the peers' comm buffers and switch the handle to the device-driven exchange.  For rank r != my rank:
+// raw_ptrs[r] != 0 -> that rank lives in THIS process (or the pointer is otherwise valid here); else its IPC
+// handle (64 bytes at ipc_handles + 64 r) is opened.
+int wendy_cuda_shard_comm_open(wendy_cuda_handle *h, const unsigned char *ipc_handles, const unsigned long long *raw_ptrs) {
+  if (!h || !h->bounds || !h->comm || !raw_ptrs) return set_err(WENDY_E_ARG, "export the comm buffer first");
+  PeerComm &pc = h->peer_host;
+  memset(&pc, 0, sizeof(pc));
+  pc.nranks = h->nranks; pc.my_rank = h->my_rank; pc.ocap = (unsigned)h->ocap;
+  auto carve = [&](void *base, unsigned long long *&inf, unsigned long long *&cntf, double *&inbox) {
+    char *b = (char *)base;
+    inf = (unsigned long long *)b;
+    cntf = inf + 2 * PEER_MAX;
+    inbox = (double *)(b + 256 + comm_flag_bytes());
+  };
+  {
+    unsigned long long *a, *b; double *c;
+    carve(h->comm, a, b, c);
+    pc.in_flag = a; pc.cnt_flag = b; pc.inbox = c;
+  }
+  for (int r = 0; r < h->nranks; r++) {
+    void *base = nullptr;
+    if (r == h->my_rank) base = h->comm;
+    else if (raw_ptrs[r]) base = (void *)(uintptr_t)raw_ptrs[r];
+    else {
+      if (!ipc_handles) return set_err(WENDY_E_ARG, "no IPC handle for a peer in another process");
+      cudaIpcMemHandle_t ih;
+      memcpy(&ih, ipc_handles + (size_t)64 * r, 64);
+      CK(cudaIpcOpenMemHandle(&base, ih, cudaIpcMemLazyEnablePeerAccess));
+      h->peer_map[r] = base;
+    }
+    carve(base, pc.peer_in_flag[r], pc.peer_cnt_flag[r], pc.peer_inbox[r]);
+  }
+  if (!h->peer_scratch) {
+    CK(dev_alloc(&h->peer_scratch, (PEER_MAX + 8) * sizeof(unsigned)));
+    CK(dev_alloc(&h->peer_n, (size_t)(PEER_NHIST + 2) * sizeof(long long)));
+    CK(dev_alloc(&h->peer_dev, sizeof(PeerComm)));
+    CK(cudaMallocHost(&h->h_peer_n, (size_t)(PEER_NHIST + 2) * sizeof(long long)));
+  }
+  CK(cudaMemsetAsync(h->peer_scratch, 0, (PEER_MAX + 8) * sizeof(unsigned), h->st));
+  CK(cudaMemsetAsync(h->peer_n, 0, (size_t)(PEER_NHIST + 2) * sizeof(long long), h->st));
+  pc.out_cnt = h->peer_scratch; pc.cta_done = h->peer_scratch + PEER_MAX; pc.peer_stat = h->peer_scratch + PEER_MAX + 2;
+  pc.n_local = h->peer_n; pc.n_hist = h->peer_n + 1;
+  {
+    const char *te = getenv("WENDY_B200_PEER_TIMEOUT_MS");
+    const long long ms = te ? atoll(te) : 20000;
+    pc.timeout_ns = (unsigned long long)(ms > 0 ? ms : 20000) * 1000000ull;
+  }
+  CK(cudaMemcpyAsync(h->peer_dev, &pc, sizeof(pc), cudaMemcpyHostToDevice, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  h->peer_on = true;
+  // the exchange lives in the persistent CTA kernel: coarse buckets from the start
+  if (h->cap != tile_coarse_cap()) {
+    h->want_cap = tile_coarse_cap();
+    h->has_split = false;
+  }
+  return 0;
+}
+
+// (Re)seed the count flags: counts[r] = particles rank r owns now (from a host collective).  Needed once after
+// the partition and after every rollback; between calls the flags of the last sub-step are already in place.
+int wendy_cuda_shard_seed_counts(wendy_cuda_handle *h, const long long *counts) {
+  if (!h || !h->peer_on || !counts) return set_err(WENDY_E_ARG, "peer exchange is not set up");
+  unsigned long long w[PEER_MAX];
+  const unsigned e = h->pepoch - 1u;
+  for (int r = 0; r < PEER_MAX; r++) w[r] = r < h->nranks ? peer_pack(e, false, (unsigned)counts[r]) : 0ull;
+  CK(cudaStreamSynchronize(h->st));
+  CK(cudaMemcpy((void *)(h->peer_host.cnt_flag + (e & 1u) * PEER_MAX), w, sizeof(w), cudaMemcpyHostToDevice));
+  const long long mine = counts[h->my_rank];
+  CK(cudaMemcpy(h->peer_n, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+  CK(cudaMemset(h->peer_scratch, 0, (PEER_MAX + 8) * sizeof(unsigned)));
+  h->peer_mig_seen = 0;
+  h->N = mine; h->seg_len = mine;
+  return 0;
+}
+
+// Enqueue sub-steps [k0, nleap) of one call on every rank's own stream; nothing here waits for a peer's HOST.
+// (A layout rebuild -- first call, changed dt, after a rollback -- is local and synchronous.)
+int wendy_cuda_shard_step_begin(wendy_cuda_handle *h, double dt, int nleap, int k0) {
+  if (!h || !h->peer_on) return set_err(WENDY_E_ARG, "peer exchange is not set up");
+  if (nleap < 1 || nleap > PEER_NHIST || k0 < 0 || k0 >= nleap) return set_err(WENDY_E_ARG, "bad nleap");
+  if (h->pending) return set_err(WENDY_E_ARG, "a call is already in flight");
+  if (k0 == 0) { h->p_seq.clear(); h->p_seq_inj.clear(); h->p_cur.clear(); h->p_ccur.clear(); }
+  h->p_seq.resize(k0); h->p_seq_inj.resize(k0); h->p_cur.resize(k0); h->p_ccur.resize(k0);
+  h->p_dt = dt; h->p_nleap = nleap; h->p_k0 = k0;
+  for (int k = k0; k < nleap; k++) {
+    const double h_pre = (k == 0) ? dt / 2. : 0.;
+    const bool last = (k == nleap - 1);
+    if (h->dense || !h->has_split || h->bucket_h != h_pre || h->rebuild_pending) {
+      if (k != k0) return set_err(WENDY_E_CUDA, "internal: layout lost inside a call");
+      int rc = rebucket(h, h_pre);
+      if (rc) return rc;
+      h->rebuild_pending = false;
+    }
+    h->p_cur.push_back(h->cur);
+    h->p_ccur.push_back(h->ccur);
+    h->p_seq.push_back(h->seq);
+    // step kernel (count prefix first)
+    {
+      TileParams p;
+      fill_tile_params(h, p);
+      p.h_pre = h_pre; p.dt_kick = dt; p.dt_drift = last ? dt / 2. : dt; p.h_next = last ? dt / 2. : 0.;
+      p.kcall = k;
+      launch_count_prefix(h->st, p.cnt_in, h->nb, h->cpre, h->cp_desc, h->cp_ticket, p.epoch);
+      p.cpre = h->cpre;
+      launch_tile(h->st, h->cap, LOAD_BUCKET, EMIT_SPLITTER, 1, p);
+      h->n_launch += 2;
+      advance_after_tile(h);
+      h->n_launch--;
+      h->cur ^= 1; h->ccur = (h->ccur + 1) % 3; h->bucket_h = p.h_next;
+      h->n_sub++;
+    }
+    // inject kernel
+    {
+      InjectParams q;
+      memset(&q, 0, sizeof(q));
+      q.peer = h->peer_dev; q.pepoch = h->pepoch; q.kcall = k; q.h = h->bucket_h;
+      q.xout = h->x[h->cur]; q.vout = h->v[h->cur]; q.idout = h->id[h->cur];
+      q.cnt_out = h->cnt[h->ccur]; q.split = h->split; q.cap = h->cap; q.nb = h->nb;
+      q.fail_seq = h->flags; q.seq = h->seq; q.stats = h->flags + 1;
+      h->p_seq_inj.push_back(h->seq);
+      h->seq++;
+      int grid = h->sm_count;
+      if (const char *ge = getenv("WENDY_B200_PERSIST_GRID")) grid = std::max(1, std::min(grid, atoi(ge)));
+      launch_peer_inject(h->st, q, grid);
+      h->n_launch++;
+    }
+    h->pepoch++;
+  }
+  h->pending = true;
+  return 0;
+}
+
+// Wait for the call; *k_fail = index of the first sub-step that did not complete on THIS rank (nleap: all did).
+// The ranks must agree on min(k_fail) (one host collective per call) and, if it is < nleap, all roll back.
+int wendy_cuda_shard_step_end(wendy_cuda_handle *h, int *k_fail, long long *n_local, long long *migrated_in) {
+  if (!h || !h->peer_on || !k_fail) return set_err(WENDY_E_ARG, "peer exchange is not set up");
+  if (!h->pending) return set_err(WENDY_E_ARG, "no call in flight");
+  h->pending = false;
+  const int nleap = h->p_nleap;
+  CK(cudaMemcpyAsync(h->h_peer_n, h->peer_n, (size_t)(nleap + 2) * sizeof(long long), cudaMemcpyDeviceToHost, h->st));
+  unsigned pstat[2] = {0u, 0u};  // [0] a wait timed out, [1] records received so far (wraps)
+  CK(cudaMemcpyAsync(pstat, h->peer_scratch + PEER_MAX + 2, sizeof(pstat), cudaMemcpyDeviceToHost, h->st));
+  if (fetch_flags(h)) return WENDY_E_CUDA;
+  if (pstat[0]) return set_err(WENDY_E_CUDA, "shard: timed out waiting for a peer GPU");
+  if (migrated_in) *migrated_in = (long long)(unsigned)(pstat[1] - h->peer_mig_seen);
+  h->peer_mig_seen = pstat[1];
+  const unsigned f = h->h_flags[0];
+  int kf = nleap;
+  if (f != 0xffffffffu) {
+    kf = -1;
+    for (int k = 0; k < nleap; k++)
+      if (h->p_seq[k] == f || h->p_seq_inj[k] == f) kf = k;
+    if (kf < 0) {
+      // flagged by the first step kernel of this call on behalf of a peer's failure in the previous call's last
+      // inject: cannot happen (that call's step_end saw it on every rank), so treat it as sub-step k0
+      kf = h->p_k0;
+    }
+    h->n_fail++;
+  } else {
+    h->N = h->h_peer_n[1 + nleap]; h->seg_len = h->N;
+    if (h->h_flags[1] > (unsigned)(h->cap - (h->cap - h->fill) / 16)) {  // nearly full bucket: re-balance (local)
+      fill_back_off(h);
+      h->rebuild_pending = true;
+    }
+    h->n_outside += outside_total(h);
+    memset(h->h_flags + 8, 0, 128 * sizeof(unsigned));
+    CK(cudaMemsetAsync(h->flags + 8, 0, 128 * sizeof(unsigned), h->st));
+  }
+  *k_fail = kf;
+  if (n_local) *n_local = (kf == nleap) ? h->N : h->h_peer_n[1 + (kf < 0 ? 0 : kf)];
+  return 0;
+}
+
+// Every rank calls this with the agreed failing sub-step: the state goes back to the input of sub-step k (still
+// intact: double buffering), the layout is rebuilt at the next step_begin(k0 = k).  Returns the particle count
+// to seed the count flags with (after a host all-gather).
+int wendy_cuda_shard_rollback(wendy_cuda_handle *h, int k, long long *n_local) {
+  if (!h || !h->peer_on || k < 0 || k >= (int)h->p_cur.size()) return set_err(WENDY_E_ARG, "bad rollback");
+  h->n_sub -= (h->p_nleap - k);
+  h->cur = h->p_cur[k]; h->ccur = h->p_ccur[k];
+  h->has_split = false;
+  fill_back_off(h);
+  h->N = h->h_peer_n[1 + k]; h->seg_len = h->N;
+  if (reset_flags(h)) return WENDY_E_CUDA;
+  if (n_local) *n_local = h->N;
   return 0;
 }
 

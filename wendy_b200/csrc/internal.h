@@ -31,6 +31,41 @@ struct __align__(16) Desc {
   long long agg_cnt, inc_cnt;
 };
 
+// ---- sharded single system, device-driven exchange over peer memory (NVLink) -------------------------------
+// Every rank owns one COMM BUFFER (plain cudaMalloc, exported to the other ranks by CUDA IPC or, for ranks
+// that share a process, by its raw pointer).  Peers write into it, the owner only reads it:
+//   in_flag [2][PEER_MAX]   word (epoch, fail, count) from source r: "my step kernel of sub-step `epoch` is
+//                           complete; `count` of my particles moved into your range, their (x, v, id)
+//                           records are in inbox[epoch & 1][r][0 .. count)"
+//   cnt_flag[2][PEER_MAX]   word (epoch, fail, n) from rank r: "after the inject of sub-step `epoch` I own n
+//                           particles" -- the prefix over lower ranks offsets the cumulative mass
+//   inbox   [2][nranks][ocap][3] doubles
+// One 64-bit store carries flag and payload, so no ordering between two words is ever needed; records are made
+// visible before the flag by __threadfence_system() in every writing CTA and in the CTA that signals.
+constexpr int PEER_MAX = 16;
+struct PeerComm {
+  int nranks, my_rank;
+  unsigned ocap;
+  // local comm buffer
+  const double *inbox;
+  const unsigned long long *in_flag;
+  const unsigned long long *cnt_flag;
+  // the same three, in every peer's comm buffer
+  double *peer_inbox[PEER_MAX];
+  unsigned long long *peer_in_flag[PEER_MAX];
+  unsigned long long *peer_cnt_flag[PEER_MAX];
+  // local scratch
+  unsigned *out_cnt;        // [nranks] records written to each peer by the step kernel in flight
+  unsigned *cta_done;       // [2] finished-CTA counters: step kernel, inject kernel
+  long long *n_local;       // particles owned after the last inject
+  long long *n_hist;        // [k] particles owned at the start of sub-step k of the call in flight (k <= nleap)
+  unsigned *peer_stat;      // [0] set when a wait for a peer timed out, [1] records received so far
+  unsigned long long timeout_ns;  // a wait for a peer gives up after this long (WENDY_B200_PEER_TIMEOUT_MS, default 20 s)
+};
+__host__ __device__ __forceinline__ unsigned long long peer_pack(unsigned epoch, bool fail, unsigned v) {
+  return ((unsigned long long)epoch << 32) | ((unsigned long long)(fail ? 1u : 0u) << 31) | (v & 0x7fffffffu);
+}
+
 enum { LOAD_BUCKET = 0, LOAD_GATHER = 1 };
 enum { EMIT_SPLITTER = 0, EMIT_RANK = 1, EMIT_NONE = 2 };
 
@@ -81,6 +116,9 @@ struct TileParams {
   unsigned *out_cnt;        // [nranks]
   unsigned ocap;
   long long pc_offset;      // particles owned by lower ranks (added to every rank)
+  const PeerComm *peer;     // device-driven exchange (PERSIST = 3 instance): pc_offset comes from the peers' flags
+  unsigned pepoch;          // ... of this sub-step (same number on every rank)
+  int kcall;                // ... index of the sub-step within the call (n_hist slot)
   // optional outputs
   int *rank_out;            // rank_out[id] = rank within the segment at this force evaluation
   double *energy_part;      // [nb][4]: kinetic, harmonic, potential, momentum partial sums
@@ -128,6 +166,24 @@ struct ScatterParams {
   unsigned seq;
 };
 void launch_scatter(cudaStream_t st, const ScatterParams &p, int sm_count);
+
+// shard inject over peer memory: wait for every peer's migrants of sub-step `pepoch`, append them to the local
+// buckets, publish the new local particle count to every peer
+struct InjectParams {
+  const PeerComm *peer;
+  unsigned pepoch;
+  int kcall;
+  double h;                 // bucket key = x + h*v
+  double *xout, *vout;
+  int *idout;
+  unsigned *cnt_out;
+  const double *split;
+  int cap, nb;
+  unsigned *fail_seq;
+  unsigned seq;
+  unsigned *stats;
+};
+void launch_peer_inject(cudaStream_t st, const InjectParams &p, int grid);
 
 // keys for the radix sort, written in compact (segment-major) order
 void launch_make_keys(cudaStream_t st, const double *x, const double *v, double h,

@@ -28,7 +28,7 @@ constexpr int SS_MAX = 320;  // pieces: 3 per binade of the running sum plus the
 
 struct SerialTab {
   int nseg;
-  int first[64];          // first[b] = piece containing index 2^b (index 0 and 1: piece 0 / first[0])
+  int first[64];          // first[b] = piece containing index 2^b (b = 0: index 0), where the search for k in [2^b, 2^(b+1)) starts
   long long i0[SS_MAX + 1];  // piece s covers sorted positions [i0[s], i0[s+1]); i0[nseg] = LLONG_MAX
   double c0[SS_MAX];
   double inc[SS_MAX];
@@ -78,7 +78,7 @@ inline int serial_tab_build(SerialTab &T, double m0, long long n_max) {
   T.i0[T.nseg] = 0x7fffffffffffffffll;
   int s = 0;
   for (int b = 0; b < 64; b++) {
-    const long long k = (b < 62) ? (1ll << b) : 0x7fffffffffffffffll - 1;
+    const long long k = (b == 0) ? 0ll : (b < 62) ? (1ll << b) : 0x7fffffffffffffffll - 1;  // (b = 0 serves k = 0 and 1)
     while (s + 1 < T.nseg && T.i0[s + 1] <= k) s++;
     T.first[b] = s;
   }

@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include "internal.h"
 #include "lookback.cuh"
+#include "peer.cuh"
 
 namespace wendy {
 
@@ -38,25 +39,10 @@ namespace wendy {
 #ifndef TK_RANK_STRAIGHT
 #define TK_RANK_STRAIGHT 4  // members of a shared sub-bucket compared by straight-line code before a loop takes over
 #endif
-// candidates prepared for the next A/B run (not measured yet; 0 = the measured default)
-#ifndef TK_SLOT_WARPPATH
-#define TK_SLOT_WARPPATH 0  // one all-home / general decision per warp and bucket instead of two votes per particle round
-#endif
-#ifndef TK_DEST_NOWIN
-#define TK_DEST_NOWIN 0     // no window-range test before the four-splitter check (the verification covers it)
-#endif
-#ifndef TK_STORE32
-#define TK_STORE32 0        // 32-bit slot arithmetic in the emission stores (slot numbers fit: checked at creation)
-#endif
+
 #ifndef TK_PERSIST_E
 #define TK_PERSIST_E 4      // particles per thread of the PERSISTENT instances (threads = CAP / TK_PERSIST_E).  2: 1024
 #endif                      // threads, 32 registers, 64 warps per SM -- measured 16 % slower
-#ifndef TK_ROUNDS
-#define TK_ROUNDS 0         // persistent instances: load / sub-bucket / grouping / sub-bucket bounds run unguarded for the
-#endif                      // rounds that are (nearly) always full, the last round behind a warp-uniform branch (candidate)
-#ifndef TK_OWNER_SORT
-#define TK_OWNER_SORT 0     // plain persistent instance: the thread that scanned a sub-bucket sorts its members in place,
-#endif                      // ranks are then positions (prepared candidate, not measured; see "owner sort" below)
 #ifndef TK_COARSE_CAP
 #define TK_COARSE_CAP 2048  // slots per bucket of the CTA kernel (E = 4 particles per thread: 512 threads at 2048)
 #endif
@@ -74,9 +60,6 @@ struct TileSmem {
   unsigned long long pad_;
   double sx[CAP];  // sort keys (positions at force time), grouped by sub-bucket
   int sid[CAP];    // particle ids, same order
-#if TK_OWNER_SORT
-  double sv[PERSIST ? CAP : 2];  // owner sort: velocities, same order
-#endif
   union {
     struct {
       unsigned cnt[(PERSIST ? 2 : 1) * PADN];  // interpolation sub-bucket counters -> start offsets (PERSIST: two sets)
@@ -134,7 +117,9 @@ tile_kernel(const TileParams p) {
   using SM = TileSmem<CAP, THREADS, PERSIST>;
   static_assert(!PERSIST || (LOAD == LOAD_BUCKET && EQM), "the persistent variant stages x, v, id only");
   // PERSIST == 2: additionally specialised for the plain case (no external force, no rank output, one GPU)
-  constexpr bool PLAIN = (PERSIST == 2);
+  // PERSIST == 3: the plain instance for one key range of a sharded system, exchanging migrants over peer memory
+  constexpr bool PLAIN = (PERSIST >= 2);
+  constexpr bool SHARDP = (PERSIST == 3);
   constexpr int E = SM::E;
   constexpr int NW = THREADS / 32;
   constexpr int BK = CAP;  // interpolation sub-buckets
@@ -146,8 +131,29 @@ tile_kernel(const TileParams p) {
   const unsigned lt = (1u << lane) - 1u;
 
   // A launch queued behind a failed one must not touch anything (host re-runs from there).
-  if (ld_volatile_u32(p.fail_seq) < p.seq) return;
+  if (ld_volatile_u32(p.fail_seq) < p.seq) {
+    if (SHARDP && blockIdx.x == 0 && tid == 0) peer_signal_step(p.peer, p.pepoch, true);  // peers must not wait
+    return;
+  }
 
+  long long pc_off = p.pc_offset;  // particles owned by lower ranks (sharded system)
+  if (SHARDP) {
+    // ... as published by the peers after the previous sub-step (their cnt_flag words, in local memory)
+    if (tid == 0) {
+      bool bad;
+      S.pre_cnt = peer_wait_counts(p.peer, p.pepoch - 1u, bad);
+      S.bucket = bad ? 1 : 0;
+    }
+    __syncthreads();
+    pc_off = S.pre_cnt;
+    if (S.bucket) {  // a peer failed (or is gone): this sub-step must not run anywhere; roll back to the PREVIOUS one
+      if (tid == 0) atomicMin(p.fail_seq, p.seq - 1u);
+      if (blockIdx.x == 0 && tid == 0) peer_signal_step(p.peer, p.pepoch, true);
+      return;
+    }
+    if (blockIdx.x == 0 && tid == 0) p.peer->n_hist[p.kcall] = *p.peer->n_local;
+    __syncthreads();  // (S.bucket is reused below)
+  }
   // stage one bucket: three bulk copies of the live part (sizes rounded up to 16 bytes, inside the bucket's slots)
   const uint32_t bar = smem_u32(&S.mbar);
   auto stage_issue = [&](int bb, unsigned nn) {
@@ -261,29 +267,6 @@ tile_kernel(const TileParams p) {
     mbar_wait(bar, phase);
     phase ^= 1u;
   }
-#if TK_ROUNDS
-  // rounds 0 .. E-2 are full in all but the emptiest buckets: their code carries no guards (values of slots
-  // beyond n are replaced by zeros, side effects are predicated); the last round, which most warps of a bucket
-  // filled to 13/16 do not have, is skipped by a warp-uniform branch
-  const bool last_round = (unsigned)((E - 1) * THREADS + (tid & ~31)) < n;
-  if (PERSIST) {
-#pragma unroll
-    for (int k = 0; k < E; k++) {
-      xk[k] = 0.0; id[k] = 0; g[k] = 0; vreg[k] = 0.0;
-      if (k == E - 1 && !last_round) continue;
-      const unsigned i = tid + k * THREADS;
-      const bool ok = i < n;
-      double x = S.stx[i];
-      const double vv = S.stv[i];
-      const int ii = S.stid[i];
-      if (p.h_pre != 0.0) x = __dadd_rn(x, __dmul_rn(p.h_pre, vv));
-      xk[k] = ok ? x : 0.0;
-      vreg[k] = ok ? vv : 0.0;
-      id[k] = ok ? ii : 0;
-      g[k] = ok ? (unsigned)b * (unsigned)CAP + i : 0u;
-    }
-  } else
-#endif
 #pragma unroll
   for (int k = 0; k < E; k++) {
     unsigned i = tid + k * THREADS;
@@ -369,21 +352,6 @@ tile_kernel(const TileParams p) {
 
   // ---- 3. interpolation sub-bucket of every key (monotone in x), arrival slot -----------
   unsigned pk[E];  // sub-bucket | arrival order << 16
-#if TK_ROUNDS
-  if (PERSIST) {
-#pragma unroll
-    for (int k = 0; k < E; k++) {
-      pk[k] = 0;
-      if (k == E - 1 && !last_round) continue;
-      const bool ok = tid + k * THREADS < n;
-      int sub = (int)((xk[k] - xmin) * scale);
-      sub = max(0, min(BK - 1, sub));
-      unsigned o = 0;
-      if (ok) o = atomicAdd(&S.u.srt.cnt[cbase + sub + sub / E], 1u);
-      pk[k] = ok ? ((unsigned)sub | (o << 16)) : 0u;
-    }
-  } else
-#endif
 #pragma unroll
   for (int k = 0; k < E; k++) {
     pk[k] = 0;
@@ -418,18 +386,6 @@ tile_kernel(const TileParams p) {
     cp_async_commit();
   }
   // ---- 4. exclusive scan of the sub-bucket counters ------------------------------------
-#if TK_OWNER_SORT
-  // Owner sort (plain instance): the thread that scans sub-buckets [E*tid, E*tid + E) knows their sizes and
-  // where they start; after the grouping it sorts the members of every shared sub-bucket in place (x, v, id
-  // move together), so that the particle at position p has rank p and the per-particle comparison loops of
-  // step 6 disappear: the work is done once per sub-bucket instead of once per member, and particles alone
-  // in their sub-bucket cost nothing.  The CTA then continues position-wise.  A sub-bucket with more than
-  // OWNER_SORT_MAX members (a pathological clump; quadratic for one thread) sends the whole bucket down the
-  // member-wise path of step 6 instead -- the verdict rides on the barrier that follows the scan.
-  constexpr int OWNER_SORT_MAX = 12;
-  unsigned own_c[E], own_o = 0;
-  int crowded = 0;
-#endif
   {
     unsigned c[E], run = 0;
     unsigned *cp = &S.u.srt.cnt[cbase + tid * (E + 1)];
@@ -445,47 +401,14 @@ tile_kernel(const TileParams p) {
     const unsigned t = lane < NW ? S.uw[lane] : 0u;
     const unsigned ti = warp_inclusive_scan_u32(t, lane);
     unsigned ex = inc - run + __shfl_sync(WENDY_FULL_MASK, ti - t, wid);
-#if TK_OWNER_SORT
-    if (PLAIN) {
-      own_o = ex;
-#pragma unroll
-      for (int q = 0; q < E; q++) {
-        own_c[q] = c[q];
-        crowded |= c[q] > (unsigned)OWNER_SORT_MAX;
-      }
-    }
-#endif
 #pragma unroll
     for (int q = 0; q < E; q++) {
       cp[q] = ex;
       ex += c[q];
     }
   }
-#if TK_OWNER_SORT
-  if (PLAIN) crowded = __syncthreads_or(crowded);  // (the barrier after the scan, with the verdict on the side)
-  else __syncthreads();
-#else
   __syncthreads();
-#endif
   // ---- 5. group load slots by sub-bucket -------------------------------------------------
-#if TK_ROUNDS
-  if (PERSIST) {
-#pragma unroll
-    for (int k = 0; k < E; k++) {
-      if (k == E - 1 && !last_round) continue;
-      const bool ok = tid + k * THREADS < n;
-      const unsigned sub = pk[k] & 0xffffu;
-      const unsigned pos = S.u.srt.cnt[cbase + sub + sub / E] + (pk[k] >> 16);
-      if (ok) {
-        S.sx[pos] = xk[k];
-        S.sid[pos] = id[k];
-#if TK_OWNER_SORT
-        if (PLAIN) S.sv[pos] = vreg[k];
-#endif
-      }
-    }
-  } else
-#endif
 #pragma unroll
   for (int k = 0; k < E; k++) {
     unsigned i = tid + k * THREADS;
@@ -494,9 +417,6 @@ tile_kernel(const TileParams p) {
       unsigned pos = S.u.srt.cnt[cbase + sub + sub / E] + (pk[k] >> 16);
       S.sx[pos] = xk[k];
       S.sid[pos] = id[k];
-#if TK_OWNER_SORT
-      if (PLAIN) S.sv[pos] = vreg[k];
-#endif
     }
   }
   __syncthreads();
@@ -515,71 +435,9 @@ tile_kernel(const TileParams p) {
       if (tid + k * THREADS < n) m[k] = p.min[g[k]];
     }
   }
-#if TK_OWNER_SORT
-  if (PLAIN && !crowded) {
-    unsigned o = own_o;
-#pragma unroll
-    for (int q = 0; q < E; q++) {
-      const unsigned c = own_c[q];
-      if (c > 1u) {  // insertion sort of positions [o, o + c) under (x, id)
-#pragma unroll 1
-        for (unsigned i = o + 1; i < o + c; i++) {
-          const double xi = S.sx[i];
-          const int idi = S.sid[i];
-          unsigned j = i;
-#pragma unroll 1
-          while (j > o) {
-            const double xj = S.sx[j - 1];
-            if (xj < xi || (xj == xi && S.sid[j - 1] < idi)) break;
-            j--;
-          }
-          if (j != i) {
-            const double vi = S.sv[i];
-#pragma unroll 1
-            for (unsigned t = i; t > j; t--) {
-              S.sx[t] = S.sx[t - 1];
-              S.sv[t] = S.sv[t - 1];
-              S.sid[t] = S.sid[t - 1];
-            }
-            S.sx[j] = xi;
-            S.sv[j] = vi;
-            S.sid[j] = idi;
-          }
-        }
-      }
-      o += c;
-    }
-    __syncthreads();
-    // from here on a thread works on the particles at positions tid, tid + THREADS, ...: rank = position
-#pragma unroll
-    for (int k = 0; k < E; k++) {
-      const unsigned pp = tid + k * THREADS;
-      const bool ok = pp < n;
-      xk[k] = ok ? S.sx[ok ? pp : 0u] : 0.0;
-      vreg[k] = ok ? S.sv[ok ? pp : 0u] : 0.0;
-      id[k] = ok ? S.sid[ok ? pp : 0u] : 0;
-      r[k] = ok ? pp : 0u;
-    }
-  } else {
-#endif
   // The sub-bucket bounds of all E particles are fetched first (independent shared-memory loads in flight
   // together); sub-buckets hold 1.75 members on average, so the first TK_RANK_STRAIGHT members are compared
   // by predicated straight-line code and a loop only runs for crowded sub-buckets.
-#if TK_ROUNDS
-  if (PERSIST) {
-#pragma unroll
-    for (int k = 0; k < E; k++) {
-      r[k] = 0;
-      if (k == E - 1 && !last_round) { pk[k] = 0; continue; }
-      const bool ok = tid + k * THREADS < n;
-      const unsigned sub = pk[k] & 0xffffu;
-      const unsigned s0 = S.u.srt.cnt[cbase + sub + sub / E];
-      const unsigned s1 = (sub + 1 < (unsigned)BK) ? S.u.srt.cnt[cbase + (sub + 1) + (sub + 1) / E] : n;
-      r[k] = ok ? s0 : 0u;
-      pk[k] = ok ? s1 - s0 : 0u;  // the sub-bucket index is not needed any more
-    }
-  } else
-#endif
 #pragma unroll
   for (int k = 0; k < E; k++) {
     r[k] = 0;
@@ -625,9 +483,6 @@ tile_kernel(const TileParams p) {
       r[k] = rr;
     }
   }
-#if TK_OWNER_SORT
-  }
-#endif
   long long Pc;
   if (EQM) {
     // Equal masses: the exact prefix sum below sorted position k is k*m0, so its correctly
@@ -699,16 +554,16 @@ tile_kernel(const TileParams p) {
   }
   // ---- 11. force, kick, drift (or diagnostics) ----------------------------------------------------
   const double tot = p.tot[seg];
-  const double PcD = (double)(Pc + p.pc_offset);  // pc_offset: particles of the lower ranks (sharded)
+  const double PcD = (double)(Pc + pc_off);  // pc_off: particles of the lower ranks (sharded)
   // Equal masses: cumulative mass below sorted position K0 + r.  With the serial table it is the reference's own
   // running sum (wendy/wendy.c:359-360) bit for bit; a bucket nearly always lies inside one linear piece.
   SerialRun SR;
   SR.c0 = 0.0; SR.inc = 0.0; SR.j0 = 0u; SR.uniform = true;
-  if (EQM && p.stab) SR = serial_run(p.stab, Pc + p.pc_offset, n);
+  if (EQM && p.stab) SR = serial_run(p.stab, Pc + pc_off, n);
   auto cum_eqm = [&](unsigned rk) -> double {
     if (p.stab) {
       if (SR.uniform) return serial_cum_run(SR, rk);
-      return serial_cum_at(p.stab, Pc + p.pc_offset + (long long)rk);
+      return serial_cum_at(p.stab, Pc + pc_off + (long long)rk);
     }
     return __dmul_rn(__dadd_rn(PcD, (double)rk), p.m0);  // exact integer sum below 2^53, one rounding
   };
@@ -854,8 +709,8 @@ tile_kernel(const TileParams p) {
   const double inv_w = (wdt > 0.0 && wdt < CUDART_INF) ? rcp_approx(wdt) : 0.0;
   const float inv_wf = (float)fmin(inv_w, 3.0e38);
   const double win_lo = S.ssplit[sbase], win_hi = S.ssplit[sbase + wn];
-  const double sh_lo = (!PLAIN && p.bounds) ? __ldg(p.bounds + p.my_rank) : 0.0;
-  const double sh_hi = (!PLAIN && p.bounds) ? __ldg(p.bounds + p.my_rank + 1) : 0.0;
+  const double sh_lo = ((!PLAIN || SHARDP) && p.bounds) ? __ldg(p.bounds + p.my_rank) : 0.0;
+  const double sh_hi = ((!PLAIN || SHARDP) && p.bounds) ? __ldg(p.bounds + p.my_rank + 1) : 0.0;
 #pragma unroll
   for (int k = 0; k < E; k++) {
     int d = -1;
@@ -878,7 +733,7 @@ tile_kernel(const TileParams p) {
         d = -3;
       } else if (key >= home_lo && key < home_hi) {
         d = b;
-      } else if (TK_DEST_NOWIN || (key >= win_lo && key < win_hi)) {
+      } else if (key >= win_lo && key < win_hi) {
         // guess from the home bucket's width (single precision is plenty: the loops below settle it)
         int lo = rel + __float2int_rd(fmaxf(-256.f, fminf(256.f, (float)(key - home_lo) * inv_wf)));
         // The guess is nearly always within one bucket of the answer: fetch the four splitters around it
@@ -891,14 +746,6 @@ tile_kernel(const TileParams p) {
           lo += (key >= s1 ? 1 : 0) - (key < s0 ? 1 : 0);
           settled = (key >= sm1) && (key < s2);
         }
-#if TK_DEST_NOWIN
-        if (!settled && !(key >= win_lo && key < win_hi)) {  // far move after all
-          double gq = fmax(-2.0e9, fmin(2.0e9, (key - home_lo) * inv_w));
-          const int g = (int)max((long long)seg_lo, min((long long)seg_hi - 1, (long long)b + (long long)floor(gq)));
-          lo = gallop_search_tile(p.split, key, g, seg_lo, seg_hi) - wlo;
-          settled = true;
-        }
-#endif
         if (!settled) {
           lo = max(0, min(wn - 1, lo));
 #pragma unroll 1
@@ -913,43 +760,31 @@ tile_kernel(const TileParams p) {
         const int g = (int)max((long long)seg_lo, min((long long)seg_hi - 1, (long long)b + (long long)floor(gq)));
         d = gallop_search_tile(p.split, key, g, seg_lo, seg_hi);
       }
+      if (SHARDP && (d == 0 || d == p.nb - 1) && (key < sh_lo || key >= sh_hi)) {
+        // Only the two edge buckets reach beyond this GPU's key range (their outer splitters are -inf / +inf):
+        // the particle now belongs to another rank -- its record goes straight into the owner's inbox (peer
+        // memory over NVLink); the count travels with the flag word at the end of the launch.
+        const PeerComm *pc = p.peer;
+        int peer = 0;
+        while (peer + 1 < p.nranks && key >= __ldg(p.bounds + peer + 1)) peer++;
+        const unsigned slot = atomicAdd(pc->out_cnt + peer, 1u);
+        if (slot < pc->ocap) {
+          double *rec = pc->peer_inbox[peer] +
+                        ((size_t)((p.pepoch & 1u) * (unsigned)p.nranks + (unsigned)p.my_rank) * pc->ocap + slot) * 3;
+          rec[0] = x2[k];
+          rec[1] = v2[k];
+          rec[2] = (double)id[k];
+        } else {
+          sh_overflow = true;
+        }
+        d = -3;
+      }
     }
     dest[k] = d;
   }
   // slot allocation, aggregated per warp and destination; the E requests are issued back to back and
   // their results consumed afterwards, so the atomics' latencies overlap
   unsigned amask[E];
-#if TK_SLOT_WARPPATH
-  bool leaves = false;
-#pragma unroll
-  for (int k = 0; k < E; k++) leaves |= (tid + k * THREADS < n) && dest[k] != b;
-  if (!__any_sync(WENDY_FULL_MASK, leaves)) {  // the whole warp stays home (common at small dt): ballots only
-#pragma unroll
-    for (int k = 0; k < E; k++) {
-      const bool ok = tid + k * THREADS < n;
-      const unsigned valid = __ballot_sync(WENDY_FULL_MASK, ok);
-      amask[k] = ok ? valid : 0u;
-      lpos[k] = 0;
-      if (ok && lane == __ffs(valid) - 1) lpos[k] = atomicAdd(&S.dcnt[rel], (unsigned)__popc(valid));
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < E; k++) {
-      const int d = dest[k];  // -1: no particle, -3: went to an outbox
-      const unsigned mask = __match_any_sync(WENDY_FULL_MASK, d);
-      amask[k] = mask;
-      lpos[k] = 0;
-      if (d >= 0 && lane == __ffs(mask) - 1) {
-        if (d >= wlo && d < wlo + wn) {
-          lpos[k] = atomicAdd(&S.dcnt[d - wlo], (unsigned)__popc(mask));
-        } else {
-          lpos[k] = atomicAdd(&p.cnt_out[d], (unsigned)__popc(mask));
-          outside += __popc(mask);
-        }
-      }
-    }
-  }
-#else
 #pragma unroll
   for (int k = 0; k < E; k++) {
     const int d = dest[k];
@@ -969,7 +804,6 @@ tile_kernel(const TileParams p) {
       }
     }
   }
-#endif
 #pragma unroll
   for (int k = 0; k < E; k++) {
     const int leader = __ffs(amask[k]) - 1;
@@ -1001,11 +835,7 @@ tile_kernel(const TileParams p) {
       unsigned pos = lpos[k];
       if (d >= wlo && d < wlo + wn) pos += S.dbase[d - wlo];
       if (pos < (unsigned)CAP) {
-#if TK_STORE32
-        const unsigned o = (unsigned)d * (unsigned)CAP + pos;
-#else
         size_t o = (size_t)d * CAP + pos;
-#endif
         p.xout[o] = x2[k];
         p.vout[o] = v2[k];
         if (!EQM) p.mout[o] = m[k];
@@ -1023,6 +853,21 @@ tile_kernel(const TileParams p) {
   n_it = n_nx;
   cur ^= 1;
   if (b_it >= p.nb) break;
+  }
+  if (SHARDP) {
+    // the last CTA to finish tells every peer how many records this launch left in its inbox; each CTA's
+    // records are made visible system-wide before it is counted as finished
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence_system();
+      const unsigned done = atomicAdd(p.peer->cta_done, 1u);
+      if (done == gridDim.x - 1) {
+        __threadfence_system();
+        *p.peer->cta_done = 0;  // (the next step kernel on this stream starts after this one has ended)
+        const bool failed = ld_volatile_u32(p.fail_seq) <= p.seq;
+        peer_signal_step(p.peer, p.pepoch, failed);
+      }
+    }
   }
 }
 
@@ -1083,6 +928,16 @@ static void launch_tile_cap(cudaStream_t st, int load, int emit, int physics, co
         set2 = true;
       }
         tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 2 * PE><<<g_use, PT, smp, st>>>(p);
+    } else if (p.peer && !p.aext && !p.rank_out) {
+      static bool set3 = false;
+      if (!set3) {
+        cudaFuncSetAttribute(tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 3 * PE>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp);
+        cudaFuncSetAttribute(tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 3 * PE>,
+                             cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        set3 = true;
+      }
+      tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 3 * PE><<<g_use, PT, smp, st>>>(p);
     } else {
       tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, PE><<<g_use, PT, smp, st>>>(p);
     }
@@ -1177,6 +1032,112 @@ void launch_scatter(cudaStream_t st, const ScatterParams &p, int sm_count) {
   long long blocks = (total + 255) / 256;
   long long maxb = (long long)sm_count * 16;
   scatter_kernel<<<(unsigned)(blocks < maxb ? blocks : maxb), 256, 0, st>>>(p);
+}
+
+// ---- shard inject over peer memory ----------------------------------------------------------------------------
+// Second launch of a sharded sub-step (peer.cuh): the migrants of sub-step `pepoch` were written into this rank's
+// inbox by the peers' step kernels; wait for their counts, append every record to the bucket its key falls in,
+// publish the new local particle count.  Record order does not matter: buckets are unordered inside.
+__global__ void __launch_bounds__(256)
+peer_inject_kernel(const InjectParams p) {
+  __shared__ unsigned s_pre[PEER_MAX + 1];
+  __shared__ int s_bad;
+  const PeerComm *pc = p.peer;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  if (ld_volatile_u32(p.fail_seq) < p.seq) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) peer_signal_count(pc, p.pepoch, true, 0);
+    return;
+  }
+  if (threadIdx.x == 0) {
+    bool bad = false;
+    unsigned run = 0;
+    for (int r = 0; r < pc->nranks; r++) {
+      s_pre[r] = run;
+      if (r == pc->my_rank) continue;
+      unsigned long long w;
+      if (!peer_wait(pc->in_flag + (p.pepoch & 1u) * PEER_MAX + r, p.pepoch, w, pc->timeout_ns)) {
+        bad = true;
+        atomicOr(pc->peer_stat, 1u);
+        continue;
+      }
+      if ((w >> 31) & 1ull) bad = true;
+      run += (unsigned)(w & 0x7fffffffull);
+    }
+    s_pre[pc->nranks] = run;
+    s_bad = bad ? 1 : 0;
+    __threadfence_system();  // the records the flags announce are read below
+  }
+  __syncthreads();
+  if (s_bad) {
+    if (threadIdx.x == 0) atomicMin(p.fail_seq, p.seq);
+    if (blockIdx.x == 0 && threadIdx.x == 0) peer_signal_count(pc, p.pepoch, true, 0);
+    return;
+  }
+  const unsigned total = s_pre[pc->nranks];
+  const unsigned span = gridDim.x * blockDim.x;
+  bool overflow = false;
+  for (unsigned i0 = blockIdx.x * blockDim.x; i0 < total; i0 += span) {  // (warp-uniform trip count)
+    const unsigned i = i0 + threadIdx.x;
+    int d = -1;
+    double x = 0., v = 0., idd = 0.;
+    if (i < total) {
+      int r = 0;
+      while (i >= s_pre[r + 1]) r++;
+      const double *rec = pc->inbox + ((size_t)((p.pepoch & 1u) * (unsigned)pc->nranks + (unsigned)r) * pc->ocap +
+                                       (i - s_pre[r])) * 3;
+      x = __ldcg(rec); v = __ldcg(rec + 1); idd = __ldcg(rec + 2);
+      const double key = (p.h != 0.0) ? __dadd_rn(x, __dmul_rn(p.h, v)) : x;
+      int lo = 0, hi = p.nb;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(p.split + mid) <= key) lo = mid; else hi = mid;
+      }
+      d = lo;
+    }
+    const unsigned mask = __match_any_sync(WENDY_FULL_MASK, d);
+    const int leader = __ffs(mask) - 1;
+    unsigned basel = 0;
+    if (lane == leader && d >= 0) basel = atomicAdd(&p.cnt_out[d], (unsigned)__popc(mask));
+    basel = __shfl_sync(WENDY_FULL_MASK, basel, leader);
+    if (d >= 0) {
+      const unsigned pos = basel + __popc(mask & lt);
+      if (pos < (unsigned)p.cap) {
+        const size_t o = (size_t)d * p.cap + pos;
+        p.xout[o] = x;
+        p.vout[o] = v;
+        p.idout[o] = (int)idd;
+        if (pos + 1 > (unsigned)(p.cap - p.cap / 16)) atomicMax(p.stats, pos + 1);
+      } else {
+        overflow = true;
+      }
+    }
+  }
+  if (overflow) atomicMin(p.fail_seq, p.seq);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned done = atomicAdd(pc->cta_done + 1, 1u);
+    if (done == gridDim.x - 1) {
+      __threadfence();
+      pc->cta_done[1] = 0;
+      long long n = *pc->n_local + (long long)total;
+      for (int r = 0; r < pc->nranks; r++) {
+        if (r == pc->my_rank) continue;
+        n -= (long long)__ldcg(pc->out_cnt + r);
+        pc->out_cnt[r] = 0;  // (the next step kernel on this stream starts after this launch has ended)
+      }
+      *pc->n_local = n;
+      pc->n_hist[p.kcall + 1] = n;
+      pc->peer_stat[1] += total;  // records received (statistic)
+      const bool failed = ld_volatile_u32(p.fail_seq) <= p.seq;
+      peer_signal_count(pc, p.pepoch, failed, n);
+    }
+  }
+}
+
+void launch_peer_inject(cudaStream_t st, const InjectParams &p, int grid) {
+  peer_inject_kernel<<<grid < 1 ? 1 : grid, 256, 0, st>>>(p);
 }
 
 // ---- radix keys in compact (segment-major) order ----------------------------------------------------------

@@ -10,8 +10,15 @@ Two modes, one process per GPU (``torch.distributed``, NCCL on GPUs, gloo in CPU
       local step on every rank (particles whose new key leaves the rank's range land in
       per-peer outboxes)  ->  all-to-all of the migrants (x, v, id)  ->  append on the receiver
       ->  all-gather of the per-rank particle counts, whose prefix offsets the cumulative mass.
-  Equal masses only in this round (cumulative mass = RN(global rank * m0), exactly what the
+  Equal masses (cumulative mass = the reference's serial sum at the GLOBAL rank, exactly what the
   single-GPU path computes, so results are independent of the number of ranks bit for bit).
+
+  On GPUs of one node the per-sub-step exchange is DEVICE-DRIVEN (``CudaShardEngine.enable_peer``):
+  the step kernel stores migrants straight into the owner's inbox over NVLink peer memory, a second
+  kernel appends them, counts travel through flag words -- no host round trip and no collective per
+  sub-step; the host runs one small collective per CALL to agree that no sub-step failed
+  (wendy_b200/csrc/peer.cuh).  The host-orchestrated exchange below (all-gather + all-to-all per
+  sub-step) remains as the portable path (gloo / numpy engine, several nodes).
 
 The host logic here is engine-agnostic: the local work is done by an *engine* object
 (``CudaShardEngine`` in the product; the tests plug in a numpy engine to run the same logic
@@ -107,16 +114,21 @@ class CudaShardEngine(object):
         self._h = ctypes.c_void_p()
         bounds = numpy.ascontiguousarray(bounds, dtype=numpy.float64)
         self.capacity = int(capacity)
-        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        # a stream of its own: kernels of the device-driven exchange wait for peers, which must never block
+        # (or be blocked by) unrelated work -- in particular other ranks living in the same process
+        self.stream = torch.cuda.Stream(device=self.device)
+        st = ctypes.c_void_p(self.stream.cuda_stream)
+        self.peer = False
         if torch.is_tensor(x):
             # the partition ran on this GPU: hand the device arrays over in place
             x = x.to(device=self.device, dtype=torch.float64).contiguous()
             v = v.to(device=self.device, dtype=torch.float64).contiguous()
             ids = ids.to(device=self.device, dtype=torch.int32).contiguous()
+            torch.cuda.current_stream().synchronize()  # the arrays were produced on torch's stream
             _lib.check(self._lib.wendy_cuda_create_shard_dev(
                 ctypes.byref(self._h), x.shape[0], self.capacity, x.data_ptr(), v.data_ptr(), ids.data_ptr(),
                 float(m0), float(totmass), float(omega2), nranks, rank, bounds, int(outbox_capacity), st))
-            torch.cuda.current_stream().synchronize()
+            self.stream.synchronize()  # ... and are copied on the engine's
         else:
             x = numpy.ascontiguousarray(x, dtype=numpy.float64)
             v = numpy.ascontiguousarray(v, dtype=numpy.float64)
@@ -138,6 +150,58 @@ class CudaShardEngine(object):
             self._h = None
 
     __del__ = close
+
+    # -- device-driven exchange over peer memory ---------------------------------------------------------
+    def enable_peer(self, comm):
+        """Exchange comm-buffer descriptors through ``comm`` and map the peers.  Ranks in the same process hand
+        over raw device pointers, other processes of the node CUDA IPC handles.  Returns False (and leaves the
+        host-orchestrated path in place) if some rank cannot export its buffer."""
+        import os
+        ptr, nbytes = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+        handle = numpy.zeros(64, dtype=numpy.uint8)
+        rc = self._lib.wendy_cuda_shard_comm_export(self._h, ctypes.byref(ptr), ctypes.byref(nbytes), handle)
+        ok = rc in (0, 1)
+        vec = numpy.concatenate(([float(os.getpid()), float(ptr.value >> 32), float(ptr.value & 0xffffffff),
+                                  1. if ok else 0., 1. if rc == 0 else 0.], handle.astype(numpy.float64)))
+        allv = comm.allgather_vec(vec)
+        if not numpy.all(allv[:, 3] == 1.):
+            return False
+        same = allv[:, 0] == float(os.getpid())
+        if not numpy.all(same | (allv[:, 4] == 1.)):
+            return False  # a peer in another process without IPC
+        raw = numpy.zeros(self.nranks, dtype=numpy.uint64)
+        for r in range(self.nranks):
+            if same[r]:
+                raw[r] = (int(allv[r, 1]) << 32) | int(allv[r, 2])
+        handles = numpy.ascontiguousarray(allv[:, 5:69].astype(numpy.uint8).ravel())
+        _lib.check(self._lib.wendy_cuda_shard_comm_open(self._h, handles, raw))
+        self.peer = True
+        return True
+
+    def seed_counts(self, counts):
+        _lib.check(self._lib.wendy_cuda_shard_seed_counts(
+            self._h, numpy.ascontiguousarray(counts, dtype=numpy.int64)))
+
+    def step_begin(self, dt_leap, nleap, k0=0):
+        _lib.check(self._lib.wendy_cuda_shard_step_begin(self._h, float(dt_leap), int(nleap), int(k0)))
+
+    def step_end(self):
+        """(first sub-step that did not complete here, or nleap; particles owned; records received)."""
+        kf, n, mig = ctypes.c_int(), ctypes.c_longlong(), ctypes.c_longlong()
+        _lib.check(self._lib.wendy_cuda_shard_step_end(self._h, ctypes.byref(kf), ctypes.byref(n), ctypes.byref(mig)))
+        return kf.value, n.value, mig.value
+
+    def rollback(self, k):
+        n = ctypes.c_longlong()
+        _lib.check(self._lib.wendy_cuda_shard_rollback(self._h, int(k), ctypes.byref(n)))
+        return n.value
+
+    def stats(self):
+        out = numpy.zeros(9, dtype=numpy.int64)
+        _lib.check(self._lib.wendy_cuda_stats(self._h, out, 9))
+        keys = ['substeps', 'rebuilds', 'failed_substeps', 'max_bucket_count', 'left_window',
+                'kernel_launches', 'cap', 'buckets', 'radix_fallbacks']
+        return dict(zip(keys, (int(o) for o in out)))
 
     def substep(self, h_pre, dt_kick, dt_drift, h_next, pc_offset):
         """Returns, per peer, an (n, 3) float64 CUDA tensor of migrants (x, v, id)."""
@@ -215,6 +279,8 @@ class ShardedSystem(object):
         self.dt_leap = None
         self.pc_offset = 0
         self.migrated = 0
+        self.peer, self.peer_tried = False, False
+        self.timing = {'substep': 0., 'allgather': 0., 'exchange+inject': 0.}
 
     # -- set-up: global sample sort on the keys of the FIRST force evaluation -------------------------
     def _partition(self, dt_leap):
@@ -276,15 +342,69 @@ class ShardedSystem(object):
         counts = self.comm.allgather_vec([self.engine.count()])[:, 0]
         self.counts = counts.astype(numpy.int64)
         self.pc_offset = int(self.counts[:self.comm.rank].sum())
+        # device-driven exchange where the engine offers it (CUDA engine, all ranks reachable by peer memory)
+        import os
+        if (not self.peer_tried and hasattr(self.engine, 'enable_peer') and self.comm.size > 1
+                and os.environ.get('WENDY_B200_SHARD_PEER', '1') != '0'):
+            self.peer_tried = True
+            self.peer = bool(self.engine.enable_peer(self.comm))
+        if self.peer:
+            self.engine.seed_counts(self.counts)
+
+    def _repartition(self, dt_leap):
+        """A new time step changes the key of the first force evaluation (x + dt/2 v), hence which rank owns the
+        particles near the range edges: partition again from the current (synchronised) state.  Rare and not
+        optimised: the state goes through the host."""
+        ids, x, v = self.engine.read()
+        self._raw = (numpy.array(x), numpy.array(v), numpy.array(ids, dtype=numpy.int32))
+        self.engine.close()
+        self.engine = None
+        self.peer, self.peer_tried = False, False
+        self._partition(dt_leap)
+
+    def _step_peer(self, dt_leap, nleap):
+        """One call with the device-driven exchange: enqueue everything, wait once, agree once."""
+        import time
+        tm = self.timing
+        eng = self.engine
+        k0, tries = 0, 0
+        while True:
+            t0 = time.perf_counter()
+            eng.step_begin(dt_leap, nleap, k0)
+            t1 = time.perf_counter()
+            kf, n_local, mig = eng.step_end()
+            t2 = time.perf_counter()
+            info = self.comm.allgather_vec([kf, n_local]).astype(numpy.int64)  # the one collective of the call
+            tm['substep'] += t1 - t0
+            tm['exchange+inject'] += t2 - t1
+            tm['allgather'] += time.perf_counter() - t2
+            self.migrated += int(mig)
+            kf_all = int(info[:, 0].min())
+            if kf_all >= nleap:
+                self.counts = info[:, 1]
+                self.pc_offset = int(self.counts[:self.comm.rank].sum())
+                return
+            # some rank could not complete sub-step kf_all (bucket or inbox overflow): everyone goes back to its
+            # input, rebuilds its layout and runs the rest of the call again
+            tries += 1
+            if tries > 8:
+                raise RuntimeError('wendy_b200: sharded sub-step keeps overflowing after re-balancing')
+            n_back = eng.rollback(kf_all)
+            self.counts = self.comm.allgather_vec([n_back])[:, 0].astype(numpy.int64)
+            eng.seed_counts(self.counts)
+            k0 = kf_all
 
     # -- one reference call: drift dt/2, nleap x [force, kick, drift] (wendy/wendy.c:385-418) ------------
     def step(self, dt_leap, nleap):
         if self.engine is None:
             self._partition(dt_leap)
         elif dt_leap != self.dt_leap:
-            raise NotImplementedError('changing dt between calls needs a global re-partition')
+            self._repartition(dt_leap)
         import time
-        tm = self.timing = getattr(self, 'timing', {'substep': 0., 'allgather': 0., 'exchange+inject': 0.})
+        tm = self.timing
+        if self.peer:
+            self._step_peer(dt_leap, nleap)
+            return self
         for k in range(nleap):
             last = k == nleap - 1
             t0 = time.perf_counter()
