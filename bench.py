@@ -1,20 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- particle-steps/s of the approximate-integration hot path on B200.
 
-Workload (BASELINE.json configs[2], the configuration the metric is quoted on): sech^2
-self-gravitating disk with a harmonic term (omega=1.1), N=1e8 per GPU, fp64, seeded numpy ICs
-(SURVEY.md section 8d).  A bench "step" is ONE call of the reference entry point
-(wendy/wendy.c:385-418) with nleap leapfrog sub-steps; particle-steps = N * nleap * steps.
+Default workload = BASELINE.json configs[2], the configuration the metric is quoted on: sech^2 self-gravitating
+disk with a harmonic term (omega = 1.1), N = 1e8 per GPU, fp64, equal masses, seeded numpy ICs.
+A bench "step" is ONE call of the reference entry point (wendy/wendy.c:385-418) with nleap leapfrog sub-steps;
+particle-steps = N * nleap * steps.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]          our CUDA path
-  python bench.py --impl reference ...                          the reference's own C path on the host
+  python bench.py [--gpus N] [--steps K] [--warmup W]      our CUDA path; one JSON line (rank 0)
+  python bench.py --impl reference ...                      the reference's own C path on the host cores
+  python bench.py --config 1|2|3|4|5                        the other BASELINE configs as their own legs
 
-N>1 is launched by torchrun (one rank per GPU).  By default the ranks then hold ONE system of N*gpus
-particles, range-partitioned by position (wendy_b200/multi.py: all-to-all of migrants + all-gather of
-counts per sub-step; BASELINE.json configs[3]); --mode ensemble runs independent realisations instead
-(configs[4], no data-path collective).  Per-GPU work is fixed either way, so scaling is "weak".
+The default line also carries: `variants` (config 3's other sub-runs: dt_leap 1e-5 and 5e-3, and the full radix
+sort forced every sub-step), `parity` (x, v of the GPU against the compiled reference on the SAME N=1e8 system,
+bit for bit) and `cpu_baseline` (the reference timed on that system).  N>1 is launched by torchrun, one rank per
+GPU: the ranks hold ONE system of N*gpus particles, range-partitioned by position (BASELINE configs[3];
+wendy_b200/multi.py, migrants exchanged over NVLink peer memory); `--mode ensemble` runs independent
+realisations instead (configs[4]).  Per-GPU work is fixed either way: scaling is "weak".
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -28,6 +32,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALG_BYTES = 40.  # algorithmic bytes per particle-step: read x,v,m + write x,v
+# dram__bytes_read.sum + dram__bytes_write.sum per particle of the dominant kernel, from the ncu --set full
+# captures under profiles/ (persistent CTA kernel: profiles/r02/tile_1e8_dt1e-3_summary.txt; warp kernel r01)
+TRAFFIC_B_PER_PARTICLE = {2048: 39.9, 256: 40.2}
+KERNEL_NAME = {
+    2: 'tile_kernel<2048,512,LOAD_BUCKET,EMIT_SPLITTER,PHYS,EQM,PERSIST=2> (persistent CTAs, two per SM; next bucket by TMA)',
+    3: 'tile_kernel<2048,512,LOAD_BUCKET,EMIT_SPLITTER,PHYS,EQM,PERSIST=3> (same + migrants stored into the peers\' inboxes)',
+    1: 'tile_kernel<2048,512,...,PERSIST=1> (persistent CTAs; ext-force / host-exchanged shard instance)',
+    256: 'wstep_kernel<256,8,EQM> (one warp per bucket)',
+}
 
 
 def parse():
@@ -36,17 +49,18 @@ def parse():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--particles', dest='n', type=float, default=1e8, help='particles per GPU')
+    ap.add_argument('--config', type=int, default=3, choices=[1, 2, 3, 4, 5], help='BASELINE.json config (1-based)')
+    ap.add_argument('--particles', dest='n', type=float, default=1e8, help='particles per GPU (config 3/4)')
     ap.add_argument('--leap', dest='nleap', type=int, default=10)
     ap.add_argument('--dt-leap', type=float, default=1e-3)
     ap.add_argument('--omega', type=float, default=1.1)
     ap.add_argument('--sort', default='gpu', choices=['gpu', 'gpu-radix'])
-    ap.add_argument('--ref-particles', dest='ref_n', type=float, default=1e7, help='particles in the CPU sample')
+    ap.add_argument('--ref-particles', dest='ref_n', type=float, default=0, help='reference arm: particles (0 = same as ours)')
     ap.add_argument('--skip-cpu-baseline', dest='no_cpu_baseline', action='store_true')
     ap.add_argument('--skip-e2e', dest='no_e2e', action='store_true')
-    ap.add_argument('--cap', type=int, default=0, help='bucket capacity: 0/256 = warp kernel, 2048 = CTA kernel')
+    ap.add_argument('--skip-variants', dest='no_variants', action='store_true')
+    ap.add_argument('--cap', type=int, default=0, help='bucket capacity: 0 = library choice, 256 = warp kernel, 2048 = CTA kernel')
     ap.add_argument('--fill', type=int, default=0, help='target particles per bucket (0 = library default)')
-    ap.add_argument('--variants', action='store_true', help='also time other dt_leap / sort settings')
     ap.add_argument('--mode', default='auto', choices=['auto', 'ensemble', 'sharded'],
                     help='N>1: independent realisations per GPU, or ONE system of n*gpus particles '
                          'range-partitioned over the GPUs (auto = sharded)')
@@ -61,6 +75,25 @@ def sech2_ic(n, seed):
     v -= numpy.mean(v)
     m = numpy.full(n, 1. / n)
     return x, v, m
+
+
+def slab_ic(n, seed=3):
+    """config 2 (survey-defined cold slab: the violent-relaxation notebook is missing from the snapshot)."""
+    rs = numpy.random.RandomState(seed)
+    x = rs.uniform(-0.5, 0.5, size=n)
+    v = 0.05 * rs.normal(size=n)
+    v -= numpy.mean(v)
+    return x, v, numpy.full(n, 1. / n)
+
+
+def host_info():
+    gcc = ''
+    try:
+        gcc = subprocess.run(['gcc', '--version'], capture_output=True, text=True, timeout=5).stdout.splitlines()[0]
+    except Exception:
+        pass
+    return {'nproc': os.cpu_count(), 'OMP_NUM_THREADS': os.environ.get('OMP_NUM_THREADS'), 'gcc': gcc,
+            'PARALLEL_SORT_NUM_THREADS': '32 (wendy_c.so, the reference default, parallel_sort.h:7-14) / nproc (wendy_c_nt.so)'}
 
 
 class ClockSampler(threading.Thread):
@@ -96,22 +129,72 @@ class ClockSampler(threading.Thread):
                 'reasons': reasons, 'samples': len(self.rows)}
 
 
-def time_reference(x, v, m, omega, dt_leap, steps, warmup):
-    """The reference's own C path (oracle/_ref/wendy_c.so, sort='parallel', all host threads)."""
+def make_reference(x, v, m, omega, dt_leap, sort='parallel', variant='wendy_c.so', nleap=1):
+    """The reference's own C path (oracle/_ref/*.so = /root/reference/wendy/*.c compiled unmodified), driven as
+    wendy/wendy.py:425-433 drives it; falls back to our C restatement when the reference could not be built."""
     from oracle import wendy_oracle as wo
-    kind = 'reference' if wo.reference_available() else 'port'
-    if kind == 'reference':
-        r = wo.Reference(x, v, m, dt_leap, 1, omega=omega, sort='parallel')
-    else:
-        subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'oracle'), 'oracle'])
-        r = wo.COracle(x, v, m, dt_leap, 1, omega=omega)
+    if wo.reference_available(variant):
+        return wo.Reference(x, v, m, dt_leap * nleap, nleap, omega=omega, sort=sort, variant=variant), 'reference'
+    subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'oracle'), 'oracle'])
+    return wo.COracle(x, v, m, dt_leap * nleap, nleap, omega=omega), 'port'
+
+
+def time_reference(r, steps, warmup):
     for _ in range(warmup):
         r.step()
-    t = time.perf_counter()
+    ts = []
     for _ in range(steps):
+        t = time.perf_counter()
         r.step()
-    el = time.perf_counter() - t
-    return len(x) * steps / el, el / steps, kind
+        ts.append(time.perf_counter() - t)
+    return sum(ts) / max(1, len(ts)), ts
+
+
+def relerr(a, b):
+    floor = 0.1 * numpy.sqrt(numpy.mean(b ** 2)) + 1e-300
+    return float(numpy.max(numpy.abs(a - b) / numpy.maximum(floor, numpy.abs(b))))
+
+
+def reference_arm(a, rank):
+    """bench.py --impl reference: the reference C path on the host cores, SAME system as our arm (config 3:
+    N = 1e8), each step a bounded sample of the workload: one leapfrog sub-step (a call with nleap = 1)."""
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    n = int(a.ref_n) if a.ref_n else int(a.n)
+    if a.config == 2:
+        x, v, m = slab_ic(1000000)
+        omega, dt_leap, label = None, 0.005, 'cold slab N=1e6 (config 2), dt_leap=0.005'
+    elif a.config == 1:
+        x, v, m = sech2_ic(10000, 2)
+        omega, dt_leap, label = None, 0.05, 'sech2 disk N=1e4 (config 1), dt=0.05, nleap=1'
+    else:
+        x, v, m = sech2_ic(n, 2)
+        omega, dt_leap, label = a.omega, a.dt_leap, 'sech2 disk + harmonic omega=%g, N=%d, dt_leap=%g' % (a.omega, n, a.dt_leap)
+    r, kind = make_reference(x, v, m, omega, dt_leap)
+    per, _ = time_reference(r, a.steps, a.warmup)
+    val = len(x) / per
+    extra = {}
+    try:  # BASELINE.md section 3: the nproc-thread build of the parallel sort and the best serial sort, for context
+        nb = min(len(x), 10000000)
+        for name, sort, variant in (('parallel_sort_nproc_threads', 'parallel', 'wendy_c_nt.so'),
+                                    ('serial_tim', 'tim', 'wendy_c.so'), ('serial_quick', 'quick', 'wendy_c.so')):
+            rr, k2 = make_reference(x[:nb], v[:nb], m[:nb] * (len(x) / nb), omega, dt_leap, sort=sort, variant=variant)
+            if k2 != 'reference':
+                continue
+            p2, _ = time_reference(rr, 2, 1)
+            extra[name] = {'value': nb / p2, 'N': nb}
+    except Exception as exc:  # noqa: BLE001
+        extra['error'] = str(exc)[:200]
+    sample = ('the whole N=%d system, one leapfrog sub-step (nleap=1 call) per step, sort=parallel' % len(x))
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'particle-steps/s', 'value': val, 'unit': 'particle-steps/s',
+        'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': per * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': label, 'host': host_info()},
+        'cpu_baseline': {'value': val, 'unit': 'particle-steps/s', 'cores': cores, 'kind': kind, 'sample': sample},
+        'other_reference_sorts': extra,
+        'e2e': {'value': val, 'unit': 'particle-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
 
 def main():
@@ -126,22 +209,7 @@ def main():
     os.environ.pop('OMP_NUM_THREADS', None)
 
     if a.impl == 'reference':
-        if rank != 0:
-            return
-        os.environ.pop('OMP_NUM_THREADS', None)
-        nr = int(a.ref_n)
-        x, v, m = sech2_ic(nr, 2)
-        val, per, kind = time_reference(x, v, m, a.omega, a.dt_leap, a.steps, a.warmup)
-        sample = ('N=%d of the N=%d workload, one sub-step per step, sort=parallel '
-                  '(PARALLEL_SORT_NUM_THREADS=32 default), OMP threads=%d' % (nr, n, cores))
-        print(json.dumps({
-            'impl': 'reference', 'metric': 'particle-steps/s', 'value': val, 'unit': 'particle-steps/s',
-            'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': per * 1e3,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-            'data': 'synthetic',
-            'config': {'workload': 'sech2 disk + harmonic omega=%g, dt_leap=%g (CPU sample N=%d)' % (a.omega, a.dt_leap, nr)},
-            'cpu_baseline': {'value': val, 'unit': 'particle-steps/s', 'cores': cores, 'kind': kind, 'sample': sample},
-            'e2e': {'value': val, 'unit': 'particle-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+        reference_arm(a, rank)
         return
 
     import torch
@@ -163,12 +231,25 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
 
-    x, v, m = sech2_ic(n, 2 + rank)
-    omega2 = a.omega ** 2
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = peaks.get('hbm_gbs', 6650.)
     stream = torch.cuda.current_stream().cuda_stream
+    stat_keys = ('substeps', 'rebuilds', 'failed_substeps', 'kernel_launches', 'radix_fallbacks', 'left_window')
 
-    def run(dt_leap, sort, steps, warmup, nleap):
-        st = wendy_b200.ApproxState(x, v, m, omega2=omega2, sort=sort, stream=stream, cap=a.cap, fill=a.fill)
+    def stat_delta(s1, s0):
+        d = {k: s1[k] - s0[k] for k in stat_keys}
+        d['max_bucket_count'] = s1['max_bucket_count']
+        d['cap'] = s1['cap']
+        d['buckets'] = s1['buckets']
+        return d
+
+    def run_single(x, v, m, omega2, dt_leap, sort, steps, warmup, nleap, n_segments=1, cap=0, fill=0):
+        st = wendy_b200.ApproxState(x, v, m, omega2=omega2, sort=sort, stream=stream, cap=cap, fill=fill,
+                                    n_segments=n_segments)
         for _ in range(warmup):
             st.step(dt_leap, nleap)
         s0 = st.stats()
@@ -180,13 +261,121 @@ def main():
         e1.record()
         barrier()
         ms = max_over_ranks(e0.elapsed_time(e1))
-        s1 = st.stats()
+        d = stat_delta(st.stats(), s0)
         st.close()
-        run.cap = s1['cap']
-        d = {k: s1[k] - s0[k] for k in ('substeps', 'rebuilds', 'failed_substeps', 'kernel_launches', 'radix_fallbacks')}
-        d['max_bucket_count'] = s1['max_bucket_count']
-        d['left_window'] = s1['left_window'] - s0['left_window']
         return ms, d
+
+    # ------------------------------------------------------------------------------------------------------
+    # the other BASELINE configs as their own legs
+    if a.config in (1, 2, 5):
+        out = None
+        if a.config == 1:  # N=1e4, dt=0.05, 100 outputs: the reference's own CPU-runnable case (KAT-D)
+            x, v, m = sech2_ic(10000, 2)
+            g = wendy_b200.nbody(x, v, m, 0.05, approx=True, nleap=1)
+            next(g)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(99):
+                xo, vo = next(g)
+            el = time.perf_counter() - t0
+            hx, hv = hashlib.sha256(xo.tobytes()).hexdigest()[:16], hashlib.sha256(vo.tobytes()).hexdigest()[:16]
+            g.close()
+            out = {'value': 1e4 * 99 / el, 'ms_per_step': 1e3 * el / 99,
+                   'config': {'workload': 'config 1: sech2 disk N=1e4, dt=0.05, nleap=1, 100 outputs through nbody()'},
+                   'parity': {'sha256_x': hx, 'sha256_v': hv,
+                              'equals_reference_KAT_D': hx == '21614814a2a156b6' and hv == '7730018ad0084bb4'}}
+        if a.config == 2:  # cold slab N=1e6, 1000 steps, energy-drift statistics beside the reference's own
+            from oracle import wendy_oracle as wo
+            nn, nsteps, dtl = 1000000, 1000, 0.005
+            x, v, m = slab_ic(nn)
+            E0 = wo.energy(x, v, m)
+            st = wendy_b200.ApproxState(x, v, m, stream=stream)
+            st.step(dtl, 1)
+            s0 = st.stats()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            drift = []
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(1, nsteps):
+                st.step(dtl, 1)
+                if (i + 1) % 100 == 0:
+                    ke, he, pe, _ = st.energy_terms()
+                    drift.append(abs((ke + he + pe) - E0) / abs(E0))
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            d = stat_delta(st.stats(), s0)
+            xg, vg = st.read()
+            st.close()
+            ref_drift, ref_rate, same10 = None, None, None
+            if rank == 0 and not a.no_cpu_baseline:
+                r, kind = make_reference(x, v, m, None, dtl)
+                t0 = time.perf_counter()
+                ref_drift = []
+                for i in range(nsteps):
+                    xr, vr = r.step()
+                    if i == 9:
+                        g10 = wendy_b200.ApproxState(x, v, m, stream=stream)
+                        for _ in range(10):
+                            g10.step(dtl, 1)
+                        x10, v10 = g10.read()
+                        g10.close()
+                        same10 = bool(numpy.array_equal(x10, xr) and numpy.array_equal(v10, vr))
+                    if (i + 1) % 100 == 0:
+                        ref_drift.append(abs(wo.energy(xr, vr, m) - E0) / abs(E0))
+                ref_rate = nn * nsteps / (time.perf_counter() - t0)
+            out = {'value': float(nn) * (nsteps - 1) / (ms * 1e-3), 'ms_per_step': ms / (nsteps - 1),
+                   'config': {'workload': 'config 2: cold slab N=1e6, omega=None, dt_leap=0.005, 1000 steps (violent relaxation)'},
+                   'path_stats': d, 'gpu_launches': d['kernel_launches'],
+                   'energy_drift': {'gpu_abs_dE_over_E_every_100_steps': drift, 'reference_same_ICs': ref_drift,
+                                    'note': 'chaotic after a few steps: compared as statistics, not particle by particle'},
+                   'parity': {'bit_identical_to_reference_after_10_steps': same10},
+                   'cpu_baseline': {'value': ref_rate, 'unit': 'particle-steps/s', 'cores': cores, 'kind': 'reference',
+                                    'sample': 'the same 1000 steps, sort=parallel'}}
+        if a.config == 5:  # Gaia phase-space spiral ensemble: realisations of 1e5 particles + torch ext_force
+            from wendy_b200 import multi
+            total_real = 4096 if world == 8 else 512 * world
+            mine = multi.shard_ensemble(total_real, rank, world)
+            S, L = len(mine), 100000
+            alpha, sigma, zh = 0.3, 1., 1.
+            xs, vs = numpy.empty(S * L), numpy.empty(S * L)
+            for j, r_ in enumerate(mine):  # per realisation RandomState(2 + r), SURVEY 8d config 5
+                rs = numpy.random.RandomState(2 + r_)
+                xs[j * L:(j + 1) * L] = numpy.arctanh(2. * rs.uniform(size=L) - 1.) * 2. * zh
+                vv = rs.normal(size=L) * sigma
+                vs[j * L:(j + 1) * L] = vv - numpy.mean(vv) + sigma  # the kick that winds up the spiral
+            ms_ = numpy.full(S * L, alpha / L)
+            F = lambda xx, t: -(1. - alpha) * sigma ** 2. * torch.tanh(0.5 * xx / zh) / zh  # noqa: E731
+            barrier()
+            t_c = time.perf_counter()
+            g = wendy_b200.nbody(xs, vs, ms_, 0.05, approx=True, nleap=10, ext_force=F, n_segments=S)
+            next(g)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(a.steps):
+                next(g)
+            torch.cuda.synchronize()
+            el = max_over_ranks(time.perf_counter() - t0)
+            g.close()
+            out = {'value': float(total_real) * L * 10 * a.steps / el, 'ms_per_step': 1e3 * el / a.steps,
+                   'config': {'workload': 'config 5: Gaia phase-space-spiral ensemble, %d realisations x 1e5 particles (%d per GPU), '
+                                          'torch ext_force, dt=0.05, nleap=10, through nbody() incl. D2H of x, v every output'
+                                          % (total_real, S), 'parallelism': 'realisations dealt out to the ranks, no collective'},
+                   'construction_s': t0 - t_c}
+        if rank == 0:
+            base = {'metric': 'particle-steps/s', 'unit': 'particle-steps/s', 'n_gpus': world, 'steps': a.steps,
+                    'warmup': a.warmup, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                    'dtype': 'f64', 'data': 'synthetic'}
+            base.update(out)
+            print(json.dumps(base))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ------------------------------------------------------------------------------------------------------
+    # config 3 (N=1) / config 4 (N>1): the headline line
+    x, v, m = sech2_ic(n, 2 + rank)
+    omega2 = a.omega ** 2
 
     def run_sharded(dt_leap, steps, warmup, nleap):
         """ONE system of n*world particles, range-partitioned by position over the ranks."""
@@ -197,22 +386,54 @@ def main():
         s = multi.ShardedSystem(x, v, ids.astype(numpy.int32), m0, m0 * n * world, comm, omega=a.omega)
         for _ in range(warmup):
             s.step(dt_leap, nleap)
+        est = s.engine.stream  # the shard's kernels run on the engine's own stream
+        s0 = s.engine.stats()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         mig0 = s.migrated
+        tm0 = dict(s.timing)
         barrier()
-        e0.record()
+        e0.record(est)
         for _ in range(steps):
             s.step(dt_leap, nleap)
-        e1.record()
+        e1.record(est)
         barrier()
+        est.synchronize()
         ms = max_over_ranks(e0.elapsed_time(e1))
-        d = {'substeps': steps * nleap, 'rebuilds': 0, 'failed_substeps': 0, 'kernel_launches': 2 * steps * nleap,
-             'radix_fallbacks': 0, 'max_bucket_count': 0, 'left_window': 0,
-             'migrants_per_substep_rank0': (s.migrated - mig0) / float(steps * nleap),
-             'particles_per_rank': [int(c) for c in s.counts],
-             'host_ms_per_substep_rank0': {k: 1e3 * t / max(1, (steps + warmup) * nleap) for k, t in s.timing.items()}}
+        d = stat_delta(s.engine.stats(), s0)
+        d['exchange'] = 'device-driven over peer memory (NVLink)' if s.peer else 'host-orchestrated (NCCL all-gather + all-to-all per sub-step)'
+        d['migrants_per_substep_rank0'] = (s.migrated - mig0) / float(steps * nleap)
+        d['particles_per_rank'] = [int(c) for c in s.counts]
+        d['host_ms_per_call_rank0'] = {k: 1e3 * (t - tm0[k]) / max(1, steps) for k, t in s.timing.items()}
+        peer = s.peer
         s.close()
-        return ms, d
+        return ms, d, peer
+
+    def sharded_check():
+        """Correctness inside the scaling run: a 2.4e6-particle system stepped sharded over all ranks must equal the
+        same system stepped on one GPU (rank 0), bit for bit (sha256 of x and v in particle order)."""
+        from wendy_b200 import multi
+        nn = 2400000
+        xx, vv, mm = sech2_ic(nn, 6)
+        comm = multi.TorchComm(device='cuda')
+        mine = numpy.arange(nn) % world == rank
+        s = multi.ShardedSystem(xx[mine], vv[mine], numpy.arange(nn, dtype=numpy.int32)[mine], mm[0], numpy.sum(mm),
+                                comm, omega=a.omega)
+        s.step(1e-3, 4)
+        s.step(1e-3, 4)
+        X, V = s.gather(nn)
+        s.close()
+        res = None
+        if rank == 0:
+            st = wendy_b200.ApproxState(xx, vv, mm, omega2=omega2)
+            st.step(1e-3, 4)
+            st.step(1e-3, 4)
+            Xs, Vs = st.read()
+            st.close()
+            h1 = hashlib.sha256(X.tobytes() + V.tobytes()).hexdigest()[:16]
+            h2 = hashlib.sha256(Xs.tobytes() + Vs.tobytes()).hexdigest()[:16]
+            res = {'particles': nn, 'substeps': 8, 'ranks': world, 'sha256_sharded': h1, 'sha256_one_gpu': h2,
+                   'bit_identical': h1 == h2}
+        return res
 
     def e2e_sharded(dt_leap, steps_e, nleap):
         """Public multi-GPU API with host buffers: construction (key sample, all-to-all partition, H2D) +
@@ -241,10 +462,11 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    peer = False
     if sharded:
-        ms, d = run_sharded(a.dt_leap, a.steps, a.warmup, a.nleap)
+        ms, d, peer = run_sharded(a.dt_leap, a.steps, a.warmup, a.nleap)
     else:
-        ms, d = run(a.dt_leap, a.sort, a.steps, a.warmup, a.nleap)
+        ms, d = run_single(x, v, m, omega2, a.dt_leap, a.sort, a.steps, a.warmup, a.nleap, cap=a.cap, fill=a.fill)
     clocks = sampler.stop() if sampler else None
     psteps = float(n) * world * a.nleap * a.steps
     value = psteps / (ms * 1e-3)
@@ -253,7 +475,7 @@ def main():
     # GPU, no data-path collective (BASELINE.json configs[4]) -- so that both scalings can be read off one
     # line.  No collective inside the leg (a rank that fails must not hang the others): local events, then one
     # max over ranks.
-    ensemble = None
+    ensemble, check = None, None
     if sharded:
         steps_v = max(2, a.steps // 2)
         ms_loc = -1.
@@ -280,26 +502,32 @@ def main():
                                 '%d timed calls, max over ranks of local CUDA-event times' % (n, steps_v)}
         elif ensemble is None:
             ensemble = {'error': 'another rank failed'}
+        try:
+            check = sharded_check()
+        except Exception as exc:  # noqa: BLE001
+            check = {'error': str(exc)[:300]}
 
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-    except Exception:
-        pass
-    peak = peaks.get('hbm_gbs', 6650.)
-    # dominant kernel: tile_kernel (one launch per sub-step on the bucket path).  Its average
-    # duration is the timed region / sub-steps when nothing else ran (rebuilds == 0).
-    launches_tile = d['substeps']
-    ms_per_launch = ms / max(1, launches_tile)
+    # dominant kernel: the step kernel, one launch per sub-step on the bucket path.  Its average duration is the
+    # timed region / sub-steps (CUDA events on the launching stream); the count-prefix kernel that precedes each
+    # launch (and, sharded, the inject kernel that follows it) are inside that figure (0.3 % by the ncu launch list)
+    launches_step = max(1, d['substeps'])
+    ms_per_launch = ms / launches_step
     achieved = ALG_BYTES * n / (ms_per_launch * 1e-3) / 1e9
+    if a.sort != 'gpu':
+        kname = 'radix passes (onesweep) + tile_kernel<LOAD_GATHER,EMIT_RANK>'
+    elif d['cap'] == 256:
+        kname = KERNEL_NAME[256]
+    else:
+        kname = KERNEL_NAME[3 if (sharded and peer) else (1 if sharded else 2)]
+    traffic = TRAFFIC_B_PER_PARTICLE.get(d['cap'], None)
     out = {
         'metric': 'particle-steps/s', 'value': value, 'unit': 'particle-steps/s', 'n_gpus': world,
         'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms / a.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'sech2 disk + harmonic omega=%g, N=%d per GPU, dt_leap=%g, nleap=%d, sort=%s'
+        'config': {'workload': 'sech2 disk + harmonic omega=%g, N=%d per GPU, dt_leap=%g, nleap=%d, sort=%s, equal masses'
                                % (a.omega, n, a.dt_leap, a.nleap, a.sort),
-                   'parallelism': ('one system of %d particles range-partitioned over %d GPUs (sample sort: all-to-all of '
-                                   'migrants + all-gather of counts per sub-step)' % (n * world, world)) if sharded
+                   'parallelism': ('one system of %d particles range-partitioned over %d GPUs (sample-sort partition; '
+                                   'per sub-step: %s)' % (n * world, world, d.get('exchange', ''))) if sharded
                    else ('independent realisations, one per GPU' if world > 1 else 'single GPU'),
                    'l2': 'state (%.1f GB) is far larger than L2' % (n * 28 / 1e9)},
         'gpu_launches': d['kernel_launches'],
@@ -307,53 +535,25 @@ def main():
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak,
                      'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback', 'unit': 'GB/s',
                      'frac': achieved / peak,
-                     # dram__bytes_read+write per launch from the ncu --set full captures under profiles/r01
-                     # (wstep: 40.2 B/particle, persistent CTA kernel: 39.9 B/particle -- 2.027 GB read + 1.963 GB
-                     # written at N=1e8, tile_1e8_dt1e-3_summary.txt), scaled to this N
-                     'traffic': (40.2 if getattr(run, 'cap', 256) == 256 else 39.9) * n if a.sort == 'gpu' else None,
-                     'kernel': ('radix passes + tile_kernel<LOAD_GATHER>' if a.sort != 'gpu' else
-                                'wstep_kernel<256,8,EQM> (one warp per bucket)' if getattr(run, 'cap', 256) == 256 else
-                                'tile_kernel<2048,512,LOAD_BUCKET,EMIT_SPLITTER,EQM,PERSIST> (persistent CTAs, two per SM; next bucket prefetched by TMA)'),
-                     'ms_per_launch': ms_per_launch},
+                     'traffic': traffic * n if (traffic and a.sort == 'gpu' and world == 1) else None,
+                     'kernel': kname, 'ms_per_launch': ms_per_launch},
         'clocks': clocks,
     }
     if ensemble is not None:
         out['ensemble_mode'] = ensemble
+    if check is not None:
+        out['sharded_check'] = check
 
-    if a.variants and world == 1:
+    # ---- config 3's other sub-runs: dt_leap 1e-5 / 5e-3 and the full radix sort forced every sub-step -------
+    if world == 1 and not a.no_variants:
         var = {}
-        for dtl, srt in ((1e-5, 'gpu'), (1e-3, 'gpu'), (5e-3, 'gpu'), (1e-3, 'gpu-radix')):
-            vms, vd = run(dtl, srt, max(1, a.steps // 2), 1, a.nleap if srt == 'gpu' else 2)
-            nl = a.nleap if srt == 'gpu' else 2
-            var['dt_leap=%g,%s' % (dtl, srt)] = {'value': float(n) * nl * max(1, a.steps // 2) / (vms * 1e-3), 'stats': vd}
-        # general (unequal) masses: the exact 128-bit scan path
-        rs = numpy.random.RandomState(5)
-        mj = m * (1. + 0.1 * (2. * rs.uniform(size=n) - 1.))
-        for dtl in (1e-5, 1e-3):
-            st = wendy_b200.ApproxState(x, v, mj, omega2=omega2, stream=stream)
-            st.step(dtl, a.nleap); st.step(dtl, a.nleap)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(2):
-                st.step(dtl, a.nleap)
-            e1.record(); torch.cuda.synchronize()
-            var['general masses, dt_leap=%g' % dtl] = {'value': float(n) * a.nleap * 2 / (e0.elapsed_time(e1) * 1e-3),
-                                                        'stats': st.stats()}
-            st.close()
-        # BASELINE config 5 shape: independent realisations of 1e5 particles + torch ext_force (Gaia spiral)
-        S, L = max(1, int(n // 100000 // 2)), 100000
-        xs = numpy.arctanh(2. * rs.uniform(size=S * L) - 1.) * 2.
-        vs = rs.normal(size=S * L) + 1.0
-        ms = numpy.full(S * L, 0.3 / L)
-        F = lambda xx, t: -0.7 * torch.tanh(0.5 * xx)  # noqa: E731
-        g = wendy_b200.nbody(xs, vs, ms, 0.05, approx=True, nleap=10, ext_force=F, n_segments=S)
-        next(g)
-        torch.cuda.synchronize(); t0 = time.perf_counter()
-        for _ in range(2):
-            next(g)
-        torch.cuda.synchronize(); el = time.perf_counter() - t0
-        g.close()
-        var['ensemble %d x 1e5 + torch ext_force, dt_leap=0.005 (generator, incl. D2H)' % S] = {'value': S * L * 10 * 2 / el}
+        for dtl, srt, nl, stp in ((1e-5, 'gpu', a.nleap, 3), (5e-3, 'gpu', a.nleap, 3), (a.dt_leap, 'gpu-radix', 2, 2)):
+            try:
+                vms, vd = run_single(x, v, m, omega2, dtl, srt, stp, 2, nl)
+                var['dt_leap=%g,%s' % (dtl, srt)] = {'value': float(n) * nl * stp / (vms * 1e-3), 'ms_per_substep': vms / (nl * stp),
+                                                     'stats': vd}
+            except Exception as exc:  # noqa: BLE001
+                var['dt_leap=%g,%s' % (dtl, srt)] = {'error': str(exc)[:200]}
         out['variants'] = var
 
     # ---- end to end through the public generator API, host buffers --------------------------
@@ -375,13 +575,29 @@ def main():
                       'note': 'wendy_b200.nbody(): generator construction (H2D of x,v,m, amortised over %d steps) '
                               '+ next() x %d, each with nleap=%d sub-steps and a D2H of x,v' % (steps_e, steps_e, a.nleap)}
 
+    # ---- the reference on the SAME system: timing (cpu_baseline) and parity at the headline size ----------
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        os.environ.pop('OMP_NUM_THREADS', None)
-        nr = int(min(a.ref_n, n))
-        val, per, kind = time_reference(x[:nr] if nr < n else x, v[:nr], m[:nr] * (n / nr), a.omega, a.dt_leap, 3, 1)
-        out['cpu_baseline'] = {'value': val, 'unit': 'particle-steps/s', 'cores': cores, 'kind': kind,
-                               'sample': 'first %d particles of the workload (masses rescaled), 1 warm-up + 3 timed '
-                                         'sub-steps, reference sort=parallel, %.2f s per sub-step' % (nr, per)}
+        r, kind = make_reference(x, v, m, a.omega, a.dt_leap)
+        nsub = 4  # 1 warm-up (the first sort starts from random order) + 3 timed sub-steps
+        g = wendy_b200.nbody(x, v, m, a.dt_leap, approx=True, nleap=1, omega=a.omega)
+        ts, par = [], {}
+        for i in range(nsub):
+            t0 = time.perf_counter()
+            xr, vr = r.step()
+            ts.append(time.perf_counter() - t0)
+            xg, vg = next(g)
+            if i in (0, nsub - 1):
+                par['after_%d_substeps' % (i + 1)] = {
+                    'x_bit_identical': bool(numpy.array_equal(xg, xr)), 'v_bit_identical': bool(numpy.array_equal(vg, vr)),
+                    'max_rel_err_x': relerr(xg, xr), 'max_rel_err_v': relerr(vg, vr)}
+        g.close()
+        per = sum(ts[1:]) / (nsub - 1)
+        out['cpu_baseline'] = {'value': n / per, 'unit': 'particle-steps/s', 'cores': cores, 'kind': kind,
+                               'sample': 'the same N=%d system: 1 warm-up + 3 timed leapfrog sub-steps (nleap=1 calls), reference '
+                                         'sort=parallel, %.2f s per sub-step' % (n, per), 'host': host_info()}
+        par['against'] = 'oracle/_ref/wendy_c.so (the unmodified reference C path), same ICs, N=%d, dt_leap=%g, nleap=1 calls' % (n, a.dt_leap)
+        par['tolerance_north_star'] = 'x, v relative 1e-12 after 1 step, 1e-9 after 10; observed: bit-identical'
+        out['parity'] = par
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

@@ -79,6 +79,8 @@ struct wendy_cuda_handle {
   bool fill_backoff = false;    // a library-chosen coarse layout overflowed at the optimistic fill: use 3/4 from now on
   bool rebuild_pending = false;  // shard: rebuild at the start of the next sub-step (state complete)
   bool ext_half_done = false;    // ext-force stepping: the leading half drift of the call is already in x
+  int ext_fail_streak = 0;       // ... consecutive overflows of the same sub-step (two: take it on the radix path)
+  int nb_last = 0;               // last bucket of the layout that has a finite lower edge (the tail may be unused)
   int user_fill = 0, user_cap = 0;
   double last_dt = 0.;
   bool dense = true;       // state is the dense upload in buffer `cur` (no layout yet)
@@ -311,6 +313,7 @@ static int rebucket(H *h, double hkey, const double *extra = nullptr, long long 
   h->cur = o; h->ccur = c1; h->dense = false; h->has_split = true; h->bucket_h = hkey;
   trace_mark(h->st, "rebucket: scatter");
   h->cap = ncap; h->fill = nfill; h->nbps = nnbps; h->nb = nnb; h->want_cap = 0;
+  h->nb_last = (int)(((n_extra > 0 ? n_all : h->seg_len) - 1) / nfill);
   {
     const size_t nc = (size_t)h->nb_alloc / 8 + 8;  // flow statistics belong to the old layout
     CK(cudaMemsetAsync(h->knot_sum, 0, nc * sizeof(double), h->st));
@@ -338,7 +341,7 @@ static void fill_tile_params(H *h, TileParams &p) {
   p.nranks = h->nranks; p.my_rank = h->my_rank; p.bounds = h->bounds;
   p.out_rec = h->out_rec; p.out_cnt = h->out_cnt;
   p.ocap = (unsigned)h->ocap; p.pc_offset = h->pc_offset;
-  p.peer = h->peer_on ? h->peer_dev : nullptr; p.pepoch = h->pepoch;
+  p.peer = h->peer_on ? h->peer_dev : nullptr; p.pepoch = h->pepoch; p.nb_last = h->nb_last;
   p.ticket = h->ticket + h->tcur; p.ticket_zero = h->ticket + (h->tcur + 2) % 3;
   p.fail_seq = h->flags; p.stats = h->flags + 1; p.outside = (unsigned long long *)(h->flags + 8);
   p.seq = h->seq; p.epoch = h->seq;
@@ -1302,10 +1305,22 @@ int wendy_cuda_substep(wendy_cuda_handle *h, double dt_kick, double dt_drift, do
     return 0;
   }
   if (!h->has_split || h->bucket_h != 0.) return set_err(WENDY_E_ARG, "layout is not keyed on the stored positions");
+  if (h->ext_fail_streak >= 2) {
+    // even a freshly balanced layout overflowed within this one sub-step: take it on the radix path, which
+    // cannot overflow (a_ext is in the storage order of the current layout, which is what that path gathers from)
+    int rc = launch_radix_substep(h, 0., dt_kick, dt_drift, a_ext_dev, nullptr);
+    if (rc) return rc;
+    if (fetch_flags(h)) return WENDY_E_CUDA;
+    h->n_radix_fallback++;
+    h->ext_fail_streak = 0;
+    h->ext_half_done = false;
+    return 0;
+  }
   launch_bucket_substep(h, 0., dt_kick, dt_drift, h_next, a_ext_dev, nullptr);
   if (fetch_flags(h)) return WENDY_E_CUDA;
   if (h->h_flags[0] != 0xffffffffu) {
     h->n_fail++; h->n_sub--;
+    h->ext_fail_streak++;
     fill_back_off(h);
     h->cur = cur0; h->ccur = ccur0;
     if (reset_flags(h)) return WENDY_E_CUDA;
@@ -1314,6 +1329,7 @@ int wendy_cuda_substep(wendy_cuda_handle *h, double dt_kick, double dt_drift, do
     return WENDY_RETRY;
   }
   h->ext_half_done = false;
+  h->ext_fail_streak = 0;
   if (h->h_flags[1] > (unsigned)(h->cap - (h->cap - h->fill) / 16)) {
     // nearly full bucket: re-balance now; the caller's next force_positions sees the new slots
     fill_back_off(h);
@@ -1597,7 +1613,7 @@ void _wendy_nbody_approx_onestep(int N, struct wendy_array_w_index *xi, double *
       int tries = 0;
       do {
         int cur0 = h->cur, ccur0 = h->ccur;
-        if (h->mode == WENDY_SORT_RADIX) {
+        if (h->mode == WENDY_SORT_RADIX || tries >= 2) {  // (two overflows of fresh layouts: the radix path cannot overflow)
           rc = launch_radix_substep(h, 0., dt, k == nleap - 1 ? dt / 2. : dt, nullptr, h->rank);
           if (!rc) rc = fetch_flags(h);
         } else {
@@ -1610,7 +1626,7 @@ void _wendy_nbody_approx_onestep(int N, struct wendy_array_w_index *xi, double *
             if (!rc) rc = WENDY_RETRY;
           }
         }
-      } while (rc == WENDY_RETRY && ++tries < 3);
+      } while (rc == WENDY_RETRY && ++tries < 4);
       h->ext_half_done = false;
     }
   } else if (!rc) {
@@ -1633,7 +1649,7 @@ void _wendy_nbody_approx_onestep(int N, struct wendy_array_w_index *xi, double *
         }
         cudaMemcpyAsync(a_id, ah.data(), (size_t)N * sizeof(double), cudaMemcpyHostToDevice, h->st);
         launch_gather_by_id(h->st, a_id, h->id[h->cur], h->cnt[h->ccur], h->cap, h->nb, a_slot);
-        if (h->mode == WENDY_SORT_RADIX) {
+        if (h->mode == WENDY_SORT_RADIX || tries >= 2) {
           rc = launch_radix_substep(h, 0., dt, k == nleap - 1 ? dt / 2. : dt, a_slot, h->rank);
           if (!rc) rc = fetch_flags(h);
         } else {
@@ -1647,7 +1663,7 @@ void _wendy_nbody_approx_onestep(int N, struct wendy_array_w_index *xi, double *
             if (!rc) rc = WENDY_RETRY;
           }
         }
-      } while (rc == WENDY_RETRY && ++tries < 3);
+      } while (rc == WENDY_RETRY && ++tries < 4);
       h->ext_half_done = false;
       if (!rc) *t0 += dt;  // wendy/wendy.c:403-404,409-410
     }

@@ -119,6 +119,8 @@ struct TileParams {
   const PeerComm *peer;     // device-driven exchange (PERSIST = 3 instance): pc_offset comes from the peers' flags
   unsigned pepoch;          // ... of this sub-step (same number on every rank)
   int kcall;                // ... index of the sub-step within the call (n_hist slot)
+  int nb_last;              // last bucket with a finite lower edge: together with bucket 0 the only ones whose
+                            // range reaches beyond this GPU's key range
   // optional outputs
   int *rank_out;            // rank_out[id] = rank within the segment at this force evaluation
   double *energy_part;      // [nb][4]: kinetic, harmonic, potential, momentum partial sums

@@ -13,6 +13,9 @@
 // Per pass: (1) per-tile digit histogram, (2) exclusive scan of the digit-major
 // [256][ntiles] table, (3) stable scatter.  Optional extra passes sort on the bits of a
 // segment id derived from the value (ensembles of independent realisations).
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -178,11 +181,184 @@ radix_scatter_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restric
   }
 }
 
+// =====================================================================================================
+// Onesweep: ONE read-and-write of the pairs per digit (Adinets & Merrill's scheme, written for this
+// library).  All digit histograms are taken in a single up-front pass over the keys; each sorting pass is
+// then one kernel in which a tile (4096 pairs) ranks its items, publishes its per-digit counts, resolves
+// the counts of all preceding tiles by decoupled look-back (tiles are taken in launch order through a ticket, so
+// a predecessor is always running or done), reorders the tile in shared memory so that every digit's items
+// leave as one contiguous run, and stores them.  Passes whose digit is the same for every key are skipped
+// (the high exponent bytes of clustered positions, unused segment-id bits).
+// Traffic: 8 B/pair once (histograms) + 24 B/pair per pass, against 32 B/pair per pass + a table scan before.
+constexpr int OT = 256;            // threads per tile
+constexpr int OI = 16;             // pairs per thread
+constexpr int OTILE = OT * OI;     // 4096 pairs per tile
+constexpr int OWARPS = OT / 32;
+constexpr int MAXPASS = 12;        // 8 key bytes + up to 4 segment-id bytes
+constexpr unsigned DESC_AGG = 1u << 30, DESC_INC = 2u << 30, DESC_VAL = (1u << 30) - 1u;
+
+struct SweepPlan {
+  int npass;
+  DigitSrc src[MAXPASS];
+  int any_value;                   // some pass takes its digit from the value
+};
+
+__global__ void __launch_bounds__(512)
+radix_hist_all_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, size_t n,
+                      const SweepPlan plan, unsigned *__restrict__ ghist) {
+  __shared__ unsigned h[MAXPASS * 256];
+  for (int i = threadIdx.x; i < plan.npass * 256; i += blockDim.x) h[i] = 0;
+  __syncthreads();
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint64_t k = keys[i];
+    const uint32_t v = plan.any_value ? vals[i] : 0u;
+    for (int p = 0; p < plan.npass; p++) {
+      const unsigned d = digit_of(k, v, plan.src[p]);
+      // neighbouring items of nearly sorted input share their high digits: one atomic per run inside a warp
+      const unsigned same = __match_any_sync(__activemask(), d);
+      if ((threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&h[p * 256 + d], (unsigned)__popc(same));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < plan.npass * 256; i += blockDim.x)
+    if (h[i]) atomicAdd(&ghist[i], h[i]);
+}
+
+// per pass: exclusive scan of the 256 global digit counts; skip[p] = 1 when one digit holds every key
+__global__ void __launch_bounds__(256)
+radix_prefix_kernel(const unsigned *__restrict__ ghist, unsigned *__restrict__ gbase, int *__restrict__ skip,
+                    int npass, unsigned n) {
+  __shared__ unsigned warp_tot[32];
+  __shared__ unsigned total;
+  for (int p = 0; p < npass; p++) {
+    const unsigned c = ghist[p * 256 + threadIdx.x];
+    const unsigned ex = block_exclusive_scan_u32(c, warp_tot, &total);
+    gbase[p * 256 + threadIdx.x] = ex;
+    if (c == n) skip[p] = 1;
+    __syncthreads();
+  }
+}
+
+struct SweepSmem {
+  uint64_t k[OTILE];
+  uint32_t v[OTILE];
+  unsigned wc[OWARPS][256];
+  unsigned dig_off[256];
+  unsigned glob_off[256];
+  unsigned warp_tot[32];
+  unsigned total;
+  unsigned tile;
+};
+
+__global__ void __launch_bounds__(OT)
+onesweep_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin, uint64_t *__restrict__ kout,
+                uint32_t *__restrict__ vout, size_t n, const DigitSrc src, const unsigned *__restrict__ gbase,
+                unsigned *desc, unsigned *ticket) {
+  extern __shared__ __align__(16) unsigned char sweep_raw[];
+  SweepSmem &S = *reinterpret_cast<SweepSmem *>(sweep_raw);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  if (tid == 0) S.tile = atomicAdd(ticket, 1u);
+  for (int i = tid; i < OWARPS * 256; i += OT) (&S.wc[0][0])[i] = 0;
+  __syncthreads();
+  const unsigned tile = S.tile;
+  const size_t tbase = (size_t)tile * OTILE;
+  const unsigned tile_n = (unsigned)((n - tbase < (size_t)OTILE) ? (n - tbase) : (size_t)OTILE);
+  // warp w owns the contiguous run [tbase + w*32*OI, ...): item j of lane l is element j*32 + l of it, so
+  // (warp, j, lane) order is input order and the ranking below is stable
+  const size_t wbase = tbase + (size_t)w * (32 * OI);
+  uint64_t key[OI];
+  uint32_t val[OI];
+  unsigned short dg[OI], rk[OI];
+#pragma unroll
+  for (int j = 0; j < OI; j++) {
+    const size_t i = wbase + (size_t)j * 32 + lane;
+    const bool ok = i < n;
+    key[j] = ok ? kin[i] : 0ull;
+    val[j] = ok ? vin[i] : 0u;
+  }
+#pragma unroll
+  for (int j = 0; j < OI; j++) {
+    const bool ok = wbase + (size_t)j * 32 + lane < n;
+    const unsigned d = ok ? digit_of(key[j], val[j], src) : 0xffffu;
+    dg[j] = (unsigned short)d;
+    const unsigned mask = __match_any_sync(WENDY_FULL_MASK, d);
+    const int leader = __ffs(mask) - 1;
+    unsigned old = 0;
+    if (lane == leader && ok) {
+      old = S.wc[w][d];
+      S.wc[w][d] = old + __popc(mask);
+    }
+    __syncwarp();
+    old = __shfl_sync(WENDY_FULL_MASK, old, leader);
+    rk[j] = (unsigned short)(old + __popc(mask & lt));
+  }
+  __syncthreads();
+  // thread d owns digit d: per-warp counts -> offsets inside the digit's run; tile count published at once
+  unsigned cnt_d = 0;
+  {
+    const unsigned d = tid;
+#pragma unroll
+    for (int ww = 0; ww < OWARPS; ww++) {
+      const unsigned t = S.wc[ww][d];
+      S.wc[ww][d] = cnt_d;
+      cnt_d += t;
+    }
+    *(volatile unsigned *)(desc + (size_t)tile * 256 + d) = (tile == 0 ? DESC_INC : DESC_AGG) | cnt_d;
+    const unsigned ex = block_exclusive_scan_u32(cnt_d, S.warp_tot, &S.total);
+    S.dig_off[d] = ex;
+  }
+  __syncthreads();
+  // reorder the tile by digit in shared memory (stable)
+#pragma unroll
+  for (int j = 0; j < OI; j++) {
+    if (dg[j] != 0xffffu) {
+      const unsigned pos = S.dig_off[dg[j]] + S.wc[w][dg[j]] + rk[j];
+      S.k[pos] = key[j];
+      S.v[pos] = val[j];
+    }
+  }
+  // decoupled look-back, one digit per thread: items of digit d in all preceding tiles
+  {
+    const unsigned d = tid;
+    unsigned excl = 0;
+    if (tile > 0) {
+      long long t = (long long)tile - 1;
+      while (true) {
+        unsigned vv;
+        do {
+          vv = *(volatile unsigned *)(desc + (size_t)t * 256 + d);
+        } while ((vv >> 30) == 0u);
+        excl += vv & DESC_VAL;
+        if ((vv >> 30) == 2u) break;
+        t--;
+      }
+      *(volatile unsigned *)(desc + (size_t)tile * 256 + d) = DESC_INC | (excl + cnt_d);
+    }
+    S.glob_off[d] = gbase[d] + excl - S.dig_off[d];
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (unsigned i = tid; i < tile_n; i += OT) {
+    const uint64_t kk = S.k[i];
+    const uint32_t vv = S.v[i];
+    const size_t pos = (size_t)S.glob_off[digit_of(kk, vv, src)] + i;
+    kout[pos] = kk;
+    vout[pos] = vv;
+  }
+}
+
 // ---- host driver ---------------------------------------------------------------------
 static inline unsigned ntiles_for(size_t n) { return (unsigned)((n + RTILE - 1) / RTILE); }
 
 size_t radix_table_entries(size_t n) { return (size_t)256 * ntiles_for(n); }
-size_t radix_sums_entries(size_t n) { return (radix_table_entries(n) + SCHUNK - 1) / SCHUNK; }
+// (the onesweep path keeps its global histograms, their prefixes, the skip flags and the tile tickets here too)
+constexpr size_t SWEEP_WORDS = (size_t)2 * MAXPASS * 256 + 2 * MAXPASS + 8;
+size_t radix_sums_entries(size_t n) {
+  const size_t a = (radix_table_entries(n) + SCHUNK - 1) / SCHUNK;
+  return a > SWEEP_WORDS ? a : SWEEP_WORDS;
+}
 
 static void one_pass(cudaStream_t st, const uint64_t *kin, const uint32_t *vin, uint64_t *kout,
                      uint32_t *vout, size_t n, DigitSrc src, uint32_t *table, uint32_t *sums) {
@@ -198,11 +374,60 @@ static void one_pass(cudaStream_t st, const uint64_t *kin, const uint32_t *vin, 
   radix_scatter_kernel<<<nt, RT, 0, st>>>(kin, vin, kout, vout, n, src, table, nt);
 }
 
+// WENDY_B200_RADIX=lsd selects the round-1 five-launch-per-pass sort (A/B runs)
+static bool sweep_allowed() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("WENDY_B200_RADIX");
+    v = !(e && e[0] == 'l');
+  }
+  return v != 0;
+}
+
+static int onesweep_sort_pairs(cudaStream_t st, RadixScratch &s, size_t n, int seg_bits, unsigned seg_div) {
+  SweepPlan plan;
+  memset(&plan, 0, sizeof(plan));
+  for (int shift = 0; shift < 64; shift += 8) plan.src[plan.npass++] = DigitSrc{0, shift, 1u};
+  for (int shift = 0; shift < seg_bits && plan.npass < MAXPASS; shift += 8) {
+    plan.src[plan.npass++] = DigitSrc{1, shift, seg_div};
+    plan.any_value = 1;
+  }
+  unsigned *ghist = s.sums, *gbase = s.sums + MAXPASS * 256, *ticket = s.sums + 2 * MAXPASS * 256;
+  int *skip = (int *)(ticket + MAXPASS);
+  cudaMemsetAsync(s.sums, 0, SWEEP_WORDS * sizeof(unsigned), st);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  size_t hb = (n + 511) / 512;
+  if (hb > (size_t)sms * 4) hb = (size_t)sms * 4;
+  radix_hist_all_kernel<<<(unsigned)hb, 512, 0, st>>>(s.key[0], s.val[0], n, plan, ghist);
+  radix_prefix_kernel<<<1, 256, 0, st>>>(ghist, gbase, skip, plan.npass, (unsigned)n);
+  int h_skip[MAXPASS];
+  cudaMemcpyAsync(h_skip, skip, sizeof(int) * MAXPASS, cudaMemcpyDeviceToHost, st);
+  cudaStreamSynchronize(st);  // (which passes can be skipped decides the buffer the result ends in)
+  const unsigned nt = (unsigned)((n + OTILE - 1) / OTILE);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem));
+    attr_set = true;
+  }
+  int cur = 0;
+  for (int p = 0; p < plan.npass; p++) {
+    if (h_skip[p]) continue;
+    cudaMemsetAsync(s.table, 0, (size_t)nt * 256 * sizeof(uint32_t), st);
+    onesweep_kernel<<<nt, OT, sizeof(SweepSmem), st>>>(s.key[cur], s.val[cur], s.key[cur ^ 1], s.val[cur ^ 1], n,
+                                                       plan.src[p], gbase + p * 256, s.table, ticket + p);
+    cur ^= 1;
+  }
+  return cur;
+}
+
 // Sorts the n pairs in (s.key[0], s.val[0]); returns the index (0/1) of the buffer pair
 // that holds the result.  seg_bits > 0 adds most-significant passes on (val / seg_div).
 int radix_sort_pairs(cudaStream_t st, RadixScratch &s, size_t n, int seg_bits, unsigned seg_div) {
   int cur = 0;
   if (n == 0) return cur;
+  if (sweep_allowed() && n < ((size_t)1 << 30) && seg_bits <= 32) return onesweep_sort_pairs(st, s, n, seg_bits, seg_div);
   for (int shift = 0; shift < 64; shift += 8) {
     DigitSrc src = {0, shift, 1u};
     one_pass(st, s.key[cur], s.val[cur], s.key[cur ^ 1], s.val[cur ^ 1], n, src, s.table, s.sums);

@@ -40,6 +40,12 @@ namespace wendy {
 #define TK_RANK_STRAIGHT 4  // members of a shared sub-bucket compared by straight-line code before a loop takes over
 #endif
 
+#ifndef TK_SUBMUL
+#define TK_SUBMUL 1         // persistent instances: interpolation sub-buckets per slot (2048 slots x SUBMUL counters): fewer
+#endif                      // shared sub-buckets, fewer comparisons in the ranking
+#ifndef TK_LAZY_GROUP
+#define TK_LAZY_GROUP 0     // only members of SHARED sub-buckets are written to the grouped key / id arrays
+#endif
 #ifndef TK_PERSIST_E
 #define TK_PERSIST_E 4      // particles per thread of the PERSISTENT instances (threads = CAP / TK_PERSIST_E).  2: 1024
 #endif                      // threads, 32 registers, 64 warps per SM -- measured 16 % slower
@@ -51,7 +57,10 @@ constexpr int DW = TK_DW;  // destination buckets tracked with shared-memory cou
 template <int CAP, int THREADS, int PERSIST = 0>
 struct TileSmem {
   static constexpr int E = CAP / THREADS;
-  static constexpr int PADN = CAP + CAP / E + 4;
+  static constexpr int SUBMUL = PERSIST ? TK_SUBMUL : 1;
+  static constexpr int BK = CAP * SUBMUL;          // interpolation sub-buckets
+  static constexpr int CPT = BK / THREADS;         // counters scanned by one thread (one padding word after each run)
+  static constexpr int PADN = BK + BK / CPT + 4;
   // PERSIST: landing zone of the TMA bulk copies of the NEXT bucket (x, v, id by load slot)
   double stx[PERSIST ? CAP : 2];
   double stv[PERSIST ? CAP : 2];
@@ -64,7 +73,7 @@ struct TileSmem {
     struct {
       unsigned cnt[(PERSIST ? 2 : 1) * PADN];  // interpolation sub-bucket counters -> start offsets (PERSIST: two sets)
     } srt;
-    double mcum[PADN];  // masses in sorted order -> cumulative mass below
+    double mcum[PERSIST ? 2 : PADN];  // masses in sorted order -> cumulative mass below (general masses)
   } u;
   double ssplit[(PERSIST ? 2 : 1) * (DW + 2)];  // destination window (PERSIST: current / next, alternating)
   double nx_lo[2], nx_hi[2];                    // PERSIST: key range of the current / next bucket
@@ -122,7 +131,8 @@ tile_kernel(const TileParams p) {
   constexpr bool SHARDP = (PERSIST == 3);
   constexpr int E = SM::E;
   constexpr int NW = THREADS / 32;
-  constexpr int BK = CAP;  // interpolation sub-buckets
+  constexpr int BK = SM::BK;    // interpolation sub-buckets
+  constexpr int CPT = SM::CPT;  // counters per thread in the scan
   static_assert(E * THREADS == CAP && (E & (E - 1)) == 0, "CAP must be a power-of-two multiple of THREADS");
   static_assert(CAP <= 65536, "load slots are stored as u16");
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -176,6 +186,7 @@ tile_kernel(const TileParams p) {
     w_n = min(DW, s_hi - w_lo);
   };
   uint32_t phase = 0;
+  int ser_piece = 0;      // PERSIST: piece of the serial cumulative-mass table the previous bucket started in
   int b_it = blockIdx.x;  // PERSIST: the launch guarantees gridDim.x <= p.nb
   unsigned n_it = 0;
   int cur = 0;            // PERSIST: which half of ssplit / nx_* belongs to the current bucket
@@ -358,7 +369,7 @@ tile_kernel(const TileParams p) {
     if (tid + k * THREADS < n) {
       int sub = (int)((xk[k] - xmin) * scale);
       sub = max(0, min(BK - 1, sub));
-      unsigned o = atomicAdd(&S.u.srt.cnt[cbase + sub + sub / E], 1u);
+      unsigned o = atomicAdd(&S.u.srt.cnt[cbase + sub + sub / CPT], 1u);
       pk[k] = (unsigned)sub | (o << 16);
     }
   }
@@ -387,10 +398,10 @@ tile_kernel(const TileParams p) {
   }
   // ---- 4. exclusive scan of the sub-bucket counters ------------------------------------
   {
-    unsigned c[E], run = 0;
-    unsigned *cp = &S.u.srt.cnt[cbase + tid * (E + 1)];
+    unsigned c[CPT], run = 0;
+    unsigned *cp = &S.u.srt.cnt[cbase + tid * (CPT + 1)];
 #pragma unroll
-    for (int q = 0; q < E; q++) {
+    for (int q = 0; q < CPT; q++) {
       c[q] = cp[q];
       run += c[q];
     }
@@ -402,27 +413,52 @@ tile_kernel(const TileParams p) {
     const unsigned ti = warp_inclusive_scan_u32(t, lane);
     unsigned ex = inc - run + __shfl_sync(WENDY_FULL_MASK, ti - t, wid);
 #pragma unroll
-    for (int q = 0; q < E; q++) {
+    for (int q = 0; q < CPT; q++) {
       cp[q] = ex;
       ex += c[q];
     }
   }
   __syncthreads();
   // ---- 5. group load slots by sub-bucket -------------------------------------------------
+  unsigned r[E];
+#if TK_LAZY_GROUP
+  // A particle alone in its sub-bucket has rank = start of the sub-bucket: nothing of it needs to be stored.  Only
+  // members of shared sub-buckets go to the grouped key / id arrays (the bounds are fetched once, here).
+#pragma unroll
+  for (int k = 0; k < E; k++) {
+    r[k] = 0;
+    const unsigned i = tid + k * THREADS;
+    if (i < n) {
+      const unsigned sub = pk[k] & 0xffffu;
+      const unsigned s0 = S.u.srt.cnt[cbase + sub + sub / CPT];
+      const unsigned s1 = (sub + 1 < (unsigned)BK) ? S.u.srt.cnt[cbase + (sub + 1) + (sub + 1) / CPT] : n;
+      const unsigned c = s1 - s0;
+      if (c > 1u) {
+        const unsigned pos = s0 + (pk[k] >> 16);
+        S.sx[pos] = xk[k];
+        S.sid[pos] = id[k];
+      }
+      r[k] = s0;
+      pk[k] = c;
+    } else {
+      pk[k] = 0;
+    }
+  }
+#else
 #pragma unroll
   for (int k = 0; k < E; k++) {
     unsigned i = tid + k * THREADS;
     if (i < n) {
       unsigned sub = pk[k] & 0xffffu;
-      unsigned pos = S.u.srt.cnt[cbase + sub + sub / E] + (pk[k] >> 16);
+      unsigned pos = S.u.srt.cnt[cbase + sub + sub / CPT] + (pk[k] >> 16);
       S.sx[pos] = xk[k];
       S.sid[pos] = id[k];
     }
   }
+#endif
   __syncthreads();
   // ---- 6. exact rank under the (x, id) order; masses are fetched meanwhile ---------------
   double m[E];
-  unsigned r[E];
   if (!PERSIST) {  // velocities are fetched now so that the load overlaps the ranking
 #pragma unroll
     for (int k = 0; k < E; k++)
@@ -438,17 +474,19 @@ tile_kernel(const TileParams p) {
   // The sub-bucket bounds of all E particles are fetched first (independent shared-memory loads in flight
   // together); sub-buckets hold 1.75 members on average, so the first TK_RANK_STRAIGHT members are compared
   // by predicated straight-line code and a loop only runs for crowded sub-buckets.
+#if !TK_LAZY_GROUP
 #pragma unroll
   for (int k = 0; k < E; k++) {
     r[k] = 0;
     if (tid + k * THREADS < n) {
       const unsigned sub = pk[k] & 0xffffu;
-      const unsigned s0 = S.u.srt.cnt[cbase + sub + sub / E];
-      const unsigned s1 = (sub + 1 < (unsigned)BK) ? S.u.srt.cnt[cbase + (sub + 1) + (sub + 1) / E] : n;
+      const unsigned s0 = S.u.srt.cnt[cbase + sub + sub / CPT];
+      const unsigned s1 = (sub + 1 < (unsigned)BK) ? S.u.srt.cnt[cbase + (sub + 1) + (sub + 1) / CPT] : n;
       r[k] = s0;
       pk[k] = s1 - s0;  // the sub-bucket index is not needed any more
     }
   }
+#endif
 #pragma unroll
   for (int k = 0; k < E; k++) {
     if (tid + k * THREADS < n && pk[k] > 1u) {  // shared sub-bucket: count the members that sort before this one
@@ -559,7 +597,21 @@ tile_kernel(const TileParams p) {
   // running sum (wendy/wendy.c:359-360) bit for bit; a bucket nearly always lies inside one linear piece.
   SerialRun SR;
   SR.c0 = 0.0; SR.inc = 0.0; SR.j0 = 0u; SR.uniform = true;
-  if (EQM && p.stab) SR = serial_run(p.stab, Pc + pc_off, n);
+  if (EQM && p.stab) {
+    if (PERSIST) {
+      // a CTA walks its buckets in ascending order, so the piece index only ever moves forward: remember it
+      // instead of searching (one L1-resident load per bucket in the common case)
+      const long long k0 = Pc + pc_off;
+      while (k0 >= __ldg(&p.stab->i0[ser_piece + 1])) ser_piece++;
+      const long long i0 = __ldg(&p.stab->i0[ser_piece]);
+      SR.c0 = __ldg(&p.stab->c0[ser_piece]);
+      SR.inc = __ldg(&p.stab->inc[ser_piece]);
+      SR.j0 = (unsigned)(k0 - i0);
+      SR.uniform = (k0 + (long long)n <= __ldg(&p.stab->i0[ser_piece + 1])) && (k0 - i0 + (long long)n < (1ll << 31));
+    } else {
+      SR = serial_run(p.stab, Pc + pc_off, n);
+    }
+  }
   auto cum_eqm = [&](unsigned rk) -> double {
     if (p.stab) {
       if (SR.uniform) return serial_cum_run(SR, rk);
@@ -760,7 +812,7 @@ tile_kernel(const TileParams p) {
         const int g = (int)max((long long)seg_lo, min((long long)seg_hi - 1, (long long)b + (long long)floor(gq)));
         d = gallop_search_tile(p.split, key, g, seg_lo, seg_hi);
       }
-      if (SHARDP && (d == 0 || d == p.nb - 1) && (key < sh_lo || key >= sh_hi)) {
+      if (SHARDP && (d == 0 || d >= p.nb_last) && (key < sh_lo || key >= sh_hi)) {
         // Only the two edge buckets reach beyond this GPU's key range (their outer splitters are -inf / +inf):
         // the particle now belongs to another rank -- its record goes straight into the owner's inbox (peer
         // memory over NVLink); the count travels with the flag word at the end of the launch.
