@@ -579,24 +579,41 @@ def main():
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         r, kind = make_reference(x, v, m, a.omega, a.dt_leap)
         nsub = 4  # 1 warm-up (the first sort starts from random order) + 3 timed sub-steps
+        # Exactly coincident keys: the reference's sort='parallel' (OpenMP merge over qsort leaves,
+        # wendy/parallel_sort.c:95-137) leaves their order unspecified, ours is (x, index).  Two tied particles whose
+        # ranks are swapped differ by 2 m0 dt in v -- not an error of either side; they are counted and excluded.
+        def tied_now(xc, vc):
+            key = xc + (a.dt_leap / 2.) * vc  # the key of the call's only force evaluation (wendy/wendy.c:398)
+            perm = wendy_b200.argsort(key)
+            ks = key[perm]
+            eq = numpy.flatnonzero(ks[1:] == ks[:-1])
+            return numpy.concatenate((perm[eq], perm[eq + 1]))
+        tied = numpy.zeros(n, dtype=bool)
         g = wendy_b200.nbody(x, v, m, a.dt_leap, approx=True, nleap=1, omega=a.omega)
         ts, par = [], {}
+        xc, vc = x, v
         for i in range(nsub):
+            tied[tied_now(xc, vc)] = True
             t0 = time.perf_counter()
             xr, vr = r.step()
             ts.append(time.perf_counter() - t0)
-            xg, vg = next(g)
+            xc, vc = next(g)
             if i in (0, nsub - 1):
+                bad = (xc != xr) | (vc != vr)
                 par['after_%d_substeps' % (i + 1)] = {
-                    'x_bit_identical': bool(numpy.array_equal(xg, xr)), 'v_bit_identical': bool(numpy.array_equal(vg, vr)),
-                    'max_rel_err_x': relerr(xg, xr), 'max_rel_err_v': relerr(vg, vr)}
+                    'x_bit_identical': bool(numpy.array_equal(xc[~tied], xr[~tied])),
+                    'v_bit_identical': bool(numpy.array_equal(vc[~tied], vr[~tied])),
+                    'particles_in_exact_key_ties_so_far': int(tied.sum()),
+                    'particles_differing': int(bad.sum()), 'of_which_tied': int((bad & tied).sum()),
+                    'max_rel_err_x': relerr(xc, xr), 'max_rel_err_v': relerr(vc, vr)}
         g.close()
         per = sum(ts[1:]) / (nsub - 1)
         out['cpu_baseline'] = {'value': n / per, 'unit': 'particle-steps/s', 'cores': cores, 'kind': kind,
                                'sample': 'the same N=%d system: 1 warm-up + 3 timed leapfrog sub-steps (nleap=1 calls), reference '
                                          'sort=parallel, %.2f s per sub-step' % (n, per), 'host': host_info()}
         par['against'] = 'oracle/_ref/wendy_c.so (the unmodified reference C path), same ICs, N=%d, dt_leap=%g, nleap=1 calls' % (n, a.dt_leap)
-        par['tolerance_north_star'] = 'x, v relative 1e-12 after 1 step, 1e-9 after 10; observed: bit-identical'
+        par['tolerance_north_star'] = ('x, v relative 1e-12 after 1 step, 1e-9 after 10; required here: bit-identical for every particle '
+                                       'outside exact key ties (x_bit_identical / v_bit_identical are evaluated on those)')
         out['parity'] = par
     if rank == 0:
         print(json.dumps(out))

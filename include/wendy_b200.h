@@ -184,6 +184,8 @@ int wendy_cuda_shard_comm_export(wendy_cuda_handle *h, unsigned long long *ptr, 
 int wendy_cuda_shard_comm_open(wendy_cuda_handle *h, const unsigned char *ipc_handles,
                                const unsigned long long *raw_ptrs);
 int wendy_cuda_shard_seed_counts(wendy_cuda_handle *h, const long long *counts);
+int wendy_cuda_shard_prepare(wendy_cuda_handle *h, double dt_leap, int k0);  /* optional: the (local, synchronous)
+                                   layout rebuild step_begin would do on demand, ahead of it */
 int wendy_cuda_shard_step_begin(wendy_cuda_handle *h, double dt_leap, int nleap, int k0);
 int wendy_cuda_shard_step_end(wendy_cuda_handle *h, int *k_fail, long long *n_local, long long *migrated_in);
 int wendy_cuda_shard_rollback(wendy_cuda_handle *h, int k, long long *n_local);

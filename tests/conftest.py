@@ -7,6 +7,12 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# several "ranks" of the sharded mode run as threads on ONE GPU in the tests, with kernels that wait for each other:
+# a lazily loaded kernel of one rank must not need a context-wide synchronisation while another rank's kernel spins
+os.environ.setdefault('CUDA_MODULE_LOADING', 'EAGER')
+# ... and their streams must not share a hardware queue (default: 8 connections; a kernel queued behind a spinning one of
+# another rank would never start)
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
 os.environ.setdefault('OMP_NUM_THREADS', '1')  # reference OpenMP regions are slow in VMs
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 

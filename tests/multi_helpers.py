@@ -66,8 +66,13 @@ class ThreadComm(object):
             self.vec = [None] * size
             self.mail = [[None] * size for _ in range(size)]
 
+    in_process = True  # the ranks share one process (and, on a GPU, one device)
+
     def __init__(self, world, rank, device='cpu'):
         self.w, self.rank, self.size, self.device = world, rank, world.size, device
+
+    def barrier(self):
+        self.w.barrier.wait()
 
     def allgather_vec(self, vec):
         self.w.vec[self.rank] = numpy.asarray(vec, dtype=numpy.float64).copy()

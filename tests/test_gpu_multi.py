@@ -99,7 +99,7 @@ def test_sharded_four_ranks_and_a_changed_time_step(exchange):
     import wendy_b200
     n = 120000
     x, v, m = wo.sech2_ic(n, seed=6)
-    st = wendy_b200.ApproxState(x, v, m, omega2=1.21)
+    st = wendy_b200.ApproxState(x, v, m, omega2=1.1 ** 2.)
     st.step(0.004, 4)
     st.step(0.009, 3)
     Xs, Vs = st.read()

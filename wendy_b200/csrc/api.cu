@@ -78,6 +78,11 @@ struct wendy_cuda_handle {
   bool coarse_default = false;  // large equal-mass systems start (and stay) on 2048-slot buckets
   bool fill_backoff = false;    // a library-chosen coarse layout overflowed at the optimistic fill: use 3/4 from now on
   bool rebuild_pending = false;  // shard: rebuild at the start of the next sub-step (state complete)
+  int shard_retry_k = -1, shard_retry_n = 0;  // shard: sub-step of the last rollback, consecutive rollbacks to it
+  // WENDY_B200_SHARD_TRACE=1: CUDA events around the three launches of every sharded sub-step (peer exchange)
+  std::vector<cudaEvent_t> tr_ev;
+  double tr_ms[3] = {0., 0., 0.};
+  long long tr_n = 0;
   bool ext_half_done = false;    // ext-force stepping: the leading half drift of the call is already in x
   int ext_fail_streak = 0;       // ... consecutive overflows of the same sub-step (two: take it on the radix path)
   int nb_last = 0;               // last bucket of the layout that has a finite lower edge (the tail may be unused)
@@ -259,6 +264,26 @@ static void fill_back_off(H *h) {
   }
 }
 
+// A sharded sub-step that overflows again on a FRESH layout (the density changes by more than the head-room within one
+// sub-step: violent relaxation at a coarse dt) has no radix path to fall back on: buy head-room instead.  Every
+// further retry halves the fill, down to what the shard's storage can hold (2 N slots for small shards = 2.5 x
+// head-room; 1.7 x for shards created coarse).
+static void fill_escalate(H *h) {
+  const int cap = h->want_cap ? h->want_cap : h->cap;
+  if (cap == 256) return;
+  const long long nb_max = (long long)(h->slots / (size_t)cap);
+  const long long need = (long long)((double)h->N * 1.02) + 1;
+  int f_min = nb_max > 0 ? (int)((need + nb_max - 1) / nb_max) + 1 : cap;
+  f_min = std::max(f_min, cap / 16);
+  const int cur = (cap == h->cap) ? h->fill : cap * 3 / 4;
+  const int nf = std::max(f_min, cur / 2);
+  if (nf < cur) {
+    h->fill_backoff = true;
+    h->user_fill = nf; h->user_cap = cap;  // (default_fill honours it when the geometry is switched as well)
+    if (cap == h->cap) h->fill = nf;
+  }
+}
+
 // (Re)build the bucket layout for key = x + hkey*v: exact quantile splitters from a radix
 // sort of the keys, then one streaming scatter of the state into the other buffer (optionally
 // together with `n_extra` packed migrant records: shard inject).
@@ -425,6 +450,12 @@ void wendy_cuda_destroy(wendy_cuda_handle *h) {
   if (h->reader.joinable()) h->reader.join();
   if (h->st_copy) cudaStreamSynchronize(h->st_copy);
   cudaStreamSynchronize(h->st);
+  if (h->tr_n > 0)
+    fprintf(stderr, "wendy_b200 shard trace rank %d: %lld sub-steps, ms per sub-step: count prefix %.4f, step kernel "
+            "(incl. wait for the peers' counts) %.4f, inject kernel (incl. wait for the peers' migrants) %.4f\n",
+            h->my_rank, h->tr_n, h->tr_ms[0] / h->tr_n, h->tr_ms[1] / h->tr_n, h->tr_ms[2] / h->tr_n);
+  for (cudaEvent_t e : h->tr_ev) cudaEventDestroy(e);
+  h->tr_ev.clear();
   ring_release(h->ring);
   h->ring = nullptr;
   for (int i = 0; i < 2; i++) {
@@ -896,9 +927,18 @@ int wendy_cuda_shard_read(wendy_cuda_handle *h, double *x_host, double *v_host, 
     launch_compact(h->st, h->x[h->cur], h->v[h->cur], h->id[h->cur], h->cnt[h->ccur], h->cpre, h->cap, h->nb,
                    h->xo, h->vo, h->cid);
     h->n_launch += 2;
-    CK(copy_split(x_host, h->xo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
-    CK(copy_split(v_host, h->vo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
-    CK(copy_split(id_host, h->cid, (size_t)h->N * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    void *const dst[3] = {x_host, v_host, id_host};
+    const void *const src[3] = {h->xo, h->vo, h->cid};
+    const size_t nby[3] = {(size_t)h->N * sizeof(double), (size_t)h->N * sizeof(double), (size_t)h->N * sizeof(int)};
+    // ordinary (pageable) destinations are filled through the page-locked bounce ring at PCIe speed, as in
+    // wendy_cuda_read: page-locking gigabytes per rank costs more than many read-outs
+    const bool bounce = nby[0] >= ((size_t)4 << 20) && bounce_allowed() && !host_range_is_pinned(x_host, nby[0]);
+    if (bounce && !h->ring) h->ring = ring_acquire(h->device);
+    if (bounce && h->ring) {
+      if (bounce_d2h(h->ring, h->st, dst, src, nby, 3)) return set_err(WENDY_E_CUDA, "device -> host copy through the bounce buffers failed");
+    } else {
+      for (int a = 0; a < 3; a++) CK(copy_split(dst[a], src[a], nby[a], cudaMemcpyDeviceToHost, h->st));
+    }
   }
   CK(cudaStreamSynchronize(h->st));
   CK(cudaGetLastError());
@@ -1009,15 +1049,37 @@ int wendy_cuda_shard_seed_counts(wendy_cuda_handle *h, const long long *counts) 
   return 0;
 }
 
+// Make sure the layout is the one sub-step k0 of a call needs (first call, changed dt, after a rollback): local and
+// synchronous.  step_begin does the same on demand; calling this first keeps every potentially device-synchronising
+// CUDA call (allocations, first-time kernel loads) out of the window in which kernels wait for peers -- which matters
+// when several ranks share ONE device (ranks as threads of a process: tests), not with one process per GPU.
+int wendy_cuda_shard_prepare(wendy_cuda_handle *h, double dt, int k0) {
+  if (!h || !h->peer_on) return set_err(WENDY_E_ARG, "peer exchange is not set up");
+  if (h->pending) return set_err(WENDY_E_ARG, "a call is already in flight");
+  const double h_pre = (k0 == 0) ? dt / 2. : 0.;
+  if (h->dense || !h->has_split || h->bucket_h != h_pre || h->rebuild_pending) {
+    int rc = rebucket(h, h_pre);
+    if (rc) return rc;
+    h->rebuild_pending = false;
+  }
+  return 0;
+}
+
 // Enqueue sub-steps [k0, nleap) of one call on every rank's own stream; nothing here waits for a peer's HOST.
 // (A layout rebuild -- first call, changed dt, after a rollback -- is local and synchronous.)
 int wendy_cuda_shard_step_begin(wendy_cuda_handle *h, double dt, int nleap, int k0) {
   if (!h || !h->peer_on) return set_err(WENDY_E_ARG, "peer exchange is not set up");
   if (nleap < 1 || nleap > PEER_NHIST || k0 < 0 || k0 >= nleap) return set_err(WENDY_E_ARG, "bad nleap");
   if (h->pending) return set_err(WENDY_E_ARG, "a call is already in flight");
-  if (k0 == 0) { h->p_seq.clear(); h->p_seq_inj.clear(); h->p_cur.clear(); h->p_ccur.clear(); }
+  if (k0 == 0) { h->p_seq.clear(); h->p_seq_inj.clear(); h->p_cur.clear(); h->p_ccur.clear(); h->shard_retry_k = -1; }
   h->p_seq.resize(k0); h->p_seq_inj.resize(k0); h->p_cur.resize(k0); h->p_ccur.resize(k0);
   h->p_dt = dt; h->p_nleap = nleap; h->p_k0 = k0;
+  static const bool trace_on = getenv("WENDY_B200_SHARD_TRACE") != nullptr;
+  if (trace_on) {
+    while (h->tr_ev.size() < (size_t)4 * PEER_NHIST) {
+      cudaEvent_t e; CK(cudaEventCreate(&e)); h->tr_ev.push_back(e);
+    }
+  }
   for (int k = k0; k < nleap; k++) {
     const double h_pre = (k == 0) ? dt / 2. : 0.;
     const bool last = (k == nleap - 1);
@@ -1036,9 +1098,12 @@ int wendy_cuda_shard_step_begin(wendy_cuda_handle *h, double dt, int nleap, int 
       fill_tile_params(h, p);
       p.h_pre = h_pre; p.dt_kick = dt; p.dt_drift = last ? dt / 2. : dt; p.h_next = last ? dt / 2. : 0.;
       p.kcall = k;
+      if (trace_on) cudaEventRecord(h->tr_ev[4 * k], h->st);
       launch_count_prefix(h->st, p.cnt_in, h->nb, h->cpre, h->cp_desc, h->cp_ticket, p.epoch);
+      if (trace_on) cudaEventRecord(h->tr_ev[4 * k + 1], h->st);
       p.cpre = h->cpre;
       launch_tile(h->st, h->cap, LOAD_BUCKET, EMIT_SPLITTER, 1, p);
+      if (trace_on) cudaEventRecord(h->tr_ev[4 * k + 2], h->st);
       h->n_launch += 2;
       advance_after_tile(h);
       h->n_launch--;
@@ -1058,6 +1123,7 @@ int wendy_cuda_shard_step_begin(wendy_cuda_handle *h, double dt, int nleap, int 
       int grid = h->sm_count;
       if (const char *ge = getenv("WENDY_B200_PERSIST_GRID")) grid = std::max(1, std::min(grid, atoi(ge)));
       launch_peer_inject(h->st, q, grid);
+      if (trace_on) cudaEventRecord(h->tr_ev[4 * k + 3], h->st);
       h->n_launch++;
     }
     h->pepoch++;
@@ -1077,6 +1143,15 @@ int wendy_cuda_shard_step_end(wendy_cuda_handle *h, int *k_fail, long long *n_lo
   unsigned pstat[2] = {0u, 0u};  // [0] a wait timed out, [1] records received so far (wraps)
   CK(cudaMemcpyAsync(pstat, h->peer_scratch + PEER_MAX + 2, sizeof(pstat), cudaMemcpyDeviceToHost, h->st));
   if (fetch_flags(h)) return WENDY_E_CUDA;
+  if (!h->tr_ev.empty()) {
+    for (int k = h->p_k0; k < nleap; k++) {
+      for (int j = 0; j < 3; j++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->tr_ev[4 * k + j], h->tr_ev[4 * k + j + 1]) == cudaSuccess) h->tr_ms[j] += ms;
+      }
+      h->tr_n++;
+    }
+  }
   if (pstat[0]) return set_err(WENDY_E_CUDA, "shard: timed out waiting for a peer GPU");
   if (migrated_in) *migrated_in = (long long)(unsigned)(pstat[1] - h->peer_mig_seen);
   h->peer_mig_seen = pstat[1];
@@ -1115,8 +1190,10 @@ int wendy_cuda_shard_rollback(wendy_cuda_handle *h, int k, long long *n_local) {
   h->n_sub -= (h->p_nleap - k);
   h->cur = h->p_cur[k]; h->ccur = h->p_ccur[k];
   h->has_split = false;
-  fill_back_off(h);
   h->N = h->h_peer_n[1 + k]; h->seg_len = h->N;
+  fill_back_off(h);
+  if (h->shard_retry_k == k) h->shard_retry_n++; else { h->shard_retry_k = k; h->shard_retry_n = 0; }
+  if (h->shard_retry_n >= 1) fill_escalate(h);  // the fresh layout of the first retry overflowed as well
   if (reset_flags(h)) return WENDY_E_CUDA;
   if (n_local) *n_local = h->N;
   return 0;

@@ -213,12 +213,8 @@ radix_hist_all_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restr
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const uint64_t k = keys[i];
     const uint32_t v = plan.any_value ? vals[i] : 0u;
-    for (int p = 0; p < plan.npass; p++) {
-      const unsigned d = digit_of(k, v, plan.src[p]);
-      // neighbouring items of nearly sorted input share their high digits: one atomic per run inside a warp
-      const unsigned same = __match_any_sync(__activemask(), d);
-      if ((threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&h[p * 256 + d], (unsigned)__popc(same));
-    }
+    for (int p = 0; p < plan.npass; p++)  // (spread shared atomics cost about as much as a shared load on sm_100a)
+      atomicAdd(&h[p * 256 + digit_of(k, v, plan.src[p])], 1u);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < plan.npass * 256; i += blockDim.x)
@@ -283,7 +279,16 @@ onesweep_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ v
     const bool ok = wbase + (size_t)j * 32 + lane < n;
     const unsigned d = ok ? digit_of(key[j], val[j], src) : 0xffffu;
     dg[j] = (unsigned short)d;
-    const unsigned mask = __match_any_sync(WENDY_FULL_MASK, d);
+    // lanes holding the same digit: eight ballots (MATCH.ANY costs ~33 SM cycles per warp instruction on sm_100a
+    // when the lanes' values differ, eight VOTEs ~5: scripts/ubench/atoms.cu)
+    unsigned mask = __ballot_sync(WENDY_FULL_MASK, ok);
+#pragma unroll
+    for (int bit = 0; bit < 8; bit++) {
+      const bool one = (d >> bit) & 1u;
+      const unsigned bb = __ballot_sync(WENDY_FULL_MASK, one);
+      mask &= one ? bb : ~bb;
+    }
+    if (!ok) mask = 1u << lane;
     const int leader = __ffs(mask) - 1;
     unsigned old = 0;
     if (lane == leader && ok) {

@@ -37,14 +37,17 @@ namespace wendy {
 #endif
 // Tunables kept as macros for A/B builds (scripts/ab_variants.py; measured values in DESIGN.md section 3.0)
 #ifndef TK_RANK_STRAIGHT
-#define TK_RANK_STRAIGHT 4  // members of a shared sub-bucket compared by straight-line code before a loop takes over
+#define TK_RANK_STRAIGHT 2  // members of a shared sub-bucket compared by straight-line code before a loop takes over
 #endif
 
 #ifndef TK_SUBMUL
-#define TK_SUBMUL 1         // persistent instances: interpolation sub-buckets per slot (2048 slots x SUBMUL counters): fewer
+#define TK_SUBMUL 2         // persistent instances: interpolation sub-buckets per slot (2048 slots x SUBMUL counters): fewer
 #endif                      // shared sub-buckets, fewer comparisons in the ranking
 #ifndef TK_LAZY_GROUP
-#define TK_LAZY_GROUP 0     // only members of SHARED sub-buckets are written to the grouped key / id arrays
+#define TK_LAZY_GROUP 1     // only members of SHARED sub-buckets are written to the grouped key / id arrays
+#endif
+#ifndef TK_EMIT
+#define TK_EMIT 0           // slot requests of one warp: 0 MATCH.ANY per destination, 1 eight ballots, 2 direct shared atomics
 #endif
 #ifndef TK_PERSIST_E
 #define TK_PERSIST_E 4      // particles per thread of the PERSISTENT instances (threads = CAP / TK_PERSIST_E).  2: 1024
@@ -836,6 +839,32 @@ tile_kernel(const TileParams p) {
   }
   // slot allocation, aggregated per warp and destination; the E requests are issued back to back and
   // their results consumed afterwards, so the atomics' latencies overlap
+#if TK_EMIT == 2
+  // MATCH.ANY costs ~33 SM cycles per warp instruction on sm_100a when the lanes' values differ (measured,
+  // scripts/ubench/atoms.cu: an LDS or a conflict-free shared atomic costs ~3): lanes that leave the bucket ask
+  // the shared counter of their destination directly (few lanes share a destination once particles spread over
+  // many buckets); only the lanes that stay home -- one address for all of them -- are aggregated by a ballot.
+#pragma unroll
+  for (int k = 0; k < E; k++) {
+    const int d = dest[k];
+    const bool ok = tid + k * THREADS < n;
+    const unsigned home = __ballot_sync(WENDY_FULL_MASK, ok && d == b);
+    unsigned pos = 0;
+    if (home) {
+      if (lane == __ffs(home) - 1) pos = atomicAdd(&S.dcnt[rel], (unsigned)__popc(home));
+      pos = __shfl_sync(WENDY_FULL_MASK, pos, __ffs(home) - 1) + __popc(home & lt);
+    }
+    if (ok && d >= 0 && d != b) {
+      if (d >= wlo && d < wlo + wn) {
+        pos = atomicAdd(&S.dcnt[d - wlo], 1u);
+      } else {
+        pos = atomicAdd(&p.cnt_out[d], 1u);
+        outside += 1;
+      }
+    }
+    lpos[k] = pos;
+  }
+#else
   unsigned amask[E];
 #pragma unroll
   for (int k = 0; k < E; k++) {
@@ -843,8 +872,27 @@ tile_kernel(const TileParams p) {
     const bool ok = tid + k * THREADS < n;
     unsigned mask;
     const unsigned valid = __ballot_sync(WENDY_FULL_MASK, ok);
-    if (__all_sync(WENDY_FULL_MASK, d == b || !ok)) mask = ok ? valid : 0u;  // whole warp stays home (common)
-    else mask = __match_any_sync(WENDY_FULL_MASK, d);
+    if (__all_sync(WENDY_FULL_MASK, d == b || !ok)) {
+      mask = ok ? valid : 0u;  // whole warp stays home (common at small dt)
+    } else {
+#if TK_EMIT == 1
+      // lanes with the same destination, by eight ballots on the window-relative bucket number instead of
+      // MATCH.ANY (~33 SM cycles per warp instruction when the values differ; eight VOTEs cost ~5); the rare
+      // lanes that leave the window (or hold no particle) form groups of one
+      const bool inw = ok && d >= wlo && d < wlo + wn;
+      const unsigned r8 = (unsigned)(d - wlo);
+      mask = __ballot_sync(WENDY_FULL_MASK, inw);
+#pragma unroll
+      for (int bit = 0; bit < 8; bit++) {
+        const bool one = (r8 >> bit) & 1u;
+        const unsigned bb = __ballot_sync(WENDY_FULL_MASK, one);
+        mask &= one ? bb : ~bb;
+      }
+      if (!inw) mask = (ok && d >= 0) ? (1u << lane) : 0u;
+#else
+      mask = __match_any_sync(WENDY_FULL_MASK, d);
+#endif
+    }
     amask[k] = mask;
     lpos[k] = 0;
     if (ok && d >= 0 && lane == __ffs(mask) - 1) {
@@ -862,6 +910,7 @@ tile_kernel(const TileParams p) {
     const unsigned basel = __shfl_sync(WENDY_FULL_MASK, lpos[k], leader < 0 ? 0 : leader);
     lpos[k] = basel + __popc(amask[k] & lt);
   }
+#endif
   __syncthreads();
   for (int i = tid; i < wn; i += THREADS)
     if (S.dcnt[i]) S.dbase[i] = atomicAdd(&p.cnt_out[wlo + i], S.dcnt[i]);

@@ -182,6 +182,9 @@ class CudaShardEngine(object):
         _lib.check(self._lib.wendy_cuda_shard_seed_counts(
             self._h, numpy.ascontiguousarray(counts, dtype=numpy.int64)))
 
+    def prepare(self, dt_leap, k0=0):
+        _lib.check(self._lib.wendy_cuda_shard_prepare(self._h, float(dt_leap), int(k0)))
+
     def step_begin(self, dt_leap, nleap, k0=0):
         _lib.check(self._lib.wendy_cuda_shard_step_begin(self._h, float(dt_leap), int(nleap), int(k0)))
 
@@ -226,12 +229,15 @@ class CudaShardEngine(object):
         return n.value
 
     def read(self):
-        """(ids, x, v) of the local particles: views of page-locked buffers this engine re-uses on
-        every call (copy them to keep a snapshot across reads)."""
+        """(ids, x, v) of the local particles: views of host buffers this engine re-uses on every call (copy
+        them to keep a snapshot across reads)."""
         if self._pinned is None:
-            t = self.torch
-            self._pinned = tuple(t.empty(self.capacity, dtype=d, pin_memory=True).numpy()
-                                 for d in (t.float64, t.float64, t.int32))
+            # ordinary numpy memory, touched once: the library fills pageable destinations through its page-locked
+            # bounce buffers at PCIe speed; page-locking capacity * 20 bytes per rank would cost about a second
+            self._pinned = (numpy.empty(self.capacity), numpy.empty(self.capacity),
+                            numpy.empty(self.capacity, dtype=numpy.int32))
+            for arr in self._pinned:
+                self._lib.wendy_host_prefault(arr.ctypes.data, arr.nbytes)
         x, v, ids = self._pinned
         n = ctypes.c_longlong()
         _lib.check(self._lib.wendy_cuda_shard_read(self._h, x, v, ids, ctypes.byref(n)))
@@ -370,6 +376,12 @@ class ShardedSystem(object):
         k0, tries = 0, 0
         while True:
             t0 = time.perf_counter()
+            if getattr(self.comm, 'in_process', False):
+                # ranks that are threads of ONE process share a device: a device-synchronising CUDA call of one
+                # rank (an allocation, a first-time kernel load inside a layout rebuild) would wait for kernels of
+                # another rank that are waiting for this one.  Rebuild first, then start together.
+                eng.prepare(dt_leap, k0)
+                self.comm.barrier()
             eng.step_begin(dt_leap, nleap, k0)
             t1 = time.perf_counter()
             kf, n_local, mig = eng.step_end()
