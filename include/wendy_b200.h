@@ -164,6 +164,11 @@ int wendy_cuda_shard_inject(wendy_cuda_handle *h, const double *records_dev, lon
 int wendy_cuda_shard_count(wendy_cuda_handle *h, long long *n_local);
 int wendy_cuda_shard_read(wendy_cuda_handle *h, double *x_host, double *v_host, int *id_host,
                           long long *n);
+/* the same, overlapped: _begin compacts on the compute stream and starts the device -> host copies on a private
+ * copy stream; the caller may step the shard before _end (which waits for the copies) */
+int wendy_cuda_shard_read_begin(wendy_cuda_handle *h, double *x_host, double *v_host, int *id_host,
+                                long long *n);
+int wendy_cuda_shard_read_end(wendy_cuda_handle *h);
 
 /* ---- sharded single system, device-driven exchange over peer memory (NVLink) ---------------------
  * With these entry points a sub-step needs NO host round trip and no host-side collective: the step kernel
@@ -218,6 +223,9 @@ void wendy_cuda_trim(void);
 
 /* Touch every page of a freshly allocated host array (contents kept) with a few threads, so that the first
  * read-out into it does not pay the page faults.  Host-only; no CUDA call. */
+void wendy_host_set_threads(int n);  /* host threads the library's own copy / validation loops may use (0: default =
+                                        OpenMP's maximum, at most 32).  One rank per GPU: cores / ranks on the node
+                                        (wendy_b200/multi.py sets it); WENDY_B200_HOST_THREADS overrides */
 void wendy_host_prefault(void *host_ptr, unsigned long long bytes);
 
 /* Test/diagnostic hook: copies the per-bucket particle counts and lower splitters of the current

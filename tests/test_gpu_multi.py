@@ -126,13 +126,17 @@ def test_sharded_peer_exchange_rolls_back_after_an_overflow(monkeypatch):
     monkeypatch.setenv('WENDY_B200_PEER_TIMEOUT_MS', '5000')
     n = 60000
     x, v, m = wo.slab_ic(n, seed=5)
-    Xs, Vs = _single_gpu(x, v, m, 0.05, 5, 4, None)
+    # three calls = 15 sub-steps: the slab's density rises by 1.3 (a stale layout overflows, a fresh one holds) and at
+    # most a few hundred particles per sub-step cross the range edge; the deep collapse that follows (thousands of
+    # crossings per sub-step, density doubling within one sub-step) is beyond what a shard's inbox and head-room
+    # are sized for and raises instead
+    Xs, Vs = _single_gpu(x, v, m, 0.05, 5, 3, None)
 
     def run(comm):
         from wendy_b200 import multi
         mine = numpy.arange(n) % comm.size == comm.rank
         s = multi.ShardedSystem(x[mine], v[mine], numpy.arange(n)[mine], m[0], numpy.sum(m), comm)
-        for _ in range(4):
+        for _ in range(3):
             s.step(0.05, 5)
         X, V = s.gather(n)
         fails = s.engine.stats()['failed_substeps']

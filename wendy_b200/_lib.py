@@ -104,6 +104,8 @@ def load():
     lib.wendy_cuda_shard_comm_open.argtypes = [vp, _nd('u1'), _nd('u8')]
     lib.wendy_cuda_shard_seed_counts.restype = ctypes.c_int
     lib.wendy_cuda_shard_seed_counts.argtypes = [vp, _nd('i8')]
+    lib.wendy_host_set_threads.restype = None
+    lib.wendy_host_set_threads.argtypes = [ctypes.c_int]
     lib.wendy_cuda_shard_prepare.restype = ctypes.c_int
     lib.wendy_cuda_shard_prepare.argtypes = [vp, ctypes.c_double, ctypes.c_int]
     lib.wendy_cuda_shard_step_begin.restype = ctypes.c_int
@@ -116,6 +118,10 @@ def load():
     lib.wendy_cuda_shard_count.argtypes = [vp, c_ll_p]
     lib.wendy_cuda_shard_read.restype = ctypes.c_int
     lib.wendy_cuda_shard_read.argtypes = [vp, _nd('f8'), _nd('f8'), _nd('i4'), c_ll_p]
+    lib.wendy_cuda_shard_read_begin.restype = ctypes.c_int
+    lib.wendy_cuda_shard_read_begin.argtypes = [vp, _nd('f8'), _nd('f8'), _nd('i4'), c_ll_p]
+    lib.wendy_cuda_shard_read_end.restype = ctypes.c_int
+    lib.wendy_cuda_shard_read_end.argtypes = [vp]
     lib.wendy_host_prefault.restype = None
     lib.wendy_host_prefault.argtypes = [vp, ctypes.c_ulonglong]
     lib.wendy_cuda_trim.restype = None
@@ -144,7 +150,7 @@ EXPORTED = ['wendy_cuda_create', 'wendy_cuda_create_dev', 'wendy_cuda_step', 'we
             'wendy_cuda_read_begin', 'wendy_cuda_read_end', 'wendy_cuda_force_positions',
             'wendy_cuda_substep', 'wendy_cuda_read', 'wendy_cuda_read_dev', 'wendy_cuda_energy',
             'wendy_cuda_stats', 'wendy_serial_cum', 'wendy_cuda_create_shard', 'wendy_cuda_create_shard_dev', 'wendy_cuda_shard_substep', 'wendy_cuda_shard_outbox',
-            'wendy_cuda_shard_inject', 'wendy_cuda_shard_comm_export', 'wendy_cuda_shard_comm_open', 'wendy_cuda_shard_seed_counts', 'wendy_cuda_shard_prepare', 'wendy_cuda_shard_step_begin', 'wendy_cuda_shard_step_end', 'wendy_cuda_shard_rollback', 'wendy_cuda_shard_count', 'wendy_cuda_shard_read', 'wendy_cuda_potential', 'wendy_cuda_energy_individual', 'wendy_cuda_set_totmass', 'wendy_cuda_trim', 'wendy_host_prefault', 'wendy_cuda_pin', 'wendy_cuda_unpin', 'wendy_cuda_debug_layout', 'wendy_cuda_destroy', 'wendy_cuda_last_error',
+            'wendy_cuda_shard_inject', 'wendy_cuda_shard_comm_export', 'wendy_cuda_shard_comm_open', 'wendy_cuda_shard_seed_counts', 'wendy_cuda_shard_prepare', 'wendy_cuda_shard_step_begin', 'wendy_cuda_shard_step_end', 'wendy_cuda_shard_rollback', 'wendy_cuda_shard_count', 'wendy_cuda_shard_read', 'wendy_cuda_shard_read_begin', 'wendy_cuda_shard_read_end', 'wendy_cuda_potential', 'wendy_cuda_energy_individual', 'wendy_cuda_set_totmass', 'wendy_cuda_trim', 'wendy_host_prefault', 'wendy_host_set_threads', 'wendy_cuda_pin', 'wendy_cuda_unpin', 'wendy_cuda_debug_layout', 'wendy_cuda_destroy', 'wendy_cuda_last_error',
             'wendy_cuda_argsort', '_wendy_nbody_approx_onestep']
 
 

@@ -82,6 +82,7 @@ struct wendy_cuda_handle {
   // WENDY_B200_SHARD_TRACE=1: CUDA events around the three launches of every sharded sub-step (peer exchange)
   std::vector<cudaEvent_t> tr_ev;
   double tr_ms[3] = {0., 0., 0.};
+  unsigned tr_wait[2] = {0u, 0u};
   long long tr_n = 0;
   bool ext_half_done = false;    // ext-force stepping: the leading half drift of the call is already in x
   int ext_fail_streak = 0;       // ... consecutive overflows of the same sub-step (two: take it on the radix path)
@@ -452,8 +453,10 @@ void wendy_cuda_destroy(wendy_cuda_handle *h) {
   cudaStreamSynchronize(h->st);
   if (h->tr_n > 0)
     fprintf(stderr, "wendy_b200 shard trace rank %d: %lld sub-steps, ms per sub-step: count prefix %.4f, step kernel "
-            "(incl. wait for the peers' counts) %.4f, inject kernel (incl. wait for the peers' migrants) %.4f\n",
-            h->my_rank, h->tr_n, h->tr_ms[0] / h->tr_n, h->tr_ms[1] / h->tr_n, h->tr_ms[2] / h->tr_n);
+            "(incl. wait for the peers' counts) %.4f, inject kernel (incl. wait for the peers' migrants) %.4f; of which "
+            "waiting (CTA 0, all sub-steps of the handle): step %.4f, inject %.4f\n",
+            h->my_rank, h->tr_n, h->tr_ms[0] / h->tr_n, h->tr_ms[1] / h->tr_n, h->tr_ms[2] / h->tr_n,
+            h->tr_wait[0] * 1.024e-3 / std::max(1ll, h->n_sub), h->tr_wait[1] * 1.024e-3 / std::max(1ll, h->n_sub));
   for (cudaEvent_t e : h->tr_ev) cudaEventDestroy(e);
   h->tr_ev.clear();
   ring_release(h->ring);
@@ -521,7 +524,7 @@ static int upload_host_arrays(cudaStream_t st, const double *const *src, double 
       if (used[bsel]) cudaEventSynchronize(ev[bsel]);  // the copy that last read this bounce buffer
       const double *sp = src[a] + off;
       double *bp = stage[bsel];
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(host_threads())
       for (long long blk = 0; blk < (long long)((len + 65535) / 65536); blk++) {
         const size_t b0 = (size_t)blk * 65536, bl = std::min((size_t)65536, len - b0);
         memcpy(bp + b0, sp + b0, bl * sizeof(double));
@@ -600,7 +603,7 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
     long long n_diff = 0;
     const double m_first = m[0];
     const long long L = h->seg_len;
-#pragma omp parallel for reduction(+ : probe, n_diff) reduction(max : sum_abs) schedule(static) if (n_segments > 1)
+#pragma omp parallel for reduction(+ : probe, n_diff) reduction(max : sum_abs) schedule(static) if (n_segments > 1) num_threads(host_threads())
     for (int s = 0; s < (n_segments > 1 ? n_segments : 0); s++) {
       double a = 0.;
       for (long long i = s * L; i < (s + 1) * L; i++) {
@@ -612,7 +615,7 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
     }
     if (n_segments == 1) {  // a single segment: parallelise over chunks instead
       probe = 0.; n_diff = 0; sum_abs = 0.;
-#pragma omp parallel for reduction(+ : probe, n_diff, sum_abs) schedule(static)
+#pragma omp parallel for reduction(+ : probe, n_diff, sum_abs) schedule(static) num_threads(host_threads())
       for (long long i = 0; i < N; i++) {
         probe += x[i] * 0. + v[i] * 0. + m[i] * 0.;
         sum_abs += fabs(m[i]);
@@ -629,9 +632,10 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
   trace_mark(h->st, "create: validation pass");
   // Geometry chosen by the library: the persistent CTA kernel (2048-slot buckets, next bucket prefetched by
   // TMA) is the fastest step for large equal-mass systems at every dt measured; small
-  // systems and general masses start on 256-slot buckets (warp kernel) and switch when the window statistic
-  // says so.
-  if (h->adaptive && h->eqm && N >= (1ll << 20)) {
+  // systems start on 256-slot buckets (warp kernel) and switch when the window statistic says so.  Large systems
+  // of unequal masses start coarse as well: their CTA kernel beats their warp kernel (128-bit scan across one warp,
+  // 11 KB slab) at every dt measured (N=2e7, dt_leap=1e-4: 0.68 against 1.08 ms, profiles/r02/kernels_tour_N1e8.md).
+  if (h->adaptive && N >= (1ll << 20)) {
     // ... and stay there, so the storage is sized for that geometry: n/(3/4) slots per particle array instead
     // of the 2n of the fine layout (less to allocate -- cudaMalloc is a visible part of the set-up time --
     // and N=1e9 needs 75 GB instead of 106 GB).  Bucket arrays are sized for the conservative fill, which
@@ -909,40 +913,61 @@ int wendy_cuda_shard_count(wendy_cuda_handle *h, long long *n_local) {
   return 0;
 }
 
+static int start_read_n(H *h, void *const *host, const void *const *src, const size_t *nby, int na, cudaStream_t st);
+static int finish_read(H *h, cudaStream_t st);
+
 // Compact (x, v, id) of the local particles to HOST arrays (capacity entries); *n = local count.
-int wendy_cuda_shard_read(wendy_cuda_handle *h, double *x_host, double *v_host, int *id_host, long long *n) {
+// _begin: compaction on the compute stream, device -> host copies on the private copy stream (a worker thread
+// drives the bounce ring for pageable destinations); the caller may step the shard meanwhile.  _end waits.
+int wendy_cuda_shard_read_begin(wendy_cuda_handle *h, double *x_host, double *v_host, int *id_host, long long *n) {
   if (!h || !h->bounds || !x_host || !v_host || !id_host || !n) return set_err(WENDY_E_ARG, "bad argument");
+  if (h->pending) return set_err(WENDY_E_ARG, "finish the call in flight first");
+  if (h->reader.joinable()) return set_err(WENDY_E_ARG, "a read-out is in flight: wendy_cuda_shard_read_end first");
+  if (!h->st_copy) {
+    CK(cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_unsort, cudaEventDisableTiming));
+  }
   if (!h->xo) {
     trace_mark(h->st, "(read: start)");
     CK(dev_alloc(&h->xo, (size_t)h->n_cap * sizeof(double)));
     CK(dev_alloc(&h->vo, (size_t)h->n_cap * sizeof(double)));
     trace_mark(h->st, "read: staging allocation");
   }
-  if (h->dense) {
-    CK(copy_split(x_host, h->x[h->cur], (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
-    CK(copy_split(v_host, h->v[h->cur], (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
-    CK(copy_split(id_host, h->id[h->cur], (size_t)h->N * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  const void *src[3] = {h->xo, h->vo, h->cid};
+  if (h->dense) {  // (staged as well: the state buffers are rewritten by the next call while the copy runs)
+    CK(cudaMemcpyAsync(h->xo, h->x[h->cur], (size_t)h->N * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    CK(cudaMemcpyAsync(h->vo, h->v[h->cur], (size_t)h->N * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    CK(cudaMemcpyAsync(h->cid, h->id[h->cur], (size_t)h->N * sizeof(int), cudaMemcpyDeviceToDevice, h->st));
   } else {
     launch_count_prefix(h->st, h->cnt[h->ccur], h->nb, h->cpre, h->cp_desc, h->cp_ticket, h->seq++);
     launch_compact(h->st, h->x[h->cur], h->v[h->cur], h->id[h->cur], h->cnt[h->ccur], h->cpre, h->cap, h->nb,
                    h->xo, h->vo, h->cid);
     h->n_launch += 2;
-    void *const dst[3] = {x_host, v_host, id_host};
-    const void *const src[3] = {h->xo, h->vo, h->cid};
-    const size_t nby[3] = {(size_t)h->N * sizeof(double), (size_t)h->N * sizeof(double), (size_t)h->N * sizeof(int)};
-    // ordinary (pageable) destinations are filled through the page-locked bounce ring at PCIe speed, as in
-    // wendy_cuda_read: page-locking gigabytes per rank costs more than many read-outs
-    const bool bounce = nby[0] >= ((size_t)4 << 20) && bounce_allowed() && !host_range_is_pinned(x_host, nby[0]);
-    if (bounce && !h->ring) h->ring = ring_acquire(h->device);
-    if (bounce && h->ring) {
-      if (bounce_d2h(h->ring, h->st, dst, src, nby, 3)) return set_err(WENDY_E_CUDA, "device -> host copy through the bounce buffers failed");
-    } else {
-      for (int a = 0; a < 3; a++) CK(copy_split(dst[a], src[a], nby[a], cudaMemcpyDeviceToHost, h->st));
-    }
   }
-  CK(cudaStreamSynchronize(h->st));
-  CK(cudaGetLastError());
+  CK(cudaEventRecord(h->ev_unsort, h->st));
+  CK(cudaStreamWaitEvent(h->st_copy, h->ev_unsort, 0));
+  void *const dst[3] = {x_host, v_host, id_host};
+  const size_t nby[3] = {(size_t)h->N * sizeof(double), (size_t)h->N * sizeof(double), (size_t)h->N * sizeof(int)};
   *n = h->N;
+  return start_read_n(h, dst, src, nby, 3, h->st_copy);
+}
+
+int wendy_cuda_shard_read_end(wendy_cuda_handle *h) {
+  if (!h || !h->bounds) return set_err(WENDY_E_ARG, "not a shard handle");
+  if (h->st_copy) {
+    int rc = finish_read(h, h->st_copy);
+    if (rc) return rc;
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int wendy_cuda_shard_read(wendy_cuda_handle *h, double *x_host, double *v_host, int *id_host, long long *n) {
+  int rc = wendy_cuda_shard_read_begin(h, x_host, v_host, id_host, n);
+  if (rc) return rc;
+  rc = wendy_cuda_shard_read_end(h);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->st));
   return 0;
 }
 
@@ -1071,7 +1096,7 @@ int wendy_cuda_shard_step_begin(wendy_cuda_handle *h, double dt, int nleap, int 
   if (!h || !h->peer_on) return set_err(WENDY_E_ARG, "peer exchange is not set up");
   if (nleap < 1 || nleap > PEER_NHIST || k0 < 0 || k0 >= nleap) return set_err(WENDY_E_ARG, "bad nleap");
   if (h->pending) return set_err(WENDY_E_ARG, "a call is already in flight");
-  if (k0 == 0) { h->p_seq.clear(); h->p_seq_inj.clear(); h->p_cur.clear(); h->p_ccur.clear(); h->shard_retry_k = -1; }
+  if (k0 == 0) { h->p_seq.clear(); h->p_seq_inj.clear(); h->p_cur.clear(); h->p_ccur.clear(); }
   h->p_seq.resize(k0); h->p_seq_inj.resize(k0); h->p_cur.resize(k0); h->p_ccur.resize(k0);
   h->p_dt = dt; h->p_nleap = nleap; h->p_k0 = k0;
   static const bool trace_on = getenv("WENDY_B200_SHARD_TRACE") != nullptr;
@@ -1140,7 +1165,8 @@ int wendy_cuda_shard_step_end(wendy_cuda_handle *h, int *k_fail, long long *n_lo
   h->pending = false;
   const int nleap = h->p_nleap;
   CK(cudaMemcpyAsync(h->h_peer_n, h->peer_n, (size_t)(nleap + 2) * sizeof(long long), cudaMemcpyDeviceToHost, h->st));
-  unsigned pstat[2] = {0u, 0u};  // [0] a wait timed out, [1] records received so far (wraps)
+  unsigned pstat[4] = {0u, 0u, 0u, 0u};  // [0] a wait timed out, [1] records received so far (wraps), [2] / [3] ~us CTA 0
+                                         // of the step / inject kernels waited for the peers' flags (wrap)
   CK(cudaMemcpyAsync(pstat, h->peer_scratch + PEER_MAX + 2, sizeof(pstat), cudaMemcpyDeviceToHost, h->st));
   if (fetch_flags(h)) return WENDY_E_CUDA;
   if (!h->tr_ev.empty()) {
@@ -1151,6 +1177,7 @@ int wendy_cuda_shard_step_end(wendy_cuda_handle *h, int *k_fail, long long *n_lo
       }
       h->tr_n++;
     }
+    h->tr_wait[0] = pstat[2]; h->tr_wait[1] = pstat[3];
   }
   if (pstat[0]) return set_err(WENDY_E_CUDA, "shard: timed out waiting for a peer GPU");
   if (migrated_in) *migrated_in = (long long)(unsigned)(pstat[1] - h->peer_mig_seen);
@@ -1168,6 +1195,7 @@ int wendy_cuda_shard_step_end(wendy_cuda_handle *h, int *k_fail, long long *n_lo
     }
     h->n_fail++;
   } else {
+    h->shard_retry_k = -1;  // (a retried sub-step may be k = 0 of a call: only a completed call resets the escalation)
     h->N = h->h_peer_n[1 + nleap]; h->seg_len = h->N;
     if (h->h_flags[1] > (unsigned)(h->cap - (h->cap - h->fill) / 16)) {  // nearly full bucket: re-balance (local)
       fill_back_off(h);
@@ -1440,36 +1468,40 @@ int wendy_cuda_read_dev(wendy_cuda_handle *h, double *x_dev, double *v_dev) {
 // Start the device -> host copy of the de-sorted staging arrays on stream st: page-locked destinations get
 // plain (split) copies; large pageable ones are filled through the bounce ring by a worker thread, so that
 // the caller can go on enqueueing work.  finish_read() waits for both.
-static int start_read(H *h, double *x_host, double *v_host, cudaStream_t st) {
+static int start_read_n(H *h, void *const *host, const void *const *src, const size_t *nby, int na, cudaStream_t st) {
   if (h->reader.joinable()) return set_err(WENDY_E_ARG, "a read-out is in flight: wendy_cuda_read_end first");
-  const size_t bytes = (size_t)h->N * sizeof(double);
-  void *dst[2] = {nullptr, nullptr};
-  const void *src[2] = {h->xo, h->vo};
-  double *host[2] = {x_host, v_host};
-  int nb = 0;
-  for (int a = 0; a < 2; a++) {
-    if (!host[a]) continue;
-    if (bytes >= ((size_t)4 << 20) && bounce_allowed() && !host_range_is_pinned(host[a], bytes)) { dst[a] = host[a]; nb++; }
-    else CK(copy_split(host[a], src[a], bytes, cudaMemcpyDeviceToHost, st));
+  std::vector<void *> d;
+  std::vector<const void *> sr;
+  std::vector<size_t> nb;
+  for (int a = 0; a < na; a++) {
+    if (!host[a] || !nby[a]) continue;
+    if (nby[a] >= ((size_t)4 << 20) && bounce_allowed() && !host_range_is_pinned(host[a], nby[a])) {
+      d.push_back(host[a]); sr.push_back(src[a]); nb.push_back(nby[a]);
+    } else {
+      CK(copy_split(host[a], src[a], nby[a], cudaMemcpyDeviceToHost, st));
+    }
   }
-  if (!nb) return 0;
+  if (d.empty()) return 0;
   if (!h->ring) h->ring = ring_acquire(h->device);
   if (!h->ring) {  // no page-locked memory to be had: let the driver stage the copies
-    for (int a = 0; a < 2; a++)
-      if (dst[a]) CK(copy_split(dst[a], src[a], bytes, cudaMemcpyDeviceToHost, st));
+    for (size_t a = 0; a < d.size(); a++) CK(copy_split(d[a], sr[a], nb[a], cudaMemcpyDeviceToHost, st));
     return 0;
   }
   h->reader_rc = 0;
   H *hh = h;
-  void *d0 = dst[0], *d1 = dst[1];
-  h->reader = std::thread([hh, d0, d1, bytes, st]() {
+  h->reader = std::thread([hh, d, sr, nb, st]() {
     cudaSetDevice(hh->device);
-    void *const d[2] = {d0, d1};
-    const void *const sr[2] = {hh->xo, hh->vo};
-    const size_t nby[2] = {bytes, bytes};
-    hh->reader_rc = bounce_d2h(hh->ring, st, d, sr, nby, 2);
+    hh->reader_rc = bounce_d2h(hh->ring, st, d.data(), sr.data(), nb.data(), (int)d.size());
   });
   return 0;
+}
+
+static int start_read(H *h, double *x_host, double *v_host, cudaStream_t st) {
+  const size_t bytes = (size_t)h->N * sizeof(double);
+  void *const host[2] = {x_host, v_host};
+  const void *const src[2] = {h->xo, h->vo};
+  const size_t nby[2] = {bytes, bytes};
+  return start_read_n(h, host, src, nby, 2, st);
 }
 
 static int finish_read(H *h, cudaStream_t st) {

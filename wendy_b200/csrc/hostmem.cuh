@@ -28,6 +28,20 @@
 
 #include "../../include/wendy_b200.h"
 
+// Host threads the library's own copy / validation loops may use.  Default: what OpenMP offers, at most 32.  A
+// multi-process job (one rank per GPU) must divide the cores between its ranks -- oversubscribed OpenMP teams spin
+// on each other -- so multi.py calls wendy_host_set_threads(cores / ranks on this node); WENDY_B200_HOST_THREADS
+// overrides both.
+static int g_host_threads = 0;
+static int host_threads() {
+  static int env = -1;
+  if (env < 0) { const char *e = getenv("WENDY_B200_HOST_THREADS"); env = e ? std::max(1, atoi(e)) : 0; }
+  if (env > 0) return env;
+  if (g_host_threads > 0) return g_host_threads;
+  return std::max(1, std::min(32, omp_get_max_threads()));
+}
+extern "C" void wendy_host_set_threads(int n) { g_host_threads = n > 0 ? n : 0; }
+
 // ---- device block cache -----------------------------------------------------------------------------------
 // cudaMalloc / cudaFree of the multi-GB state arrays cost 30-100 ms per GB on this platform (measured:
 // profiles/r01/e2e_phases_N1e8.txt), which dominates the set-up of a generator.  Blocks of >= 32 MB released
@@ -264,7 +278,7 @@ int bounce_d2h(BounceRing *r, cudaStream_t st, void *const *dst, const void *con
     const char *bp = (const char *)r->buf[sl];
     char *dp = pieces[i].d;
     const long long nblk = (long long)((pieces[i].n + 262143) / 262144);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(host_threads())
     for (long long blk = 0; blk < nblk; blk++) {
       const size_t b0 = (size_t)blk * 262144, bl = std::min((size_t)262144, pieces[i].n - b0);
       stream_copy(dp + b0, bp + b0, bl);
@@ -281,7 +295,7 @@ extern "C" void wendy_host_prefault(void *host_ptr, unsigned long long bytes) {
   if (!host_ptr || !bytes) return;
   const size_t page = 4096;
   const long long np = (long long)((bytes + page - 1) / page);
-  int nt = omp_get_max_threads();
+  int nt = host_threads();
   if (nt > 8) nt = 8;
 #pragma omp parallel for schedule(static) num_threads(nt)
   for (long long i = 0; i < np; i++) {
@@ -293,7 +307,7 @@ extern "C" void wendy_host_prefault(void *host_ptr, unsigned long long bytes) {
 // test hook (tests/test_abi.py): the host-side copy used by the bounce-buffered read-out, multi-threaded
 extern "C" void wendy_host_stream_copy(void *dst, const void *src, unsigned long long bytes) {
   const long long nblk = (long long)((bytes + 262143) / 262144);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(host_threads())
   for (long long blk = 0; blk < nblk; blk++) {
     const size_t b0 = (size_t)blk * 262144, bl = std::min((size_t)262144, (size_t)bytes - b0);
     stream_copy((char *)dst + b0, (const char *)src + b0, bl);

@@ -37,7 +37,7 @@ namespace wendy {
 #endif
 // Tunables kept as macros for A/B builds (scripts/ab_variants.py; measured values in DESIGN.md section 3.0)
 #ifndef TK_RANK_STRAIGHT
-#define TK_RANK_STRAIGHT 2  // members of a shared sub-bucket compared by straight-line code before a loop takes over
+#define TK_RANK_STRAIGHT 3  // members of a shared sub-bucket compared by straight-line code before a loop takes over
 #endif
 
 #ifndef TK_SUBMUL
@@ -154,8 +154,10 @@ tile_kernel(const TileParams p) {
     // ... as published by the peers after the previous sub-step (their cnt_flag words, in local memory)
     if (tid == 0) {
       bool bad;
+      const unsigned long long tw0 = (blockIdx.x == 0) ? peer_now_ns() : 0ull;
       S.pre_cnt = peer_wait_counts(p.peer, p.pepoch - 1u, bad);
       S.bucket = bad ? 1 : 0;
+      if (blockIdx.x == 0) p.peer->peer_stat[2] += (unsigned)((peer_now_ns() - tw0) >> 10);  // ~microseconds waited
     }
     __syncthreads();
     pc_off = S.pre_cnt;
@@ -1153,6 +1155,7 @@ peer_inject_kernel(const InjectParams p) {
   if (threadIdx.x == 0) {
     bool bad = false;
     unsigned run = 0;
+    const unsigned long long tw0 = (blockIdx.x == 0) ? peer_now_ns() : 0ull;
     for (int r = 0; r < pc->nranks; r++) {
       s_pre[r] = run;
       if (r == pc->my_rank) continue;
@@ -1167,6 +1170,7 @@ peer_inject_kernel(const InjectParams p) {
     }
     s_pre[pc->nranks] = run;
     s_bad = bad ? 1 : 0;
+    if (blockIdx.x == 0) pc->peer_stat[3] += (unsigned)((peer_now_ns() - tw0) >> 10);
     __threadfence_system();  // the records the flags announce are read below
   }
   __syncthreads();

@@ -228,20 +228,44 @@ class CudaShardEngine(object):
         _lib.check(self._lib.wendy_cuda_shard_count(self._h, ctypes.byref(n)))
         return n.value
 
-    def read(self):
-        """(ids, x, v) of the local particles: views of host buffers this engine re-uses on every call (copy
-        them to keep a snapshot across reads)."""
+    def _host_buffers(self):
+        """Ordinary numpy memory: the library fills pageable destinations through its page-locked bounce buffers
+        at PCIe speed (page-locking capacity * 20 bytes per rank would cost about a second).  Two sets, the second
+        made on first use: one is being filled (read_begin) while the caller still looks at the other.  Only the
+        part a read-out will touch is pre-faulted."""
         if self._pinned is None:
-            # ordinary numpy memory, touched once: the library fills pageable destinations through its page-locked
-            # bounce buffers at PCIe speed; page-locking capacity * 20 bytes per rank would cost about a second
-            self._pinned = (numpy.empty(self.capacity), numpy.empty(self.capacity),
-                            numpy.empty(self.capacity, dtype=numpy.int32))
-            for arr in self._pinned:
-                self._lib.wendy_host_prefault(arr.ctypes.data, arr.nbytes)
-        x, v, ids = self._pinned
+            self._pinned, self._pin_sel = [None, None], 0
+        if self._pinned[self._pin_sel] is None:
+            bufs = (numpy.empty(self.capacity), numpy.empty(self.capacity),
+                    numpy.empty(self.capacity, dtype=numpy.int32))
+            touch = min(self.capacity, int(self.count() * 1.05) + 4096)
+            for arr in bufs:
+                self._lib.wendy_host_prefault(arr.ctypes.data, touch * arr.itemsize)
+            self._pinned[self._pin_sel] = bufs
+        return self._pinned[self._pin_sel]
+
+    def read_begin(self):
+        """Start the read-out of the local particles (compaction on the compute stream, device -> host copies on
+        a copy stream); the shard may be stepped before ``read_end``."""
+        x, v, ids = self._host_buffers()
         n = ctypes.c_longlong()
-        _lib.check(self._lib.wendy_cuda_shard_read(self._h, x, v, ids, ctypes.byref(n)))
-        return ids[:n.value], x[:n.value], v[:n.value]
+        _lib.check(self._lib.wendy_cuda_shard_read_begin(self._h, x, v, ids, ctypes.byref(n)))
+        self._reading = (ids[:n.value], x[:n.value], v[:n.value])
+        self._pin_sel ^= 1
+
+    def read_end(self):
+        """(ids, x, v) started by ``read_begin``: views of host buffers that are re-used two read-outs later."""
+        _lib.check(self._lib.wendy_cuda_shard_read_end(self._h))
+        out, self._reading = self._reading, None
+        return out
+
+    def read(self):
+        """(ids, x, v) of the local particles: views of host buffers this engine re-uses (copy them to keep a
+        snapshot across more than one further read)."""
+        self.read_begin()
+        out = self.read_end()
+        self.stream.synchronize()
+        return out
 
     def to_device(self, arr):
         return self.torch.as_tensor(numpy.ascontiguousarray(arr), device=self.device)
@@ -276,8 +300,9 @@ class ShardedSystem(object):
         self.comm = comm
         self.m0, self.totmass = float(m0), float(totmass)
         self.omega2 = -1. if omega is None else float(omega) ** 2.
-        self._raw = (numpy.array(x, dtype=numpy.float64), numpy.array(v, dtype=numpy.float64),
-                     numpy.array(ids, dtype=numpy.int32))
+        # (only read, at the first step: no copies -- 2 GB per rank at 1e8 particles)
+        self._raw = (numpy.ascontiguousarray(x, dtype=numpy.float64), numpy.ascontiguousarray(v, dtype=numpy.float64),
+                     numpy.ascontiguousarray(ids, dtype=numpy.int32))
         self.engine_factory = engine_factory or CudaShardEngine
         self.capacity_factor, self.outbox_fraction, self.n_sample = capacity_factor, outbox_fraction, n_sample
         self.engine = None
@@ -287,6 +312,11 @@ class ShardedSystem(object):
         self.migrated = 0
         self.peer, self.peer_tried = False, False
         self.timing = {'substep': 0., 'allgather': 0., 'exchange+inject': 0.}
+        if self.engine_factory is CudaShardEngine:
+            # one rank per GPU: the library's host-side copy threads must share the node's cores between the ranks
+            import os
+            local = int(os.environ.get('LOCAL_WORLD_SIZE', comm.size) or comm.size)
+            _lib.load().wendy_host_set_threads(max(1, min(32, (os.cpu_count() or 1) // max(1, local))))
 
     # -- set-up: global sample sort on the keys of the FIRST force evaluation -------------------------
     def _partition(self, dt_leap):
@@ -350,8 +380,9 @@ class ShardedSystem(object):
         self.pc_offset = int(self.counts[:self.comm.rank].sum())
         # device-driven exchange where the engine offers it (CUDA engine, all ranks reachable by peer memory)
         import os
-        if (not self.peer_tried and hasattr(self.engine, 'enable_peer') and self.comm.size > 1
-                and os.environ.get('WENDY_B200_SHARD_PEER', '1') != '0'):
+        mode = os.environ.get('WENDY_B200_SHARD_PEER', '1')  # 'force': also with one rank (kernel diagnostics)
+        if (not self.peer_tried and hasattr(self.engine, 'enable_peer') and mode != '0'
+                and (self.comm.size > 1 or mode == 'force')):
             self.peer_tried = True
             self.peer = bool(self.engine.enable_peer(self.comm))
         if self.peer:
@@ -400,7 +431,10 @@ class ShardedSystem(object):
             # input, rebuilds its layout and runs the rest of the call again
             tries += 1
             if tries > 8:
-                raise RuntimeError('wendy_b200: sharded sub-step keeps overflowing after re-balancing')
+                raise RuntimeError('wendy_b200: sharded sub-step keeps overflowing after re-balancing (the density changes '
+                                   'by more than the head-room of a fresh layout, or more particles cross a range '
+                                   'edge than the inbox holds, within ONE sub-step: use a smaller dt or a larger '
+                                   'outbox_fraction)')
             n_back = eng.rollback(kf_all)
             self.counts = self.comm.allgather_vec([n_back])[:, 0].astype(numpy.int64)
             eng.seed_counts(self.counts)
@@ -441,6 +475,14 @@ class ShardedSystem(object):
     def read_local(self):
         """(ids, x, v) of the particles this rank currently owns (synchronised state)."""
         return self.engine.read()
+
+    def read_local_begin(self):
+        """Overlapped read-out: start copying the particles this rank owns NOW to the host; ``step`` may be called
+        before ``read_local_end`` returns them (the copy runs beside the next call's kernels)."""
+        self.engine.read_begin()
+
+    def read_local_end(self):
+        return self.engine.read_end()
 
     def gather(self, n_total):
         """Full (x, v) in particle-index order on every rank (diagnostics / tests)."""

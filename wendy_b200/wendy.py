@@ -330,11 +330,16 @@ def _nbody_approx(x, v, m, dt, nleap, t0=0., omega=None, ext_force=None, sort='g
                     yield (x, v, te)
                 else:
                     yield (x, v)
+        # External force: the same speculation as above -- the de-sort + D2H of output k runs on the copy stream
+        # (and the library's reader thread) while the sub-steps of call k+1, F evaluations included, are issued.
+        t0 = state.step_ext(dt_leap, nleap, ext_force, t0)
         while True:
+            te = state.time_elapsed
+            state.read_begin(x, v)
             t0 = state.step_ext(dt_leap, nleap, ext_force, t0)
-            state.read(x, v)
+            state.read_end()
             if full_output:
-                yield (x, v, state.time_elapsed)
+                yield (x, v, te)
             else:
                 yield (x, v)
     finally:
