@@ -307,6 +307,18 @@ def main():
             d = stat_delta(st.stats(), s0)
             xg, vg = st.read()
             st.close()
+            # the same system with the full radix sort every step (no bucket layout to rebuild): at this size the
+            # whole state lives in L2 and a step is a dozen short launches
+            st = wendy_b200.ApproxState(x, v, m, stream=stream, sort='gpu-radix')
+            st.step(dtl, 1)
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(300):
+                st.step(dtl, 1)
+            e1.record()
+            torch.cuda.synchronize()
+            radix_rate = float(nn) * 300 / (e0.elapsed_time(e1) * 1e-3)
+            st.close()
             ref_drift, ref_rate, same10 = None, None, None
             if rank == 0 and not a.no_cpu_baseline:
                 r, kind = make_reference(x, v, m, None, dtl)
@@ -327,6 +339,7 @@ def main():
             out = {'value': float(nn) * (nsteps - 1) / (ms * 1e-3), 'ms_per_step': ms / (nsteps - 1),
                    'config': {'workload': 'config 2: cold slab N=1e6, omega=None, dt_leap=0.005, 1000 steps (violent relaxation)'},
                    'path_stats': d, 'gpu_launches': d['kernel_launches'],
+                   'variants': {'sort=gpu-radix (first 300 steps)': {'value': radix_rate}},
                    'energy_drift': {'gpu_abs_dE_over_E_every_100_steps': drift, 'reference_same_ICs': ref_drift,
                                     'note': 'chaotic after a few steps: compared as statistics, not particle by particle'},
                    'parity': {'bit_identical_to_reference_after_10_steps': same10},

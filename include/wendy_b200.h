@@ -114,6 +114,15 @@ int wendy_cuda_force_positions(wendy_cuda_handle *h, double dt_leap, int first_s
                                double **x_dev, long long *n_slots);
 int wendy_cuda_substep(wendy_cuda_handle *h, double dt_kick, double dt_drift, double h_next,
                        const double *a_ext_dev);
+/* The same without a host round trip per sub-step: wendy_cuda_ext_begin; per sub-step wendy_cuda_force_positions,
+ * the caller's F evaluation on the handle's stream, wendy_cuda_substep_async; then wendy_cuda_ext_end waits once.
+ * *k_done = sub-steps completed; if it is less than the number enqueued, sub-step k_done overflowed a bucket: its
+ * input has been restored and the layout rebuilt, and the caller runs the remaining sub-steps through
+ * wendy_cuda_force_positions / wendy_cuda_substep.  The a_ext arrays must stay alive until wendy_cuda_ext_end. */
+int wendy_cuda_ext_begin(wendy_cuda_handle *h);
+int wendy_cuda_substep_async(wendy_cuda_handle *h, double dt_kick, double dt_drift, double h_next,
+                             const double *a_ext_dev);
+int wendy_cuda_ext_end(wendy_cuda_handle *h, int *k_done);
 
 /* De-sort (wendy/wendy.c:413-415) and copy to HOST arrays of N doubles (either may be NULL). */
 int wendy_cuda_read(wendy_cuda_handle *h, double *x_host, double *v_host);

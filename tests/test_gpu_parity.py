@@ -390,6 +390,31 @@ def test_segments_equal_independent_runs(sort):
         assert numpy.array_equal(X[s * L:(s + 1) * L], x1) and numpy.array_equal(V[s * L:(s + 1) * L], v1)
 
 
+def test_large_ensemble_on_the_persistent_kernel_equals_the_oracle():
+    """Segments on 2048-slot buckets with MORE buckets than resident CTAs: a persistent CTA then walks buckets of
+    several segments one after the other, and everything it carries between buckets (the piece of the serial
+    cumulative-mass table, the splitter window, the prefetched counts) must follow the segment change.  Equal
+    masses: bit-identical to the C restatement of the reference, per segment; no sub-step may fail over."""
+    import wendy_b200
+    S, L = 4, 300000  # 1.2e6 particles: the library chooses the coarse geometry; 4 x 181 buckets > 2 x 148 CTAs
+    ics = [wo.sech2_ic(L, seed=60 + s) for s in range(S)]
+    X = numpy.concatenate([i[0] for i in ics]); V = numpy.concatenate([i[1] for i in ics])
+    M = numpy.concatenate([i[2] for i in ics])
+    st = wendy_b200.ApproxState(X, V, M, omega2=1.1 ** 2., n_segments=S)
+    for _ in range(2):
+        st.step(0.004, 3)
+    Xg, Vg = st.read()
+    stats = st.stats()
+    st.close()
+    assert stats['cap'] == 2048 and stats['buckets'] > 296
+    assert stats['failed_substeps'] == 0 and stats['radix_fallbacks'] == 0, stats
+    for s in range(S):
+        ref = wo.COracle(ics[s][0], ics[s][1], ics[s][2], 0.012, 3, omega=1.1)
+        for _ in range(2):
+            xr, vr = ref.step()
+        assert numpy.array_equal(Xg[s * L:(s + 1) * L], xr) and numpy.array_equal(Vg[s * L:(s + 1) * L], vr), s
+
+
 # ---- compat export: the reference's own C entry point --------------------------------------------
 def _compat_call(lib, xi, x, v, m, tot, dt, nleap, t0, omega2, cb):
     from wendy_b200 import _lib
@@ -538,17 +563,21 @@ def test_overflow_recovery_by_rebalancing():
     assert numpy.array_equal(xg, xo) and numpy.array_equal(vg, vo)
 
 
-def test_ext_force_with_overflow_on_the_first_substep_applies_the_half_drift_once():
-    """A bucket overflow on the first sub-step of an output step makes wendy_cuda_substep return WENDY_RETRY
-    after the leading half drift was materialised; the retry must not drift again (round-1 advisor finding)."""
+@pytest.mark.parametrize('nleap,calls,async_ext', [(1, 8, '1'), (4, 2, '1'), (4, 2, '0')])
+def test_ext_force_with_overflow_on_the_first_substep_applies_the_half_drift_once(nleap, calls, async_ext, monkeypatch):
+    """A bucket overflow on the first sub-step of an output step makes the library restore that sub-step's input
+    after the leading half drift was materialised; the retry must not drift again (round-1 advisor finding).
+    nleap = 4: the overflow hits a later sub-step of a call that was enqueued asynchronously (wendy_cuda_ext_begin /
+    _substep_async / _ext_end): the launches behind it are void and the call is finished synchronously."""
     import wendy_b200
+    monkeypatch.setenv('WENDY_B200_EXT_ASYNC', async_ext)
     x, v, m = wo.slab_ic(20000, seed=5)
     F = lambda xx, t: -0.3 * xx + 0.05 * t  # noqa: E731  (linear: bit-identical in torch and numpy)
     st = wendy_b200.ApproxState(x, v, m, cap=256, fill=250)
     xo, vo, t0, tg = x, v, 0.1, 0.1
-    for _ in range(8):
-        tg = st.step_ext(0.05, 1, F, tg)
-        xo, vo, t0, _ = wo.numpy_onestep(xo, vo, m, numpy.sum(m), 0.05, 1, -1., F, t0)
+    for _ in range(calls):
+        tg = st.step_ext(0.05, nleap, F, tg)
+        xo, vo, t0, _ = wo.numpy_onestep(xo, vo, m, numpy.sum(m), 0.05, nleap, -1., F, t0)
     xg, vg = st.read()
     s = st.stats()
     st.close()

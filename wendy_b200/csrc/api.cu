@@ -84,6 +84,7 @@ struct wendy_cuda_handle {
   double tr_ms[3] = {0., 0., 0.};
   unsigned tr_wait[2] = {0u, 0u};
   long long tr_n = 0;
+  bool ext_async = false;        // ext-force stepping: between wendy_cuda_ext_begin and wendy_cuda_ext_end
   bool ext_half_done = false;    // ext-force stepping: the leading half drift of the call is already in x
   int ext_fail_streak = 0;       // ... consecutive overflows of the same sub-step (two: take it on the radix path)
   int nb_last = 0;               // last bucket of the layout that has a finite lower edge (the tail may be unused)
@@ -1439,6 +1440,62 @@ int wendy_cuda_substep(wendy_cuda_handle *h, double dt_kick, double dt_drift, do
     // nearly full bucket: re-balance now; the caller's next force_positions sees the new slots
     fill_back_off(h);
     int rc = rebucket(h, h_next);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+// ---- external force, asynchronous: the sub-steps of one call are enqueued without a host round trip each ----------
+// wendy_cuda_ext_begin; per sub-step wendy_cuda_force_positions -> (caller evaluates F on the stream) ->
+// wendy_cuda_substep_async; then wendy_cuda_ext_end waits once.  A bucket overflow in sub-step k makes every launch
+// queued behind it a no-op (fail_seq); ext_end then restores the input of sub-step k, rebuilds the layout and
+// reports k: the caller re-runs sub-steps k.. through the synchronous wendy_cuda_substep (which may retry or take the
+// radix path).  The a_ext arrays must stay alive until ext_end.
+int wendy_cuda_ext_begin(wendy_cuda_handle *h) {
+  if (!h) return set_err(WENDY_E_ARG, "null handle");
+  if (h->pending) return set_err(WENDY_E_ARG, "a call is already in flight");
+  h->p_seq.clear(); h->p_cur.clear(); h->p_ccur.clear();
+  h->ext_async = true;
+  return 0;
+}
+
+int wendy_cuda_substep_async(wendy_cuda_handle *h, double dt_kick, double dt_drift, double h_next,
+                             const double *a_ext_dev) {
+  if (!h || !h->ext_async) return set_err(WENDY_E_ARG, "wendy_cuda_ext_begin first");
+  if (h->dense || h->mode == WENDY_SORT_RADIX || !h->has_split || h->bucket_h != 0.)
+    return set_err(WENDY_E_ARG, "layout is not keyed on the stored positions");
+  h->p_seq.push_back(h->seq); h->p_cur.push_back(h->cur); h->p_ccur.push_back(h->ccur);
+  launch_bucket_substep(h, 0., dt_kick, dt_drift, h_next, a_ext_dev, nullptr);
+  return 0;
+}
+
+// *k_done = number of sub-steps (since ext_begin) that completed; == the number enqueued unless one overflowed.
+int wendy_cuda_ext_end(wendy_cuda_handle *h, int *k_done) {
+  if (!h || !k_done || !h->ext_async) return set_err(WENDY_E_ARG, "no asynchronous call in flight");
+  h->ext_async = false;
+  const int nq = (int)h->p_seq.size();
+  if (fetch_flags(h)) return WENDY_E_CUDA;
+  *k_done = nq;
+  if (h->h_flags[0] != 0xffffffffu) {
+    int kf = 0;
+    for (int k = 0; k < nq; k++)
+      if (h->p_seq[k] == h->h_flags[0]) kf = k;
+    h->n_fail++;
+    h->n_sub -= (nq - kf);
+    h->ext_fail_streak = 1;
+    fill_back_off(h);
+    h->cur = h->p_cur[kf]; h->ccur = h->p_ccur[kf];
+    if (reset_flags(h)) return WENDY_E_CUDA;
+    int rc = rebucket(h, 0.);
+    if (rc) return rc;
+    *k_done = kf;
+    return 0;
+  }
+  h->ext_half_done = false;
+  h->ext_fail_streak = 0;
+  if (nq > 0 && h->h_flags[1] > (unsigned)(h->cap - (h->cap - h->fill) / 16)) {
+    fill_back_off(h);  // nearly full bucket: re-balance now (the layout is keyed on bucket_h = the last h_next)
+    int rc = rebucket(h, h->bucket_h);
     if (rc) return rc;
   }
   return 0;

@@ -194,9 +194,11 @@ tile_kernel(const TileParams p) {
   int ser_piece = 0;      // PERSIST: piece of the serial cumulative-mass table the previous bucket started in
   int b_it = blockIdx.x;  // PERSIST: the launch guarantees gridDim.x <= p.nb
   unsigned n_it = 0;
+  unsigned n_pf = 0;      // PERSIST: count of the NEXT bucket, fetched one iteration ahead of its use
   int cur = 0;            // PERSIST: which half of ssplit / nx_* belongs to the current bucket
   if (PERSIST) {
     n_it = p.cnt_in[b_it];
+    if (b_it + (int)gridDim.x < p.nb) n_pf = p.cnt_in[b_it + (int)gridDim.x];
     if (tid == 0) {
       mbar_init(bar, 1);
       if (n_it) stage_issue(b_it, n_it);
@@ -233,7 +235,11 @@ tile_kernel(const TileParams p) {
   const int b_nx = b + (int)gridDim.x;
   unsigned n_nx = 0, pc_reg = 0;
   if (PERSIST) {
-    if (b_nx < p.nb) n_nx = p.cnt_in[b_nx];
+    // (the count of the next bucket was requested during the previous iteration: thread 0 needs it right after
+    // the first barrier to issue the bulk copies, and a load issued here would still be in flight then)
+    n_nx = n_pf;
+    n_pf = 0;
+    if (b_nx + (int)gridDim.x < p.nb) n_pf = p.cnt_in[b_nx + (int)gridDim.x];
     pc_reg = p.cpre[b] - (unsigned)((long long)seg * p.seg_len);
   }
 
@@ -607,6 +613,8 @@ tile_kernel(const TileParams p) {
       // a CTA walks its buckets in ascending order, so the piece index only ever moves forward: remember it
       // instead of searching (one L1-resident load per bucket in the common case)
       const long long k0 = Pc + pc_off;
+      // (an ensemble's ranks start again at 0 in every segment: the next bucket of this CTA may lie in another one)
+      while (ser_piece > 0 && k0 < __ldg(&p.stab->i0[ser_piece])) ser_piece--;
       while (k0 >= __ldg(&p.stab->i0[ser_piece + 1])) ser_piece++;
       const long long i0 = __ldg(&p.stab->i0[ser_piece]);
       SR.c0 = __ldg(&p.stab->c0[ser_piece]);
@@ -817,27 +825,42 @@ tile_kernel(const TileParams p) {
         const int g = (int)max((long long)seg_lo, min((long long)seg_hi - 1, (long long)b + (long long)floor(gq)));
         d = gallop_search_tile(p.split, key, g, seg_lo, seg_hi);
       }
-      if (SHARDP && (d == 0 || d >= p.nb_last) && (key < sh_lo || key >= sh_hi)) {
-        // Only the two edge buckets reach beyond this GPU's key range (their outer splitters are -inf / +inf):
-        // the particle now belongs to another rank -- its record goes straight into the owner's inbox (peer
-        // memory over NVLink); the count travels with the flag word at the end of the launch.
-        const PeerComm *pc = p.peer;
-        int peer = 0;
-        while (peer + 1 < p.nranks && key >= __ldg(p.bounds + peer + 1)) peer++;
-        const unsigned slot = atomicAdd(pc->out_cnt + peer, 1u);
-        if (slot < pc->ocap) {
-          double *rec = pc->peer_inbox[peer] +
-                        ((size_t)((p.pepoch & 1u) * (unsigned)p.nranks + (unsigned)p.my_rank) * pc->ocap + slot) * 3;
-          rec[0] = x2[k];
-          rec[1] = v2[k];
-          rec[2] = (double)id[k];
-        } else {
-          sh_overflow = true;
-        }
-        d = -3;
-      }
     }
     dest[k] = d;
+  }
+  if (SHARDP) {
+    // Only the two edge buckets reach beyond this GPU's key range (their outer splitters are -inf / +inf): a
+    // particle sent there may belong to another rank -- its record goes straight into the owner's inbox (peer
+    // memory over NVLink); the count travels with the flag word at the end of the launch.  Kept OUT of the
+    // destination loop above: the atomics and peer stores in it would order that loop's shared-memory loads
+    // (four particles searched one after the other instead of together); here a warp-uniform test skips it
+    // for all but the few warps near a range edge.
+    bool edge = false;
+#pragma unroll
+    for (int k = 0; k < E; k++) edge |= (dest[k] == 0 || dest[k] >= p.nb_last);
+    if (__any_sync(WENDY_FULL_MASK, edge)) {
+#pragma unroll
+      for (int k = 0; k < E; k++) {
+        const int d = dest[k];
+        const double key = xb[k];
+        if ((d == 0 || d >= p.nb_last) && (key < sh_lo || key >= sh_hi)) {
+          const PeerComm *pc = p.peer;
+          int peer = 0;
+          while (peer + 1 < p.nranks && key >= __ldg(p.bounds + peer + 1)) peer++;
+          const unsigned slot = atomicAdd(pc->out_cnt + peer, 1u);
+          if (slot < pc->ocap) {
+            double *rec = pc->peer_inbox[peer] +
+                          ((size_t)((p.pepoch & 1u) * (unsigned)p.nranks + (unsigned)p.my_rank) * pc->ocap + slot) * 3;
+            rec[0] = x2[k];
+            rec[1] = v2[k];
+            rec[2] = (double)id[k];
+          } else {
+            sh_overflow = true;
+          }
+          dest[k] = -3;
+        }
+      }
+    }
   }
   // slot allocation, aggregated per warp and destination; the E requests are issued back to back and
   // their results consumed afterwards, so the atomics' latencies overlap

@@ -64,6 +64,7 @@ class ApproxState(object):
             return numpy.ascontiguousarray(numpy.sum(m.reshape(self.n_segments, -1), axis=1))
 
         self._h = ctypes.c_void_p()
+        self._sort, self._stream = sort, int(stream or 0)
         flags = _lib.SORT_FLAGS[sort] | (0x10 if general_masses else 0) | (0x20 if exact_scan else 0)
         st = ctypes.c_void_p(stream) if stream else None
         if self.N < (1 << 22) or self.N % self.n_segments:
@@ -109,6 +110,7 @@ class ApproxState(object):
         if sort in _REFERENCE_SORTS:
             sort = 'gpu'
         self._h = ctypes.c_void_p()
+        self._sort, self._stream = sort, int(torch.cuda.current_stream().cuda_stream)
         torch.cuda.current_stream().synchronize()
         _lib.check(self._lib.wendy_cuda_create_dev(
             ctypes.byref(self._h), self.N, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(v.data_ptr()), mptr, m0,
@@ -158,15 +160,47 @@ class ApproxState(object):
         import torch
         tb = time.perf_counter()
         xptr, ns = ctypes.c_void_p(), ctypes.c_longlong()
-        k = 0
-        while k < nleap:
+
+        # F runs on torch's current stream, the library on the handle's: the same stream unless the caller entered a
+        # torch.cuda.stream() context (then every hand-over is fenced by a device synchronisation, and the
+        # asynchronous path is not used)
+        same_stream = int(torch.cuda.current_stream().cuda_stream) == self._stream
+
+        def force(k, t):
             _lib.check(self._lib.wendy_cuda_force_positions(self._h, dt_leap, int(k == 0),
                                                             ctypes.byref(xptr), ctypes.byref(ns)))
+            if not same_stream:
+                torch.cuda.synchronize()
             xs = torch.as_tensor(_CudaArrayView(xptr.value, ns.value), device='cuda')
-            a = ext_force(xs, t0)
+            a = ext_force(xs, t)
             if not torch.is_tensor(a):
                 a = torch.as_tensor(a, dtype=torch.float64, device=xs.device)
             a = a.to(dtype=torch.float64).expand_as(xs).contiguous()
+            if not same_stream:
+                torch.cuda.synchronize()
+            return a
+
+        k = 0
+        if same_stream and self._sort != 'gpu-radix' and os.environ.get('WENDY_B200_EXT_ASYNC', '1') != '0':
+            # all sub-steps of the call are enqueued without a host round trip each (the F evaluations are stream
+            # work like the kernels); one wait at the end.  An overflowing sub-step voids the launches behind it:
+            # the library restores its input and the loop below finishes the call synchronously.
+            _lib.check(self._lib.wendy_cuda_ext_begin(self._h))
+            keep = []
+            for kk in range(nleap):
+                a = force(kk, t0 + kk * dt_leap)
+                keep.append(a)  # alive until the kernels that read it have run
+                last = kk == nleap - 1
+                _lib.check(self._lib.wendy_cuda_substep_async(
+                    self._h, dt_leap, dt_leap / 2. if last else dt_leap, dt_leap / 2. if last else 0.,
+                    ctypes.c_void_p(a.data_ptr())))
+            done = ctypes.c_int(0)
+            _lib.check(self._lib.wendy_cuda_ext_end(self._h, ctypes.byref(done)))
+            del keep
+            k = done.value
+            t0 += k * dt_leap
+        while k < nleap:
+            a = force(k, t0)
             last = k == nleap - 1
             rc = _lib.check(self._lib.wendy_cuda_substep(
                 self._h, dt_leap, dt_leap / 2. if last else dt_leap, dt_leap / 2. if last else 0.,
