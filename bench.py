@@ -218,6 +218,10 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     import wendy_b200
+    if world > 1:
+        # one rank per GPU: the library's host-side copy threads share the node's cores between the ranks
+        from wendy_b200 import _lib as _wl
+        _wl.load().wendy_host_set_threads(max(1, min(32, cores // int(os.environ.get('LOCAL_WORLD_SIZE', world)))))
 
     def barrier():
         if world > 1:

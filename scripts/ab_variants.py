@@ -20,7 +20,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-DTS = (1e-3, 1e-4, 1e-5)
+DTS = [float(t) for t in os.environ.get("AB_DTS", "1e-3,1e-4,1e-5").split(",")]
 
 
 def worker(n, cap=0, fill=0):
@@ -109,7 +109,9 @@ def main():
             r['accepted'] = False
             continue
         vals = r['values']
-        score = vals['dt=0.001'] ** 0.5 * vals['dt=0.0001'] ** 0.25 * vals['dt=1e-05'] ** 0.25
+        score = 1.
+        for vv in vals.values():
+            score *= vv ** (1. / len(vals))
         r['score'], r['accepted'] = score, True
         if score > best_score:
             best, best_score = r, score

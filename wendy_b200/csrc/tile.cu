@@ -820,7 +820,10 @@ tile_kernel(const TileParams p) {
         }
         d = wlo + lo;
       } else {  // far move (split[seg_lo] is -inf)
-        // interpolated guess from the home bucket's width, then a galloping search around it
+        // interpolated guess from the home bucket's width, then a galloping search around it.  (Measured: a
+        // four-splitter check on the global table with L1 prefetch of its lines is 3-5 % SLOWER at dt_leap 1e-3 ...
+        // 5e-3, profiles/r02/ab_far_movers.json -- the cost of large displacements is not this search but the emission into
+        // hundreds of destinations per bucket.)
         double gq = fmax(-2.0e9, fmin(2.0e9, (key - home_lo) * inv_w));
         const int g = (int)max((long long)seg_lo, min((long long)seg_hi - 1, (long long)b + (long long)floor(gq)));
         d = gallop_search_tile(p.split, key, g, seg_lo, seg_hi);
