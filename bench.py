@@ -221,7 +221,7 @@ def main():
     if world > 1:
         # one rank per GPU: the library's host-side copy threads share the node's cores between the ranks
         from wendy_b200 import _lib as _wl
-        _wl.load().wendy_host_set_threads(max(1, min(32, cores // int(os.environ.get('LOCAL_WORLD_SIZE', world)))))
+        _wl.load().wendy_host_set_threads(max(1, min(32, cores // int(os.environ.get('LOCAL_WORLD_SIZE', world)) - 1)))
 
     def barrier():
         if world > 1:
@@ -504,7 +504,20 @@ def main():
     # GPU, no data-path collective (BASELINE.json configs[4]) -- so that both scalings can be read off one
     # line.  No collective inside the leg (a rank that fails must not hang the others): local events, then one
     # max over ranks.
-    ensemble, check = None, None
+    ensemble, check, regime = None, None, None
+    if sharded and not a.no_variants:
+        # The cost of a sub-step grows with the displacement per sub-step measured in ranks, N_total * rho * v * dt:
+        # at a fixed dt a system of `world` times more particles sends every particle across `world` times more
+        # buckets (path_stats.left_window: particles leaving the 256-bucket destination window).  The same run
+        # with dt_leap / world keeps that displacement -- the regime of the N=1 line -- and isolates what the
+        # exchange itself costs.
+        try:
+            vms, vd, _ = run_sharded(a.dt_leap / world, 3, 2, a.nleap)
+            regime = {'dt_leap': a.dt_leap / world, 'value': float(n) * world * a.nleap * 3 / (vms * 1e-3),
+                      'ms_per_substep': vms / (3 * a.nleap), 'left_window': vd['left_window'],
+                      'note': 'same system, dt_leap / n_gpus: displacement per sub-step in ranks as in the N=1 run'}
+        except Exception as exc:  # noqa: BLE001
+            regime = {'error': str(exc)[:200]}
     if sharded:
         steps_v = max(2, a.steps // 2)
         ms_loc = -1.
@@ -572,6 +585,8 @@ def main():
         out['ensemble_mode'] = ensemble
     if check is not None:
         out['sharded_check'] = check
+    if regime is not None:
+        out['variants'] = {'dt_leap/n_gpus': regime}
 
     # ---- config 3's other sub-runs: dt_leap 1e-5 / 5e-3 and the full radix sort forced every sub-step -------
     if world == 1 and not a.no_variants:

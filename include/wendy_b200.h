@@ -166,6 +166,19 @@ int wendy_cuda_create_shard_dev(wendy_cuda_handle **h, long long n_local, long l
                                 const double *x_dev, const double *v_dev, const int *ids_dev,
                                 double m0, double totmass, double omega2, int nranks, int rank,
                                 const double *bounds, long long outbox_capacity, void *cuda_stream);
+/* Unequal masses (host-orchestrated exchange; the reference's force takes arbitrary m, wendy/wendy.c:375-383):
+ * m[n_local] already times twopiG; sum_abs_m_global = sum |m| over ALL ranks (fixes the shared 128-bit fixed-point
+ * scale, so that the ranks' exact mass totals add exactly and the result does not depend on the number of ranks).
+ * Migrant records are then (x, v, id, m), four doubles.  Before every sub-step: wendy_cuda_shard_mass_total on
+ * every rank (exact total of the masses it holds, two 64-bit words), an all-gather of those by the host language,
+ * wendy_cuda_shard_set_mass_offset(sum over the lower ranks); then wendy_cuda_shard_substep as for equal masses. */
+int wendy_cuda_create_shard_m(wendy_cuda_handle **h, long long n_local, long long n_capacity,
+                              const double *x, const double *v, const double *m, const int *ids,
+                              double sum_abs_m_global, double totmass, double omega2, int nranks, int rank,
+                              const double *bounds, long long outbox_capacity, void *cuda_stream);
+int wendy_cuda_shard_mass_total(wendy_cuda_handle *h, double h_pre, unsigned long long *total2);
+int wendy_cuda_shard_set_mass_offset(wendy_cuda_handle *h, unsigned long long lo, unsigned long long hi);
+int wendy_cuda_shard_read_masses(wendy_cuda_handle *h, double *m_host);  /* order of the last shard_read */
 int wendy_cuda_shard_substep(wendy_cuda_handle *h, double h_pre, double dt_kick, double dt_drift,
                              double h_next, long long pc_offset, unsigned *out_counts);
 int wendy_cuda_shard_outbox(wendy_cuda_handle *h, double **records, long long *ocap);

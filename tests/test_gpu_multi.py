@@ -118,6 +118,43 @@ def test_sharded_four_ranks_and_a_changed_time_step(exchange):
         assert numpy.array_equal(X, Xs) and numpy.array_equal(V, Vs)
 
 
+@pytest.mark.parametrize('ranks', [2, 3])
+def test_sharded_unequal_masses_equal_the_single_gpu_general_path(ranks, monkeypatch):
+    """Unequal masses over several ranks (the reference's force takes arbitrary m, wendy/wendy.c:375-383):
+    every rank offsets its exact 128-bit mass scan by the exact total of the lower ranks, migrant records carry the
+    mass, and the result equals the single-GPU general path bit for bit whatever the number of ranks.  The peer
+    exchange is equal-mass only: asked for, it must decline by itself and leave the host-orchestrated path.  The third
+    call uses another dt (re-partition, masses read back with the particles)."""
+    import wendy_b200
+    monkeypatch.setenv('WENDY_B200_SHARD_PEER', '1')
+    n = 90000
+    x, v, m = wo.sech2_ic(n, seed=8, mass_jitter=0.3)
+    st = wendy_b200.ApproxState(x, v, m, omega2=1.1 ** 2.)
+    st.step(0.004, 4)
+    st.step(0.004, 4)
+    st.step(0.007, 3)
+    Xs, Vs = st.read()
+    st.close()
+
+    def run(comm):
+        from wendy_b200 import multi
+        mine = numpy.arange(n) % comm.size == comm.rank
+        s = multi.ShardedSystem(x[mine], v[mine], numpy.arange(n)[mine], 0., numpy.sum(m), comm, omega=1.1, m=m[mine])
+        s.step(0.004, 4)
+        s.step(0.004, 4)
+        peer = s.peer
+        s.step(0.007, 3)
+        X, V = s.gather(n)
+        mig = s.migrated
+        s.close()
+        return X, V, mig, peer
+    res = run_threads(ranks, run, device='cuda')
+    for X, V, mig, peer in res:
+        assert not peer
+        assert numpy.array_equal(X, Xs) and numpy.array_equal(V, Vs)
+    assert sum(r[2] for r in res) > 0
+
+
 def test_sharded_peer_exchange_rolls_back_after_an_overflow(monkeypatch):
     """A collapsing cold slab overflows buckets in the middle of a call: the failing rank's flag words stop every
     rank within one exchange, all roll back to the input of that sub-step, rebuild, and finish the call."""

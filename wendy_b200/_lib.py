@@ -90,6 +90,17 @@ def load():
                                                 vp, vp, vp, ctypes.c_double,
                                                 ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int,
                                                 _nd('f8'), ctypes.c_longlong, vp]
+    lib.wendy_cuda_create_shard_m.restype = ctypes.c_int
+    lib.wendy_cuda_create_shard_m.argtypes = [ctypes.POINTER(vp), ctypes.c_longlong, ctypes.c_longlong,
+                                              _nd('f8'), _nd('f8'), _nd('f8'), _nd('i4'), ctypes.c_double,
+                                              ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int,
+                                              _nd('f8'), ctypes.c_longlong, vp]
+    lib.wendy_cuda_shard_mass_total.restype = ctypes.c_int
+    lib.wendy_cuda_shard_mass_total.argtypes = [vp, ctypes.c_double, _nd('u8')]
+    lib.wendy_cuda_shard_set_mass_offset.restype = ctypes.c_int
+    lib.wendy_cuda_shard_set_mass_offset.argtypes = [vp, ctypes.c_ulonglong, ctypes.c_ulonglong]
+    lib.wendy_cuda_shard_read_masses.restype = ctypes.c_int
+    lib.wendy_cuda_shard_read_masses.argtypes = [vp, _nd('f8')]
     lib.wendy_cuda_potential.restype = ctypes.c_int
     lib.wendy_cuda_potential.argtypes = [vp, ctypes.c_longlong, vp, vp, ctypes.c_longlong, ctypes.c_double,
                                          ctypes.c_double, vp, vp]
@@ -155,7 +166,7 @@ def load():
 EXPORTED = ['wendy_cuda_create', 'wendy_cuda_create_dev', 'wendy_cuda_step', 'wendy_cuda_step_begin', 'wendy_cuda_step_end',
             'wendy_cuda_read_begin', 'wendy_cuda_read_end', 'wendy_cuda_force_positions',
             'wendy_cuda_substep', 'wendy_cuda_ext_begin', 'wendy_cuda_substep_async', 'wendy_cuda_ext_end', 'wendy_cuda_read', 'wendy_cuda_read_dev', 'wendy_cuda_energy',
-            'wendy_cuda_stats', 'wendy_serial_cum', 'wendy_cuda_create_shard', 'wendy_cuda_create_shard_dev', 'wendy_cuda_shard_substep', 'wendy_cuda_shard_outbox',
+            'wendy_cuda_stats', 'wendy_serial_cum', 'wendy_cuda_create_shard', 'wendy_cuda_create_shard_dev', 'wendy_cuda_create_shard_m', 'wendy_cuda_shard_mass_total', 'wendy_cuda_shard_set_mass_offset', 'wendy_cuda_shard_read_masses', 'wendy_cuda_shard_substep', 'wendy_cuda_shard_outbox',
             'wendy_cuda_shard_inject', 'wendy_cuda_shard_comm_export', 'wendy_cuda_shard_comm_open', 'wendy_cuda_shard_seed_counts', 'wendy_cuda_shard_prepare', 'wendy_cuda_shard_step_begin', 'wendy_cuda_shard_step_end', 'wendy_cuda_shard_rollback', 'wendy_cuda_shard_count', 'wendy_cuda_shard_read', 'wendy_cuda_shard_read_begin', 'wendy_cuda_shard_read_end', 'wendy_cuda_potential', 'wendy_cuda_energy_individual', 'wendy_cuda_set_totmass', 'wendy_cuda_trim', 'wendy_host_prefault', 'wendy_host_set_threads', 'wendy_cuda_pin', 'wendy_cuda_unpin', 'wendy_cuda_debug_layout', 'wendy_cuda_destroy', 'wendy_cuda_last_error',
             'wendy_cuda_argsort', '_wendy_nbody_approx_onestep']
 

@@ -46,7 +46,7 @@ void launch_iota(cudaStream_t st, int *id, long long n);
 void launch_gather_by_id(cudaStream_t st, const double *a_by_id, const int *id, const unsigned *cnt,
                          int cap, int nb, double *a_slots);
 void launch_validate(cudaStream_t st, const double *x, const double *v, const double *m, long long n, double *out3);
-void launch_make_keys_packed(cudaStream_t st, const double *packed, double h, long long n, uint64_t *keys,
+void launch_make_keys_packed(cudaStream_t st, const double *packed, int prec, double h, long long n, uint64_t *keys,
                              uint32_t *vals);
 void launch_make_keys_by_id(cudaStream_t st, const double *x, const double *v, const int *id, const unsigned *cnt,
                             int cap, int nb, long long n, double h, uint32_t *inv_scratch, uint64_t *keys,
@@ -78,6 +78,9 @@ struct wendy_cuda_handle {
   bool coarse_default = false;  // large equal-mass systems start (and stay) on 2048-slot buckets
   bool fill_backoff = false;    // a library-chosen coarse layout overflowed at the optimistic fill: use 3/4 from now on
   bool rebuild_pending = false;  // shard: rebuild at the start of the next sub-step (state complete)
+  int orec = 3;                          // doubles per migrant record: (x, v, id) or, general masses, (x, v, id, m)
+  unsigned long long pm_lo = 0, pm_hi = 0;  // general masses, sharded: exact 128-bit mass owned by the lower ranks
+  bool mpre_ready = false;               // magg / mpre already hold the bucket masses of the CURRENT state
   int shard_retry_k = -1, shard_retry_n = 0;  // shard: sub-step of the last rollback, consecutive rollbacks to it
   // WENDY_B200_SHARD_TRACE=1: CUDA events around the three launches of every sharded sub-step (peer exchange)
   std::vector<cudaEvent_t> tr_ev;
@@ -305,7 +308,7 @@ static int rebucket(H *h, double hkey, const double *extra = nullptr, long long 
   trace_mark(h->st, "rebucket: radix scratch");
   if (make_keys(h, hkey, VAL_SEGMENT)) return WENDY_E_CUDA;
   if (n_extra > 0)  // shard inject: the layout is built from the union of local state and inbox
-    launch_make_keys_packed(h->st, extra, hkey, n_extra, h->rs.key[0] + h->N, h->rs.val[0] + h->N);
+    launch_make_keys_packed(h->st, extra, h->orec, hkey, n_extra, h->rs.key[0] + h->N, h->rs.val[0] + h->N);
   const long long n_all = h->N + n_extra;
   int res = radix_sort_pairs(h->st, h->rs, (size_t)n_all, seg_bits(h), 1u);
   h->n_launch += 5 * (8 + (seg_bits(h) + 7) / 8);
@@ -326,7 +329,7 @@ static int rebucket(H *h, double hkey, const double *extra = nullptr, long long 
   sp.seg_len = h->seg_len; sp.fail_seq = h->flags; sp.seq = h->seq++;
   launch_scatter(h->st, sp, h->sm_count);
   if (n_extra > 0) {
-    sp.packed_in = extra; sp.cnt_in = nullptr; sp.n_dense = n_extra; sp.min = nullptr;
+    sp.packed_in = extra; sp.prec = h->orec; sp.cnt_in = nullptr; sp.n_dense = n_extra; sp.min = nullptr;
     sp.seg_len = h->n_cap + n_extra + 1; sp.seq = h->seq++;
     launch_scatter(h->st, sp, h->sm_count);
   }
@@ -337,7 +340,7 @@ static int rebucket(H *h, double hkey, const double *extra = nullptr, long long 
     return set_err(WENDY_E_OVERFLOW, "bucket overflow while building the layout: too many exactly "
                                      "coincident particles for one bucket");
   }
-  h->cur = o; h->ccur = c1; h->dense = false; h->has_split = true; h->bucket_h = hkey;
+  h->cur = o; h->ccur = c1; h->dense = false; h->has_split = true; h->bucket_h = hkey; h->mpre_ready = false;
   trace_mark(h->st, "rebucket: scatter");
   h->cap = ncap; h->fill = nfill; h->nbps = nnbps; h->nb = nnb; h->want_cap = 0;
   h->nb_last = (int)(((n_extra > 0 ? n_all : h->seg_len) - 1) / nfill);
@@ -366,7 +369,7 @@ static void fill_tile_params(H *h, TileParams &p) {
   p.status = h->status; p.desc = h->desc;
   p.eqm = h->eqm ? 1 : 0; p.m0 = h->m0; p.stab = h->stab;
   p.nranks = h->nranks; p.my_rank = h->my_rank; p.bounds = h->bounds;
-  p.out_rec = h->out_rec; p.out_cnt = h->out_cnt;
+  p.out_rec = h->out_rec; p.out_cnt = h->out_cnt; p.orec = h->orec; p.pm_lo = h->pm_lo; p.pm_hi = h->pm_hi;
   p.ocap = (unsigned)h->ocap; p.pc_offset = h->pc_offset;
   p.peer = h->peer_on ? h->peer_dev : nullptr; p.pepoch = h->pepoch; p.nb_last = h->nb_last;
   p.ticket = h->ticket + h->tcur; p.ticket_zero = h->ticket + (h->tcur + 2) % 3;
@@ -401,9 +404,12 @@ static void launch_bucket_substep(H *h, double h_pre, double dt_kick, double dt_
   h->n_launch++;
   p.cpre = h->cpre;
   if (!h->eqm) {
-    launch_mass_prefix(h->st, p.min, p.cnt_in, h->cap, h->nb, h->fxE, h->magg, h->mpre, h->mp_desc, h->mp_status,
-                       h->mp_ticket, p.epoch);
-    h->n_launch += 2;
+    if (!h->mpre_ready) {  // (a shard has just computed them for wendy_cuda_shard_mass_total)
+      launch_mass_prefix(h->st, p.min, p.cnt_in, h->cap, h->nb, h->fxE, h->magg, h->mpre, h->mp_desc, h->mp_status,
+                         h->mp_ticket, p.epoch);
+      h->n_launch += 2;
+    }
+    h->mpre_ready = false;
     p.mpre = h->mpre;
   }
   if (wstep_cap_supported(h->cap)) launch_wstep(h->st, h->cap, p);
@@ -452,12 +458,14 @@ void wendy_cuda_destroy(wendy_cuda_handle *h) {
   if (h->reader.joinable()) h->reader.join();
   if (h->st_copy) cudaStreamSynchronize(h->st_copy);
   cudaStreamSynchronize(h->st);
-  if (h->tr_n > 0)
-    fprintf(stderr, "wendy_b200 shard trace rank %d: %lld sub-steps, ms per sub-step: count prefix %.4f, step kernel "
-            "(incl. wait for the peers' counts) %.4f, inject kernel (incl. wait for the peers' migrants) %.4f; of which "
-            "waiting (CTA 0, all sub-steps of the handle): step %.4f, inject %.4f\n",
-            h->my_rank, h->tr_n, h->tr_ms[0] / h->tr_n, h->tr_ms[1] / h->tr_n, h->tr_ms[2] / h->tr_n,
-            h->tr_wait[0] * 1.024e-3 / std::max(1ll, h->n_sub), h->tr_wait[1] * 1.024e-3 / std::max(1ll, h->n_sub));
+  if (h->tr_n > 0) {
+    char line[512];  // one write(2): the ranks' lines must not interleave
+    int len = snprintf(line, sizeof(line), "wendy_b200 shard trace rank %d: %lld sub-steps, ms each: prefix %.4f step %.4f "
+                       "inject %.4f; waiting (CTA 0): step %.4f inject %.4f\n", h->my_rank, h->tr_n, h->tr_ms[0] / h->tr_n,
+                       h->tr_ms[1] / h->tr_n, h->tr_ms[2] / h->tr_n,
+                       h->tr_wait[0] * 1.024e-3 / std::max(1ll, h->n_sub), h->tr_wait[1] * 1.024e-3 / std::max(1ll, h->n_sub));
+    if (len > 0 && fwrite(line, 1, (size_t)std::min(len, (int)sizeof(line) - 1), stderr) > 0) fflush(stderr);
+  }
   for (cudaEvent_t e : h->tr_ev) cudaEventDestroy(e);
   h->tr_ev.clear();
   ring_release(h->ring);
@@ -775,7 +783,7 @@ int wendy_cuda_create_dev(wendy_cuda_handle **out, long long N, const double *x_
 static int create_shard_impl(wendy_cuda_handle **out, long long n_local, long long n_capacity, const double *x,
                              const double *v, const int *ids, double m0, double totmass, double omega2,
                              int nranks, int rank, const double *bounds, long long outbox_capacity,
-                             void *cuda_stream, bool dev);
+                             void *cuda_stream, bool dev, const double *m_general, double sum_abs_global);
 int wendy_cuda_create_shard(wendy_cuda_handle **out, long long n_local, long long n_capacity, const double *x,
                             const double *v, const int *ids, double m0, double totmass, double omega2,
                             int nranks, int rank, const double *bounds, long long outbox_capacity,
@@ -783,7 +791,20 @@ int wendy_cuda_create_shard(wendy_cuda_handle **out, long long n_local, long lon
   if (!ids || !bounds || nranks < 1 || rank < 0 || rank >= nranks || outbox_capacity < 1)
     return set_err(WENDY_E_ARG, "bad shard argument");
   return create_shard_impl(out, n_local, n_capacity, x, v, ids, m0, totmass, omega2, nranks, rank, bounds,
-                           outbox_capacity, cuda_stream, false);
+                           outbox_capacity, cuda_stream, false, nullptr, 0.);
+}
+
+// Unequal masses (host-orchestrated exchange only): m[n_local] already times twopiG; sum_abs_m_global = sum of |m|
+// over ALL ranks (any common upper bound will do: it fixes the shared 128-bit fixed-point scale).  Migrant records
+// are (x, v, id, m); the cumulative mass of a rank is offset by the exact total of the lower ranks
+// (wendy_cuda_shard_mass_total / wendy_cuda_shard_set_mass_offset).
+int wendy_cuda_create_shard_m(wendy_cuda_handle **out, long long n_local, long long n_capacity, const double *x,
+                              const double *v, const double *m, const int *ids, double sum_abs_m_global,
+                              double totmass, double omega2, int nranks, int rank, const double *bounds,
+                              long long outbox_capacity, void *cuda_stream) {
+  if (!m || !(sum_abs_m_global > 0.)) return set_err(WENDY_E_ARG, "bad shard argument");
+  return create_shard_impl(out, n_local, n_capacity, x, v, ids, 0., totmass, omega2, nranks, rank, bounds,
+                           outbox_capacity, cuda_stream, false, m, sum_abs_m_global);
 }
 
 // Same, from DEVICE arrays (the partition of multi.py runs on the GPU and hands its result over in place).
@@ -792,17 +813,22 @@ int wendy_cuda_create_shard_dev(wendy_cuda_handle **out, long long n_local, long
                                 double totmass, double omega2, int nranks, int rank, const double *bounds,
                                 long long outbox_capacity, void *cuda_stream) {
   return create_shard_impl(out, n_local, n_capacity, x_dev, v_dev, ids_dev, m0, totmass, omega2, nranks, rank,
-                           bounds, outbox_capacity, cuda_stream, true);
+                           bounds, outbox_capacity, cuda_stream, true, nullptr, 0.);
 }
 
 static int create_shard_impl(wendy_cuda_handle **out, long long n_local, long long n_capacity, const double *x,
                              const double *v, const int *ids, double m0, double totmass, double omega2,
                              int nranks, int rank, const double *bounds, long long outbox_capacity,
-                             void *cuda_stream, bool dev) {
+                             void *cuda_stream, bool dev, const double *m_general, double sum_abs_global) {
   if (!ids || !bounds || nranks < 1 || rank < 0 || rank >= nranks || outbox_capacity < 1)
     return set_err(WENDY_E_ARG, "bad shard argument");
   int rc;
-  if (dev) {
+  if (m_general) {
+    // unequal masses: the general path even if THIS range happens to hold equal ones; coarse buckets (the warp
+    // kernel's sharded instance is equal-mass only)
+    rc = create_impl(out, n_local, n_capacity, x, v, m_general, ids, &totmass, omega2, 1, WENDY_FLAG_GENERAL_MASSES,
+                     tile_coarse_cap(), 0, cuda_stream);
+  } else if (dev) {
     rc = create_impl(out, n_local, n_capacity, x, v, nullptr, ids, &totmass, omega2, 1, 0, 0, 0, cuda_stream,
                      true, m0);
   } else {
@@ -816,7 +842,12 @@ static int create_shard_impl(wendy_cuda_handle **out, long long n_local, long lo
   if (e == cudaSuccess) e = dev_alloc(&h->bounds, (size_t)(nranks + 1) * sizeof(double));
   if (e == cudaSuccess) e = cudaMemcpy(h->bounds, bounds, (size_t)(nranks + 1) * sizeof(double), cudaMemcpyHostToDevice);
   size_t ob = (size_t)nranks * (size_t)outbox_capacity;
-  if (e == cudaSuccess) e = dev_alloc(&h->out_rec, ob * 3 * sizeof(double));
+  if (m_general) {
+    h->orec = 4;
+    // one fixed-point scale for the whole system: the ranks' 128-bit mass totals must add exactly
+    h->fxE = choose_fx_exponent(sum_abs_global);
+  }
+  if (e == cudaSuccess) e = dev_alloc(&h->out_rec, ob * (size_t)h->orec * sizeof(double));
   if (e == cudaSuccess) e = dev_alloc(&h->out_cnt, (size_t)nranks * sizeof(unsigned));
   if (e == cudaSuccess) e = cudaMallocHost(&h->h_out_cnt, (size_t)nranks * sizeof(unsigned));
   if (e == cudaSuccess) e = dev_alloc(&h->cid, (size_t)n_capacity * sizeof(int));
@@ -866,6 +897,62 @@ int wendy_cuda_shard_substep(wendy_cuda_handle *h, double h_pre, double dt_kick,
   return set_err(WENDY_E_OVERFLOW, "shard: bucket or outbox overflow persists after re-balancing");
 }
 
+// General masses: the exact 128-bit fixed-point total of the masses this rank holds NOW (low, high word), for the
+// layout keyed on x + h_pre*v that the next wendy_cuda_shard_substep(h_pre, ...) will use (rebuilt here if needed, so
+// that the bucket masses computed for the total are the ones that sub-step consumes).  The host adds the totals of
+// the lower ranks (128-bit integer addition) and hands the sum back through wendy_cuda_shard_set_mass_offset.
+int wendy_cuda_shard_mass_total(wendy_cuda_handle *h, double h_pre, unsigned long long *total2) {
+  if (!h || !h->bounds || !total2) return set_err(WENDY_E_ARG, "not a shard handle");
+  total2[0] = total2[1] = 0ull;
+  if (h->eqm) return set_err(WENDY_E_ARG, "equal masses: the particle count is the offset");
+  if (h->dense || !h->has_split || h->bucket_h != h_pre || h->rebuild_pending) {
+    int rc = rebucket(h, h_pre);
+    if (rc) return rc;
+    h->rebuild_pending = false;
+  }
+  launch_mass_prefix(h->st, h->m[h->cur], h->cnt[h->ccur], h->cap, h->nb, h->fxE, h->magg, h->mpre, h->mp_desc,
+                     h->mp_status, h->mp_ticket, h->seq++);
+  h->n_launch += 2;
+  ulonglong2 last[2];
+  CK(cudaMemcpyAsync(&last[0], h->mpre + (h->nb - 1), sizeof(ulonglong2), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaMemcpyAsync(&last[1], h->magg + (h->nb - 1), sizeof(ulonglong2), cudaMemcpyDeviceToHost, h->st));
+  CK(cudaStreamSynchronize(h->st));
+  const unsigned __int128 t = (((unsigned __int128)last[0].y << 64) | last[0].x) + (((unsigned __int128)last[1].y << 64) | last[1].x);
+  total2[0] = (unsigned long long)t;
+  total2[1] = (unsigned long long)(t >> 64);
+  h->mpre_ready = true;
+  return 0;
+}
+
+int wendy_cuda_shard_set_mass_offset(wendy_cuda_handle *h, unsigned long long lo, unsigned long long hi) {
+  if (!h || !h->bounds) return set_err(WENDY_E_ARG, "not a shard handle");
+  h->pm_lo = lo; h->pm_hi = hi;
+  return 0;
+}
+
+// General masses: the masses of the local particles in the order of the LAST wendy_cuda_shard_read (compacted by
+// the same kernel), for a global re-partition through the host.
+int wendy_cuda_shard_read_masses(wendy_cuda_handle *h, double *m_host) {
+  if (!h || !h->bounds || !m_host) return set_err(WENDY_E_ARG, "bad argument");
+  if (h->eqm) return set_err(WENDY_E_ARG, "equal masses");
+  if (h->pending || h->reader.joinable()) return set_err(WENDY_E_ARG, "finish the call / read-out in flight first");
+  if (!h->xo) {
+    CK(dev_alloc(&h->xo, (size_t)h->n_cap * sizeof(double)));
+    CK(dev_alloc(&h->vo, (size_t)h->n_cap * sizeof(double)));
+  }
+  if (h->dense) {
+    CK(copy_split(m_host, h->m[h->cur], (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  } else {
+    launch_count_prefix(h->st, h->cnt[h->ccur], h->nb, h->cpre, h->cp_desc, h->cp_ticket, h->seq++);
+    launch_compact(h->st, h->m[h->cur], h->m[h->cur], h->id[h->cur], h->cnt[h->ccur], h->cpre, h->cap, h->nb,
+                   h->xo, h->vo, h->cid);
+    h->n_launch += 2;
+    CK(copy_split(m_host, h->xo, (size_t)h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  }
+  CK(cudaStreamSynchronize(h->st));
+  return 0;
+}
+
 int wendy_cuda_shard_outbox(wendy_cuda_handle *h, double **records, long long *ocap) {
   if (!h || !h->bounds || !records || !ocap) return set_err(WENDY_E_ARG, "not a shard handle");
   *records = h->out_rec; *ocap = h->ocap;
@@ -877,13 +964,14 @@ int wendy_cuda_shard_inject(wendy_cuda_handle *h, const double *records_dev, lon
   if (!h || !h->bounds) return set_err(WENDY_E_ARG, "not a shard handle");
   if (n <= 0) return 0;
   if (h->N + n > h->n_cap) return set_err(WENDY_E_OVERFLOW, "shard capacity exceeded (global re-partition needed)");
+  h->mpre_ready = false;
   if (h->dense || !h->has_split) return set_err(WENDY_E_ARG, "inject needs a layout");
   ScatterParams sp;
   memset(&sp, 0, sizeof(sp));
-  sp.packed_in = records_dev; sp.min = nullptr;
+  sp.packed_in = records_dev; sp.prec = h->orec; sp.min = nullptr;
   sp.cnt_in = nullptr; sp.n_dense = n; sp.h = h->bucket_h;
   int c = h->cur;
-  sp.xout = h->x[c]; sp.vout = h->v[c]; sp.mout = nullptr; sp.idout = h->id[c];
+  sp.xout = h->x[c]; sp.vout = h->v[c]; sp.mout = h->eqm ? nullptr : h->m[c]; sp.idout = h->id[c];
   sp.cnt_out = h->cnt[h->ccur]; sp.split = h->split; sp.cap_out = h->cap; sp.nbps_out = h->nbps;
   sp.seg_len = h->n_cap + 1; sp.fail_seq = h->flags; sp.seq = h->seq++;
   // snapshot of the counts: an overflowing append is rolled back (slots beyond the counts are dead)

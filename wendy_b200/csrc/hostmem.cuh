@@ -278,7 +278,9 @@ int bounce_d2h(BounceRing *r, cudaStream_t st, void *const *dst, const void *con
     const char *bp = (const char *)r->buf[sl];
     char *dp = pieces[i].d;
     const long long nblk = (long long)((pieces[i].n + 262143) / 262144);
-#pragma omp parallel for schedule(static) num_threads(host_threads())
+    // (dynamic: with one rank per GPU the cores are shared with the other ranks' threads; a static split would wait
+    // for whichever thread was descheduled)
+#pragma omp parallel for schedule(dynamic, 2) num_threads(host_threads())
     for (long long blk = 0; blk < nblk; blk++) {
       const size_t b0 = (size_t)blk * 262144, bl = std::min((size_t)262144, pieces[i].n - b0);
       stream_copy(dp + b0, bp + b0, bl);

@@ -112,7 +112,9 @@ struct TileParams {
   // [bounds[my_rank], bounds[my_rank+1]) are appended to the outbox of the owning peer
   int nranks, my_rank;
   const double *bounds;     // nranks+1 ascending range edges (first -inf, last +inf), device
-  double *out_rec;          // [nranks][ocap][3] outboxes of packed (x, v, id) records
+  double *out_rec;          // [nranks][ocap][orec] outboxes of packed (x, v, id[, m]) records
+  int orec;                 // doubles per record: 3, or 4 with general masses
+  unsigned long long pm_lo, pm_hi;  // general masses, sharded: exact 128-bit mass of the lower ranks
   unsigned *out_cnt;        // [nranks]
   unsigned ocap;
   long long pc_offset;      // particles owned by lower ranks (added to every rank)
@@ -154,7 +156,8 @@ struct ScatterParams {
   const double *xin, *vin, *min;
   const int *idin;
   const unsigned *cnt_in;   // null: source is dense (n_dense elements, segment = i / seg_len)
-  const double *packed_in;  // non-null: dense source of packed (x, v, id) triples (migrants)
+  const double *packed_in;  // non-null: dense source of packed (x, v, id[, m]) records (migrants)
+  int prec;                 // doubles per packed record (3; 4 with general masses)
   long long n_dense;
   int cap_in, nb_in, nbps_in;
   double h;                 // bucket key = x + h*v

@@ -580,7 +580,7 @@ tile_kernel(const TileParams p) {
       long long Pcm;
       if (p.mpre) {  // bucket mass prefix precomputed (bucket_mass + mass_prefix kernels): no look-back
         const ulonglong2 a = p.mpre[b], z = p.mpre[seg_lo];
-        P = make_i128(a.x, a.y) - make_i128(z.x, z.y);
+        P = make_i128(a.x, a.y) - make_i128(z.x, z.y) + make_i128(p.pm_lo, p.pm_hi);  // (+ the lower ranks' mass)
       } else {
         lookback(p.desc, p.status, p.epoch, b, seg_lo, agg, (long long)n, lane, P, Pcm);
       }
@@ -788,10 +788,11 @@ tile_kernel(const TileParams p) {
         while (peer + 1 < p.nranks && key >= __ldg(p.bounds + peer + 1)) peer++;
         const unsigned slot = atomicAdd(p.out_cnt + peer, 1u);
         if (slot < p.ocap) {
-          double *rec = p.out_rec + ((size_t)peer * p.ocap + slot) * 3;
+          double *rec = p.out_rec + ((size_t)peer * p.ocap + slot) * (EQM ? 3 : p.orec);
           rec[0] = x2[k];
           rec[1] = v2[k];
           rec[2] = (double)id[k];
+          if (!EQM) rec[3] = m[k];
         } else {
           sh_overflow = true;
         }
@@ -1119,8 +1120,8 @@ scatter_kernel(const ScatterParams p) {
       }
       if (ok) {
         if (p.packed_in) {
-          x = p.packed_in[3 * i];
-          v = p.packed_in[3 * i + 1];
+          x = p.packed_in[(size_t)p.prec * i];
+          v = p.packed_in[(size_t)p.prec * i + 1];
         } else {
           x = p.xin[i];
           v = p.vin[i];
@@ -1145,8 +1146,13 @@ scatter_kernel(const ScatterParams p) {
         size_t o = (size_t)d * p.cap_out + pos;
         p.xout[o] = x;
         p.vout[o] = v;
-        if (p.min) p.mout[o] = p.min[i];
-        p.idout[o] = p.packed_in ? (int)p.packed_in[3 * i + 2] : p.idin[i];
+        if (p.packed_in) {
+          p.idout[o] = (int)p.packed_in[(size_t)p.prec * i + 2];
+          if (p.mout && p.prec > 3) p.mout[o] = p.packed_in[(size_t)p.prec * i + 3];
+        } else {
+          if (p.min) p.mout[o] = p.min[i];
+          p.idout[o] = p.idin[i];
+        }
       } else {
         overflow = true;
       }
@@ -1346,22 +1352,22 @@ void launch_make_keys_by_id(cudaStream_t st, const double *x, const double *v, c
 }
 
 // keys of packed (x, v, id) migrant records (segment 0)
-__global__ void make_keys_packed_kernel(const double *__restrict__ packed, double h, long long n,
+__global__ void make_keys_packed_kernel(const double *__restrict__ packed, int prec, double h, long long n,
                                         uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
-    double xx = packed[3 * i];
-    if (h != 0.0) xx = __dadd_rn(xx, __dmul_rn(h, packed[3 * i + 1]));
+    double xx = packed[(size_t)prec * i];
+    if (h != 0.0) xx = __dadd_rn(xx, __dmul_rn(h, packed[(size_t)prec * i + 1]));
     keys[i] = key_from_double(xx);
     vals[i] = 0u;
   }
 }
-void launch_make_keys_packed(cudaStream_t st, const double *packed, double h, long long n, uint64_t *keys,
+void launch_make_keys_packed(cudaStream_t st, const double *packed, int prec, double h, long long n, uint64_t *keys,
                              uint32_t *vals) {
   if (n <= 0) return;
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  make_keys_packed_kernel<<<(unsigned)blocks, 256, 0, st>>>(packed, h, n, keys, vals);
+  make_keys_packed_kernel<<<(unsigned)blocks, 256, 0, st>>>(packed, prec, h, n, keys, vals);
 }
 
 // exclusive scan of the bucket counts (single block; nb is N/fill, at most a few 1e5)

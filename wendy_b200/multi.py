@@ -59,26 +59,28 @@ class TorchComm(object):
         return numpy.stack([o.cpu().numpy() for o in out])
 
     def exchange(self, send, counts=None):
-        """send[p]: (n_p, 3) float64 tensor for peer p (send[rank] is delivered locally).
-        counts[src][dst] may be passed when it is already known (saves one all-gather).
-        Returns ONE contiguous (m, 3) tensor with everything received from the other ranks."""
+        """send[p]: (n_p, w) float64 tensor for peer p (send[rank] is delivered locally); w = 3 (x, v, id) or
+        4 (x, v, id, m).  counts[src][dst] may be passed when it is already known (saves one all-gather).
+        Returns ONE contiguous (m, w) tensor with everything received from the other ranks."""
         torch, dist = self.torch, self.dist
+        w = int(send[0].shape[1])
         if counts is None:
             counts = self.allgather_vec([s.shape[0] for s in send]).astype(numpy.int64)  # [src][dst]
         n_in = [int(counts[p][self.rank]) if p != self.rank else 0 for p in range(self.size)]
         n_out = [int(send[p].shape[0]) if p != self.rank else 0 for p in range(self.size)]
         total = sum(n_in)
         if total > (1 << 22):  # the one-off initial partition: do not keep gigabytes around
-            inbox = torch.empty((total, 3), dtype=torch.float64, device=self.device)
+            inbox = torch.empty((total, w), dtype=torch.float64, device=self.device)
         else:
-            if getattr(self, '_inbox', None) is None or self._inbox.shape[0] < total:
-                self._inbox = torch.empty((max(total, 1024) * 2, 3), dtype=torch.float64, device=self.device)
+            if (getattr(self, '_inbox', None) is None or self._inbox.shape[0] < total
+                    or self._inbox.shape[1] != w):
+                self._inbox = torch.empty((max(total, 1024) * 2, w), dtype=torch.float64, device=self.device)
             inbox = self._inbox[:total]
         if total == 0 and sum(n_out) == 0:
             return inbox
         if dist.get_backend(self.group) == 'nccl':
             sendbuf = torch.cat([send[p] for p in range(self.size) if n_out[p]], dim=0) if sum(n_out) \
-                else torch.empty((0, 3), dtype=torch.float64, device=self.device)
+                else torch.empty((0, w), dtype=torch.float64, device=self.device)
             dist.all_to_all_single(inbox, sendbuf, output_split_sizes=n_in, input_split_sizes=n_out,
                                    group=self.group)
             return inbox
@@ -105,7 +107,7 @@ class CudaShardEngine(object):
     """One key range on one GPU, over the shard entry points of libwendy_b200.so."""
 
     def __init__(self, x, v, ids, m0, totmass, omega2, nranks, rank, bounds, capacity,
-                 outbox_capacity, device=None):
+                 outbox_capacity, device=None, m=None, sum_abs_m=0.):
         import torch
         self.torch = torch
         self._lib = _lib.load()
@@ -119,7 +121,17 @@ class CudaShardEngine(object):
         self.stream = torch.cuda.Stream(device=self.device)
         st = ctypes.c_void_p(self.stream.cuda_stream)
         self.peer = False
-        if torch.is_tensor(x):
+        self.width = 3 if m is None else 4  # doubles per migrant record
+        if m is not None:
+            # unequal masses: host arrays, host-orchestrated exchange (wendy_cuda_create_shard_m)
+            if torch.is_tensor(x):
+                x, v, ids, m = (t.cpu().numpy() for t in (x, v, ids, m))
+            _lib.check(self._lib.wendy_cuda_create_shard_m(
+                ctypes.byref(self._h), len(x), self.capacity, numpy.ascontiguousarray(x, dtype=numpy.float64),
+                numpy.ascontiguousarray(v, dtype=numpy.float64), numpy.ascontiguousarray(m, dtype=numpy.float64),
+                numpy.ascontiguousarray(ids, dtype=numpy.int32), float(sum_abs_m), float(totmass), float(omega2),
+                nranks, rank, bounds, int(outbox_capacity), st))
+        elif torch.is_tensor(x):
             # the partition ran on this GPU: hand the device arrays over in place
             x = x.to(device=self.device, dtype=torch.float64).contiguous()
             v = v.to(device=self.device, dtype=torch.float64).contiguous()
@@ -140,9 +152,9 @@ class CudaShardEngine(object):
         pr, oc = ctypes.c_void_p(), ctypes.c_longlong()
         _lib.check(self._lib.wendy_cuda_shard_outbox(self._h, ctypes.byref(pr), ctypes.byref(oc)))
         self._ocap = oc.value
-        # zero-copy view of the packed (x, v, id) outbox records: [peer][slot][3]
-        self._orec = torch.as_tensor(_DevView(pr.value, nranks * oc.value * 3, '<f8'),
-                                     device=self.device).view(nranks, oc.value, 3)
+        # zero-copy view of the packed (x, v, id[, m]) outbox records: [peer][slot][width]
+        self._orec = torch.as_tensor(_DevView(pr.value, nranks * oc.value * self.width, '<f8'),
+                                     device=self.device).view(nranks, oc.value, self.width)
 
     def close(self):
         if getattr(self, '_h', None):
@@ -159,6 +171,7 @@ class CudaShardEngine(object):
         import os
         ptr, nbytes = ctypes.c_ulonglong(), ctypes.c_ulonglong()
         handle = numpy.zeros(64, dtype=numpy.uint8)
+        # (unequal masses: the export refuses, every rank sees it in the all-gather below, all stay host-orchestrated)
         rc = self._lib.wendy_cuda_shard_comm_export(self._h, ctypes.byref(ptr), ctypes.byref(nbytes), handle)
         ok = rc in (0, 1)
         vec = numpy.concatenate(([float(os.getpid()), float(ptr.value >> 32), float(ptr.value & 0xffffffff),
@@ -228,6 +241,22 @@ class CudaShardEngine(object):
         _lib.check(self._lib.wendy_cuda_shard_count(self._h, ctypes.byref(n)))
         return n.value
 
+    def mass_total(self, h_pre):
+        """Exact 128-bit fixed-point total of the masses held now, as a Python int (unequal masses)."""
+        t = numpy.zeros(2, dtype=numpy.uint64)
+        _lib.check(self._lib.wendy_cuda_shard_mass_total(self._h, float(h_pre), t))
+        return int(t[0]) | (int(t[1]) << 64)
+
+    def set_mass_offset(self, total):
+        total &= (1 << 128) - 1
+        _lib.check(self._lib.wendy_cuda_shard_set_mass_offset(self._h, total & 0xffffffffffffffff, total >> 64))
+
+    def read_masses(self):
+        """Masses in the order of the last read()."""
+        m = numpy.empty(self.capacity)
+        _lib.check(self._lib.wendy_cuda_shard_read_masses(self._h, m))
+        return m[:self.count()]
+
     def _host_buffers(self):
         """Ordinary numpy memory: the library fills pageable destinations through its page-locked bounce buffers
         at PCIe speed (page-locking capacity * 20 bytes per rank would cost about a second).  Two sets, the second
@@ -293,12 +322,20 @@ class ShardedSystem(object):
 
     Every rank passes the particles it happens to hold (any subset, with their GLOBAL ids);
     ``m0`` is the common particle mass ALREADY times twopiG, ``totmass`` the global total as the
-    reference computes it (numpy.sum of the scaled masses, wendy/wendy.py:383)."""
+    reference computes it (numpy.sum of the scaled masses, wendy/wendy.py:383).
+
+    Unequal masses: pass ``m=`` (the masses of the particles given, times twopiG; ``m0`` is then ignored).  The
+    cumulative mass becomes the correctly rounded exact prefix sum of the general single-GPU path -- every rank
+    adds the exact 128-bit total of the lower ranks to its own scan, so the result is again independent of the
+    number of ranks bit for bit.  The exchange is host-orchestrated in this mode (records carry the mass)."""
 
     def __init__(self, x, v, ids, m0, totmass, comm, omega=None, engine_factory=None,
-                 capacity_factor=1.3, outbox_fraction=0.05, n_sample=65536):
+                 capacity_factor=1.3, outbox_fraction=0.05, n_sample=65536, m=None):
         self.comm = comm
         self.m0, self.totmass = float(m0), float(totmass)
+        self._m = None if m is None else numpy.ascontiguousarray(m, dtype=numpy.float64)
+        self.general = m is not None
+        self.sum_abs_m = 0.
         self.omega2 = -1. if omega is None else float(omega) ** 2.
         # (only read, at the first step: no copies -- 2 GB per rank at 1e8 particles)
         self._raw = (numpy.ascontiguousarray(x, dtype=numpy.float64), numpy.ascontiguousarray(v, dtype=numpy.float64),
@@ -316,7 +353,7 @@ class ShardedSystem(object):
             # one rank per GPU: the library's host-side copy threads must share the node's cores between the ranks
             import os
             local = int(os.environ.get('LOCAL_WORLD_SIZE', comm.size) or comm.size)
-            _lib.load().wendy_host_set_threads(max(1, min(32, (os.cpu_count() or 1) // max(1, local))))
+            _lib.load().wendy_host_set_threads(max(1, min(32, (os.cpu_count() or 1) // max(1, local) - 1)))
 
     # -- set-up: global sample sort on the keys of the FIRST force evaluation -------------------------
     def _partition(self, dt_leap):
@@ -329,19 +366,26 @@ class ShardedSystem(object):
         sample[:len(take)] = key[take] if len(key) else []  # a strided subset is an unbiased key sample
         self.bounds = choose_bounds(comm.allgather_vec(sample), comm.size)
         cap = int(self.capacity_factor * n_tot / comm.size) + 1024
-        if str(comm.device).startswith('cuda') and self.engine_factory is CudaShardEngine:
+        if str(comm.device).startswith('cuda') and self.engine_factory is CudaShardEngine and not self.general:
             return self._partition_device(dt_leap, cap)
         owner = route(key, self.bounds)
         # the engine's tensors decide where the exchange buffers live (cuda for NCCL, cpu for gloo)
         import torch
-        send = [torch.as_tensor(numpy.stack((x[owner == p], v[owner == p], ids[owner == p].astype(numpy.float64)),
-                                            axis=1), device=comm.device) for p in range(comm.size)]
+        cols = [x, v, ids.astype(numpy.float64)] + ([self._m] if self.general else [])
+        send = [torch.as_tensor(numpy.stack([c[owner == p] for c in cols], axis=1), device=comm.device)
+                for p in range(comm.size)]
         keep = send[comm.rank]
         mine = torch.cat((keep, comm.exchange(send)), dim=0).cpu().numpy()
+        extra = {}
+        if self.general:
+            # one fixed-point scale for all ranks: the global sum of |m| (same additions in the same order everywhere)
+            self.sum_abs_m = float(numpy.sum(comm.allgather_vec([float(numpy.sum(numpy.abs(self._m)))])[:, 0]))
+            extra = {'m': mine[:, 3].copy(), 'sum_abs_m': self.sum_abs_m}
         self.engine = self.engine_factory(mine[:, 0].copy(), mine[:, 1].copy(), mine[:, 2].astype(numpy.int32),
                                           self.m0, self.totmass, self.omega2, comm.size, comm.rank,
-                                          self.bounds, cap, max(1024, int(self.outbox_fraction * cap)))
+                                          self.bounds, cap, max(1024, int(self.outbox_fraction * cap)), **extra)
         self._raw = None
+        self._m = None
         self.dt_leap = dt_leap
         self._update_offset()
 
@@ -394,6 +438,8 @@ class ShardedSystem(object):
         optimised: the state goes through the host."""
         ids, x, v = self.engine.read()
         self._raw = (numpy.array(x), numpy.array(v), numpy.array(ids, dtype=numpy.int32))
+        if self.general:
+            self._m = numpy.array(self.engine.read_masses())
         self.engine.close()
         self.engine = None
         self.peer, self.peer_tried = False, False
@@ -454,6 +500,13 @@ class ShardedSystem(object):
         for k in range(nleap):
             last = k == nleap - 1
             t0 = time.perf_counter()
+            if self.general:
+                # exact mass of the lower ranks: every rank's 128-bit total, all-gathered as four 32-bit pieces
+                # (exact in float64), summed as Python integers
+                tot = self.engine.mass_total(dt_leap / 2. if k == 0 else 0.)
+                parts = self.comm.allgather_vec([float((tot >> (32 * j)) & 0xffffffff) for j in range(4)])
+                below = sum(sum(int(parts[r, j]) << (32 * j) for j in range(4)) for r in range(self.comm.rank))
+                self.engine.set_mass_offset(below)
             out = self.engine.substep(dt_leap / 2. if k == 0 else 0., dt_leap,
                                       dt_leap / 2. if last else dt_leap,
                                       dt_leap / 2. if last else 0., self.pc_offset)
