@@ -288,67 +288,69 @@ def main():
                    'config': {'workload': 'config 1: sech2 disk N=1e4, dt=0.05, nleap=1, 100 outputs through nbody()'},
                    'parity': {'sha256_x': hx, 'sha256_v': hv,
                               'equals_reference_KAT_D': hx == '21614814a2a156b6' and hv == '7730018ad0084bb4'}}
-        if a.config == 2:  # cold slab N=1e6, 1000 steps, energy-drift statistics beside the reference's own
+        if a.config == 2:  # cold slab N=1e6, 1000 leapfrog steps, energy-drift statistics beside the reference's own
             from oracle import wendy_oracle as wo
-            nn, nsteps, dtl = 1000000, 1000, 0.005
+            nn, nsteps, dtl, nl = 1000000, 1000, 0.005, 10  # 100 calls of nleap = 10 (the host syncs once per call)
             x, v, m = slab_ic(nn)
             E0 = wo.energy(x, v, m)
             st = wendy_b200.ApproxState(x, v, m, stream=stream)
-            st.step(dtl, 1)
+            st.step(dtl, nl)
             s0 = st.stats()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             drift = []
             torch.cuda.synchronize()
             e0.record()
-            for i in range(1, nsteps):
-                st.step(dtl, 1)
-                if (i + 1) % 100 == 0:
+            for i in range(1, nsteps // nl):
+                st.step(dtl, nl)
+                if (i + 1) % 10 == 0:
                     ke, he, pe, _ = st.energy_terms()
                     drift.append(abs((ke + he + pe) - E0) / abs(E0))
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)
             d = stat_delta(st.stats(), s0)
-            xg, vg = st.read()
             st.close()
-            # the same system with the full radix sort every step (no bucket layout to rebuild): at this size the
-            # whole state lives in L2 and a step is a dozen short launches
-            st = wendy_b200.ApproxState(x, v, m, stream=stream, sort='gpu-radix')
-            st.step(dtl, 1)
-            torch.cuda.synchronize()
-            e0.record()
-            for i in range(300):
-                st.step(dtl, 1)
-            e1.record()
-            torch.cuda.synchronize()
-            radix_rate = float(nn) * 300 / (e0.elapsed_time(e1) * 1e-3)
-            st.close()
+
+            def timed(nleap_v, calls, **kw):
+                stv = wendy_b200.ApproxState(x, v, m, stream=stream, **kw)
+                stv.step(dtl, nleap_v)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(calls):
+                    stv.step(dtl, nleap_v)
+                e1.record()
+                torch.cuda.synchronize()
+                r_ = float(nn) * nleap_v * calls / (e0.elapsed_time(e1) * 1e-3)
+                stv.close()
+                return r_
+            var = {'300 calls of nleap=1 (a host round trip per leapfrog step)': {'value': timed(1, 300)},
+                   'sort=gpu-radix, 30 calls of nleap=10 (full sort every step, no layout to rebuild)':
+                       {'value': timed(nl, 30, sort='gpu-radix')}}
             ref_drift, ref_rate, same10 = None, None, None
             if rank == 0 and not a.no_cpu_baseline:
-                r, kind = make_reference(x, v, m, None, dtl)
+                r, kind = make_reference(x, v, m, None, dtl, nleap=nl)
                 t0 = time.perf_counter()
                 ref_drift = []
-                for i in range(nsteps):
+                for i in range(nsteps // nl):
                     xr, vr = r.step()
-                    if i == 9:
+                    if i == 0:
                         g10 = wendy_b200.ApproxState(x, v, m, stream=stream)
-                        for _ in range(10):
-                            g10.step(dtl, 1)
+                        g10.step(dtl, nl)
                         x10, v10 = g10.read()
                         g10.close()
                         same10 = bool(numpy.array_equal(x10, xr) and numpy.array_equal(v10, vr))
-                    if (i + 1) % 100 == 0:
+                    if (i + 1) % 10 == 0:
                         ref_drift.append(abs(wo.energy(xr, vr, m) - E0) / abs(E0))
                 ref_rate = nn * nsteps / (time.perf_counter() - t0)
-            out = {'value': float(nn) * (nsteps - 1) / (ms * 1e-3), 'ms_per_step': ms / (nsteps - 1),
-                   'config': {'workload': 'config 2: cold slab N=1e6, omega=None, dt_leap=0.005, 1000 steps (violent relaxation)'},
-                   'path_stats': d, 'gpu_launches': d['kernel_launches'],
-                   'variants': {'sort=gpu-radix (first 300 steps)': {'value': radix_rate}},
+            out = {'value': float(nn) * (nsteps - nl) / (ms * 1e-3), 'ms_per_step': ms / (nsteps - nl),
+                   'config': {'workload': 'config 2: cold slab N=1e6, omega=None, dt_leap=0.005, 1000 leapfrog steps as 100 calls '
+                                          'of nleap=10 (violent relaxation)'},
+                   'path_stats': d, 'gpu_launches': d['kernel_launches'], 'variants': var,
                    'energy_drift': {'gpu_abs_dE_over_E_every_100_steps': drift, 'reference_same_ICs': ref_drift,
                                     'note': 'chaotic after a few steps: compared as statistics, not particle by particle'},
                    'parity': {'bit_identical_to_reference_after_10_steps': same10},
                    'cpu_baseline': {'value': ref_rate, 'unit': 'particle-steps/s', 'cores': cores, 'kind': 'reference',
-                                    'sample': 'the same 1000 steps, sort=parallel'}}
+                                    'sample': 'the same 1000 steps (100 calls of nleap=10), sort=parallel'}}
         if a.config == 5:  # Gaia phase-space spiral ensemble: realisations of 1e5 particles + torch ext_force
             from wendy_b200 import multi
             total_real = 4096 if world == 8 else 512 * world
@@ -598,6 +600,15 @@ def main():
                                                      'stats': vd}
             except Exception as exc:  # noqa: BLE001
                 var['dt_leap=%g,%s' % (dtl, srt)] = {'error': str(exc)[:200]}
+        # unequal masses (the reference's force takes arbitrary m): the general path -- exact 128-bit mass scan
+        try:
+            mg = m * (1. + 0.3 * (2. * numpy.random.RandomState(7).uniform(size=n) - 1.))
+            vms, vd = run_single(x, v, mg, omega2, a.dt_leap, 'gpu', 3, 2, a.nleap)
+            var['unequal masses,dt_leap=%g' % a.dt_leap] = {'value': float(n) * a.nleap * 3 / (vms * 1e-3),
+                                                            'ms_per_substep': vms / (a.nleap * 3), 'stats': vd}
+            del mg
+        except Exception as exc:  # noqa: BLE001
+            var['unequal masses'] = {'error': str(exc)[:200]}
         out['variants'] = var
 
     # ---- end to end through the public generator API, host buffers --------------------------

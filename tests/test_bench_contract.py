@@ -65,6 +65,6 @@ def test_our_arm_line_carries_every_contract_key_live():
     if c['kind'] == 'reference':  # equal masses: bit-identical to the compiled reference on the same system
         for k in ('after_1_substeps', 'after_4_substeps'):
             assert p[k]['x_bit_identical'] and p[k]['v_bit_identical'], p
-    assert set(d['variants']) == {'dt_leap=1e-05,gpu', 'dt_leap=0.005,gpu', 'dt_leap=0.001,gpu-radix'}
+    assert set(d['variants']) == {'dt_leap=1e-05,gpu', 'dt_leap=0.005,gpu', 'dt_leap=0.001,gpu-radix', 'unequal masses,dt_leap=0.001'}
     for vv in d['variants'].values():
         assert vv.get('value', 0) > 0, vv

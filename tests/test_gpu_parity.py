@@ -492,6 +492,29 @@ def test_adversarial_distributions_bit_exact(kind, cap):
     gen.close()
 
 
+@pytest.mark.parametrize('by_id', ['', '1'])
+@pytest.mark.parametrize('kind', ['duplicates', 'signed_zero', 'tiny_scale'])
+def test_radix_path_orders_exact_ties_by_particle_index(kind, by_id, monkeypatch):
+    """sort='gpu-radix' from the second sub-step on sorts keys taken in STORAGE order; the stable sort would leave
+    exactly coincident keys in slot order, so the sorted values of every tie run are re-ordered by particle index
+    (fix_ties_kernel: runs of 20 by insertion, runs of hundreds by heap sort).  Unequal masses make any wrong tie
+    order visible in x, v.  WENDY_B200_RADIX_BYID=1: the earlier scheme (keys generated in id order), same answer."""
+    import wendy_b200
+    if by_id:
+        monkeypatch.setenv('WENDY_B200_RADIX_BYID', by_id)
+    rs = numpy.random.RandomState(98)
+    n = 4000
+    x, v = _nasty(kind, n, rs)
+    m = rs.uniform(0.5, 1.5, size=n) / n
+    gen = wendy_b200.nbody(x, v, m, 0.03, approx=True, nleap=3, omega=0.3, sort='gpu-radix')
+    xo, vo = x, v
+    for _ in range(3):
+        xg, vg = next(gen)
+        xo, vo, _, _ = wo.numpy_onestep(xo, vo, m, numpy.sum(m), 0.01, 3, 0.09, exact_scan=True)
+        assert numpy.array_equal(xg, xo) and numpy.array_equal(vg, vo), kind
+    gen.close()
+
+
 def test_ext_force_on_an_ensemble_matches_separate_runs():
     """Config-5 shape in miniature: several realisations, torch-vectorised external force."""
     import torch

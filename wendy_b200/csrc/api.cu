@@ -48,6 +48,8 @@ void launch_gather_by_id(cudaStream_t st, const double *a_by_id, const int *id, 
 void launch_validate(cudaStream_t st, const double *x, const double *v, const double *m, long long n, double *out3);
 void launch_make_keys_packed(cudaStream_t st, const double *packed, int prec, double h, long long n, uint64_t *keys,
                              uint32_t *vals);
+void launch_fix_ties(cudaStream_t st, const uint64_t *keys, uint32_t *vals, const int *id_by_slot, long long n,
+                     unsigned seg_div);
 void launch_make_keys_by_id(cudaStream_t st, const double *x, const double *v, const int *id, const unsigned *cnt,
                             int cap, int nb, long long n, double h, uint32_t *inv_scratch, uint64_t *keys,
                             uint32_t *vals);
@@ -81,6 +83,7 @@ struct wendy_cuda_handle {
   int orec = 3;                          // doubles per migrant record: (x, v, id) or, general masses, (x, v, id, m)
   unsigned long long pm_lo = 0, pm_hi = 0;  // general masses, sharded: exact 128-bit mass owned by the lower ranks
   bool mpre_ready = false;               // magg / mpre already hold the bucket masses of the CURRENT state
+  double fail_score = 0.;                // recent bucket overflows (decays with every clean call): sparser buckets at 3
   int shard_retry_k = -1, shard_retry_n = 0;  // shard: sub-step of the last rollback, consecutive rollbacks to it
   // WENDY_B200_SHARD_TRACE=1: CUDA events around the three launches of every sharded sub-step (peer exchange)
   std::vector<cudaEvent_t> tr_ev;
@@ -276,8 +279,8 @@ static void fill_back_off(H *h) {
 static void fill_escalate(H *h) {
   const int cap = h->want_cap ? h->want_cap : h->cap;
   if (cap == 256) return;
-  const long long nb_max = (long long)(h->slots / (size_t)cap);
-  const long long need = (long long)((double)h->N * 1.02) + 1;
+  const long long nb_max = (long long)(h->slots / (size_t)cap) / h->nseg;  // buckets one segment can have
+  const long long need = h->bounds ? (long long)((double)h->N * 1.02) + 1 : h->n_cap / h->nseg;  // (as rebucket sizes it)
   int f_min = nb_max > 0 ? (int)((need + nb_max - 1) / nb_max) + 1 : cap;
   f_min = std::max(f_min, cap / 16);
   const int cur = (cap == h->cap) ? h->fill : cap * 3 / 4;
@@ -423,8 +426,12 @@ static void launch_bucket_substep(H *h, double h_pre, double dt_kick, double dt_
 // through the sorted permutation; the output is a compact sorted layout.
 static int launch_radix_substep(H *h, double h_pre, double dt_kick, double dt_drift, const double *aext,
                                 int *rank_out) {
-  if (h->dense || h->bounds) {
-    // dense upload: slots ARE particle ids, so the stable sort already breaks ties by index
+  // keys in storage order, value = storage slot.  A dense upload stores particle i in slot i, so the stable sort
+  // already breaks ties by index; a bucket layout does not -- its (rare) ties are put right after the sort.
+  // WENDY_B200_RADIX_BYID=1 restores the earlier scheme (keys generated in particle-id order) for A/B runs.
+  static const bool by_id = getenv("WENDY_B200_RADIX_BYID") != nullptr;
+  const bool fix = !(h->dense || h->bounds) && !by_id;
+  if (h->dense || h->bounds || fix) {
     if (make_keys(h, h_pre, VAL_SLOT)) return WENDY_E_CUDA;
   } else {
     // keys generated in particle-id order (segment-major, ids are contiguous per segment)
@@ -436,6 +443,10 @@ static int launch_radix_substep(H *h, double h_pre, double dt_kick, double dt_dr
   unsigned seg_div = h->dense ? (unsigned)h->seg_len : (unsigned)((long long)h->nbps * h->cap);
   int res = radix_sort_pairs(h->st, h->rs, (size_t)h->N, seg_bits(h), seg_div);
   h->n_launch += 5 * (8 + (seg_bits(h) + 7) / 8);
+  if (fix) {
+    launch_fix_ties(h->st, h->rs.key[res], h->rs.val[res], h->id[h->cur], h->N, seg_bits(h) ? seg_div : 0u);
+    h->n_launch++;
+  }
   TileParams p;
   fill_tile_params(h, p);
   p.perm = h->rs.val[res];
@@ -579,6 +590,10 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
   h->adaptive = adaptive && h->mode != WENDY_SORT_RADIX;
   h->small_ok = h->adaptive && !dev_inputs_shard(ids) && (N / n_segments) <= small_max_particles();
   h->nbps = (int)(((n_cap / n_segments) + fill - 1) / fill);
+  // mid-size systems (the whole state is a few tens of MB): half as many slots again, so that a system whose
+  // density keeps changing faster than the layout's head-room (violent relaxation) can be given sparser buckets
+  // (fill_escalate) instead of a rebuild every other sub-step
+  if (adaptive && N >= (1ll << 16) && N < (1ll << 20)) h->nbps += h->nbps / 2;
   long long nb = (long long)h->nbps * n_segments;
   if (nb * cap >= (1ll << 32)) { delete h; return set_err(WENDY_E_ARG, "too many storage slots for u32 indices"); }
   h->nb = (int)nb; h->nb_alloc = (int)nb; h->slots = (size_t)nb * cap;
@@ -653,6 +668,7 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
     h->cap = tile_coarse_cap();
     h->fill = default_fill(h, h->cap);
     h->nbps = (int)(((n_cap / n_segments) + (h->cap * 3 / 4) - 1) / (h->cap * 3 / 4));
+    if (N < (1ll << 23)) h->nbps *= 2;  // (mid-size: room for sparser buckets, see above; 53 -> 107 B/particle)
     h->nb = h->nbps * n_segments;
     h->nb_alloc = h->nb;
     h->slots = (size_t)h->nb * h->cap;
@@ -1377,6 +1393,11 @@ static int finish_substeps(H *h) {
     if (kf < 0) return set_err(WENDY_E_CUDA, "internal: unknown failing launch");
     h->n_fail++;
     fill_back_off(h);
+    h->fail_score += 1.;
+    if (h->adaptive && h->fail_score >= 3.) {  // overflows keep coming: buy head-room with sparser buckets, if the storage allows
+      fill_escalate(h);
+      h->fail_score = 0.;
+    }
     if (h->nseg == 1 && advect_allowed()) h->advect_on = true;  // bucket edges could not keep up with the flow: let them move with it
     h->n_sub -= (nleap - kf);
     h->cur = h->p_cur[kf - h->p_k0];
@@ -1406,6 +1427,7 @@ static int finish_substeps(H *h) {
     if (rc) return rc;
   }
   if (last_fail < 0 && h->radix_left == 0 && h->n_fail == h->fail_mark) h->radix_streak = 0;  // a clean call
+  if (h->n_fail == h->fail_mark) h->fail_score *= 0.97;
   h->fail_mark = h->n_fail;
   // adaptive layout: when most particles leave the 32-bucket window of the warp kernel every
   // sub-step (large N*dt), 2048-slot buckets with CTA-aggregated emission are faster

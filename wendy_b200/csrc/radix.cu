@@ -191,8 +191,11 @@ radix_scatter_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restric
 // (the high exponent bytes of clustered positions, unused segment-id bits).
 // Traffic: 8 B/pair once (histograms) + 24 B/pair per pass, against 32 B/pair per pass + a table scan before.
 constexpr int OT = 256;            // threads per tile
-constexpr int OI = 16;             // pairs per thread
-constexpr int OTILE = OT * OI;     // 4096 pairs per tile
+constexpr int OI_BIG = 16;         // pairs per thread: 4096 pairs per tile (large inputs: bandwidth-bound passes)
+constexpr int OI_SMALL = 4;        // ... 1024 pairs per tile for inputs that live in L2 (a pass is then bound by the
+                                   // serial work of one thread and by launch latency: four times the tiles, a
+                                   // quarter of the work each; N=1e6: 20 -> 6 us per pass)
+constexpr size_t SWEEP_SMALL_N = (size_t)1 << 22;
 constexpr int OWARPS = OT / 32;
 constexpr int MAXPASS = 12;        // 8 key bytes + up to 4 segment-id bytes
 constexpr unsigned DESC_AGG = 1u << 30, DESC_INC = 2u << 30, DESC_VAL = (1u << 30) - 1u;
@@ -236,7 +239,9 @@ radix_prefix_kernel(const unsigned *__restrict__ ghist, unsigned *__restrict__ g
   }
 }
 
+template <int OI>
 struct SweepSmem {
+  static constexpr int OTILE = OT * OI;
   uint64_t k[OTILE];
   uint32_t v[OTILE];
   unsigned wc[OWARPS][256];
@@ -247,12 +252,14 @@ struct SweepSmem {
   unsigned tile;
 };
 
+template <int OI>
 __global__ void __launch_bounds__(OT)
 onesweep_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin, uint64_t *__restrict__ kout,
                 uint32_t *__restrict__ vout, size_t n, const DigitSrc src, const unsigned *__restrict__ gbase,
                 unsigned *desc, unsigned *ticket) {
+  constexpr int OTILE = OT * OI;
   extern __shared__ __align__(16) unsigned char sweep_raw[];
-  SweepSmem &S = *reinterpret_cast<SweepSmem *>(sweep_raw);
+  SweepSmem<OI> &S = *reinterpret_cast<SweepSmem<OI> *>(sweep_raw);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const unsigned lt = (1u << lane) - 1u;
   if (tid == 0) S.tile = atomicAdd(ticket, 1u);
@@ -357,7 +364,14 @@ onesweep_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ v
 // ---- host driver ---------------------------------------------------------------------
 static inline unsigned ntiles_for(size_t n) { return (unsigned)((n + RTILE - 1) / RTILE); }
 
-size_t radix_table_entries(size_t n) { return (size_t)256 * ntiles_for(n); }
+size_t radix_table_entries(size_t n) {
+  // small inputs: look-back descriptors of ALL passes of the onesweep sort at 1024 pairs per tile (one clear per sort)
+  // (scratch allocated for n also serves every smaller sort: the bound is monotone in n)
+  const size_t ns = n < SWEEP_SMALL_N ? n : SWEEP_SMALL_N;
+  const size_t small = (size_t)256 * MAXPASS * ((ns + OT * OI_SMALL - 1) / (OT * OI_SMALL) + 1);
+  const size_t big = (size_t)256 * ntiles_for(n);
+  return small > big ? small : big;
+}
 // (the onesweep path keeps its global histograms, their prefixes, the skip flags and the tile tickets here too)
 constexpr size_t SWEEP_WORDS = (size_t)2 * MAXPASS * 256 + 2 * MAXPASS + 8;
 size_t radix_sums_entries(size_t n) {
@@ -407,21 +421,35 @@ static int onesweep_sort_pairs(cudaStream_t st, RadixScratch &s, size_t n, int s
   if (hb > (size_t)sms * 4) hb = (size_t)sms * 4;
   radix_hist_all_kernel<<<(unsigned)hb, 512, 0, st>>>(s.key[0], s.val[0], n, plan, ghist);
   radix_prefix_kernel<<<1, 256, 0, st>>>(ghist, gbase, skip, plan.npass, (unsigned)n);
-  int h_skip[MAXPASS];
-  cudaMemcpyAsync(h_skip, skip, sizeof(int) * MAXPASS, cudaMemcpyDeviceToHost, st);
-  cudaStreamSynchronize(st);  // (which passes can be skipped decides the buffer the result ends in)
-  const unsigned nt = (unsigned)((n + OTILE - 1) / OTILE);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem));
+    cudaFuncSetAttribute(onesweep_kernel<OI_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem<OI_BIG>));
+    cudaFuncSetAttribute(onesweep_kernel<OI_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem<OI_SMALL>));
     attr_set = true;
   }
   int cur = 0;
+  if (n < SWEEP_SMALL_N) {
+    // Latency-bound regime: no host round trip (single-digit passes are not skipped -- a pass costs microseconds
+    // here -- so the result buffer is known in advance) and one clear of the descriptors of all passes.
+    const unsigned nt = (unsigned)((n + OT * OI_SMALL - 1) / (OT * OI_SMALL));
+    cudaMemsetAsync(s.table, 0, (size_t)nt * 256 * plan.npass * sizeof(uint32_t), st);
+    for (int p = 0; p < plan.npass; p++) {
+      onesweep_kernel<OI_SMALL><<<nt, OT, sizeof(SweepSmem<OI_SMALL>), st>>>(
+          s.key[cur], s.val[cur], s.key[cur ^ 1], s.val[cur ^ 1], n, plan.src[p], gbase + p * 256,
+          s.table + (size_t)p * nt * 256, ticket + p);
+      cur ^= 1;
+    }
+    return cur;
+  }
+  int h_skip[MAXPASS];
+  cudaMemcpyAsync(h_skip, skip, sizeof(int) * MAXPASS, cudaMemcpyDeviceToHost, st);
+  cudaStreamSynchronize(st);  // (which passes can be skipped decides the buffer the result ends in)
+  const unsigned nt = (unsigned)((n + OT * OI_BIG - 1) / (OT * OI_BIG));
   for (int p = 0; p < plan.npass; p++) {
     if (h_skip[p]) continue;
     cudaMemsetAsync(s.table, 0, (size_t)nt * 256 * sizeof(uint32_t), st);
-    onesweep_kernel<<<nt, OT, sizeof(SweepSmem), st>>>(s.key[cur], s.val[cur], s.key[cur ^ 1], s.val[cur ^ 1], n,
-                                                       plan.src[p], gbase + p * 256, s.table, ticket + p);
+    onesweep_kernel<OI_BIG><<<nt, OT, sizeof(SweepSmem<OI_BIG>), st>>>(
+        s.key[cur], s.val[cur], s.key[cur ^ 1], s.val[cur ^ 1], n, plan.src[p], gbase + p * 256, s.table, ticket + p);
     cur ^= 1;
   }
   return cur;

@@ -1351,6 +1351,62 @@ void launch_make_keys_by_id(cudaStream_t st, const double *x, const double *v, c
   make_keys_by_id_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, v, h, inv_scratch, n, keys, vals);
 }
 
+// ---- ties after a sort that started from STORAGE order -----------------------------------------------------------
+// The stable radix sort orders exactly coincident keys by their input position -- the storage slot, not the particle
+// index the reference's order demands (ties broken by index).  Coincidences are rare (about one pair per sort at
+// N=1e8), so instead of generating the keys in particle-id order (a scatter and a gather of the whole state per
+// sort: 6.5 ms at N=1e8) the sorted output is fixed up: the thread that finds the start of a run of equal keys (same
+// segment) orders the run's values by particle id.  Runs of up to 32 by insertion, longer ones by heap sort.
+__device__ __forceinline__ int tie_id(const int *__restrict__ id_by_slot, uint32_t slot) { return id_by_slot[slot]; }
+
+__global__ void __launch_bounds__(256)
+fix_ties_kernel(const uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, const int *__restrict__ id_by_slot,
+                long long n, unsigned seg_div) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r + 1 < n;
+       r += (long long)gridDim.x * blockDim.x) {
+    const uint64_t k = keys[r];
+    if (keys[r + 1] != k) continue;
+    const unsigned sg = vals[r] / seg_div;
+    if (vals[r + 1] / seg_div != sg) continue;
+    if (r > 0 && keys[r - 1] == k && vals[r - 1] / seg_div == sg) continue;  // not the start of the run
+    long long e = r + 2;
+    while (e < n && keys[e] == k && vals[e] / seg_div == sg) e++;
+    const long long len = e - r;
+    uint32_t *a = vals + r;
+    if (len <= 32) {
+      for (long long i = 1; i < len; i++) {
+        const uint32_t s = a[i];
+        const int si = tie_id(id_by_slot, s);
+        long long j = i;
+        while (j > 0 && tie_id(id_by_slot, a[j - 1]) > si) { a[j] = a[j - 1]; j--; }
+        a[j] = s;
+      }
+    } else {
+      auto sift = [&](long long root, long long end) {
+        while (2 * root + 1 < end) {
+          long long c = 2 * root + 1;
+          if (c + 1 < end && tie_id(id_by_slot, a[c]) < tie_id(id_by_slot, a[c + 1])) c++;
+          if (tie_id(id_by_slot, a[root]) >= tie_id(id_by_slot, a[c])) return;
+          const uint32_t t = a[root]; a[root] = a[c]; a[c] = t;
+          root = c;
+        }
+      };
+      for (long long st = len / 2 - 1; st >= 0; st--) sift(st, len);
+      for (long long end = len - 1; end > 0; end--) {
+        const uint32_t t = a[0]; a[0] = a[end]; a[end] = t;
+        sift(0, end);
+      }
+    }
+  }
+}
+void launch_fix_ties(cudaStream_t st, const uint64_t *keys, uint32_t *vals, const int *id_by_slot, long long n,
+                     unsigned seg_div) {
+  if (n < 2) return;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  fix_ties_kernel<<<(unsigned)blocks, 256, 0, st>>>(keys, vals, id_by_slot, n, seg_div ? seg_div : 0xffffffffu);
+}
+
 // keys of packed (x, v, id) migrant records (segment 0)
 __global__ void make_keys_packed_kernel(const double *__restrict__ packed, int prec, double h, long long n,
                                         uint64_t *__restrict__ keys, uint32_t *__restrict__ vals) {
