@@ -515,6 +515,31 @@ def test_radix_path_orders_exact_ties_by_particle_index(kind, by_id, monkeypatch
     gen.close()
 
 
+@pytest.mark.parametrize('jitter', [0., 0.2])
+def test_launch_sequence_numbers_are_renewed_before_the_lookback_epoch_wraps(jitter, monkeypatch):
+    """The look-back words keep 30 bits of the launch sequence number (round-1 advisor finding: a handle that had
+    issued 2^30 launches would hang).  The handle starts again from 1 with clean look-back words long before that;
+    here after every 40 launches, on the bucket path (count-prefix look-back; unequal masses: mass-prefix look-back
+    too) and with an external force."""
+    import torch
+    import wendy_b200
+    monkeypatch.setenv('WENDY_B200_EPOCH_RENEW_AT', '40')
+    x, v, m = wo.sech2_ic(30000, seed=21, mass_jitter=jitter)
+    st = wendy_b200.ApproxState(x, v, m, omega2=0.09)
+    xo, vo = x, v
+    for _ in range(12):
+        st.step(0.01, 3)
+        xo, vo, _, _ = wo.numpy_onestep(xo, vo, m, numpy.sum(m), 0.01, 3, 0.09, exact_scan=bool(jitter))
+    F = lambda xx, t: -0.3 * xx  # noqa: E731
+    t0 = 0.
+    for _ in range(6):
+        t0 = st.step_ext(0.01, 3, F, t0)
+        xo, vo, _, _ = wo.numpy_onestep(xo, vo, m, numpy.sum(m), 0.01, 3, 0.09, F, 0., exact_scan=bool(jitter))
+    xg, vg = st.read()
+    st.close()
+    assert numpy.array_equal(xg, xo) and numpy.array_equal(vg, vo)
+
+
 def test_ext_force_on_an_ensemble_matches_separate_runs():
     """Config-5 shape in miniature: several realisations, torch-vectorised external force."""
     import torch

@@ -227,6 +227,25 @@ static int reset_flags(H *h) {
   return 0;
 }
 
+// The launch sequence number doubles as the epoch of the look-back protocols, which keep 30 bits of it
+// (lookback.cuh: status = epoch << 2 | state; count prefix: epoch << 34).  Long before it wraps -- after about 2^30
+// launches, hours of stepping a small system -- start again from 1 with clean look-back words.  Called at the
+// start of a stepping call, when nothing of this handle is in flight.
+static int renew_epochs(H *h) {
+  static const unsigned limit = [] {  // (WENDY_B200_EPOCH_RENEW_AT: tests exercise the renewal after a few launches)
+    const char *e = getenv("WENDY_B200_EPOCH_RENEW_AT");
+    return e ? (unsigned)strtoul(e, nullptr, 10) : 0x3f000000u;
+  }();
+  if (h->seq < limit) return 0;
+  CK(cudaStreamSynchronize(h->st));
+  CK(cudaMemsetAsync(h->status, 0, (size_t)h->nb_alloc * sizeof(unsigned), h->st));
+  CK(cudaMemsetAsync(h->cp_desc, 0, (size_t)(count_prefix_tiles(h->nb_alloc) + 1) * sizeof(unsigned long long), h->st));
+  if (h->mp_status)
+    CK(cudaMemsetAsync(h->mp_status, 0, ((size_t)mass_prefix_tiles(h->nb_alloc) + 1) * sizeof(unsigned), h->st));
+  h->seq = 1;
+  return reset_flags(h);
+}
+
 // keys (x + hkey*v) of the current state -> radix scratch buffer 0, compact segment-major order
 static int make_keys(H *h, double hkey, int val_mode) {
   if (alloc_radix(h, (size_t)h->N)) return WENDY_E_CUDA;
@@ -876,6 +895,7 @@ static int create_shard_impl(wendy_cuda_handle **out, long long n_local, long lo
 int wendy_cuda_shard_substep(wendy_cuda_handle *h, double h_pre, double dt_kick, double dt_drift, double h_next,
                              long long pc_offset, unsigned *out_counts) {
   if (!h || !out_counts || !h->bounds) return set_err(WENDY_E_ARG, "not a shard handle");
+  if (renew_epochs(h)) return WENDY_E_CUDA;
   h->pc_offset = pc_offset;
   for (int attempt = 0; attempt < 3; attempt++) {
     if (h->dense || !h->has_split || h->bucket_h != h_pre || h->rebuild_pending) {
@@ -1201,7 +1221,10 @@ int wendy_cuda_shard_step_begin(wendy_cuda_handle *h, double dt, int nleap, int 
   if (!h || !h->peer_on) return set_err(WENDY_E_ARG, "peer exchange is not set up");
   if (nleap < 1 || nleap > PEER_NHIST || k0 < 0 || k0 >= nleap) return set_err(WENDY_E_ARG, "bad nleap");
   if (h->pending) return set_err(WENDY_E_ARG, "a call is already in flight");
-  if (k0 == 0) { h->p_seq.clear(); h->p_seq_inj.clear(); h->p_cur.clear(); h->p_ccur.clear(); }
+  if (k0 == 0) {
+    if (renew_epochs(h)) return WENDY_E_CUDA;
+    h->p_seq.clear(); h->p_seq_inj.clear(); h->p_cur.clear(); h->p_ccur.clear();
+  }
   h->p_seq.resize(k0); h->p_seq_inj.resize(k0); h->p_cur.resize(k0); h->p_ccur.resize(k0);
   h->p_dt = dt; h->p_nleap = nleap; h->p_k0 = k0;
   static const bool trace_on = getenv("WENDY_B200_SHARD_TRACE") != nullptr;
@@ -1346,6 +1369,7 @@ static int enqueue_substeps(H *h, double dt, int nleap, int k0) {
     return 0;
   }
   if (k0 == 0) {
+    if (renew_epochs(h)) return WENDY_E_CUDA;
     h->n_outside += outside_total(h);
     memset(h->h_flags + 8, 0, 128 * sizeof(unsigned));
     CK(cudaMemsetAsync(h->flags + 8, 0, 128 * sizeof(unsigned), h->st));  // per-call window statistic
@@ -1488,6 +1512,7 @@ int wendy_cuda_force_positions(wendy_cuda_handle *h, double dt_leap, int first_s
   if (!h || !x_dev || !n_slots) return set_err(WENDY_E_ARG, "null argument");
   // The leading half drift is materialised in the stored positions below; a caller that comes back for the same
   // sub-step after WENDY_RETRY (the layout overflowed and was rebuilt) must not have it applied a second time.
+  if (first_substep && !h->ext_async && renew_epochs(h)) return WENDY_E_CUDA;
   double need_h = (first_substep && !h->ext_half_done) ? dt_leap / 2. : 0.;
   if (h->mode == WENDY_SORT_RADIX) {
     // radix mode keeps no splitters; give it a (compact or bucketed) layout to expose
@@ -1564,6 +1589,7 @@ int wendy_cuda_substep(wendy_cuda_handle *h, double dt_kick, double dt_drift, do
 int wendy_cuda_ext_begin(wendy_cuda_handle *h) {
   if (!h) return set_err(WENDY_E_ARG, "null handle");
   if (h->pending) return set_err(WENDY_E_ARG, "a call is already in flight");
+  if (renew_epochs(h)) return WENDY_E_CUDA;
   h->p_seq.clear(); h->p_cur.clear(); h->p_ccur.clear();
   h->ext_async = true;
   return 0;

@@ -15,6 +15,18 @@ typedef unsigned __int128 u128;
 
 #define WENDY_FULL_MASK 0xffffffffu
 
+// Per-function attributes (dynamic shared-memory size, carve-out) are per DEVICE: a process that steps systems on
+// two GPUs must set them on both.  flags: a static array owned by the call site; true the first time the current
+// device comes by.  (One cudaGetDevice per launch; a race between threads only sets the attribute twice.)
+static inline bool first_use_on_device(bool (&flags)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (flags[dev]) return false;
+  flags[dev] = true;
+  return true;
+}
+
 // ---------------------------------------------------------------------------------
 // key transform: ascending u64 order == ascending fp64 order; -0.0 is canonicalised to
 // +0.0 first because the reference comparator (wendy/wendy.c:21) treats them as equal.

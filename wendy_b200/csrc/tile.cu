@@ -1017,11 +1017,10 @@ static void launch_tile_cap(cudaStream_t st, int load, int emit, int physics, co
   size_t sm = sizeof(TileSmem<CAP, THREADS>);
 #define WENDY_LAUNCH(L, EM, PH)                                                                   \
   do {                                                                                              \
-    static bool attr_set = false;                                                                   \
-    if (!attr_set) {                                                                                \
+    static bool attr_set[64];                                                                       \
+    if (first_use_on_device(attr_set)) {                                                            \
       cudaFuncSetAttribute(tile_kernel<CAP, THREADS, L, EM, PH, EQM>,                               \
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                   \
-      attr_set = true;                                                                              \
     }                                                                                               \
     tile_kernel<CAP, THREADS, L, EM, PH, EQM><<<p.nb, THREADS, sm, st>>>(p);                        \
   } while (0)
@@ -1031,8 +1030,9 @@ static void launch_tile_cap(cudaStream_t st, int load, int emit, int physics, co
     constexpr int PQ = PE ? EQM : 1;
     constexpr int PT = PE ? CAP / TK_PERSIST_E : THREADS;  // threads of the persistent instances
     static int grid = 0;
+    static bool grid_set[64];
     const size_t smp = sizeof(TileSmem<CAP, PT, PE>);
-    if (!grid) {
+    if (first_use_on_device(grid_set)) {
       int dev = 0, sms = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1049,23 +1049,21 @@ static void launch_tile_cap(cudaStream_t st, int load, int emit, int physics, co
     int g_use = min(grid, p.nb);
     if (const char *ge = getenv("WENDY_B200_PERSIST_GRID")) g_use = max(1, min(g_use, atoi(ge)));
     if (!p.aext && !p.rank_out && !p.bounds) {
-      static bool set2 = false;
-      if (!set2) {
+      static bool set2[64];
+      if (first_use_on_device(set2)) {
         cudaFuncSetAttribute(tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 2 * PE>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp);
         cudaFuncSetAttribute(tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 2 * PE>,
                              cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-        set2 = true;
       }
         tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 2 * PE><<<g_use, PT, smp, st>>>(p);
     } else if (p.peer && !p.aext && !p.rank_out) {
-      static bool set3 = false;
-      if (!set3) {
+      static bool set3[64];
+      if (first_use_on_device(set3)) {
         cudaFuncSetAttribute(tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 3 * PE>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp);
         cudaFuncSetAttribute(tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 3 * PE>,
                              cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-        set3 = true;
       }
       tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 3 * PE><<<g_use, PT, smp, st>>>(p);
     } else {

@@ -687,11 +687,10 @@ void launch_count_prefix(cudaStream_t st, const unsigned *cnt, int nb, unsigned 
 
 template <int WCAP, int WARPS, int EQM, int SHARD>
 static void launch_wstep_t(cudaStream_t st, const TileParams &p) {
-  static bool attr_set = false;
+  static bool attr_set[64];
   const size_t sm = sizeof(WarpSlab<WCAP, EQM>) * WARPS;
-  if (!attr_set) {
+  if (first_use_on_device(attr_set)) {
     cudaFuncSetAttribute(wstep_kernel<WCAP, WARPS, EQM, SHARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    attr_set = true;
   }
   const int grid = (p.nb + WARPS - 1) / WARPS;
   wstep_kernel<WCAP, WARPS, EQM, SHARD><<<grid, WARPS * 32, sm, st>>>(p);
