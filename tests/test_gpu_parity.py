@@ -540,6 +540,23 @@ def test_launch_sequence_numbers_are_renewed_before_the_lookback_epoch_wraps(jit
     assert numpy.array_equal(xg, xo) and numpy.array_equal(vg, vo)
 
 
+@pytest.mark.parametrize('ext', [False, True])
+def test_device_output_yields_the_same_numbers_without_leaving_the_gpu(ext):
+    """nbody(..., output='device') yields CUDA tensors (de-sorted on the device): same values as the host arrays."""
+    import torch
+    import wendy_b200
+    x, v, m = wo.sech2_ic(50000, seed=31)
+    F = (lambda xx, t: -0.3 * xx + 0.01 * t) if ext else None  # noqa: E731
+    gh = wendy_b200.nbody(x, v, m, 0.03, approx=True, nleap=3, omega=0.7, ext_force=F)
+    gd = wendy_b200.nbody(x, v, m, 0.03, approx=True, nleap=3, omega=0.7, ext_force=F, output='device')
+    for _ in range(3):
+        xh, vh = next(gh)
+        xd, vd = next(gd)
+        assert xd.is_cuda and xd.dtype == torch.float64
+        assert numpy.array_equal(xd.cpu().numpy(), xh) and numpy.array_equal(vd.cpu().numpy(), vh)
+    gh.close(); gd.close()
+
+
 def test_ext_force_on_an_ensemble_matches_separate_runs():
     """Config-5 shape in miniature: several realisations, torch-vectorised external force."""
     import torch
@@ -635,7 +652,8 @@ def test_ext_force_with_overflow_on_the_first_substep_applies_the_half_drift_onc
 
 def test_optimistic_fill_backs_off_after_an_overflow():
     """Large equal-mass systems start on 2048-slot buckets filled to 13/16; the first overflow (here: a
-    collapsing cold slab) moves the handle back to 3/4 for good.  Results equal the radix path bit for bit."""
+    collapsing cold slab) moves the handle back to 3/4 for good, and overflows that keep coming buy sparser
+    buckets still (half the fill, as far as the storage goes).  Results equal the radix path bit for bit."""
     import wendy_b200
     n = 1 << 20
     x, v, m = wo.slab_ic(n, seed=8)
@@ -651,7 +669,7 @@ def test_optimistic_fill_backs_off_after_an_overflow():
     s1 = a.stats()
     xa, va = a.read(); xb, vb = b.read()
     a.close(); b.close()
-    assert s1['failed_substeps'] > 0 and s1['buckets'] == -(-n // 1536), s1
+    assert s1['failed_substeps'] > 0 and s1['buckets'] >= -(-n // 1536), s1
     assert numpy.array_equal(xa, xb) and numpy.array_equal(va, vb)
 
 

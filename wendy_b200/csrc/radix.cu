@@ -191,7 +191,10 @@ radix_scatter_kernel(const uint64_t *__restrict__ kin, const uint32_t *__restric
 // (the high exponent bytes of clustered positions, unused segment-id bits).
 // Traffic: 8 B/pair once (histograms) + 24 B/pair per pass, against 32 B/pair per pass + a table scan before.
 constexpr int OT = 256;            // threads per tile
-constexpr int OI_BIG = 16;         // pairs per thread: 4096 pairs per tile (large inputs: bandwidth-bound passes)
+#ifndef WENDY_OI_BIG
+#define WENDY_OI_BIG 16
+#endif
+constexpr int OI_BIG = WENDY_OI_BIG;  // pairs per thread: 4096 pairs per tile (large inputs: bandwidth-bound passes)
 constexpr int OI_SMALL = 4;        // ... 1024 pairs per tile for inputs that live in L2 (a pass is then bound by the
                                    // serial work of one thread and by launch latency: four times the tiles, a
                                    // quarter of the work each; N=1e6: 20 -> 6 us per pass)

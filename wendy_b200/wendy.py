@@ -246,7 +246,8 @@ class ApproxState(object):
 def nbody(x, v, m, dt, t0=0., twopiG=1., omega=None, ext_force=None,
           approx=False, nleap=None, sort='gpu',
           maxcoll=100000, warn_maxcoll=False,
-          full_output=False, n_segments=1, _cap=0, _fill=0, _general_masses=False, _exact_scan=False):
+          full_output=False, n_segments=1, output='host', _cap=0, _fill=0, _general_masses=False,
+          _exact_scan=False):
     """
     NAME:
        nbody
@@ -264,6 +265,9 @@ def nbody(x, v, m, dt, t0=0., twopiG=1., omega=None, ext_force=None,
        sort= reference names accepted; 'gpu' (default), 'gpu-radix'
        full_output= (False) also yield the wall time of the step (reference: time_elapsed)
        n_segments= (1) treat the input as that many independent, equal-size realisations
+       output= ('host') 'device': yield CUDA torch tensors (de-sorted on the GPU, no copy to the host) for
+               consumers that stay on the device; as with the host arrays the SAME two tensors are yielded
+               every time
     OUTPUT:
        Generator: each iteration returns (x,v) [+ time_elapsed]; as in the reference the SAME
        two ndarrays are yielded every time, updated in place
@@ -276,13 +280,13 @@ def nbody(x, v, m, dt, t0=0., twopiG=1., omega=None, ext_force=None,
     for item in _nbody_approx(x, v, m, dt, nleap, t0=t0, sort=sort, omega=omega,
                               ext_force=ext_force, twopiG=twopiG, full_output=full_output,
                               n_segments=n_segments, _cap=_cap, _fill=_fill,
-                              _general_masses=_general_masses, _exact_scan=_exact_scan):
+                              _general_masses=_general_masses, _exact_scan=_exact_scan, output=output):
         yield item
 
 
 def _nbody_approx(x, v, m, dt, nleap, t0=0., omega=None, ext_force=None, sort='gpu',
                   twopiG=1., full_output=False, n_segments=1, _cap=0, _fill=0, _general_masses=False,
-                  _exact_scan=False):
+                  _exact_scan=False, output='host'):
     """Setup follows reference wendy/wendy.py:363-387,422; loop follows :424-437."""
     omega2 = -1. if omega is None else omega ** 2.
     # The inputs are only read (the reference copies them, wendy/wendy.py:369-370; here the "copy" is the
@@ -324,6 +328,32 @@ def _nbody_approx(x, v, m, dt, nleap, t0=0., omega=None, ext_force=None, sort='g
                     out['pinned'].append(a)
             else:
                 lib.wendy_host_prefault(a.ctypes.data, a.nbytes)  # page faults now, not inside the first read-out
+
+    if output == 'device':
+        # The consumer stays on the GPU: de-sort into two CUDA tensors (wendy/wendy.c:413-415), nothing crosses
+        # PCIe.  The library works on torch's current stream, so the tensors are ready for torch ops in stream order.
+        import torch
+        state = None
+        try:
+            cs = torch.cuda.current_stream().cuda_stream
+            state = ApproxState(xin, vin, ms, omega2=omega2, n_segments=n_segments, sort=sort, cap=_cap, fill=_fill,
+                                general_masses=_general_masses, exact_scan=_exact_scan, stream=cs)
+            xt = torch.empty(n, dtype=torch.float64, device='cuda')
+            vt = torch.empty(n, dtype=torch.float64, device='cuda')
+            dt_leap = dt / nleap
+            while True:
+                if ext_force is None:
+                    state.step(dt_leap, nleap)
+                else:
+                    t0 = state.step_ext(dt_leap, nleap, ext_force, t0)
+                _lib.check(lib.wendy_cuda_read_dev(state._h, ctypes.c_void_p(xt.data_ptr()), ctypes.c_void_p(vt.data_ptr())))
+                yield (xt, vt, state.time_elapsed) if full_output else (xt, vt)
+        finally:
+            if state is not None:
+                state.close()
+        return
+    if output != 'host':
+        raise ValueError("output must be 'host' or 'device'")
 
     import threading
     helpers = [threading.Thread(target=alloc_outputs)]
