@@ -44,7 +44,7 @@ def exchange(request, monkeypatch):
     monkeypatch.setenv('WENDY_B200_SHARD_PEER', '1' if request.param == 'peer' else '0')
     if request.param == 'peer':
         monkeypatch.setenv('WENDY_B200_PERSIST_GRID', '12')
-        monkeypatch.setenv('WENDY_B200_PEER_TIMEOUT_MS', '5000')  # a protocol bug fails the test instead of hanging it
+        monkeypatch.setenv('WENDY_B200_PEER_TIMEOUT_MS', '15000')  # a protocol bug fails the test instead of hanging it
     return request.param
 
 
@@ -160,7 +160,7 @@ def test_sharded_peer_exchange_rolls_back_after_an_overflow(monkeypatch):
     rank within one exchange, all roll back to the input of that sub-step, rebuild, and finish the call."""
     monkeypatch.setenv('WENDY_B200_SHARD_PEER', '1')
     monkeypatch.setenv('WENDY_B200_PERSIST_GRID', '12')
-    monkeypatch.setenv('WENDY_B200_PEER_TIMEOUT_MS', '5000')
+    monkeypatch.setenv('WENDY_B200_PEER_TIMEOUT_MS', '15000')
     n = 60000
     x, v, m = wo.slab_ic(n, seed=5)
     # three calls = 15 sub-steps: the slab's density rises by 1.3 (a stale layout overflows, a fresh one holds) and at

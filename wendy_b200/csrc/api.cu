@@ -1173,6 +1173,7 @@ int wendy_cuda_shard_comm_open(wendy_cuda_handle *h, const unsigned char *ipc_ha
   }
   CK(cudaMemcpyAsync(h->peer_dev, &pc, sizeof(pc), cudaMemcpyHostToDevice, h->st));
   CK(cudaStreamSynchronize(h->st));
+  tile_prepare_persistent();  // (no first-use set-up call behind a kernel that is waiting for a peer)
   h->peer_on = true;
   // the exchange lives in the persistent CTA kernel: coarse buckets from the start
   if (h->cap != tile_coarse_cap()) {

@@ -150,6 +150,7 @@ void launch_mass_prefix(cudaStream_t st, const double *m, const unsigned *cnt, i
 int mass_prefix_tiles(int nb);
 bool wstep_cap_supported(int cap);
 bool tile_cap_supported(int cap);
+void tile_prepare_persistent();  // attributes + grid of the persistent instances, ahead of their first launch
 int tile_coarse_cap();  // slots per bucket of the CTA kernel (2048)
 
 struct ScatterParams {

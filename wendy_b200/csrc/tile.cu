@@ -47,7 +47,9 @@ namespace wendy {
 #define TK_LAZY_GROUP 1     // only members of SHARED sub-buckets are written to the grouped key / id arrays
 #endif
 #ifndef TK_EMIT
-#define TK_EMIT 0           // slot requests of one warp: 0 MATCH.ANY per destination, 1 eight ballots, 2 direct shared atomics
+#define TK_EMIT 3           // 3: warp-direct emission (one GLOBAL atomic per warp and destination, no CTA-level counts, no
+                            // barrier in the emission); 0: slots counted per CTA and destination in shared memory, one global
+                            // atomic per CTA and destination between two barriers (the kernel up to round 2; A/B runs)
 #endif
 #ifndef TK_PERSIST_E
 #define TK_PERSIST_E 4      // particles per thread of the PERSISTENT instances (threads = CAP / TK_PERSIST_E).  2: 1024
@@ -467,6 +469,16 @@ tile_kernel(const TileParams p) {
     }
   }
 #endif
+#if TK_EMIT == 3
+  if (PERSIST && EMIT == EMIT_SPLITTER) {
+    // (warp-direct emission has no barrier after this one: what the NEXT iteration touches before its first barrier
+    // is prepared here -- its counter set, last read during the previous bucket's ranking, is cleared, and its
+    // splitter window / key range (cp.async issued after the first barrier) have landed)
+    uint4 *c4 = reinterpret_cast<uint4 *>(S.u.srt.cnt + (cur ^ 1) * SM::PADN);
+    for (int i = tid; i < SM::PADN / 4; i += THREADS) c4[i] = make_uint4(0u, 0u, 0u, 0u);
+    cp_async_wait_all();
+  }
+#endif
   __syncthreads();
   // ---- 6. exact rank under the (x, id) order; masses are fetched meanwhile ---------------
   double m[E];
@@ -868,30 +880,53 @@ tile_kernel(const TileParams p) {
   }
   // slot allocation, aggregated per warp and destination; the E requests are issued back to back and
   // their results consumed afterwards, so the atomics' latencies overlap
-#if TK_EMIT == 2
-  // MATCH.ANY costs ~33 SM cycles per warp instruction on sm_100a when the lanes' values differ (measured,
-  // scripts/ubench/atoms.cu: an LDS or a conflict-free shared atomic costs ~3): lanes that leave the bucket ask
-  // the shared counter of their destination directly (few lanes share a destination once particles spread over
-  // many buckets); only the lanes that stay home -- one address for all of them -- are aggregated by a ballot.
+#if TK_EMIT == 3
+  // Warp-direct emission: every warp allocates its slots with ONE global atomicAdd per destination it feeds, and
+  // stores.  No counts per CTA, hence no barrier pair around per-destination global atomics whose L2 round trip the
+  // whole CTA waits for (10 % of the stall samples at dt_leap = 1e-3, 20 % at 5e-3): a warp waits for its own
+  // atomics only, the other warps run on.  More global atomics (one per warp and destination instead of one per CTA
+  // and destination) and shorter store runs are the price.
+  {
+    unsigned amask[E];
 #pragma unroll
-  for (int k = 0; k < E; k++) {
-    const int d = dest[k];
-    const bool ok = tid + k * THREADS < n;
-    const unsigned home = __ballot_sync(WENDY_FULL_MASK, ok && d == b);
-    unsigned pos = 0;
-    if (home) {
-      if (lane == __ffs(home) - 1) pos = atomicAdd(&S.dcnt[rel], (unsigned)__popc(home));
-      pos = __shfl_sync(WENDY_FULL_MASK, pos, __ffs(home) - 1) + __popc(home & lt);
-    }
-    if (ok && d >= 0 && d != b) {
-      if (d >= wlo && d < wlo + wn) {
-        pos = atomicAdd(&S.dcnt[d - wlo], 1u);
-      } else {
-        pos = atomicAdd(&p.cnt_out[d], 1u);
-        outside += 1;
+    for (int k = 0; k < E; k++) {
+      const int d = dest[k];
+      const bool ok = tid + k * THREADS < n;
+      unsigned mask;
+      const unsigned valid = __ballot_sync(WENDY_FULL_MASK, ok);
+      if (__all_sync(WENDY_FULL_MASK, d == b || !ok)) mask = ok ? valid : 0u;
+      else mask = __match_any_sync(WENDY_FULL_MASK, d);
+      amask[k] = mask;
+      lpos[k] = 0;
+      if (ok && d >= 0 && lane == __ffs(mask) - 1) {
+        lpos[k] = atomicAdd(&p.cnt_out[d], (unsigned)__popc(mask));
+        if (!(d >= wlo && d < wlo + wn)) outside += __popc(mask);
       }
     }
-    lpos[k] = pos;
+    {
+      const unsigned wsum = __reduce_add_sync(WENDY_FULL_MASK, outside);
+      if (lane == 0 && wsum) atomicAdd(p.outside + (b & 63), (unsigned long long)wsum);
+    }
+    bool overflow = false;
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+      const int leader = __ffs(amask[k]) - 1;
+      const unsigned basel = __shfl_sync(WENDY_FULL_MASK, lpos[k], leader < 0 ? 0 : leader);
+      const unsigned pos = basel + __popc(amask[k] & lt);
+      const int d = dest[k];
+      if (d >= 0) {
+        if (pos < (unsigned)CAP) {
+          size_t o = (size_t)d * CAP + pos;
+          p.xout[o] = x2[k];
+          p.vout[o] = v2[k];
+          if (!EQM) p.mout[o] = m[k];
+          p.idout[o] = id[k];
+        } else {
+          overflow = true;
+        }
+      }
+    }
+    if (overflow || sh_overflow) atomicMin(p.fail_seq, p.seq);
   }
 #else
   unsigned amask[E];
@@ -904,23 +939,7 @@ tile_kernel(const TileParams p) {
     if (__all_sync(WENDY_FULL_MASK, d == b || !ok)) {
       mask = ok ? valid : 0u;  // whole warp stays home (common at small dt)
     } else {
-#if TK_EMIT == 1
-      // lanes with the same destination, by eight ballots on the window-relative bucket number instead of
-      // MATCH.ANY (~33 SM cycles per warp instruction when the values differ; eight VOTEs cost ~5); the rare
-      // lanes that leave the window (or hold no particle) form groups of one
-      const bool inw = ok && d >= wlo && d < wlo + wn;
-      const unsigned r8 = (unsigned)(d - wlo);
-      mask = __ballot_sync(WENDY_FULL_MASK, inw);
-#pragma unroll
-      for (int bit = 0; bit < 8; bit++) {
-        const bool one = (r8 >> bit) & 1u;
-        const unsigned bb = __ballot_sync(WENDY_FULL_MASK, one);
-        mask &= one ? bb : ~bb;
-      }
-      if (!inw) mask = (ok && d >= 0) ? (1u << lane) : 0u;
-#else
       mask = __match_any_sync(WENDY_FULL_MASK, d);
-#endif
     }
     amask[k] = mask;
     lpos[k] = 0;
@@ -939,7 +958,6 @@ tile_kernel(const TileParams p) {
     const unsigned basel = __shfl_sync(WENDY_FULL_MASK, lpos[k], leader < 0 ? 0 : leader);
     lpos[k] = basel + __popc(amask[k] & lt);
   }
-#endif
   __syncthreads();
   for (int i = tid; i < wn; i += THREADS)
     if (S.dcnt[i]) S.dbase[i] = atomicAdd(&p.cnt_out[wlo + i], S.dcnt[i]);
@@ -976,6 +994,7 @@ tile_kernel(const TileParams p) {
     }
   }
   if (overflow || sh_overflow) atomicMin(p.fail_seq, p.seq);
+#endif  // TK_EMIT == 3
   // no barrier needed here: everything the next iteration touches before its first barrier was prepared
   // before the last barrier of the emission
   if (!PERSIST) break;
@@ -1012,6 +1031,36 @@ static bool persist_allowed() {
   return v != 0;
 }
 
+// Shared-memory size / carve-out of the three persistent instances and the grid (CTAs that fit the device), once per
+// device.  Done for all three at once and also callable ahead of the first launch (tile_prepare_persistent): when
+// several ranks of a sharded system live in ONE process their kernels wait for each other, and a first-use attribute
+// call of one rank behind a spinning kernel of another must not happen.
+template <int CAP, int PT, int PQ, int PE>
+static int persist_setup() {
+  static int grid[64];
+  static bool grid_set[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (first_use_on_device(grid_set)) {
+    const size_t smp = sizeof(TileSmem<CAP, PT, PE>);
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    auto setup = [&](auto kern) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp);
+      cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    };
+    setup(tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, PE>);
+    setup(tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 2 * PE>);
+    setup(tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 3 * PE>);
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &per_sm, tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, PE>, PT, smp);
+    grid[dev] = max(1, per_sm) * sms;
+  }
+  return grid[dev];
+}
+
 template <int CAP, int THREADS, int EQM>
 static void launch_tile_cap(cudaStream_t st, int load, int emit, int physics, const TileParams &p) {
   size_t sm = sizeof(TileSmem<CAP, THREADS>);
@@ -1029,42 +1078,14 @@ static void launch_tile_cap(cudaStream_t st, int load, int emit, int physics, co
     constexpr int PE = (EQM && CAP >= 1024) ? 1 : 0;  // (keeps the other instantiations out of the binary)
     constexpr int PQ = PE ? EQM : 1;
     constexpr int PT = PE ? CAP / TK_PERSIST_E : THREADS;  // threads of the persistent instances
-    static int grid = 0;
-    static bool grid_set[64];
     const size_t smp = sizeof(TileSmem<CAP, PT, PE>);
-    if (first_use_on_device(grid_set)) {
-      int dev = 0, sms = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      cudaFuncSetAttribute(tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, PE>,
-                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp);
-      cudaFuncSetAttribute(tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, PE>,
-                           cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-      int per_sm = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          &per_sm, tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, PE>, PT, smp);
-      grid = max(1, per_sm) * sms;
-    }
+    const int grid = persist_setup<CAP, PT, PQ, PE>();
     // WENDY_B200_PERSIST_GRID=<n> shrinks the grid (tests: many buckets per CTA even for small systems)
     int g_use = min(grid, p.nb);
     if (const char *ge = getenv("WENDY_B200_PERSIST_GRID")) g_use = max(1, min(g_use, atoi(ge)));
     if (!p.aext && !p.rank_out && !p.bounds) {
-      static bool set2[64];
-      if (first_use_on_device(set2)) {
-        cudaFuncSetAttribute(tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 2 * PE>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp);
-        cudaFuncSetAttribute(tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 2 * PE>,
-                             cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-      }
         tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 2 * PE><<<g_use, PT, smp, st>>>(p);
     } else if (p.peer && !p.aext && !p.rank_out) {
-      static bool set3[64];
-      if (first_use_on_device(set3)) {
-        cudaFuncSetAttribute(tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 3 * PE>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp);
-        cudaFuncSetAttribute(tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 3 * PE>,
-                             cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-      }
       tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, 3 * PE><<<g_use, PT, smp, st>>>(p);
     } else {
       tile_kernel<CAP, PT, LOAD_BUCKET, EMIT_SPLITTER, 1, PQ, PE><<<g_use, PT, smp, st>>>(p);
@@ -1073,6 +1094,11 @@ static void launch_tile_cap(cudaStream_t st, int load, int emit, int physics, co
   else if (load == LOAD_GATHER && emit == EMIT_RANK && physics) WENDY_LAUNCH(LOAD_GATHER, EMIT_RANK, 1);
   else if (load == LOAD_GATHER && emit == EMIT_NONE && !physics) WENDY_LAUNCH(LOAD_GATHER, EMIT_NONE, 0);
 #undef WENDY_LAUNCH
+}
+
+void tile_prepare_persistent() {
+  constexpr int CAP = TK_COARSE_CAP;
+  persist_setup<CAP, CAP / TK_PERSIST_E, 1, 1>();
 }
 
 bool tile_cap_supported(int cap) { return cap == TK_COARSE_CAP || cap == 256; }
