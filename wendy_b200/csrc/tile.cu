@@ -421,7 +421,8 @@ tile_kernel(const TileParams p) {
     unsigned inc = warp_inclusive_scan_u32(run, lane);
     if (lane == 31) S.uw[wid] = inc;
     __syncthreads();
-    // every warp scans the (<= 32) warp totals itself: cheaper than a second block-wide barrier
+    // every warp scans the (<= 32) warp totals itself: cheaper than a second block-wide barrier.  (Passing the totals
+    // through tagged shared-memory words that the warps poll, instead of this barrier, is 3 % slower.)
     const unsigned t = lane < NW ? S.uw[lane] : 0u;
     const unsigned ti = warp_inclusive_scan_u32(t, lane);
     unsigned ex = inc - run + __shfl_sync(WENDY_FULL_MASK, ti - t, wid);
@@ -779,6 +780,9 @@ tile_kernel(const TileParams p) {
   int dest[E];
   unsigned lpos[E];
   unsigned outside = 0;
+#if TK_EMIT == 3
+  unsigned amask[E];
+#endif
   const int rel = b - wlo;
   const double home_lo = S.ssplit[sbase + rel], home_hi = S.ssplit[sbase + rel + 1];
   bool sh_overflow = false;
@@ -887,20 +891,25 @@ tile_kernel(const TileParams p) {
   // atomics only, the other warps run on.  More global atomics (one per warp and destination instead of one per CTA
   // and destination) and shorter store runs are the price.
   {
-    unsigned amask[E];
+    {
+      // (issuing each request inside the destination loop, to overlap its round trip with the searches that
+      // follow, is 4 % SLOWER: the atomics order that loop's shared-memory loads -- profiles/r02/ab_variants_5.json;
+      // one atomic per LEAVER instead of MATCH.ANY aggregation is 44 % slower at dt_leap = 1e-3: the L2 serves about
+      // 3.6e10 atomics with return per second -- profiles/r02/ab_variants_6.json)
 #pragma unroll
-    for (int k = 0; k < E; k++) {
-      const int d = dest[k];
-      const bool ok = tid + k * THREADS < n;
-      unsigned mask;
-      const unsigned valid = __ballot_sync(WENDY_FULL_MASK, ok);
-      if (__all_sync(WENDY_FULL_MASK, d == b || !ok)) mask = ok ? valid : 0u;
-      else mask = __match_any_sync(WENDY_FULL_MASK, d);
-      amask[k] = mask;
-      lpos[k] = 0;
-      if (ok && d >= 0 && lane == __ffs(mask) - 1) {
-        lpos[k] = atomicAdd(&p.cnt_out[d], (unsigned)__popc(mask));
-        if (!(d >= wlo && d < wlo + wn)) outside += __popc(mask);
+      for (int k = 0; k < E; k++) {
+        const int d = dest[k];
+        const bool ok = tid + k * THREADS < n;
+        unsigned mask;
+        const unsigned valid = __ballot_sync(WENDY_FULL_MASK, ok);
+        if (__all_sync(WENDY_FULL_MASK, d == b || !ok)) mask = ok ? valid : 0u;
+        else mask = __match_any_sync(WENDY_FULL_MASK, d);
+        amask[k] = mask;
+        lpos[k] = 0;
+        if (ok && d >= 0 && lane == __ffs(mask) - 1) {
+          lpos[k] = atomicAdd(&p.cnt_out[d], (unsigned)__popc(mask));
+          if ((unsigned)(d - wlo) >= (unsigned)wn) outside += __popc(mask);
+        }
       }
     }
     {
