@@ -278,8 +278,9 @@ static bool advect_allowed() {
 static int default_fill(const H *h, int cap) {
   if (h->user_fill > 0 && cap == h->user_cap) return h->user_fill;
   if (cap == 256) return 128;
-  // (shards keep 3/4: their edge buckets also take the migrants of the neighbouring ranks)
-  return (h->adaptive && !h->fill_backoff && !h->bounds) ? cap * WENDY_COARSE_FILL_16THS / 16 : cap * 3 / 4;
+  // (shards too: migrants land in the buckets their keys fall in, spread over the same +-15 buckets as everybody
+  // else's movers, and an overflow is rolled back like any other -- +5 % per sub-step at 1e8 particles per rank)
+  return (h->adaptive && !h->fill_backoff) ? cap * WENDY_COARSE_FILL_16THS / 16 : cap * 3 / 4;
 }
 
 // called when a bucket of the current layout overflowed or came close: give up the optimistic fill
@@ -887,7 +888,7 @@ static int create_shard_impl(wendy_cuda_handle **out, long long n_local, long lo
   if (e == cudaSuccess) e = cudaMallocHost(&h->h_out_cnt, (size_t)nranks * sizeof(unsigned));
   if (e == cudaSuccess) e = dev_alloc(&h->cid, (size_t)n_capacity * sizeof(int));
   if (e != cudaSuccess) { std::string msg = cudaGetErrorString(e); wendy_cuda_destroy(h); *out = nullptr; return set_err(WENDY_E_CUDA, msg); }
-  if (h->cap != 256) h->fill = default_fill(h, h->cap);  // shards keep the conservative fill (bounds is known now)
+  if (h->cap != 256) h->fill = default_fill(h, h->cap);
   return 0;
 }
 

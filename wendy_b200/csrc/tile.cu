@@ -151,7 +151,6 @@ tile_kernel(const TileParams p) {
     return;
   }
 
-  long long pc_off = p.pc_offset;  // particles owned by lower ranks (sharded system)
   if (SHARDP) {
     // ... as published by the peers after the previous sub-step (their cnt_flag words, in local memory)
     if (tid == 0) {
@@ -162,7 +161,6 @@ tile_kernel(const TileParams p) {
       if (blockIdx.x == 0) p.peer->peer_stat[2] += (unsigned)((peer_now_ns() - tw0) >> 10);  // ~microseconds waited
     }
     __syncthreads();
-    pc_off = S.pre_cnt;
     if (S.bucket) {  // a peer failed (or is gone): this sub-step must not run anywhere; roll back to the PREVIOUS one
       if (tid == 0) atomicMin(p.fail_seq, p.seq - 1u);
       if (blockIdx.x == 0 && tid == 0) peer_signal_step(p.peer, p.pepoch, true);
@@ -616,7 +614,11 @@ tile_kernel(const TileParams p) {
   }
   // ---- 11. force, kick, drift (or diagnostics) ----------------------------------------------------
   const double tot = p.tot[seg];
-  const double PcD = (double)(Pc + pc_off);  // pc_off: particles of the lower ranks (sharded)
+  // particles owned by the lower ranks (sharded system).  The peer instance reads it from shared memory where the
+  // kernel's first wait left it (S.pre_cnt: not written again by a persistent instance) instead of carrying two more
+  // registers through the bucket loop -- the instance is at the register limit and spilled
+  const long long pc_off = SHARDP ? S.pre_cnt : p.pc_offset;
+  const double PcD = (double)(Pc + pc_off);
   // Equal masses: cumulative mass below sorted position K0 + r.  With the serial table it is the reference's own
   // running sum (wendy/wendy.c:359-360) bit for bit; a bucket nearly always lies inside one linear piece.
   SerialRun SR;
@@ -790,8 +792,8 @@ tile_kernel(const TileParams p) {
   const double inv_w = (wdt > 0.0 && wdt < CUDART_INF) ? rcp_approx(wdt) : 0.0;
   const float inv_wf = (float)fmin(inv_w, 3.0e38);
   const double win_lo = S.ssplit[sbase], win_hi = S.ssplit[sbase + wn];
-  const double sh_lo = ((!PLAIN || SHARDP) && p.bounds) ? __ldg(p.bounds + p.my_rank) : 0.0;
-  const double sh_hi = ((!PLAIN || SHARDP) && p.bounds) ? __ldg(p.bounds + p.my_rank + 1) : 0.0;
+  const double sh_lo = (!PLAIN && p.bounds) ? __ldg(p.bounds + p.my_rank) : 0.0;
+  const double sh_hi = (!PLAIN && p.bounds) ? __ldg(p.bounds + p.my_rank + 1) : 0.0;
 #pragma unroll
   for (int k = 0; k < E; k++) {
     int d = -1;
@@ -859,6 +861,7 @@ tile_kernel(const TileParams p) {
 #pragma unroll
     for (int k = 0; k < E; k++) edge |= (dest[k] == 0 || dest[k] >= p.nb_last);
     if (__any_sync(WENDY_FULL_MASK, edge)) {
+      const double sh_lo = __ldg(p.bounds + p.my_rank), sh_hi = __ldg(p.bounds + p.my_rank + 1);
 #pragma unroll
       for (int k = 0; k < E; k++) {
         const int d = dest[k];
