@@ -70,12 +70,34 @@ def test_sharded_system_three_thread_ranks_matches_oracle():
 
 
 def test_choose_bounds_and_route():
-    b = multi.choose_bounds(numpy.linspace(0., 1., 1000), 4)
+    b, share = multi.choose_bounds(numpy.linspace(0., 1., 1000), 4)
+    assert numpy.allclose(share, 0.25, atol=2e-3)
     assert b[0] == -numpy.inf and b[-1] == numpy.inf and numpy.all(numpy.diff(b) >= 0)
     keys = numpy.array([-5., 0.1, 0.26, 0.6, 0.99, 7.])
     assert list(multi.route(keys, b)) == [0, 0, 1, 2, 3, 3]
     # a key equal to an edge belongs to the upper range (same convention as the bucket splitters)
     assert multi.route(numpy.array([b[2]]), b)[0] == 2
+
+
+def test_cost_balanced_bounds_give_dense_ranges_fewer_particles():
+    """Large N dt: a particle of the dense centre costs more (it crosses more buckets per sub-step), so the central
+    ranks get fewer particles; without a displacement estimate the split is by count."""
+    rs = numpy.random.RandomState(3)
+    keys = numpy.arctanh(2. * rs.uniform(size=200000) - 1.) * 2.
+    b0, s0 = multi.choose_bounds(keys, 8)
+    assert numpy.allclose(s0, 0.125, atol=1e-3)
+    b1, s1 = multi.choose_bounds(keys, 8, n_total=800000000, disp=1e-3)
+    assert numpy.all(numpy.diff(b1) >= 0) and abs(s1.sum() - 1.) < 1e-12
+    assert s1[3] < 0.115 and s1[4] < 0.115 and s1[0] > 0.135 and s1[7] > 0.135  # centre lighter, wings heavier
+    # equal COST: weight 1 + 0.008 D_b per particle, D_b = density * disp / 1664
+    ks = numpy.sort(keys)
+    dens = 800000000 * 0.25 / numpy.cosh(0.5 * ks) ** 2
+    w = 1. + 0.008 * dens * 1e-3 / 1664.
+    cost = numpy.array([w[(ks >= b1[r]) & (ks < b1[r + 1])].sum() for r in range(8)])
+    assert cost.max() / cost.min() < 1.05
+    # small systems / small dt: nothing to balance
+    b2, s2 = multi.choose_bounds(keys, 8, n_total=800000000, disp=1e-7)
+    assert numpy.allclose(s2, 0.125, atol=2e-3)
 
 
 def test_shard_ensemble_covers_everything_once():

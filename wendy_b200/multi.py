@@ -301,15 +301,40 @@ class CudaShardEngine(object):
 
 
 # ---- the sharded system ------------------------------------------------------------------------------
-def choose_bounds(all_samples, nranks):
-    """Range edges from the pooled key sample: equal-count quantiles, -inf / +inf at the ends."""
+def choose_bounds(all_samples, nranks, n_total=0, disp=0., per_bucket=1664., slope=0.008):
+    """Range edges from the pooled key sample, -inf / +inf at the ends; returns (bounds, share) with share[r] the
+    fraction of the particles rank r is expected to own.
+
+    Default: equal-count quantiles.  With ``n_total`` and ``disp`` (= sigma_v * dt_leap, the typical displacement per
+    sub-step) the quantiles are weighted by the estimated COST of a particle instead: the step kernel's time per
+    particle grows with the displacement measured in buckets, D_b = (number density) * disp / (particles per bucket)
+    -- about 1 + 0.008 D_b, fitted to the single-GPU dt series and to the per-rank kernel times of the 8-GPU run
+     -- so the dense central ranges of a large system get fewer particles and every rank's
+    sub-step takes about the same time."""
     s = numpy.sort(numpy.asarray(all_samples, dtype=numpy.float64).ravel())
     s = s[numpy.isfinite(s)]
     b = numpy.empty(nranks + 1)
     b[0], b[-1] = -numpy.inf, numpy.inf
-    for k in range(1, nranks):
-        b[k] = s[min(len(s) - 1, (k * len(s)) // nranks)] if len(s) else 0.
-    return numpy.maximum.accumulate(b)
+    share = numpy.full(nranks, 1. / nranks)
+    if len(s) == 0:
+        b[1:-1] = 0.
+        return b, share
+    w = numpy.ones(len(s))
+    if n_total > 0 and disp > 0. and len(s) > 256:
+        k = 32
+        idx = numpy.arange(len(s))
+        lo, hi = numpy.maximum(idx - k, 0), numpy.minimum(idx + k, len(s) - 1)
+        span = numpy.maximum(s[hi] - s[lo], 1e-300)
+        dens = float(n_total) / len(s) * (hi - lo) / span  # particles per unit length around every sample point
+        w = 1. + slope * numpy.minimum(dens * disp / per_bucket, 1024.)
+    cw = numpy.cumsum(w)
+    cut = numpy.searchsorted(cw, cw[-1] * numpy.arange(1, nranks) / nranks)
+    cut = numpy.minimum(cut, len(s) - 1)
+    b[1:-1] = s[cut]
+    b = numpy.maximum.accumulate(b)
+    edges = numpy.concatenate(([0], cut, [len(s)])).astype(float)
+    share = numpy.maximum(numpy.diff(edges), 0.) / len(s)
+    return b, share
 
 
 def route(keys, bounds):
@@ -330,8 +355,9 @@ class ShardedSystem(object):
     number of ranks bit for bit.  The exchange is host-orchestrated in this mode (records carry the mass)."""
 
     def __init__(self, x, v, ids, m0, totmass, comm, omega=None, engine_factory=None,
-                 capacity_factor=1.3, outbox_fraction=0.05, n_sample=65536, m=None):
+                 capacity_factor=1.3, outbox_fraction=0.05, n_sample=65536, m=None, balance='cost'):
         self.comm = comm
+        self.balance = balance  # 'cost' (default; only acts on systems of >= 2^24 particles) or 'count'
         self.m0, self.totmass = float(m0), float(totmass)
         self._m = None if m is None else numpy.ascontiguousarray(m, dtype=numpy.float64)
         self.general = m is not None
@@ -364,8 +390,16 @@ class ShardedSystem(object):
         take = numpy.linspace(0, max(len(key) - 1, 0), num=min(self.n_sample, len(key))).astype(int)
         sample = numpy.full(self.n_sample, numpy.nan)
         sample[:len(take)] = key[take] if len(key) else []  # a strided subset is an unbiased key sample
-        self.bounds = choose_bounds(comm.allgather_vec(sample), comm.size)
-        cap = int(self.capacity_factor * n_tot / comm.size) + 1024
+        disp = 0.
+        if self.balance == 'cost' and n_tot >= (1 << 24):
+            # typical displacement per sub-step: global velocity dispersion * dt_leap
+            mom = comm.allgather_vec([float(len(v)), float(numpy.sum(v)), float(numpy.sum(v * v))]).sum(axis=0)
+            disp = float(numpy.sqrt(max(mom[2] / mom[0] - (mom[1] / mom[0]) ** 2., 0.))) * abs(dt_leap)
+        self.bounds, share = choose_bounds(comm.allgather_vec(sample), comm.size, n_tot, disp)
+        # (head-room over the share of the particles this rank is expected to own, not over the mean)
+        cap = int(self.capacity_factor * n_tot * max(float(share[comm.rank]), 0.5 / comm.size)) + 1024
+        # (the same on every rank: a sender addresses the receiver's inbox with its own outbox capacity)
+        self._ocap = max(1024, int(self.outbox_fraction * self.capacity_factor * n_tot / comm.size))
         if str(comm.device).startswith('cuda') and self.engine_factory is CudaShardEngine and not self.general:
             return self._partition_device(dt_leap, cap)
         owner = route(key, self.bounds)
@@ -383,7 +417,7 @@ class ShardedSystem(object):
             extra = {'m': mine[:, 3].copy(), 'sum_abs_m': self.sum_abs_m}
         self.engine = self.engine_factory(mine[:, 0].copy(), mine[:, 1].copy(), mine[:, 2].astype(numpy.int32),
                                           self.m0, self.totmass, self.omega2, comm.size, comm.rank,
-                                          self.bounds, cap, max(1024, int(self.outbox_fraction * cap)), **extra)
+                                          self.bounds, cap, self._ocap, **extra)
         self._raw = None
         self._m = None
         self.dt_leap = dt_leap
@@ -412,7 +446,7 @@ class ShardedSystem(object):
         del send, packed
         self.engine = CudaShardEngine(mine[:, 0], mine[:, 1], mine[:, 2].to(torch.int32),
                                       self.m0, self.totmass, self.omega2, comm.size, comm.rank,
-                                      self.bounds, cap, max(1024, int(self.outbox_fraction * cap)))
+                                      self.bounds, cap, self._ocap)
         del mine
         self._raw = None
         self.dt_leap = dt_leap
