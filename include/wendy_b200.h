@@ -99,6 +99,7 @@ int wendy_cuda_step(wendy_cuda_handle *h, double dt_leap, int nleap, double *tim
  * wendy_cuda_read_end joins); the same holds for wendy_cuda_read. */
 int wendy_cuda_step_begin(wendy_cuda_handle *h, double dt_leap, int nleap);
 int wendy_cuda_step_end(wendy_cuda_handle *h);
+int wendy_cuda_last_call_seconds(wendy_cuda_handle *h, double *seconds);  /* device time of the last begin/end call */
 int wendy_cuda_read_begin(wendy_cuda_handle *h, double *x_host, double *v_host);
 int wendy_cuda_read_end(wendy_cuda_handle *h);
 

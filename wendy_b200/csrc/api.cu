@@ -156,6 +156,8 @@ struct wendy_cuda_handle {
   std::vector<int> p_cur, p_ccur;
   cudaStream_t st_copy = nullptr;
   cudaEvent_t ev_unsort = nullptr;
+  cudaEvent_t ev_call[2] = {nullptr, nullptr};  // asynchronous call: device time from the first to the last launch
+  double call_host_s = 0.;                      // ... plus the host time of layout rebuilds inside begin / end
   int device = 0;               // CUDA device of the handle (worker threads select it)
   std::thread reader;           // bounce-buffered read-out in flight (wendy_cuda_read_begin / _end)
   int reader_rc = 0;
@@ -523,6 +525,7 @@ void wendy_cuda_destroy(wendy_cuda_handle *h) {
   if (h->h_out_cnt) cudaFreeHost(h->h_out_cnt);
   if (h->st_copy) cudaStreamDestroy(h->st_copy);
   if (h->ev_unsort) cudaEventDestroy(h->ev_unsort);
+  for (int i = 0; i < 2; i++) if (h->ev_call[i]) cudaEventDestroy(h->ev_call[i]);
   if (h->h_flags) cudaFreeHost(h->h_flags);
   if (h->h_eout) cudaFreeHost(h->h_eout);
   delete h;
@@ -1485,8 +1488,14 @@ int wendy_cuda_step_begin(wendy_cuda_handle *h, double dt_leap, int nleap) {
   if (!h) return set_err(WENDY_E_ARG, "null handle");
   if (nleap < 1) return set_err(WENDY_E_ARG, "nleap must be >= 1");
   if (h->pending) return set_err(WENDY_E_ARG, "a call is already in flight");
+  // time of the call as the reference reports it (wendy/wendy.c time_begin / time_end around the integration):
+  // device time between two events around the enqueued sub-steps; a caller that overlaps its read-out and its own
+  // work with the call (as the generator does) must not see those in time_elapsed (round-1 advisor finding)
+  if (!h->ev_call[0]) { CK(cudaEventCreate(&h->ev_call[0])); CK(cudaEventCreate(&h->ev_call[1])); }
+  CK(cudaEventRecord(h->ev_call[0], h->st));
   int rc = enqueue_substeps(h, dt_leap, nleap, 0);
   if (rc) return rc;
+  CK(cudaEventRecord(h->ev_call[1], h->st));
   h->pending = true;
   return 0;
 }
@@ -1496,6 +1505,18 @@ int wendy_cuda_step_end(wendy_cuda_handle *h) {
   if (!h->pending) return 0;
   h->pending = false;
   return finish_substeps(h);
+}
+
+// Seconds the last wendy_cuda_step_begin / _step_end call spent on the device (between its first and last launch as
+// enqueued; sub-steps re-run after an overflow are not included).  Call after wendy_cuda_step_end.
+int wendy_cuda_last_call_seconds(wendy_cuda_handle *h, double *seconds) {
+  if (!h || !seconds) return set_err(WENDY_E_ARG, "null argument");
+  *seconds = 0.;
+  if (!h->ev_call[0]) return 0;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, h->ev_call[0], h->ev_call[1]) != cudaSuccess) { cudaGetLastError(); return 0; }
+  *seconds = 1e-3 * (double)ms;
+  return 0;
 }
 
 int wendy_cuda_step(wendy_cuda_handle *h, double dt_leap, int nleap, double *time_elapsed) {

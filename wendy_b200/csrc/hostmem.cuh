@@ -174,11 +174,17 @@ cudaError_t copy_split(void *dst, const void *src, size_t bytes, cudaMemcpyKind 
 // page-locked is therefore filled through a small ring of page-locked bounce buffers: the copy engine writes
 // piece i+1.. while all host threads copy piece i into the caller's array (the mirror image of
 // upload_host_arrays).  Rings are pooled per process; a handle borrows one for its lifetime.
+#ifndef WENDY_BOUNCE_NB
+#define WENDY_BOUNCE_NB 4
+#endif
+#ifndef WENDY_BOUNCE_MB
+#define WENDY_BOUNCE_MB 16
+#endif
 struct BounceRing {
-  static constexpr int NB = 4;
-  static constexpr size_t BYTES = (size_t)16 << 20;
-  void *buf[NB] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev[NB] = {nullptr, nullptr, nullptr, nullptr};
+  static constexpr int NB = WENDY_BOUNCE_NB;
+  static constexpr size_t BYTES = (size_t)WENDY_BOUNCE_MB << 20;
+  void *buf[NB] = {};
+  cudaEvent_t ev[NB] = {};
   int device = 0;
 };
 namespace {

@@ -141,9 +141,13 @@ class ApproxState(object):
         _lib.check(self._lib.wendy_cuda_step_begin(self._h, dt_leap, nleap))
 
     def step_end(self):
-        import time
         _lib.check(self._lib.wendy_cuda_step_end(self._h))
-        self.time_elapsed = time.perf_counter() - getattr(self, '_t_begin', time.perf_counter())
+        # the reference reports the time of the integration only (wendy/wendy.c: time_begin / time_end around it):
+        # device time between the first and the last launch of the call, not the wall time since step_begin
+        # (which would include the overlapped read-out and whatever the consumer did between two next() calls)
+        t = ctypes.c_double(0.)
+        _lib.check(self._lib.wendy_cuda_last_call_seconds(self._h, ctypes.byref(t)))
+        self.time_elapsed = t.value
 
     def read_begin(self, x_out, v_out):
         _lib.check(self._lib.wendy_cuda_read_begin(self._h, x_out.ctypes.data, v_out.ctypes.data))
