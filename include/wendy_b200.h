@@ -100,6 +100,8 @@ int wendy_cuda_step(wendy_cuda_handle *h, double dt_leap, int nleap, double *tim
 int wendy_cuda_step_begin(wendy_cuda_handle *h, double dt_leap, int nleap);
 int wendy_cuda_step_end(wendy_cuda_handle *h);
 int wendy_cuda_last_call_seconds(wendy_cuda_handle *h, double *seconds);  /* device time of the last begin/end call */
+int wendy_cuda_stage_ahead(wendy_cuda_handle *h);  /* after wendy_cuda_step_begin: de-sort the state that call will leave
+                                   into a spare staging set, so that the next read_begin starts its copy at once */
 int wendy_cuda_read_begin(wendy_cuda_handle *h, double *x_host, double *v_host);
 int wendy_cuda_read_end(wendy_cuda_handle *h);
 

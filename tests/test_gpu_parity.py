@@ -557,6 +557,28 @@ def test_device_output_yields_the_same_numbers_without_leaving_the_gpu(ext):
     gh.close(); gd.close()
 
 
+@pytest.mark.parametrize('kind', ['steady', 'overflowing'])
+def test_desort_ahead_of_the_readout_yields_the_same_outputs(kind, monkeypatch):
+    """WENDY_B200_STAGE_AHEAD=1: the generator queues the de-sort of output k+1 behind the sub-steps of call k+1 (into
+    a second staging set) while output k is still being copied.  Every yielded output must equal the oracle's --
+    also when a sub-step of the call has to be re-run after a bucket overflow (the staged copy is then dropped)."""
+    import wendy_b200
+    monkeypatch.setenv('WENDY_B200_STAGE_AHEAD', '1')
+    if kind == 'steady':
+        x, v, m = wo.sech2_ic(30000, seed=33)
+        kw, om, dtl = {}, 0.7, 0.01
+    else:
+        x, v, m = wo.slab_ic(20000, seed=5)
+        kw, om, dtl = {'_cap': 256, '_fill': 250}, None, 0.05
+    gen = wendy_b200.nbody(x, v, m, dtl * 5, approx=True, nleap=5, omega=om, **kw)
+    xo, vo = x, v
+    for _ in range(6):
+        xg, vg = next(gen)
+        xo, vo, _, _ = wo.numpy_onestep(xo, vo, m, numpy.sum(m), dtl, 5, -1. if om is None else om ** 2.)
+        assert numpy.array_equal(xg, xo) and numpy.array_equal(vg, vo), kind
+    gen.close()
+
+
 def test_ext_force_on_an_ensemble_matches_separate_runs():
     """Config-5 shape in miniature: several realisations, torch-vectorised external force."""
     import torch

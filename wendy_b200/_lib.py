@@ -53,6 +53,8 @@ def load():
     lib.wendy_cuda_step.argtypes = [vp, ctypes.c_double, ctypes.c_int, c_double_p]
     lib.wendy_cuda_step_begin.restype = ctypes.c_int
     lib.wendy_cuda_step_begin.argtypes = [vp, ctypes.c_double, ctypes.c_int]
+    lib.wendy_cuda_stage_ahead.restype = ctypes.c_int
+    lib.wendy_cuda_stage_ahead.argtypes = [vp]
     lib.wendy_cuda_last_call_seconds.restype = ctypes.c_int
     lib.wendy_cuda_last_call_seconds.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     lib.wendy_cuda_step_end.restype = ctypes.c_int
@@ -166,7 +168,7 @@ def load():
 
 #: every symbol include/wendy_b200.h declares (checked by tests/test_abi.py)
 EXPORTED = ['wendy_cuda_create', 'wendy_cuda_create_dev', 'wendy_cuda_step', 'wendy_cuda_step_begin', 'wendy_cuda_step_end', 'wendy_cuda_last_call_seconds',
-            'wendy_cuda_read_begin', 'wendy_cuda_read_end', 'wendy_cuda_force_positions',
+            'wendy_cuda_stage_ahead', 'wendy_cuda_read_begin', 'wendy_cuda_read_end', 'wendy_cuda_force_positions',
             'wendy_cuda_substep', 'wendy_cuda_ext_begin', 'wendy_cuda_substep_async', 'wendy_cuda_ext_end', 'wendy_cuda_read', 'wendy_cuda_read_dev', 'wendy_cuda_energy',
             'wendy_cuda_stats', 'wendy_serial_cum', 'wendy_cuda_create_shard', 'wendy_cuda_create_shard_dev', 'wendy_cuda_create_shard_m', 'wendy_cuda_shard_mass_total', 'wendy_cuda_shard_set_mass_offset', 'wendy_cuda_shard_read_masses', 'wendy_cuda_shard_substep', 'wendy_cuda_shard_outbox',
             'wendy_cuda_shard_inject', 'wendy_cuda_shard_comm_export', 'wendy_cuda_shard_comm_open', 'wendy_cuda_shard_seed_counts', 'wendy_cuda_shard_prepare', 'wendy_cuda_shard_step_begin', 'wendy_cuda_shard_step_end', 'wendy_cuda_shard_rollback', 'wendy_cuda_shard_count', 'wendy_cuda_shard_read', 'wendy_cuda_shard_read_begin', 'wendy_cuda_shard_read_end', 'wendy_cuda_potential', 'wendy_cuda_energy_individual', 'wendy_cuda_set_totmass', 'wendy_cuda_trim', 'wendy_host_prefault', 'wendy_host_set_threads', 'wendy_cuda_pin', 'wendy_cuda_unpin', 'wendy_cuda_debug_layout', 'wendy_cuda_destroy', 'wendy_cuda_last_error',

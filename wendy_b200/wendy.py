@@ -149,6 +149,10 @@ class ApproxState(object):
         _lib.check(self._lib.wendy_cuda_last_call_seconds(self._h, ctypes.byref(t)))
         self.time_elapsed = t.value
 
+    def stage_ahead(self):
+        """After step_begin: de-sort the state that call will leave ahead of its read-out (wendy_cuda_stage_ahead)."""
+        _lib.check(self._lib.wendy_cuda_stage_ahead(self._h))
+
     def read_begin(self, x_out, v_out):
         _lib.check(self._lib.wendy_cuda_read_begin(self._h, x_out.ctypes.data, v_out.ctypes.data))
 
@@ -359,6 +363,9 @@ def _nbody_approx(x, v, m, dt, nleap, t0=0., omega=None, ext_force=None, sort='g
     if output != 'host':
         raise ValueError("output must be 'host' or 'device'")
 
+    # de-sort ahead of the read-out (a second staging set, 16 B per particle) where the read-out is long enough to
+    # matter; WENDY_B200_STAGE_AHEAD=0 / 1 forces it off / on
+    stage = os.environ.get('WENDY_B200_STAGE_AHEAD', '1' if n >= (1 << 20) else '0') != '0'
     import threading
     helpers = [threading.Thread(target=alloc_outputs)]
     for t in helpers:
@@ -371,6 +378,8 @@ def _nbody_approx(x, v, m, dt, nleap, t0=0., omega=None, ext_force=None, sort='g
                                 fill=_fill, general_masses=_general_masses, exact_scan=_exact_scan)
             if ext_force is None:
                 state.step_begin(dt_leap, nleap)
+                if stage:
+                    state.stage_ahead()
         finally:
             for t in helpers:
                 t.join()
@@ -385,6 +394,9 @@ def _nbody_approx(x, v, m, dt, nleap, t0=0., omega=None, ext_force=None, sort='g
                 te = state.time_elapsed
                 state.read_begin(x, v)
                 state.step_begin(dt_leap, nleap)
+                if stage:
+                    # ... and its de-sort, behind its sub-steps: output k+1's copy will start the moment the call ends
+                    state.stage_ahead()
                 state.read_end()
                 n_out += 1
                 if pin_later and n_out == 2 and x.nbytes >= (1 << 20):
