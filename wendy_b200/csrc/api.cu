@@ -540,12 +540,19 @@ static inline bool dev_inputs_shard(const int *ids) { return ids != nullptr; }  
 // (what a numpy caller normally has) are staged: all host threads copy 32 MB chunks into two page-locked
 // bounce buffers while the previous chunk is in flight, which beats the driver's single-threaded staging
 // several times over on many-core hosts.
+// Pageable host arrays -> device through page-locked staging: all host threads fill piece i+1 while the copy engine
+// moves piece i.  `ring`: the pooled bounce ring of the read-out (four 16 MB buffers: nothing to allocate -- obtaining
+// and releasing 64 MB of page-locked memory per upload cost as much as the copies); without one, two private buffers.
 static int upload_host_arrays(cudaStream_t st, const double *const *src, double *const *dst, int narr, size_t n,
-                              std::string &err) {
-  const size_t CH = (size_t)4 << 20;  // doubles per chunk
-  double *stage[2] = {nullptr, nullptr};
-  cudaEvent_t ev[2] = {nullptr, nullptr};
-  bool used[2] = {false, false};
+                              std::string &err, BounceRing *ring = nullptr) {
+  constexpr int MAXB = BounceRing::NB > 2 ? BounceRing::NB : 2;
+  const int nbuf = ring ? BounceRing::NB : 2;
+  const size_t CH = ring ? BounceRing::BYTES / sizeof(double) : ((size_t)4 << 20);  // doubles per chunk
+  double *stage[MAXB] = {};
+  cudaEvent_t ev[MAXB] = {};
+  bool used[MAXB] = {};
+  if (ring)
+    for (int i = 0; i < nbuf; i++) { stage[i] = (double *)ring->buf[i]; ev[i] = ring->ev[i]; }
   int rc = 0, turn = 0;
   auto fail = [&](cudaError_t e, const char *what) { err = std::string(what) + ": " + cudaGetErrorString(e); rc = -1; };
   for (int a = 0; a < narr && !rc; a++) {
@@ -560,7 +567,7 @@ static int upload_host_arrays(cudaStream_t st, const double *const *src, double 
     }
     for (size_t off = 0; off < n && !rc; off += CH) {
       const size_t len = std::min(CH, n - off);
-      const int bsel = turn & 1;
+      const int bsel = turn % nbuf;
       turn++;
       if (!stage[bsel]) {
         cudaError_t e = cudaMallocHost(&stage[bsel], CH * sizeof(double));
@@ -581,10 +588,12 @@ static int upload_host_arrays(cudaStream_t st, const double *const *src, double 
       used[bsel] = true;
     }
   }
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < nbuf; i++) {
     if (used[i]) cudaEventSynchronize(ev[i]);
-    if (ev[i]) cudaEventDestroy(ev[i]);
-    if (stage[i]) cudaFreeHost(stage[i]);
+    if (!ring) {
+      if (ev[i]) cudaEventDestroy(ev[i]);
+      if (stage[i]) cudaFreeHost(stage[i]);
+    }
   }
   return rc;
 }
@@ -629,6 +638,44 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
   CKD(cudaGetDevice(&dev));
   h->device = dev;
   CKD(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev));
+  // Geometry chosen by the library: the persistent CTA kernel (2048-slot buckets, next bucket prefetched by
+  // TMA) is the fastest step for large equal-mass systems at every dt measured (DESIGN.md section 8); small
+  // systems start on 256-slot buckets (warp kernel) and switch when the window statistic says so.  Large systems
+  // of unequal masses start coarse as well: their CTA kernel beats their warp kernel (128-bit scan across one warp,
+  // 11 KB slab) at every dt measured (N=2e7, dt_leap=1e-4: 0.68 against 1.08 ms, profiles/r02/kernels_tour_N1e8.md).
+  if (h->adaptive && N >= (1ll << 20)) {
+    // ... and stay there, so the storage is sized for that geometry: n/(3/4) slots per particle array instead
+    // of the 2n of the fine layout (less to allocate -- cudaMalloc is a visible part of the set-up time --
+    // and N=1e9 needs 75 GB instead of 106 GB).  Bucket arrays are sized for the conservative fill, which
+    // the handle falls back to after an overflow (fill_back_off).
+    h->coarse_default = true;
+    h->cap = tile_coarse_cap();
+    h->fill = default_fill(h, h->cap);
+    h->nbps = (int)(((n_cap / n_segments) + (h->cap * 3 / 4) - 1) / (h->cap * 3 / 4));
+    if (N < (1ll << 23)) h->nbps *= 2;  // (mid-size: room for sparser buckets, see above; 53 -> 107 B/particle)
+    h->nb = h->nbps * n_segments;
+    h->nb_alloc = h->nb;
+    h->slots = (size_t)h->nb * h->cap;
+  }
+  // The bulk of the device memory (both state buffers) is allocated by a helper thread while this one validates
+  // the host arrays: 40-55 ms of cudaMalloc at N=1e8 that used to sit between validation and upload.
+  struct AllocJob {
+    std::thread th;
+    cudaError_t err = cudaSuccess;
+    ~AllocJob() { if (th.joinable()) th.join(); }
+  } alloc_job;
+  if (!dev_inputs && (size_t)N >= ((size_t)1 << 22)) {
+    H *hh = h;
+    AllocJob *job = &alloc_job;
+    alloc_job.th = std::thread([hh, job]() {
+      cudaSetDevice(hh->device);
+      for (int i = 0; i < 2 && job->err == cudaSuccess; i++) {
+        job->err = dev_alloc(&hh->x[i], hh->slots * sizeof(double));
+        if (job->err == cudaSuccess) job->err = dev_alloc(&hh->v[i], hh->slots * sizeof(double));
+        if (job->err == cudaSuccess) job->err = dev_alloc(&hh->id[i], hh->slots * sizeof(int));
+      }
+    });
+  }
   double sum_abs = 0.;
   if (dev_inputs) {
     // device inputs: one validation kernel (finiteness, sum |m|, equal-mass test)
@@ -673,6 +720,7 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
       }
     }
     if (!(probe == 0.)) {
+      if (alloc_job.th.joinable()) alloc_job.th.join();
       wendy_cuda_destroy(h);
       return set_err(WENDY_E_ARG, "x, v, m must be finite (NaN keys are undefined in the reference sort too)");
     }
@@ -680,25 +728,8 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
   }
   h->fxE = choose_fx_exponent(sum_abs);
   trace_mark(h->st, "create: validation pass");
-  // Geometry chosen by the library: the persistent CTA kernel (2048-slot buckets, next bucket prefetched by
-  // TMA) is the fastest step for large equal-mass systems at every dt measured (DESIGN.md section 8); small
-  // systems start on 256-slot buckets (warp kernel) and switch when the window statistic says so.  Large systems
-  // of unequal masses start coarse as well: their CTA kernel beats their warp kernel (128-bit scan across one warp,
-  // 11 KB slab) at every dt measured (N=2e7, dt_leap=1e-4: 0.68 against 1.08 ms, profiles/r02/kernels_tour_N1e8.md).
-  if (h->adaptive && N >= (1ll << 20)) {
-    // ... and stay there, so the storage is sized for that geometry: n/(3/4) slots per particle array instead
-    // of the 2n of the fine layout (less to allocate -- cudaMalloc is a visible part of the set-up time --
-    // and N=1e9 needs 75 GB instead of 106 GB).  Bucket arrays are sized for the conservative fill, which
-    // the handle falls back to after an overflow (fill_back_off).
-    h->coarse_default = true;
-    h->cap = tile_coarse_cap();
-    h->fill = default_fill(h, h->cap);
-    h->nbps = (int)(((n_cap / n_segments) + (h->cap * 3 / 4) - 1) / (h->cap * 3 / 4));
-    if (N < (1ll << 23)) h->nbps *= 2;  // (mid-size: room for sparser buckets, see above; 53 -> 107 B/particle)
-    h->nb = h->nbps * n_segments;
-    h->nb_alloc = h->nb;
-    h->slots = (size_t)h->nb * h->cap;
-  }
+  // (joined here: every error path below releases the handle)
+  if (alloc_job.th.joinable()) alloc_job.th.join();
   if (dev_inputs) {
     h->m0 = m0_dev;
     if (m) CKD(cudaMemcpy(&h->m0, m, sizeof(double), cudaMemcpyDeviceToHost));
@@ -721,11 +752,13 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
     }
     delete T;
   }
+  if (alloc_job.th.joinable()) alloc_job.th.join();
+  CKD(alloc_job.err);
   for (int i = 0; i < 2; i++) {
-    CKD(dev_alloc(&h->x[i], h->slots * sizeof(double)));
-    CKD(dev_alloc(&h->v[i], h->slots * sizeof(double)));
+    if (!h->x[i]) CKD(dev_alloc(&h->x[i], h->slots * sizeof(double)));
+    if (!h->v[i]) CKD(dev_alloc(&h->v[i], h->slots * sizeof(double)));
     if (!h->eqm) CKD(dev_alloc(&h->m[i], h->slots * sizeof(double)));
-    CKD(dev_alloc(&h->id[i], h->slots * sizeof(int)));
+    if (!h->id[i]) CKD(dev_alloc(&h->id[i], h->slots * sizeof(int)));
     CKD(cudaMemsetAsync(h->x[i], 0, h->slots * sizeof(double), h->st));
     CKD(cudaMemsetAsync(h->v[i], 0, h->slots * sizeof(double), h->st));
   }
@@ -781,7 +814,9 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
     const double *src[3] = {x, v, h->eqm ? nullptr : m};
     double *dst[3] = {h->x[0], h->v[0], h->eqm ? nullptr : h->m[0]};
     std::string uerr;
-    if (upload_host_arrays(h->st, src, dst, 3, (size_t)N, uerr)) { wendy_cuda_destroy(h); return set_err(WENDY_E_CUDA, uerr); }
+    // (large systems: through the read-out's bounce ring, which this handle keeps for its read-outs)
+    if ((size_t)N * sizeof(double) >= ((size_t)64 << 20) && bounce_allowed() && !h->ring) h->ring = ring_acquire(h->device);
+    if (upload_host_arrays(h->st, src, dst, 3, (size_t)N, uerr, h->ring)) { wendy_cuda_destroy(h); return set_err(WENDY_E_CUDA, uerr); }
   }
   CKD(cudaMemcpyAsync(h->tot, totmass, (size_t)n_segments * sizeof(double), cudaMemcpyHostToDevice, h->st));
   if (ids) CKD(cudaMemcpyAsync(h->id[0], ids, (size_t)N * sizeof(int), cudaMemcpyDefault, h->st));
