@@ -630,23 +630,6 @@ def main():
                       'note': 'wendy_b200.nbody(): generator construction (H2D of x,v,m, amortised over %d steps) '
                               '+ next() x %d, each with nleap=%d sub-steps and a D2H of x,v' % (steps_e, steps_e, a.nleap)}
 
-    # ---- the same generator for a consumer that stays on the GPU (output='device': no D2H) -- NOT the e2e figure
-    if not a.no_e2e and not sharded and not a.no_variants:
-        try:
-            steps_e = max(2, min(a.steps, 10))
-            t0 = time.perf_counter()
-            g = wendy_b200.nbody(x, v, m, a.dt_leap * a.nleap, approx=True, nleap=a.nleap, omega=a.omega, output='device')
-            for _ in range(steps_e):
-                xt, vt = next(g)
-            chk = float(xt[:8].sum().item())  # a device -> host read of a few results ends the region
-            el = time.perf_counter() - t0
-            g.close()
-            out['e2e_device_output'] = {'value': float(n) * a.nleap * steps_e / el, 'unit': 'particle-steps/s',
-                                        'note': "nbody(..., output='device'): construction from host arrays + %d outputs "
-                                                'de-sorted into CUDA tensors, nothing copied back' % steps_e}
-        except Exception as exc:  # noqa: BLE001
-            out['e2e_device_output'] = {'error': str(exc)[:200]}
-
     # ---- the reference on the SAME system: timing (cpu_baseline) and parity at the headline size ----------
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         r, kind = make_reference(x, v, m, a.omega, a.dt_leap)
