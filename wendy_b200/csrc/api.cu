@@ -76,6 +76,9 @@ struct wendy_cuda_handle {
   int ccur = 0;
   bool small_ok = false;   // systems of <= 1024 particles: resident kernel while the state is dense
   bool adaptive = false;   // cap chosen by the library: 256 (warp kernel) <-> 2048 (CTA kernel)
+  int dw = 256;            // destination window of the persistent CTA kernel, in buckets: doubled (up to tile_window_max())
+  bool dw_fixed = false;   // while more than 0.2 % of the particles leave it per sub-step (WENDY_B200_DW=<n> pins it)
+  long long dw_out_mark = 0, dw_sub_mark = 0;
   int want_cap = 0;        // geometry to switch to at the next layout rebuild (0: keep)
   bool coarse_default = false;  // large equal-mass systems start (and stay) on 2048-slot buckets
   bool fill_backoff = false;    // a library-chosen coarse layout overflowed at the optimistic fill: use 3/4 from now on
@@ -204,12 +207,14 @@ static int seg_bits(const H *h) {
   return h->nseg > 1 ? bits : 0;
 }
 
+static void adapt_window(H *h);
 // Sync and fetch {fail_seq, max count, outside count}.
 static int fetch_flags(H *h) {
   CK(cudaMemcpyAsync(h->h_flags, h->flags, 136 * sizeof(unsigned), cudaMemcpyDeviceToHost, h->st));
   CK(cudaStreamSynchronize(h->st));
   CK(cudaGetLastError());
   if (h->h_flags[1] > h->max_cnt) h->max_cnt = h->h_flags[1];
+  adapt_window(h);
   return 0;
 }
 
@@ -218,6 +223,24 @@ static long long outside_total(const H *h) {
   const unsigned long long *c = (const unsigned long long *)(h->h_flags + 8);
   for (int i = 0; i < 64; i++) t += (long long)c[i];
   return t;
+}
+
+// Destination window of the persistent CTA kernel (tile.cu): particles whose new key falls outside the window of
+// splitters held in shared memory take a galloping search in the global table, which a whole warp executes for a few
+// lanes.  Large N dt (long sub-steps, or one system over many GPUs) sends a noticeable share there; a wider window
+// costs a little at small displacements (more splitters staged per bucket), so it is only widened on evidence.
+// Called wherever the flags have just been fetched; results never depend on the window.
+static void adapt_window(H *h) {
+  if (h->dw_fixed || h->cap == 256) return;
+  const long long out = h->n_outside + outside_total(h), sub = h->n_sub;
+  const long long dsub = sub - h->dw_sub_mark, dout = out - h->dw_out_mark;
+  if (dsub <= 0) {
+    if (dsub < 0) { h->dw_sub_mark = sub; h->dw_out_mark = out; }
+    return;
+  }
+  if (h->dw < tile_window_max() && (double)dout > 0.002 * (double)h->N * (double)dsub) h->dw = std::min(2 * h->dw, tile_window_max());
+  h->dw_sub_mark = sub;
+  h->dw_out_mark = out;
 }
 
 static int reset_flags(H *h) {
@@ -392,7 +415,7 @@ static void fill_tile_params(H *h, TileParams &p) {
   p.cnt_out = h->cnt[(h->ccur + 1) % 3];
   p.cnt_zero = h->cnt[(h->ccur + 2) % 3];
   p.split = h->split; p.split_in = h->split;
-  p.nb = h->nb; p.nbps = h->nbps; p.seg_len = h->seg_len;
+  p.nb = h->nb; p.nbps = h->nbps; p.seg_len = h->seg_len; p.dw = h->dw;
   p.omega2 = h->omega2; p.tot = h->tot; p.fxE = h->fxE;
   p.status = h->status; p.desc = h->desc;
   p.eqm = h->eqm ? 1 : 0; p.m0 = h->m0; p.stab = h->stab;
@@ -623,6 +646,10 @@ static int create_impl(wendy_cuda_handle **out, long long N, long long n_cap, co
   h->N = N; h->n_cap = n_cap; h->nseg = n_segments; h->seg_len = N / n_segments; h->omega2 = omega2;
   h->mode = flags & 0xf; h->cap = cap; h->fill = fill;
   h->adaptive = adaptive && h->mode != WENDY_SORT_RADIX;
+  if (const char *edw = getenv("WENDY_B200_DW")) {  // A/B runs: a fixed destination window
+    h->dw = std::max(8, std::min(tile_window_max(), atoi(edw)));
+    h->dw_fixed = true;
+  }
   h->small_ok = h->adaptive && !dev_inputs_shard(ids) && (N / n_segments) <= small_max_particles();
   h->nbps = (int)(((n_cap / n_segments) + fill - 1) / fill);
   // mid-size systems (the whole state is a few tens of MB): half as many slots again, so that a system whose
@@ -1420,6 +1447,7 @@ static int enqueue_substeps(H *h, double dt, int nleap, int k0) {
       h->want_cap = 256;  // a new time step: start again from the fine layout and re-measure
       h->has_split = false;
     }
+    if (h->last_dt != 0. && dt != h->last_dt && !h->dw_fixed) h->dw = 256;  // ... and from the narrow destination window
     h->last_dt = dt;
   }
   for (int kk = k0; kk < nleap; kk++) {

@@ -140,6 +140,23 @@ __device__ __forceinline__ unsigned warp_inclusive_scan_u32(unsigned v, int lane
   }
   return v;
 }
+// The same scan with the shuffle's own "source lane in range" predicate guarding the addition (no compare and
+// select per step: three instructions per step instead of four)
+__device__ __forceinline__ unsigned warp_inclusive_scan_u32_p(unsigned v) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .u32 t;\n\t"
+        "shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t"
+        "@p add.u32 %0, %0, t;\n\t"
+        "}"
+        : "+r"(v)
+        : "r"(o));
+  }
+  return v;
+}
 
 // global loads that must not hit a stale L1 line (cross-CTA communication)
 // ---- TMA bulk copies (global -> shared) completing on an mbarrier ----------------------------------------
@@ -178,6 +195,12 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ double rcp_approx(double x) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return r;
+}
+
+__device__ __forceinline__ float rcp_approx_f(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
 

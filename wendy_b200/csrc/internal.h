@@ -88,6 +88,7 @@ struct TileParams {
   int knot_g;
   // geometry
   int nb, nbps;             // buckets in total / per segment
+  int dw;                   // persistent instances: destination window in buckets (<= tile_window_max(); 0 = smallest)
   long long seg_len;        // particles per segment
   // physics (reference wendy/wendy.c:375-383 and :324-333)
   double h_pre, dt_kick, dt_drift, h_next, omega2;
@@ -129,6 +130,7 @@ struct TileParams {
 };
 
 void launch_tile(cudaStream_t st, int cap, int load, int emit, int physics, const TileParams &p);
+int tile_window_max();  // widest destination window of the persistent instances (TK_DWP)
 // small.cu: resident kernel, one CTA per small system, all nleap sub-steps of a call in one launch
 void launch_small(cudaStream_t st, double *x, double *v, const double *m, long long seg_len, int nseg,
                   const double *tot_seg, int eqm, double m0, const SerialTab *stab, double omega2, int fxE,

@@ -33,7 +33,36 @@
 namespace wendy {
 
 #ifndef TK_DW
-#define TK_DW 256
+#define TK_DW 256           // destination window (buckets around the home bucket whose splitters sit in shared memory) of the
+#endif                      // one-CTA-per-bucket instances
+#ifndef TK_DWP
+#define TK_DWP 1024         // ... of the persistent instances.  Particles whose new key leaves the window take the far-mover path
+#endif                      // (a galloping search in the global table, executed by the whole warp for a few lanes)
+#ifndef TK_WIN_SINGLE
+#define TK_WIN_SINGLE 1     // persistent instances: ONE window buffer, filled for the CURRENT bucket behind its first barrier
+#endif                      // (0: two buffers, the next bucket's window prefetched -- the kernel up to round 2)
+#ifndef TK_GUESS_REFINE
+#define TK_GUESS_REFINE 2   // a window guess that fails the four-splitter check is refined by one secant step and checked
+#endif                      // again before the linear walk takes over (1: refine every guess further than 48 buckets from
+                            // home BEFORE the first check; 0: never)
+// Instruction-count trims of the persistent instances (each measured on its own: profiles/r02/ab_variants_7*.json)
+#ifndef TK_SCAN_PRED
+#define TK_SCAN_PRED 1      // warp scan: the shuffle's own predicate guards the addition
+#endif
+#ifndef TK_TOTALS_REDUX
+#define TK_TOTALS_REDUX 1   // prefix of the warp totals: one masked REDUX.SUM per warp instead of a second shuffle scan
+#endif
+#ifndef TK_POSMAX
+#define TK_POSMAX 1         // emission: overflow detected from the largest slot number instead of a flag per store
+#endif
+#ifndef TK_FLOAT_RCP
+#define TK_FLOAT_RCP 1      // binning scale and search guess from a single-precision reciprocal (both only steer)
+#endif
+#ifndef TK_SENTINEL
+#define TK_SENTINEL 1       // the scan leaves n behind the last sub-bucket offset: no end-of-table test in the bound fetch
+#endif
+#ifndef TK_LOAD_UNGUARDED
+#define TK_LOAD_UNGUARDED 1 // staged loads without the i < n guard (slots beyond n hold stale data nobody consumes)
 #endif
 // Tunables kept as macros for A/B builds (scripts/ab_variants.py; measured values in DESIGN.md section 3.0)
 #ifndef TK_RANK_STRAIGHT
@@ -57,7 +86,6 @@ namespace wendy {
 #ifndef TK_COARSE_CAP
 #define TK_COARSE_CAP 2048  // slots per bucket of the CTA kernel (E = 4 particles per thread: 512 threads at 2048)
 #endif
-constexpr int DW = TK_DW;  // destination buckets tracked with shared-memory counters
 
 template <int CAP, int THREADS, int PERSIST = 0>
 struct TileSmem {
@@ -66,6 +94,10 @@ struct TileSmem {
   static constexpr int BK = CAP * SUBMUL;          // interpolation sub-buckets
   static constexpr int CPT = BK / THREADS;         // counters scanned by one thread (one padding word after each run)
   static constexpr int PADN = BK + BK / CPT + 4;
+  static constexpr int DW = PERSIST ? TK_DWP : TK_DW;  // destination window
+  static constexpr int NWIN = (PERSIST && !TK_WIN_SINGLE) ? 2 : 1;
+  // (the persistent instances with warp-direct emission keep no per-destination counts)
+  static constexpr int NDC = (PERSIST && TK_EMIT == 3) ? 4 : DW;
   // PERSIST: landing zone of the TMA bulk copies of the NEXT bucket (x, v, id by load slot)
   double stx[PERSIST ? CAP : 2];
   double stv[PERSIST ? CAP : 2];
@@ -80,9 +112,9 @@ struct TileSmem {
     } srt;
     double mcum[PERSIST ? 2 : PADN];  // masses in sorted order -> cumulative mass below (general masses)
   } u;
-  double ssplit[(PERSIST ? 2 : 1) * (DW + 2)];  // destination window (PERSIST: current / next, alternating)
+  double ssplit[NWIN * (DW + 2)];  // destination window (two buffers: current / next, alternating)
   double nx_lo[2], nx_hi[2];                    // PERSIST: key range of the current / next bucket
-  unsigned dcnt[DW], dbase[DW];
+  unsigned dcnt[NDC], dbase[NDC];
   unsigned long long wlo[32], whi[32];
   unsigned uw[32];
   double dred[4][32];
@@ -141,6 +173,8 @@ tile_kernel(const TileParams p) {
   constexpr int NW = THREADS / 32;
   constexpr int BK = SM::BK;    // interpolation sub-buckets
   constexpr int CPT = SM::CPT;  // counters per thread in the scan
+  constexpr int DW = SM::DW;    // destination window
+  constexpr bool WIN1 = PERSIST && TK_WIN_SINGLE;
   static_assert(E * THREADS == CAP && (E & (E - 1)) == 0, "CAP must be a power-of-two multiple of THREADS");
   static_assert(CAP <= 65536, "load slots are stored as u16");
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -184,14 +218,16 @@ tile_kernel(const TileParams p) {
     tma_load_1d(S.stid, p.idin + base, b4, bar);
   };
   // destination window of bucket bb: DW buckets around it, clipped to its segment
+  // (persistent instances: the host widens the window up to DW when particles keep leaving it -- large N dt)
+  const int dwr = PERSIST ? max(8, min(DW, p.dw)) : DW;
   auto window_of = [&](int bb, int &w_lo, int &w_n, int &s_hi) {
     const int sg = (p.nbps == p.nb) ? 0 : bb / p.nbps;
     const int s_lo = sg * p.nbps;
     s_hi = s_lo + p.nbps;
-    w_lo = bb - DW / 2;
-    if (w_lo > s_hi - DW) w_lo = s_hi - DW;
+    w_lo = bb - dwr / 2;
+    if (w_lo > s_hi - dwr) w_lo = s_hi - dwr;
     if (w_lo < s_lo) w_lo = s_lo;
-    w_n = min(DW, s_hi - w_lo);
+    w_n = min(dwr, s_hi - w_lo);
   };
   uint32_t phase = 0;
   int ser_piece = 0;      // PERSIST: piece of the serial cumulative-mass table the previous bucket started in
@@ -208,7 +244,8 @@ tile_kernel(const TileParams p) {
     }
     int w_lo, w_n, s_hi;
     window_of(b_it, w_lo, w_n, s_hi);
-    for (int i = tid; i <= w_n; i += THREADS) S.ssplit[i] = (w_lo + i < s_hi) ? p.split[w_lo + i] : CUDART_INF;
+    if (!WIN1)  // (one window buffer: every iteration fetches its own window behind its first barrier)
+      for (int i = tid; i <= w_n; i += THREADS) S.ssplit[i] = (w_lo + i < s_hi) ? p.split[w_lo + i] : CUDART_INF;
     if (tid == 0) {
       S.nx_lo[0] = __ldg(p.split_in + b_it);
       S.nx_hi[0] = (b_it + 1 < s_hi) ? __ldg(p.split_in + b_it + 1) : CUDART_INF;
@@ -218,7 +255,8 @@ tile_kernel(const TileParams p) {
   if (PERSIST) {  // both counter sets start clean; inside the loop each is cleared while the other is in use
     uint4 *c4 = reinterpret_cast<uint4 *>(S.u.srt.cnt);
     for (int i = tid; i < 2 * SM::PADN / 4; i += THREADS) c4[i] = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = tid; i < DW; i += THREADS) S.dcnt[i] = 0;
+    if (!WARP_EMIT)
+      for (int i = tid; i < DW; i += THREADS) S.dcnt[i] = 0;
     __syncthreads();
   }
   for (;;) {  // one bucket per iteration (a single iteration unless PERSIST)
@@ -272,12 +310,12 @@ tile_kernel(const TileParams p) {
 
   // destination window of splitters (EMIT_SPLITTER)
   int wlo = 0, wn = 0;
-  const int sbase = PERSIST ? cur * (DW + 2) : 0;
+  const int sbase = (PERSIST && !WIN1) ? cur * (DW + 2) : 0;
   if (EMIT == EMIT_SPLITTER) {
-    wlo = b - DW / 2;
-    if (wlo > seg_hi - DW) wlo = seg_hi - DW;
+    wlo = b - dwr / 2;
+    if (wlo > seg_hi - dwr) wlo = seg_hi - dwr;
     if (wlo < seg_lo) wlo = seg_lo;
-    wn = min(DW, seg_hi - wlo);
+    wn = min(dwr, seg_hi - wlo);
     if (!PERSIST)  // (PERSIST: written during the previous iteration)
       for (int i = tid; i <= wn; i += THREADS)
         S.ssplit[sbase + i] = (wlo + i < seg_hi) ? p.split[wlo + i] : CUDART_INF;
@@ -299,7 +337,15 @@ tile_kernel(const TileParams p) {
     id[k] = 0;
     g[k] = 0;
     vreg[k] = 0.0;
-    if (i < n) {
+    if (PERSIST && TK_LOAD_UNGUARDED) {
+      // (slots beyond n hold stale data of an earlier bucket: every consumer is guarded or stores nothing)
+      g[k] = (unsigned)b * (unsigned)CAP + i;
+      double x = S.stx[i];
+      id[k] = S.stid[i];
+      vreg[k] = S.stv[i];
+      if (p.h_pre != 0.0) x = __dadd_rn(x, __dmul_rn(p.h_pre, vreg[k]));
+      xk[k] = x;
+    } else if (i < n) {
       if (LOAD == LOAD_BUCKET)
         g[k] = (unsigned)b * (unsigned)CAP + i;
       else
@@ -373,7 +419,11 @@ tile_kernel(const TileParams p) {
     xmax = S.dred[2][1];
   }
   const double range = xmax - xmin;
-  const double scale = (range > 0.0 && range < CUDART_INF) ? (double)(BK - 1) * rcp_approx(range) : 0.0;
+  // (any positive scale gives a monotone binning; PERSIST: a single-precision reciprocal is plenty)
+  const double scale = (range > 0.0 && range < CUDART_INF)
+                           ? ((PERSIST && TK_FLOAT_RCP) ? (double)fminf((float)(BK - 1) * rcp_approx_f((float)range), 3.0e38f)
+                                                        : (double)(BK - 1) * rcp_approx(range))
+                           : 0.0;
 
   // ---- 3. interpolation sub-bucket of every key (monotone in x), arrival slot -----------
   unsigned pk[E];  // sub-bucket | arrival order << 16
@@ -392,7 +442,27 @@ tile_kernel(const TileParams p) {
   if (PERSIST && tid == 0 && n_nx) stage_issue(b_nx, n_nx);
   // ... and its splitter window and key range: per-thread asynchronous copies (cp.async, no registers
   // held), waited for at the end of this iteration
-  if (PERSIST && b_nx < p.nb) {
+  if (WIN1) {
+    // One window buffer: the splitters around THIS bucket.  Every warp has left the previous bucket's emission (the
+    // window's only reader) before the barrier above, and the copies are waited for before the barrier that precedes
+    // the ranking -- the same two points the prefetch of the next bucket's window used, so nothing new is waited for,
+    // and the window can be four times as wide in the same shared memory.
+    // (a loop over the window in use, not an unrolled one over the widest: at the narrow default the predicated-off
+    // copies of the unrolled form cost 1.9 %)
+#pragma unroll 1
+    for (int i = tid; i <= wn; i += THREADS) {
+      if (wlo + i < seg_hi) cp_async_8(&S.ssplit[i], p.split + wlo + i);
+      else S.ssplit[i] = CUDART_INF;
+    }
+    if (b_nx < p.nb && tid == THREADS - 1) {
+      int w_lo, w_n, s_hi;
+      window_of(b_nx, w_lo, w_n, s_hi);
+      cp_async_8(&S.nx_lo[cur ^ 1], p.split_in + b_nx);
+      if (b_nx + 1 < s_hi) cp_async_8(&S.nx_hi[cur ^ 1], p.split_in + b_nx + 1);
+      else S.nx_hi[cur ^ 1] = CUDART_INF;
+    }
+    cp_async_commit();
+  } else if (PERSIST && b_nx < p.nb) {
     int w_lo, w_n, s_hi;
     window_of(b_nx, w_lo, w_n, s_hi);
     const int nb_ = (cur ^ 1) * (DW + 2);
@@ -419,19 +489,27 @@ tile_kernel(const TileParams p) {
       c[q] = cp[q];
       run += c[q];
     }
-    unsigned inc = warp_inclusive_scan_u32(run, lane);
+    unsigned inc = (PERSIST && TK_SCAN_PRED) ? warp_inclusive_scan_u32_p(run) : warp_inclusive_scan_u32(run, lane);
     if (lane == 31) S.uw[wid] = inc;
     __syncthreads();
-    // every warp scans the (<= 32) warp totals itself: cheaper than a second block-wide barrier.  (Passing the totals
-    // through tagged shared-memory words that the warps poll, instead of this barrier, is 3 % slower.)
-    const unsigned t = lane < NW ? S.uw[lane] : 0u;
-    const unsigned ti = warp_inclusive_scan_u32(t, lane);
-    unsigned ex = inc - run + __shfl_sync(WENDY_FULL_MASK, ti - t, wid);
+    // every warp sums the totals of the warps before it itself: cheaper than a second block-wide barrier.  (Passing
+    // the totals through tagged shared-memory words that the warps poll, instead of this barrier, is 3 % slower.)
+    unsigned ex;
+    if (PERSIST && TK_TOTALS_REDUX) {
+      const unsigned t = lane < wid ? S.uw[lane] : 0u;  // (wid < NW <= 32)
+      ex = inc - run + __reduce_add_sync(WENDY_FULL_MASK, t);
+    } else {
+      const unsigned t = lane < NW ? S.uw[lane] : 0u;
+      const unsigned ti = warp_inclusive_scan_u32(t, lane);
+      ex = inc - run + __shfl_sync(WENDY_FULL_MASK, ti - t, wid);
+    }
 #pragma unroll
     for (int q = 0; q < CPT; q++) {
       cp[q] = ex;
       ex += c[q];
     }
+    // (the word behind the last run -- padded index of sub-bucket BK, inside the 4 spare words -- receives the total)
+    if (PERSIST && TK_SENTINEL && tid == THREADS - 1) cp[CPT + 1] = ex;
   }
   __syncthreads();
   // ---- 5. group load slots by sub-bucket -------------------------------------------------
@@ -446,7 +524,8 @@ tile_kernel(const TileParams p) {
     if (i < n) {
       const unsigned sub = pk[k] & 0xffffu;
       const unsigned s0 = S.u.srt.cnt[cbase + sub + sub / CPT];
-      const unsigned s1 = (sub + 1 < (unsigned)BK) ? S.u.srt.cnt[cbase + (sub + 1) + (sub + 1) / CPT] : n;
+      const unsigned s1 = (PERSIST && TK_SENTINEL) ? S.u.srt.cnt[cbase + (sub + 1) + (sub + 1) / CPT]
+                                                    : ((sub + 1 < (unsigned)BK) ? S.u.srt.cnt[cbase + (sub + 1) + (sub + 1) / CPT] : n);
       const unsigned c = s1 - s0;
       if (c > 1u) {
         const unsigned pos = s0 + (pk[k] >> 16);
@@ -480,6 +559,8 @@ tile_kernel(const TileParams p) {
     for (int i = tid; i < SM::PADN / 4; i += THREADS) c4[i] = make_uint4(0u, 0u, 0u, 0u);
     cp_async_wait_all();
   }
+  } else if (WIN1) {
+    cp_async_wait_all();  // (this bucket's window is read by the destination search below)
   }
   __syncthreads();
   // ---- 6. exact rank under the (x, id) order; masses are fetched meanwhile ---------------
@@ -621,7 +702,6 @@ tile_kernel(const TileParams p) {
   // kernel's first wait left it (S.pre_cnt: not written again by a persistent instance) instead of carrying two more
   // registers through the bucket loop -- the instance is at the register limit and spilled
   const long long pc_off = SHARDP ? S.pre_cnt : p.pc_offset;
-  const double PcD = (double)(Pc + pc_off);
   // Equal masses: cumulative mass below sorted position K0 + r.  With the serial table it is the reference's own
   // running sum (wendy/wendy.c:359-360) bit for bit; a bucket nearly always lies inside one linear piece.
   SerialRun SR;
@@ -648,7 +728,7 @@ tile_kernel(const TileParams p) {
       if (SR.uniform) return serial_cum_run(SR, rk);
       return serial_cum_at(p.stab, Pc + pc_off + (long long)rk);
     }
-    return __dmul_rn(__dadd_rn(PcD, (double)rk), p.m0);  // exact integer sum below 2^53, one rounding
+    return __dmul_rn(__dadd_rn((double)(Pc + pc_off), (double)rk), p.m0);  // exact integer sum below 2^53, one rounding
   };
   double x2[E], v2[E], xb[E];
   double e_ke = 0.0, e_he = 0.0, e_pe = 0.0, e_mom = 0.0;
@@ -792,8 +872,15 @@ tile_kernel(const TileParams p) {
   const double home_lo = S.ssplit[sbase + rel], home_hi = S.ssplit[sbase + rel + 1];
   bool sh_overflow = false;
   const double wdt = home_hi - home_lo;
-  const double inv_w = (wdt > 0.0 && wdt < CUDART_INF) ? rcp_approx(wdt) : 0.0;
-  const float inv_wf = (float)fmin(inv_w, 3.0e38);
+  float inv_wf;
+  double inv_w;
+  if (PERSIST && TK_FLOAT_RCP) {  // (an infinite width gives 0)
+    inv_wf = (wdt > 0.0) ? fminf(rcp_approx_f((float)wdt), 3.0e38f) : 0.f;
+    inv_w = (double)inv_wf;
+  } else {
+    inv_w = (wdt > 0.0 && wdt < CUDART_INF) ? rcp_approx(wdt) : 0.0;
+    inv_wf = (float)fmin(inv_w, 3.0e38);
+  }
   const double win_lo = S.ssplit[sbase], win_hi = S.ssplit[sbase + wn];
   const double sh_lo = (!PLAIN && p.bounds) ? __ldg(p.bounds + p.my_rank) : 0.0;
   const double sh_hi = (!PLAIN && p.bounds) ? __ldg(p.bounds + p.my_rank + 1) : 0.0;
@@ -822,16 +909,36 @@ tile_kernel(const TileParams p) {
         d = b;
       } else if (key >= win_lo && key < win_hi) {
         // guess from the home bucket's width (single precision is plenty: the loops below settle it)
-        int lo = rel + __float2int_rd(fmaxf(-256.f, fminf(256.f, (float)(key - home_lo) * inv_wf)));
+        int lo = rel + __float2int_rd(fmaxf(-(float)DW, fminf((float)DW, (float)(key - home_lo) * inv_wf)));
         // The guess is nearly always within one bucket of the answer: fetch the four splitters around it
         // (independent loads), correct by at most one, and verify; the search loops only run if that fails.
         bool settled = false;
         if (wn >= 3) {
           lo = max(1, min(wn - 2, lo));
+#if TK_GUESS_REFINE == 1
+          if (PERSIST && abs(lo - rel) > 48) {
+            const double sg = S.ssplit[sbase + lo];
+            lo += __float2int_rd(fmaxf(-64.f, fminf(64.f, (float)(key - sg) * inv_wf)));
+            lo = max(1, min(wn - 2, lo));
+          }
+#endif
           const double *sp = &S.ssplit[sbase + lo];
           const double sm1 = sp[-1], s0 = sp[0], s1 = sp[1], s2 = sp[2];
-          lo += (key >= s1 ? 1 : 0) - (key < s0 ? 1 : 0);
           settled = (key >= sm1) && (key < s2);
+#if TK_GUESS_REFINE == 2
+          // Far from home the bucket widths differ from the home bucket's by a few per cent and the guess is off by a
+          // few buckets (wide windows): one secant step from the splitter at the guess brings it back within one, and
+          // the check is repeated -- off the common path, and any result is verified, so this only saves the walk
+          if (PERSIST && !settled) {
+            lo += __float2int_rd(fmaxf(-64.f, fminf(64.f, (float)(key - s0) * inv_wf)));
+            lo = max(1, min(wn - 2, lo));
+            const double *sq = &S.ssplit[sbase + lo];
+            const double tm1 = sq[-1], t0 = sq[0], t1 = sq[1], t2 = sq[2];
+            lo += (key >= t1 ? 1 : 0) - (key < t0 ? 1 : 0);
+            settled = (key >= tm1) && (key < t2);
+          } else
+#endif
+          lo += (key >= s1 ? 1 : 0) - (key < s0 ? 1 : 0);
         }
         if (!settled) {
           lo = max(0, min(wn - 1, lo));
@@ -849,6 +956,9 @@ tile_kernel(const TileParams p) {
         double gq = fmax(-2.0e9, fmin(2.0e9, (key - home_lo) * inv_w));
         const int g = (int)max((long long)seg_lo, min((long long)seg_hi - 1, (long long)b + (long long)floor(gq)));
         d = gallop_search_tile(p.split, key, g, seg_lo, seg_hi);
+        outside++;  // (statistic: particles whose key left the destination window; counted here, off the common path.
+                    // One atomic per far mover instead of the warp reduction below: -43 % when a fifth of the particles
+                    // are far movers, nothing gained otherwise -- profiles/r02/ab_variants_9.json)
       }
     }
     dest[k] = d;
@@ -907,14 +1017,13 @@ tile_kernel(const TileParams p) {
         const int d = dest[k];
         const bool ok = tid + k * THREADS < n;
         unsigned mask;
-        const unsigned valid = __ballot_sync(WENDY_FULL_MASK, ok);
-        if (__all_sync(WENDY_FULL_MASK, d == b || !ok)) mask = ok ? valid : 0u;
-        else mask = __match_any_sync(WENDY_FULL_MASK, d);
+        // (a shortcut for warps whose particles all stay home -- ballot instead of MATCH.ANY -- gains nothing even at
+        // dt_leap = 1e-5: MATCH.ANY on uniform values is fast -- profiles/r02/ab_variants_9.json)
+        mask = __match_any_sync(WENDY_FULL_MASK, d);
         amask[k] = mask;
         lpos[k] = 0;
         if (ok && d >= 0 && lane == __ffs(mask) - 1) {
           lpos[k] = atomicAdd(&p.cnt_out[d], (unsigned)__popc(mask));
-          if ((unsigned)(d - wlo) >= (unsigned)wn) outside += __popc(mask);
         }
       }
     }
@@ -923,13 +1032,24 @@ tile_kernel(const TileParams p) {
       if (lane == 0 && wsum) atomicAdd(p.outside + (b & 63), (unsigned long long)wsum);
     }
     bool overflow = false;
+    unsigned posmax = 0;
 #pragma unroll
     for (int k = 0; k < E; k++) {
       const int leader = __ffs(amask[k]) - 1;
       const unsigned basel = __shfl_sync(WENDY_FULL_MASK, lpos[k], leader < 0 ? 0 : leader);
       const unsigned pos = basel + __popc(amask[k] & lt);
       const int d = dest[k];
-      if (d >= 0) {
+      if (TK_POSMAX) {
+        // (lanes without a particle to store -- d < 0 -- got no slots: their `pos` is a lane count, below 32)
+        posmax = max(posmax, pos);
+        if ((d >= 0) & (pos < (unsigned)CAP)) {
+          size_t o = (size_t)d * CAP + pos;
+          p.xout[o] = x2[k];
+          p.vout[o] = v2[k];
+          if (!EQM) p.mout[o] = m[k];
+          p.idout[o] = id[k];
+        }
+      } else if (d >= 0) {
         if (pos < (unsigned)CAP) {
           size_t o = (size_t)d * CAP + pos;
           p.xout[o] = x2[k];
@@ -941,6 +1061,7 @@ tile_kernel(const TileParams p) {
         }
       }
     }
+    if (TK_POSMAX) overflow = posmax >= (unsigned)CAP;
     if (overflow || sh_overflow) atomicMin(p.fail_seq, p.seq);
   }
   } else {
@@ -963,7 +1084,6 @@ tile_kernel(const TileParams p) {
         lpos[k] = atomicAdd(&S.dcnt[d - wlo], (unsigned)__popc(mask));
       } else {
         lpos[k] = atomicAdd(&p.cnt_out[d], (unsigned)__popc(mask));
-        outside += __popc(mask);
       }
     }
   }
@@ -1059,6 +1179,8 @@ static int persist_setup() {
   dev &= 63;
   if (first_use_on_device(grid_set)) {
     const size_t smp = sizeof(TileSmem<CAP, PT, PE>);
+    // two CTAs of the 2048-slot instance per SM: 228 KB of shared memory, 1 KB of it reserved per CTA
+    static_assert(CAP != 2048 || sizeof(TileSmem<CAP, PT, PE>) <= (228 * 1024 - 2 * 1024) / 2, "window / counters too large");
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     auto setup = [&](auto kern) {
@@ -1118,6 +1240,7 @@ void tile_prepare_persistent() {
 
 bool tile_cap_supported(int cap) { return cap == TK_COARSE_CAP || cap == 256; }
 int tile_coarse_cap() { return TK_COARSE_CAP; }
+int tile_window_max() { return TK_DWP; }
 
 void launch_tile(cudaStream_t st, int cap, int load, int emit, int physics, const TileParams &p) {
   if (p.nb <= 0) return;
