@@ -510,7 +510,7 @@ def main():
     if sharded and not a.no_variants:
         # The cost of a sub-step grows with the displacement per sub-step measured in ranks, N_total * rho * v * dt:
         # at a fixed dt a system of `world` times more particles sends every particle across `world` times more
-        # buckets (path_stats.left_window: particles leaving the 256-bucket destination window).  The same run
+        # buckets (path_stats.left_window: particles leaving the destination window, which the library widens from 256 to at most 1024 buckets on that evidence).  The same run
         # with dt_leap / world keeps that displacement -- the regime of the N=1 line -- and isolates what the
         # exchange itself costs.
         try:
@@ -613,9 +613,9 @@ def main():
 
     # ---- end to end through the public generator API, host buffers --------------------------
     if not a.no_e2e and sharded:
-        out['e2e'] = e2e_sharded(a.dt_leap, max(2, min(a.steps, 10)), a.nleap)
+        out['e2e'] = e2e_sharded(a.dt_leap, max(2, min(a.steps, 20)), a.nleap)
     if not a.no_e2e and not sharded:
-        steps_e = max(2, min(a.steps, 10))
+        steps_e = max(2, min(a.steps, 40))  # the K steps of the contract (bounded: each yields 1.6 GB to the host)
         barrier()
         t0 = time.perf_counter()
         g = wendy_b200.nbody(x, v, m, a.dt_leap * a.nleap, approx=True, nleap=a.nleap, omega=a.omega, sort=a.sort)

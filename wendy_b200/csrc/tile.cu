@@ -58,6 +58,22 @@ namespace wendy {
 #ifndef TK_FLOAT_RCP
 #define TK_FLOAT_RCP 1      // binning scale and search guess from a single-precision reciprocal (both only steer)
 #endif
+#ifndef TK_COARSE_TOTALS
+#define TK_COARSE_TOTALS 1  // persistent instances: the sub-bucket pass also counts per scan-warp range, so the block scan
+#endif                      // needs no barrier between the warp scans and the prefix of the warp totals (3 barriers per bucket)
+#ifndef TK_SER_TOP
+#define TK_SER_TOP 12       // persistent instances: warp that looks up the piece of the serial cumulative-mass table at the top
+#endif                      // of the iteration for everyone (shared memory); 0: every thread looks it up itself
+#ifndef TK_CLEAR_TOP
+#define TK_CLEAR_TOP 8      // persistent instances: the idle counter set is cleared at the top of the iteration by the warps
+#endif                      // from this one up -- the lower warps hold the bucket's fourth round of particles (0: by everyone
+                            // between the scan and the ranking, as before)
+#ifndef TK_PACK_CNT
+#define TK_PACK_CNT 1       // persistent instances: the scan leaves start | count << 16 in every counter word: the bounds of
+#endif                      // a particle's sub-bucket take ONE random shared-memory load instead of two
+#ifndef TK_STAGE_TID
+#define TK_STAGE_TID (THREADS - 64)  // thread that issues the next bucket's bulk copies behind the first barrier: lane 0 of a
+#endif                               // warp that has no share of the window copies (thread 0's warp has one)
 #ifndef TK_SENTINEL
 #define TK_SENTINEL 1       // the scan leaves n behind the last sub-bucket offset: no end-of-table test in the bound fetch
 #endif
@@ -94,6 +110,10 @@ struct TileSmem {
   static constexpr int BK = CAP * SUBMUL;          // interpolation sub-buckets
   static constexpr int CPT = BK / THREADS;         // counters scanned by one thread (one padding word after each run)
   static constexpr int PADN = BK + BK / CPT + 4;
+  // word of sub-bucket counter s: one spare word after each thread's run keeps the scan free of bank conflicts.  (Unpadded
+  // counters scanned with 128-bit loads / stores -- 4 instructions with two-way conflicts instead of 16 without, and no
+  // padding arithmetic -- are 2.4 % SLOWER: the kernel is sensitive to shared-memory wavefronts, profiles/r02/ab_variants_11.json)
+  static __device__ __forceinline__ int cidx(int s) { return s + s / CPT; }
   static constexpr int DW = PERSIST ? TK_DWP : TK_DW;  // destination window
   static constexpr int NWIN = (PERSIST && !TK_WIN_SINGLE) ? 2 : 1;
   // (the persistent instances with warp-direct emission keep no per-destination counts)
@@ -117,6 +137,10 @@ struct TileSmem {
   unsigned dcnt[NDC], dbase[NDC];
   unsigned long long wlo[32], whi[32];
   unsigned uw[32];
+  double ser_c0[2], ser_inc[2];  // PERSIST: piece of the serial cumulative-mass table this bucket starts in (TK_SER_TOP),
+  unsigned ser_j0[2];            // double-buffered like the counters
+  int ser_uni[2];
+  unsigned ctot[2][32];  // PERSIST: particles per scan-warp range of sub-buckets (two sets, like the counters)
   double dred[4][32];
   unsigned long long pre_lo, pre_hi;
   long long pre_cnt;
@@ -177,6 +201,7 @@ tile_kernel(const TileParams p) {
   constexpr bool WIN1 = PERSIST && TK_WIN_SINGLE;
   static_assert(E * THREADS == CAP && (E & (E - 1)) == 0, "CAP must be a power-of-two multiple of THREADS");
   static_assert(CAP <= 65536, "load slots are stored as u16");
+  static_assert(!(TK_PACK_CNT) || (TK_LAZY_GROUP && CAP < 65536), "packed counters: start and count in 16 bits each");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SM &S = *reinterpret_cast<SM *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -257,6 +282,7 @@ tile_kernel(const TileParams p) {
     for (int i = tid; i < 2 * SM::PADN / 4; i += THREADS) c4[i] = make_uint4(0u, 0u, 0u, 0u);
     if (!WARP_EMIT)
       for (int i = tid; i < DW; i += THREADS) S.dcnt[i] = 0;
+    if (tid < 64) (&S.ctot[0][0])[tid] = 0;
     __syncthreads();
   }
   for (;;) {  // one bucket per iteration (a single iteration unless PERSIST)
@@ -268,6 +294,17 @@ tile_kernel(const TileParams p) {
     __syncthreads();
   }
   const int cbase = PERSIST ? cur * SM::PADN : 0;  // this bucket's counter set
+  if (PERSIST && WARP_EMIT && TK_CLEAR_TOP && wid >= TK_CLEAR_TOP) {
+    // The OTHER counter set (the next bucket's) was last read between the scan and the ranking of the previous bucket
+    // (lazy grouping: the ranking itself works from registers and the grouped keys), so it can be cleared from here on;
+    // it must be clean before the barrier that precedes this bucket's ranking -- the last one before the next bucket's
+    // sub-bucket pass.  Done by the upper warps: the bucket's fourth round of particles (tid + 3 THREADS < n, a
+    // quarter more work behind the last barrier) belongs to the lowest ones.
+    constexpr int T0 = 32 * TK_CLEAR_TOP;
+    uint4 *c4 = reinterpret_cast<uint4 *>(S.u.srt.cnt + (cur ^ 1) * SM::PADN);
+    for (int i = tid - T0; i < SM::PADN / 4; i += THREADS - T0) c4[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (TK_COARSE_TOTALS && tid - T0 < 32) S.ctot[cur ^ 1][tid - T0] = 0;
+  }
   const int b = PERSIST ? b_it : S.bucket;
   const int seg = (p.nbps == p.nb) ? 0 : b / p.nbps;
   const int kb = b - seg * p.nbps;
@@ -282,6 +319,25 @@ tile_kernel(const TileParams p) {
     n_pf = 0;
     if (b_nx + (int)gridDim.x < p.nb) n_pf = p.cnt_in[b_nx + (int)gridDim.x];
     pc_reg = p.cpre[b] - (unsigned)((long long)seg * p.seg_len);
+  }
+  unsigned n_top = 0;
+  if (PERSIST) n_top = min(n_it, (unsigned)CAP);
+  if (PERSIST && TK_SER_TOP && EQM && p.stab && wid == TK_SER_TOP) {
+    // Piece of the serial cumulative-mass table this bucket starts in (a CTA walks its buckets in ascending order, so
+    // the index nearly always stays or moves on by one): looked up once per bucket by one of the upper warps -- which
+    // wait at the first barrier for the warps holding the bucket's fourth round anyway -- and read by all behind that
+    // barrier.  (S.pre_cnt: particles of the lower ranks, left there by the peer instance's first wait.  The words are
+    // double-buffered by `cur`: the slower warps may still be in the previous bucket's physics, behind its last barrier.)
+    const long long k0 = (long long)pc_reg + (SHARDP ? S.pre_cnt : p.pc_offset);
+    while (ser_piece > 0 && k0 < __ldg(&p.stab->i0[ser_piece])) ser_piece--;
+    while (k0 >= __ldg(&p.stab->i0[ser_piece + 1])) ser_piece++;
+    if (lane == 0) {
+      const long long i0 = __ldg(&p.stab->i0[ser_piece]);
+      S.ser_c0[cur] = __ldg(&p.stab->c0[ser_piece]);
+      S.ser_inc[cur] = __ldg(&p.stab->inc[ser_piece]);
+      S.ser_j0[cur] = (unsigned)(k0 - i0);
+      S.ser_uni[cur] = ((k0 + (long long)n_top <= __ldg(&p.stab->i0[ser_piece + 1])) && (k0 - i0 + (long long)n_top < (1ll << 31))) ? 1 : 0;
+    }
   }
 
   unsigned n;
@@ -433,13 +489,14 @@ tile_kernel(const TileParams p) {
     if (tid + k * THREADS < n) {
       int sub = (int)((xk[k] - xmin) * scale);
       sub = max(0, min(BK - 1, sub));
-      unsigned o = atomicAdd(&S.u.srt.cnt[cbase + sub + sub / CPT], 1u);
+      unsigned o = atomicAdd(&S.u.srt.cnt[cbase + SM::cidx(sub)], 1u);
+      if (PERSIST && TK_COARSE_TOTALS) atomicAdd(&S.ctot[cur][sub / (CPT * 32)], 1u);  // (the range warp sub/(32 CPT) scans)
       pk[k] = (unsigned)sub | (o << 16);
     }
   }
   __syncthreads();
   // everyone has taken its share of the staged bucket into registers: fetch the next one
-  if (PERSIST && tid == 0 && n_nx) stage_issue(b_nx, n_nx);
+  if (PERSIST && tid == (TK_STAGE_TID) && n_nx) stage_issue(b_nx, n_nx);
   // ... and its splitter window and key range: per-thread asynchronous copies (cp.async, no registers
   // held), waited for at the end of this iteration
   if (WIN1) {
@@ -490,13 +547,16 @@ tile_kernel(const TileParams p) {
       run += c[q];
     }
     unsigned inc = (PERSIST && TK_SCAN_PRED) ? warp_inclusive_scan_u32_p(run) : warp_inclusive_scan_u32(run, lane);
-    if (lane == 31) S.uw[wid] = inc;
-    __syncthreads();
+    if (!(PERSIST && TK_COARSE_TOTALS)) {
+      if (lane == 31) S.uw[wid] = inc;
+      __syncthreads();
+    }
     // every warp sums the totals of the warps before it itself: cheaper than a second block-wide barrier.  (Passing
     // the totals through tagged shared-memory words that the warps poll, instead of this barrier, is 3 % slower.)
     unsigned ex;
-    if (PERSIST && TK_TOTALS_REDUX) {
-      const unsigned t = lane < wid ? S.uw[lane] : 0u;  // (wid < NW <= 32)
+    if (PERSIST && (TK_TOTALS_REDUX || TK_COARSE_TOTALS)) {
+      // (wid < NW <= 32; with TK_COARSE_TOTALS the totals were counted by the sub-bucket pass, before the last barrier)
+      const unsigned t = lane < wid ? (TK_COARSE_TOTALS ? S.ctot[cur][lane] : S.uw[lane]) : 0u;
       ex = inc - run + __reduce_add_sync(WENDY_FULL_MASK, t);
     } else {
       const unsigned t = lane < NW ? S.uw[lane] : 0u;
@@ -505,11 +565,11 @@ tile_kernel(const TileParams p) {
     }
 #pragma unroll
     for (int q = 0; q < CPT; q++) {
-      cp[q] = ex;
+      cp[q] = (PERSIST && TK_PACK_CNT) ? (ex | (c[q] << 16)) : ex;  // (start < CAP <= 65536 by the static_assert above)
       ex += c[q];
     }
-    // (the word behind the last run -- padded index of sub-bucket BK, inside the 4 spare words -- receives the total)
-    if (PERSIST && TK_SENTINEL && tid == THREADS - 1) cp[CPT + 1] = ex;
+    // (the word of sub-bucket BK -- behind the last run, inside the 4 spare words -- receives the total)
+    if (PERSIST && TK_SENTINEL && !TK_PACK_CNT && tid == THREADS - 1) S.u.srt.cnt[cbase + SM::cidx(BK)] = ex;
   }
   __syncthreads();
   // ---- 5. group load slots by sub-bucket -------------------------------------------------
@@ -523,10 +583,17 @@ tile_kernel(const TileParams p) {
     const unsigned i = tid + k * THREADS;
     if (i < n) {
       const unsigned sub = pk[k] & 0xffffu;
-      const unsigned s0 = S.u.srt.cnt[cbase + sub + sub / CPT];
-      const unsigned s1 = (PERSIST && TK_SENTINEL) ? S.u.srt.cnt[cbase + (sub + 1) + (sub + 1) / CPT]
-                                                    : ((sub + 1 < (unsigned)BK) ? S.u.srt.cnt[cbase + (sub + 1) + (sub + 1) / CPT] : n);
-      const unsigned c = s1 - s0;
+      unsigned s0, c;
+      if (PERSIST && TK_PACK_CNT) {
+        const unsigned w = S.u.srt.cnt[cbase + SM::cidx(sub)];
+        s0 = w & 0xffffu;
+        c = w >> 16;
+      } else {
+        s0 = S.u.srt.cnt[cbase + SM::cidx(sub)];
+        const unsigned s1 = (PERSIST && TK_SENTINEL) ? S.u.srt.cnt[cbase + SM::cidx(sub + 1)]
+                                                      : ((sub + 1 < (unsigned)BK) ? S.u.srt.cnt[cbase + SM::cidx(sub + 1)] : n);
+        c = s1 - s0;
+      }
       if (c > 1u) {
         const unsigned pos = s0 + (pk[k] >> 16);
         S.sx[pos] = xk[k];
@@ -544,7 +611,7 @@ tile_kernel(const TileParams p) {
     unsigned i = tid + k * THREADS;
     if (i < n) {
       unsigned sub = pk[k] & 0xffffu;
-      unsigned pos = S.u.srt.cnt[cbase + sub + sub / CPT] + (pk[k] >> 16);
+      unsigned pos = S.u.srt.cnt[cbase + SM::cidx(sub)] + (pk[k] >> 16);
       S.sx[pos] = xk[k];
       S.sid[pos] = id[k];
     }
@@ -555,8 +622,11 @@ tile_kernel(const TileParams p) {
     // (warp-direct emission has no barrier after this one: what the NEXT iteration touches before its first barrier
     // is prepared here -- its counter set, last read during the previous bucket's ranking, is cleared, and its
     // splitter window / key range (cp.async issued after the first barrier) have landed)
-    uint4 *c4 = reinterpret_cast<uint4 *>(S.u.srt.cnt + (cur ^ 1) * SM::PADN);
-    for (int i = tid; i < SM::PADN / 4; i += THREADS) c4[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (!TK_CLEAR_TOP) {
+      uint4 *c4 = reinterpret_cast<uint4 *>(S.u.srt.cnt + (cur ^ 1) * SM::PADN);
+      for (int i = tid; i < SM::PADN / 4; i += THREADS) c4[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (TK_COARSE_TOTALS && tid < 32) S.ctot[cur ^ 1][tid] = 0;
+    }
     cp_async_wait_all();
   }
   } else if (WIN1) {
@@ -586,8 +656,8 @@ tile_kernel(const TileParams p) {
     r[k] = 0;
     if (tid + k * THREADS < n) {
       const unsigned sub = pk[k] & 0xffffu;
-      const unsigned s0 = S.u.srt.cnt[cbase + sub + sub / CPT];
-      const unsigned s1 = (sub + 1 < (unsigned)BK) ? S.u.srt.cnt[cbase + (sub + 1) + (sub + 1) / CPT] : n;
+      const unsigned s0 = S.u.srt.cnt[cbase + SM::cidx(sub)];
+      const unsigned s1 = (sub + 1 < (unsigned)BK) ? S.u.srt.cnt[cbase + SM::cidx(sub + 1)] : n;
       r[k] = s0;
       pk[k] = s1 - s0;  // the sub-bucket index is not needed any more
     }
@@ -707,7 +777,12 @@ tile_kernel(const TileParams p) {
   SerialRun SR;
   SR.c0 = 0.0; SR.inc = 0.0; SR.j0 = 0u; SR.uniform = true;
   if (EQM && p.stab) {
-    if (PERSIST) {
+    if (PERSIST && TK_SER_TOP) {
+      SR.c0 = S.ser_c0[cur];
+      SR.inc = S.ser_inc[cur];
+      SR.j0 = S.ser_j0[cur];
+      SR.uniform = S.ser_uni[cur] != 0;
+    } else if (PERSIST) {
       // a CTA walks its buckets in ascending order, so the piece index only ever moves forward: remember it
       // instead of searching (one L1-resident load per bucket in the common case)
       const long long k0 = Pc + pc_off;
@@ -1019,6 +1094,9 @@ tile_kernel(const TileParams p) {
         unsigned mask;
         // (a shortcut for warps whose particles all stay home -- ballot instead of MATCH.ANY -- gains nothing even at
         // dt_leap = 1e-5: MATCH.ANY on uniform values is fast -- profiles/r02/ab_variants_9.json)
+        // (grouping by RUNS of equal destination among consecutive lanes -- shuffle + ballot + bit arithmetic instead of
+        // MATCH.ANY -- is 14 % slower at dt_leap = 1e-3: lanes with one destination are not neighbours often enough, and
+        // every extra group is a global atomic -- profiles/r02/ab_variants_14.json)
         mask = __match_any_sync(WENDY_FULL_MASK, d);
         amask[k] = mask;
         lpos[k] = 0;
@@ -1105,6 +1183,7 @@ tile_kernel(const TileParams p) {
     // previous bucket's ranking) is cleared, its splitter window / key range (cp.async) have landed
     uint4 *c4 = reinterpret_cast<uint4 *>(S.u.srt.cnt + (cur ^ 1) * SM::PADN);
     for (int i = tid; i < SM::PADN / 4; i += THREADS) c4[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (TK_COARSE_TOTALS && tid < 32) S.ctot[cur ^ 1][tid] = 0;
     cp_async_wait_all();
   }
   __syncthreads();
