@@ -10,22 +10,54 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <mutex>
+
 typedef __int128 i128;
 typedef unsigned __int128 u128;
 
 #define WENDY_FULL_MASK 0xffffffffu
 
 // Per-function attributes (dynamic shared-memory size, carve-out) are per DEVICE: a process that steps systems on
-// two GPUs must set them on both.  flags: a static array owned by the call site; true the first time the current
-// device comes by.  (One cudaGetDevice per launch; a race between threads only sets the attribute twice.)
-static inline bool first_use_on_device(bool (&flags)[64]) {
-  int dev = 0;
-  cudaGetDevice(&dev);
-  dev &= 63;
-  if (flags[dev]) return false;
-  flags[dev] = true;
-  return true;
-}
+// two GPUs must set them on both.  flags: a static object owned by the call site (one cudaGetDevice per launch).
+// Once-per-device set-up of a kernel (cudaFuncSetAttribute ...), safe when several host threads drive handles of one
+// device (the ranks of a sharded system living in one process, tests/multi_helpers.py): a thread that finds the set-up
+// under way waits for it instead of launching a kernel whose attributes are not set yet ("invalid argument").
+//   static OnceFlags flags;  WENDY_ONCE_PER_DEVICE(flags) { cudaFuncSetAttribute(...); }
+struct OnceFlags {
+  std::atomic<int> done[64];
+};
+class OnceGuard {
+ public:
+  explicit OnceGuard(OnceFlags &f) : f_(f) {
+    cudaGetDevice(&dev_);
+    dev_ &= 63;
+    if (f_.done[dev_].load(std::memory_order_acquire)) return;
+    mutex().lock();
+    locked_ = true;
+    todo_ = f_.done[dev_].load(std::memory_order_relaxed) == 0;
+  }
+  ~OnceGuard() {
+    if (locked_) mutex().unlock();
+  }
+  OnceGuard(const OnceGuard &) = delete;
+  OnceGuard &operator=(const OnceGuard &) = delete;
+  bool run() const { return todo_; }
+  void done() {
+    f_.done[dev_].store(1, std::memory_order_release);
+    todo_ = false;
+  }
+
+ private:
+  static std::mutex &mutex() {
+    static std::mutex m;
+    return m;
+  }
+  OnceFlags &f_;
+  int dev_ = 0;
+  bool locked_ = false, todo_ = false;
+};
+#define WENDY_ONCE_PER_DEVICE(flags) for (::OnceGuard once_guard_(flags); once_guard_.run(); once_guard_.done())
 
 // ---------------------------------------------------------------------------------
 // key transform: ascending u64 order == ascending fp64 order; -0.0 is canonicalised to

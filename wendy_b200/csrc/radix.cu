@@ -424,8 +424,8 @@ static int onesweep_sort_pairs(cudaStream_t st, RadixScratch &s, size_t n, int s
   if (hb > (size_t)sms * 4) hb = (size_t)sms * 4;
   radix_hist_all_kernel<<<(unsigned)hb, 512, 0, st>>>(s.key[0], s.val[0], n, plan, ghist);
   radix_prefix_kernel<<<1, 256, 0, st>>>(ghist, gbase, skip, plan.npass, (unsigned)n);
-  static bool attr_set[64];
-  if (first_use_on_device(attr_set)) {
+  static OnceFlags attr_set;
+  WENDY_ONCE_PER_DEVICE(attr_set) {
     cudaFuncSetAttribute(onesweep_kernel<OI_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem<OI_BIG>));
     cudaFuncSetAttribute(onesweep_kernel<OI_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SweepSmem<OI_SMALL>));
   }

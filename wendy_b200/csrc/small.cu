@@ -233,15 +233,15 @@ void launch_small(cudaStream_t st, double *x, double *v, const double *m, long l
   if (nseg <= 0 || seg_len <= 0) return;
   if (eqm) {
     const size_t sm = sizeof(SmallSmem<1024, 256, 1>);
-    static bool set1[64];
-    if (first_use_on_device(set1)) {
+    static OnceFlags set1;
+    WENDY_ONCE_PER_DEVICE(set1) {
       cudaFuncSetAttribute(small_kernel<1024, 256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     }
     small_kernel<1024, 256, 1><<<nseg, 256, sm, st>>>(x, v, m, seg_len, tot_seg, m0, stab, omega2, fxE, dt, nleap);
   } else {
     const size_t sm = sizeof(SmallSmem<1024, 256, 0>);
-    static bool set0[64];
-    if (first_use_on_device(set0)) {
+    static OnceFlags set0;
+    WENDY_ONCE_PER_DEVICE(set0) {
       cudaFuncSetAttribute(small_kernel<1024, 256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     }
     small_kernel<1024, 256, 0><<<nseg, 256, sm, st>>>(x, v, m, seg_len, tot_seg, m0, nullptr, omega2, fxE, dt, nleap);

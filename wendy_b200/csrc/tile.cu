@@ -61,6 +61,8 @@ namespace wendy {
 #ifndef TK_COARSE_TOTALS
 #define TK_COARSE_TOTALS 1  // persistent instances: the sub-bucket pass also counts per scan-warp range, so the block scan
 #endif                      // needs no barrier between the warp scans and the prefix of the warp totals (3 barriers per bucket)
+// (Measured and removed: the same warp also fetching the NEXT bucket's key range and deriving its binning scale, so that
+// no thread runs the reciprocal chain at the top of its iteration: -2.7 % -- profiles/r02/ab_variants_16.json.)
 #ifndef TK_SER_TOP
 #define TK_SER_TOP 12       // persistent instances: warp that looks up the piece of the serial cumulative-mass table at the top
 #endif                      // of the iteration for everyone (shared memory); 0: every thread looks it up itself
@@ -92,7 +94,7 @@ namespace wendy {
 #define TK_LAZY_GROUP 1     // only members of SHARED sub-buckets are written to the grouped key / id arrays
 #endif
 #ifndef TK_EMIT
-#define TK_EMIT 3           // 3: warp-direct emission (one GLOBAL atomic per warp and destination, no CTA-level counts, no
+#define TK_EMIT 3           // (0 needs -DTK_DWP=512 or less: the per-destination counts) 3: warp-direct emission (one GLOBAL atomic per warp and destination, no CTA-level counts, no
                             // barrier in the emission); 0: slots counted per CTA and destination in shared memory, one global
                             // atomic per CTA and destination between two barriers (the kernel up to round 2; A/B runs)
 #endif
@@ -1252,11 +1254,11 @@ static bool persist_allowed() {
 template <int CAP, int PT, int PQ, int PE>
 static int persist_setup() {
   static int grid[64];
-  static bool grid_set[64];
+  static OnceFlags grid_set;
   int dev = 0;
   cudaGetDevice(&dev);
   dev &= 63;
-  if (first_use_on_device(grid_set)) {
+  WENDY_ONCE_PER_DEVICE(grid_set) {
     const size_t smp = sizeof(TileSmem<CAP, PT, PE>);
     // two CTAs of the 2048-slot instance per SM: 228 KB of shared memory, 1 KB of it reserved per CTA
     static_assert(CAP != 2048 || sizeof(TileSmem<CAP, PT, PE>) <= (228 * 1024 - 2 * 1024) / 2, "window / counters too large");
@@ -1282,8 +1284,8 @@ static void launch_tile_cap(cudaStream_t st, int load, int emit, int physics, co
   size_t sm = sizeof(TileSmem<CAP, THREADS>);
 #define WENDY_LAUNCH(L, EM, PH)                                                                   \
   do {                                                                                              \
-    static bool attr_set[64];                                                                       \
-    if (first_use_on_device(attr_set)) {                                                            \
+    static OnceFlags attr_set;                                                                      \
+    WENDY_ONCE_PER_DEVICE(attr_set) {                                                               \
       cudaFuncSetAttribute(tile_kernel<CAP, THREADS, L, EM, PH, EQM>,                               \
                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                   \
     }                                                                                               \

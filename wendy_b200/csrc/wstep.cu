@@ -687,9 +687,9 @@ void launch_count_prefix(cudaStream_t st, const unsigned *cnt, int nb, unsigned 
 
 template <int WCAP, int WARPS, int EQM, int SHARD>
 static void launch_wstep_t(cudaStream_t st, const TileParams &p) {
-  static bool attr_set[64];
+  static OnceFlags attr_set;
   const size_t sm = sizeof(WarpSlab<WCAP, EQM>) * WARPS;
-  if (first_use_on_device(attr_set)) {
+  WENDY_ONCE_PER_DEVICE(attr_set) {
     cudaFuncSetAttribute(wstep_kernel<WCAP, WARPS, EQM, SHARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
   }
   const int grid = (p.nb + WARPS - 1) / WARPS;
