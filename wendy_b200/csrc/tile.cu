@@ -315,8 +315,8 @@ tile_kernel(const TileParams p) {
   const int b_nx = b + (int)gridDim.x;
   unsigned n_nx = 0, pc_reg = 0;
   if (PERSIST) {
-    // (the count of the next bucket was requested during the previous iteration: thread 0 needs it right after
-    // the first barrier to issue the bulk copies, and a load issued here would still be in flight then)
+    // (the count of the next bucket was requested during the previous iteration: the issuing thread needs it right
+    // after the first barrier for the bulk copies, and a load issued here would still be in flight then)
     n_nx = n_pf;
     n_pf = 0;
     if (b_nx + (int)gridDim.x < p.nb) n_pf = p.cnt_in[b_nx + (int)gridDim.x];
@@ -621,9 +621,10 @@ tile_kernel(const TileParams p) {
 #endif
   if (WARP_EMIT) {
   if (PERSIST && EMIT == EMIT_SPLITTER) {
-    // (warp-direct emission has no barrier after this one: what the NEXT iteration touches before its first barrier
-    // is prepared here -- its counter set, last read during the previous bucket's ranking, is cleared, and its
-    // splitter window / key range (cp.async issued after the first barrier) have landed)
+    // (warp-direct emission has no barrier after this one: what this bucket's emission and the NEXT iteration's first
+    // phase touch must be in place here -- this bucket's splitter window and the next one's key range (cp.async issued
+    // after the first barrier) have landed; the next bucket's counter set is clean: with TK_CLEAR_TOP the upper warps
+    // cleared it at the top of this iteration, otherwise everybody does it now)
     if (!TK_CLEAR_TOP) {
       uint4 *c4 = reinterpret_cast<uint4 *>(S.u.srt.cnt + (cur ^ 1) * SM::PADN);
       for (int i = tid; i < SM::PADN / 4; i += THREADS) c4[i] = make_uint4(0u, 0u, 0u, 0u);
