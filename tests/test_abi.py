@@ -109,3 +109,32 @@ def test_host_prefault_keeps_contents():
     lib.wendy_host_prefault(c.ctypes.data, c.nbytes)
     c[:] = 1.
     assert c.sum() == 5000000.
+
+
+def test_library_is_sm100a_with_tma_in_the_step_kernels_and_no_spills_in_the_plain_one(lib):
+    """What DESIGN.md section 3.0 says about the built library, read from its SASS: sm_100a cubins only, bulk
+    copies (UBLKCP) and mbarrier waits (SYNCS) in the persistent step kernel, whose plain instance -- the
+    dominant kernel of the bench -- does not touch local memory (no register spills)."""
+    import shutil
+    import subprocess
+    if shutil.which('cuobjdump') is None:
+        pytest.skip('cuobjdump is not installed')
+    so = os.path.join(ROOT, 'wendy_b200', 'libwendy_b200.so')
+    archs = set(re.findall(r'arch = (sm_\w+)', subprocess.run(['cuobjdump', '-lelf', so], capture_output=True, text=True).stdout
+                           + subprocess.run(['cuobjdump', so], capture_output=True, text=True).stdout))
+    assert archs <= {'sm_100a'}, archs
+    sass = subprocess.run(['cuobjdump', '-sass', so], capture_output=True, text=True).stdout
+    fn, body = None, {}
+    for line in sass.splitlines():
+        m = re.search(r'Function : (\S+)', line)
+        if m:
+            fn = m.group(1)
+            body[fn] = []
+        elif fn is not None:
+            body[fn].append(line)
+    plain = [k for k in body if re.search(r'tile_kernelILi2048ELi512ELi0ELi0ELi1ELi1ELi2E', k)]
+    assert len(plain) == 1, plain
+    text = '\n'.join(body[plain[0]])
+    assert 'UBLKCP' in text and 'SYNCS' in text
+    assert not re.search(r'\b(STL|LDL)\b', text)
+    assert any('UBLKCP' in '\n'.join(v) for k, v in body.items() if 'wstep_kernel' in k)
