@@ -609,6 +609,25 @@ def main():
             del mg
         except Exception as exc:  # noqa: BLE001
             var['unequal masses'] = {'error': str(exc)[:200]}
+        # GPU yard-stick for the radix path: torch.sort of N fp64 keys on this GPU -- CUB's
+        # DeviceRadixSort on 64-bit keys with 64-bit indices -- beside the library's own (u64 key, u32 index)
+        # onesweep sort, which the forced-radix leg above runs once per sub-step (8.8 ms at N=1e8 on its own,
+        # profiles/r02/kernels_tour_N1e8.md).  Library code: a reference point, not on any product path.
+        try:
+            keys = torch.randn(n, dtype=torch.float64, device='cuda')
+            torch.sort(keys)
+            y0, y1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            y0.record()
+            for _ in range(3):
+                torch.sort(keys)
+            y1.record()
+            torch.cuda.synchronize()
+            var['yardstick: torch.sort of N fp64 keys (CUB radix sort, library code)'] = {'ms_per_sort': y0.elapsed_time(y1) / 3.}
+            del keys
+            torch.cuda.empty_cache()
+        except Exception as exc:  # noqa: BLE001
+            var['yardstick: torch.sort'] = {'error': str(exc)[:200]}
         out['variants'] = var
 
     # ---- end to end through the public generator API, host buffers --------------------------
