@@ -623,11 +623,12 @@ def main():
                 torch.sort(keys)
             y1.record()
             torch.cuda.synchronize()
-            var['yardstick: torch.sort of N fp64 keys (CUB radix sort, library code)'] = {'ms_per_sort': y0.elapsed_time(y1) / 3.}
+            out['yardstick'] = {'what': 'torch.sort of N fp64 keys on this GPU (CUB radix sort; library code, a reference point only)',
+                                'ms_per_sort': y0.elapsed_time(y1) / 3.}
             del keys
             torch.cuda.empty_cache()
         except Exception as exc:  # noqa: BLE001
-            var['yardstick: torch.sort'] = {'error': str(exc)[:200]}
+            out['yardstick'] = {'error': str(exc)[:200]}
         out['variants'] = var
 
     # ---- end to end through the public generator API, host buffers --------------------------
